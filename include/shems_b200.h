@@ -1,0 +1,271 @@
+/*
+ * shems_b200.h — flat C ABI of libshems_b200.so (CUDA, sm_100a).
+ *
+ * This is the drop-in boundary for ONE hot path of RL-SHEMS: the batched
+ * `shems_LU1` environment step/reset and the DDPG minibatch update.  The
+ * reference has no FFI of its own (it is Julia multiple dispatch on the
+ * Reinforce.jl protocol); every entry point below names the reference
+ * function (file:line under /root/reference/RL-SHEMS/) it stands in for.  A
+ * Julia maintainer binds these with `ccall((:sym, "libshems_b200"), Cint, …)`
+ * — see INTEGRATION.md and the shim in <package>/julia/ShemsB200.jl.
+ *
+ * Conventions
+ *   - Every function returns an int32 status: 0 = ok, <0 = error (enum below).
+ *     A human-readable message for the last error on the calling thread is
+ *     returned by shems_last_error().  Nothing throws or aborts across the ABI.
+ *   - Handles are opaque; the library owns all device memory it allocates.
+ *   - Pointers named *_dev are DEVICE pointers borrowed for the call (async:
+ *     until the handle's stream is synchronised); pointers named *_host are
+ *     host pointers, copied before return.
+ *   - Batched arrays are structure-of-arrays: a "[k][N]" array stores field k
+ *     of env n at offset k*N + n (coalesced over n).
+ *   - A handle is not thread-safe; one handle <-> one CUDA stream.  Different
+ *     handles may be used from different threads.
+ *   - There is NO CPU fallback: on a box without a CUDA device every compute
+ *     entry point fails with SHEMS_ERR_CUDA.
+ */
+#ifndef SHEMS_B200_H
+#define SHEMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHEMS_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------ status */
+enum {
+  SHEMS_OK = 0,
+  SHEMS_ERR_INVALID = -1,  /* bad argument (NULL, size, range)                         */
+  SHEMS_ERR_CUDA = -2,     /* CUDA runtime error, or no device                          */
+  SHEMS_ERR_BOUNDS = -3,   /* row idx+1 > nrows: Julia BoundsError, shems_LU1.jl:266-268 */
+  SHEMS_ERR_KEY = -4,      /* unknown charger id: Julia KeyError, shems_LU1.jl:95        */
+  SHEMS_ERR_STATE = -5,    /* call order (e.g. step before reset, sample from empty)    */
+  SHEMS_ERR_NCCL = -6
+};
+
+SHEMS_API const char* shems_last_error(void);
+SHEMS_API int32_t shems_version(void);
+/* number of visible CUDA devices (0 on a CPU-only box; never an error) */
+SHEMS_API int32_t shems_device_count(void);
+
+/* ------------------------------------------------------------- environment */
+#define SHEMS_STATE_SIZE 9   /* ShemsState, shems_LU1.jl:101-111 */
+#define SHEMS_ACTION_SIZE 2  /* ShemsAction, shems_LU1.jl:146-149 */
+#define SHEMS_TRACE_COLS 23  /* results row, shems_LU1.jl:476-478 */
+#define SHEMS_SERIES_COLS 8
+
+/* state field order (ShemsState, shems_LU1.jl:101-111) */
+enum {
+  SHEMS_S_SOC_B = 0, SHEMS_S_SOC_EV, SHEMS_S_C_EV, SHEMS_S_D_E, SHEMS_S_G_E,
+  SHEMS_S_P_BUY, SHEMS_S_H_COS, SHEMS_S_H_SIN, SHEMS_S_SEASON
+};
+
+/* input-series columns the env reads (shems_LU1.jl:251-260, 268-279), in the
+ * order of state fields 1..8.  Host layout handed to shems_create is
+ * [SHEMS_SERIES_COLS][nrows] float32 (CSV Float64/Int values converted to
+ * Float32 exactly as `env.state.x = df[idx, :col]` converts them). */
+enum {
+  SHEMS_COL_SOC_EV = 0,     /* :soc_ev        */
+  SHEMS_COL_H_COUNTDOWN,    /* :h_countdown   */
+  SHEMS_COL_ELECTKWH,       /* :electkwh      */
+  SHEMS_COL_PV_GENERATION,  /* :PV_generation */
+  SHEMS_COL_P_BUY,          /* :p_buy         */
+  SHEMS_COL_HOUR_COS,       /* :hour_cos      */
+  SHEMS_COL_HOUR_SIN,       /* :hour_sin      */
+  SHEMS_COL_SEASON          /* :season        */
+};
+
+/* trace columns (shems_LU1.jl:476-478; CSV header memory_plotting_saving.jl:172-174) */
+enum {
+  SHEMS_T_INDEX = 0, SHEMS_T_C_EV, SHEMS_T_EV_TARGET, SHEMS_T_EV, SHEMS_T_SOC_EV,
+  SHEMS_T_REWARD, SHEMS_T_PROFIT, SHEMS_T_DISCOMFORT, SHEMS_T_PENALTY, SHEMS_T_PV_DE,
+  SHEMS_T_B_DE, SHEMS_T_GR_DE, SHEMS_T_PV_B, SHEMS_T_PV_GR, SHEMS_T_PV_EV, SHEMS_T_B_EV,
+  SHEMS_T_GR_EV, SHEMS_T_EX_EV, SHEMS_T_GR_B, SHEMS_T_B_GR, SHEMS_T_B, SHEMS_T_B_TARGET,
+  SHEMS_T_SOC_B
+};
+
+/* Module-level constants of shems_LU1.jl:40-43, 67-99 with their Julia types
+ * (the Float64 fields matter: they drive the Float32->Float64 promotions). */
+typedef struct ShemsParams {
+  float pv_eta;                /* PV(1f0)                         :92  */
+  float b_eta;                 /* Battery.eta = 0.95f0            :95  */
+  float b_soc_min;             /* 0f0                             :95  */
+  float b_soc_max;             /* capacities[id][2]               :47-59 */
+  double b_rate_max;           /* capacities[id][3] (Float64)     :75  */
+  float b_loss;                /* 0.00003f0                       :95  */
+  float ev_soc_min;            /* 0f0                             :97  */
+  float ev_soc_max;            /* capacities[id][1]               :47-59 */
+  float ev_rate_max;           /* 11f0                            :97  */
+  float penalty_weight;        /* 0.1f0                           :43  */
+  double sell_discount;        /* Float64(0.2f0)                  :99, :86 */
+  double discomfort_weight_ev; /* Float64(0.01f0)                 :40, :87 */
+  double disc_pot;             /* Float64(2f0)                    :41, :88 */
+} ShemsParams;
+
+/* capacities[charger_id] lookup (shems_LU1.jl:45-59, 92-99).  Unknown id ->
+ * SHEMS_ERR_KEY (the reference raises KeyError at module load). */
+SHEMS_API int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* out);
+
+typedef struct ShemsEnv ShemsEnv; /* N instances of `Shems` (shems_LU1.jl:169-177) */
+
+/* Shems(maxsteps, path) for n_envs instances (shems_LU1.jl:203) — the series
+ * is parsed ONCE by the caller and uploaded here (the reference re-parses the
+ * CSV at :217 and :265 on every reset/step).  device = CUDA ordinal. */
+SHEMS_API int32_t shems_create(const ShemsParams* params, const float* series_host,
+                               int32_t nrows, int32_t maxsteps, int64_t n_envs,
+                               int32_t device, ShemsEnv** out);
+SHEMS_API int32_t shems_destroy(ShemsEnv* env);
+/* use an existing CUDA stream (cudaStream_t) for all launches of this handle */
+SHEMS_API int32_t shems_set_stream(ShemsEnv* env, void* cuda_stream);
+SHEMS_API int32_t shems_sync(ShemsEnv* env);
+
+/* reset!(env; rng) for all instances (shems_LU1.jl:206-262).
+ *   mode SHEMS_RESET_DETERMINISTIC  == `rng == -1`: idx = 1, Soc_b = 0.5*(soc_min+soc_max).
+ *   mode SHEMS_RESET_HOST_DRAWS     : the caller supplies the two draws the reference
+ *        takes from MersenneTwister(rng) (:224-225): idx0_host[n] in 1..nrows-maxsteps and
+ *        socb0_host[n]; the window-shift loop (:227-246) runs on the device.
+ *   mode SHEMS_RESET_DEVICE_PHILOX  : draws come from Philox4x32-10 keyed by (seed, global
+ *        env id) — Julia's MersenneTwister stream is not reproduced.
+ * env_id_base offsets the global env id (multi-GPU sharding: results do not depend on the
+ * number of ranks). */
+enum { SHEMS_RESET_DETERMINISTIC = 0, SHEMS_RESET_HOST_DRAWS = 1, SHEMS_RESET_DEVICE_PHILOX = 2 };
+SHEMS_API int32_t shems_reset(ShemsEnv* env, int32_t mode, const int32_t* idx0_host,
+                              const float* socb0_host, uint64_t seed, int64_t env_id_base);
+
+/* step!(env, s, a; track) for all instances (shems_LU1.jl:343-485).
+ *   act_dev   [2][N] float: track >= 0 -> (B_target, EV_target) in [0,1]; track < 0 -> (B, EV) kWh.
+ *   track     0 learning, 1 DRL inference, <0 rule-based bookkeeping (only the sign is used, :346-354, :466-471).
+ *   reward_dev[N] float or NULL: Float32(env.reward).
+ *   obs_dev   [9][N] float or NULL: Vector{Float32}(env.state) after the step (NULL: read it
+ *             later through shems_state_ptr — the handle's own state IS that array).
+ *   trace_dev [23][N] double or NULL: the `results` row (:476-478).
+ * Fails with SHEMS_ERR_BOUNDS (nothing launched) when any instance would read row idx+1 > nrows. */
+SHEMS_API int32_t shems_step(ShemsEnv* env, const float* act_dev, int32_t track,
+                             float* reward_dev, float* obs_dev, double* trace_dev);
+
+/* action(env, track) — the rule-based controller (shems_LU1.jl:318-340) -> (B, EV) [2][N] */
+SHEMS_API int32_t shems_action_rule(ShemsEnv* env, float* bev_dev);
+/* action(env, a::ShemsAction) (shems_LU1.jl:283-316): targets [2][N] -> feasible (B, EV) [2][N] */
+SHEMS_API int32_t shems_action_drl(ShemsEnv* env, const float* target_dev, float* bev_dev);
+/* finished(env, s') (shems_LU1.jl:487-502): always 0, kept for API completeness */
+SHEMS_API int32_t shems_finished(const ShemsEnv* env, int32_t* out);
+
+/* env.state / env.idx / env.step accessors (shems_LU1.jl:169-177) */
+SHEMS_API int32_t shems_state_ptr(ShemsEnv* env, float** obs_dev /* [9][N] */, int32_t** idx_dev /* [N], 1-based */);
+SHEMS_API int32_t shems_get_state(ShemsEnv* env, float* obs_host /* [9][N] */, int32_t* idx_host /* [N] or NULL */);
+SHEMS_API int32_t shems_set_state(ShemsEnv* env, const float* obs_host /* [9][N] */, const int32_t* idx_host /* [N] */);
+SHEMS_API int32_t shems_get_step(const ShemsEnv* env, int32_t* step);
+SHEMS_API int64_t shems_num_envs(const ShemsEnv* env);
+
+/* Fused T-step rollout: episode!/populate_memory/inference loops with the policy evaluated
+ * on the device (DDPG.jl:186-242, memory_plotting_saving.jl:9-29, 62-89).  State stays in
+ * registers for T steps; what is written per step is chosen by the sink pointers. */
+enum {
+  SHEMS_POLICY_RULE = 0,    /* a = action(env, track); step!(env, s, a, track=-0.5)  (DDPG.jl:209-212) */
+  SHEMS_POLICY_RANDOM = 1,  /* a = 2U-1 (stored), scaled to [0,1]^2, track=0        (memory_plotting_saving.jl:14-21) */
+  SHEMS_POLICY_TAPE = 2     /* scaled targets read from tape_dev [T][2][N], track=0 */
+};
+typedef struct ShemsReplay ShemsReplay;
+typedef struct ShemsRolloutArgs {
+  int32_t policy;
+  int32_t n_steps;            /* T */
+  uint64_t seed;              /* Philox key for SHEMS_POLICY_RANDOM */
+  int64_t env_id_base;        /* global env id offset (sharding) */
+  const float* tape_dev;      /* [T][2][N] or NULL */
+  double* ep_return_dev;      /* [N] sum of rewards (Float64, DDPG.jl:223) or NULL */
+  ShemsReplay* replay;        /* push (s, a, r, s', done=0) per env-step or NULL */
+  double* trace_dev;          /* [T][23][N] or NULL */
+  float* obs_traj_dev;        /* [T][9][N] post-step observations or NULL */
+  float* reward_traj_dev;     /* [T][N] or NULL */
+} ShemsRolloutArgs;
+SHEMS_API int32_t shems_rollout(ShemsEnv* env, const ShemsRolloutArgs* args);
+
+/* ----------------------------------------------------------- replay memory */
+/* memory = CircularBuffer{Any}(MEM_SIZE) of [s, a, r, s', done] (input.jl:140,
+ * memory_plotting_saving.jl:46-47), device-resident SoA ring. */
+SHEMS_API int32_t replay_create(int64_t capacity, int32_t device, ShemsReplay** out);
+SHEMS_API int32_t replay_destroy(ShemsReplay* rp);
+SHEMS_API int32_t replay_set_stream(ShemsReplay* rp, void* cuda_stream);
+SHEMS_API int64_t replay_length(const ShemsReplay* rp);
+SHEMS_API int64_t replay_capacity(const ShemsReplay* rp);
+/* remember(s, a, r, s', done) for n transitions (memory_plotting_saving.jl:46-47);
+ * a is the UNSCALED action in [-1,1] (DDPG.jl:229). done_dev may be NULL (finished == false). */
+SHEMS_API int32_t replay_push(ShemsReplay* rp, const float* s_dev /*[9][n]*/, const float* a_dev /*[2][n]*/,
+                              const float* r_dev /*[n]*/, const float* s2_dev /*[9][n]*/,
+                              const float* done_dev /*[n] or NULL*/, int64_t n);
+/* getData(batch) (memory_plotting_saving.jl:31-42): i.i.d. WITH replacement.
+ * idx_host != NULL: the caller's 0-based logical indices (0 = oldest), else Philox(seed).
+ * Outputs are device arrays [9][B], [2][B], [B], [9][B], [B]. */
+SHEMS_API int32_t replay_sample(ShemsReplay* rp, int32_t batch, const int32_t* idx_host, uint64_t seed,
+                                float* s_dev, float* a_dev, float* r_dev, float* s2_dev, float* done_dev);
+/* min_max_buffer(n) (memory_plotting_saving.jl:50-53): min/max of s over a with-replacement
+ * sample of size n_samples -> s_min_host[9], s_max_host[9]. */
+SHEMS_API int32_t replay_minmax(ShemsReplay* rp, int64_t n_samples, const int32_t* idx_host, uint64_t seed,
+                                float* s_min_host, float* s_max_host);
+/* host copies for tests / checkpoints: logical order, oldest first; arrays [k][len] */
+SHEMS_API int32_t replay_get(ShemsReplay* rp, float* s_host, float* a_host, float* r_host,
+                             float* s2_host, float* done_host);
+
+/* ----------------------------------------------------------- DDPG learner */
+typedef struct DdpgParams {
+  int32_t state_size;   /* STATE_SIZE = 9            input.jl:180 */
+  int32_t action_size;  /* ACTION_SIZE = 2           input.jl:181 */
+  int32_t l1, l2;       /* L1, L2 (250, 500 tuned)   README.md:68-86 */
+  int32_t batch;        /* BATCH_SIZE (120 tuned)    */
+  float gamma;          /* γ   DDPG.jl:133 */
+  float tau;            /* τ   DDPG.jl:142-143 */
+  float lr_actor;       /* η_act,  ADAM(η_act)   input.jl:126-127 */
+  float lr_critic;      /* η_crit, ADAM(η_crit) */
+  double adam_beta1;    /* 0.9   (Flux.ADAM default) */
+  double adam_beta2;    /* 0.999 */
+  double adam_eps;      /* 1e-8  (Flux 0.12.1 const ϵ) */
+  float act_lo[2];      /* ACTION_BOUND_LO input.jl:183 */
+  float act_hi[2];      /* ACTION_BOUND_HI input.jl:182 */
+  int32_t use_tensor_cores; /* 0: fp32 SIMT GEMMs (parity path); 1: TF32 tensor cores where the batch allows */
+} DdpgParams;
+
+enum { DDPG_NET_ACTOR = 0, DDPG_NET_CRITIC = 1, DDPG_NET_ACTOR_TARGET = 2, DDPG_NET_CRITIC_TARGET = 3 };
+
+typedef struct Ddpg Ddpg;
+SHEMS_API int32_t ddpg_default_params(DdpgParams* out);
+/* builds actor/critic and their targets (DDPG.jl:30-46) with zero weights; call ddpg_init or ddpg_set_params */
+SHEMS_API int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out);
+SHEMS_API int32_t ddpg_destroy(Ddpg* h);
+SHEMS_API int32_t ddpg_set_stream(Ddpg* h, void* cuda_stream);
+SHEMS_API int32_t ddpg_sync(Ddpg* h);
+/* glorot_uniform hidden layers, U(-3e-3,3e-3) last layers, zero biases, targets = copies
+ * (DDPG.jl:21-22, 30-46) from Philox(seed) (Julia's MersenneTwister stream is not reproduced). */
+SHEMS_API int32_t ddpg_init(Ddpg* h, uint64_t seed);
+/* Flux layout: layer weight is out×in column-major (element (o,i) at o + out*i), bias[out].
+ * layer in 0..2.  Setting ACTOR/CRITIC does not touch the targets. */
+SHEMS_API int32_t ddpg_set_layer(Ddpg* h, int32_t net, int32_t layer, const float* w_host, const float* b_host);
+SHEMS_API int32_t ddpg_get_layer(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host);
+SHEMS_API int64_t ddpg_num_params(const Ddpg* h, int32_t net);
+/* s_min, s_max of normalize() (memory_plotting_saving.jl:55-57; frozen after driver:30) */
+SHEMS_API int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* s_max_host);
+/* act(normalize(s); train) + scale_action (DDPG.jl:148-184) for n states:
+ *   obs_dev [9][n] raw states; a_dev [2][n] clamp(actor(s_n)+noise,-1,1); scaled_dev [2][n] or NULL.
+ *   noise_dev [2][n]: caller-provided noise (added as is) or NULL -> sigma*N(0,1) from Philox(seed, step)
+ *   when sigma > 0 (GNoise, DDPG.jl:57-61), no noise when sigma == 0 (train == false). */
+SHEMS_API int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step,
+                           int64_t env_id_base, const float* noise_dev, float* a_dev, float* scaled_dev);
+/* replay() (DDPG.jl:121-145) n_updates times: sample -> TD target -> critic step -> actor step
+ * -> Polyak.  idx_host ([n_updates][batch], 0-based logical indices) or NULL -> Philox(seed, update counter). */
+SHEMS_API int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed);
+/* the same update on a caller-supplied minibatch (device, [9][B],[2][B],[B],[9][B],[B]) */
+SHEMS_API int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev,
+                                    const float* s2_dev, const float* done_dev);
+/* last update's loss_crit / loss_act values (DDPG.jl:114-119) */
+SHEMS_API int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act);
+/* gradients of the last update (Flux layout, like ddpg_get_layer); net = ACTOR or CRITIC */
+SHEMS_API int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host);
+/* flat fp32 gradient buffer on the device (critic params then actor params) */
+SHEMS_API int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHEMS_B200_H */

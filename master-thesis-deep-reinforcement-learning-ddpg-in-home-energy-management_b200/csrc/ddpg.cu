@@ -1,0 +1,713 @@
+// ddpg.cu — the DDPG minibatch update of RL-SHEMS/algorithms/DDPG.jl (replay :121-145, act :148-176,
+// soft_update! :99-103, update_model! :105-108, losses :114-119) on one GPU.
+//
+// Design (B200):
+//  * All four nets live in flat fp32 buffers  [W1|b1|W2|b2|W3|b3]; a layer weight is stored exactly
+//    as Flux stores it (out×in column-major == Wt[in][out] row-major, `out` contiguous), so
+//    get/set_layer are plain copies and every GEMM reads weights coalesced along `out`.
+//  * Activations are sample-major [B][width].
+//  * One generic tiled SGEMM kernel (32×32×32 tiles, 128 threads, 2×4 register blocking, register
+//    double buffering) runs every contraction; a launch carries up to 4 independent problems
+//    (blockIdx.z) so that e.g. actor_target-L1, critic-L1 and actor-L1 share one dependent phase.
+//    Bias/ReLU/tanh, ReLU-mask, tanh-grad, TD-target and the bias-gradient column sums are fused
+//    into its epilogue.  At B=120 the update is launch/latency bound (308 MFLOP ≈ 4 µs of fp32
+//    SIMT peak) so the whole sequence (21 dependent phases) is captured once in a CUDA graph.
+//  * Adam (+ Polyak for both targets) is one fused elementwise kernel over the flat buffers, with
+//    the Float64 element math Flux.ADAM performs when β, ϵ are Float64.
+//  * Minibatch sampling is on the device: Philox indices -> gather from the replay ring ->
+//    normalize() fused, so no host round trip per update (the reference does 5 H2D copies).
+#include <new>
+#include <vector>
+#include <string.h>
+#include <stddef.h>
+#include <math.h>
+
+#include "common.h"
+#include "philox.cuh"
+
+// ----------------------------------------------------------------------------- GEMM
+enum { EPI_NONE = 0, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_ID, EPI_RELU_MASK, EPI_TD_TARGET, EPI_TANH_GRAD, EPI_SCALE_MASK };
+
+struct GemmProblem {
+  const float* A; long long sAm, sAk;  // A(m,k) = A[m*sAm + k*sAk]
+  const float* B; long long sBk, sBn;  // B(k,n) = B[k*sBk + n*sBn]
+  float* C; long long ldc;             // C(m,n) = C[m*ldc + n]
+  int M, N, K;
+  int epi;
+  const float* bias;   // [N]                         (BIAS_*, TD_TARGET)
+  const float* aux;    // RELU_MASK/SCALE_MASK: H(m,n) with ld auxld; TANH_GRAD: Y(m,n); TD_TARGET: r[m]
+  long long auxld;
+  const float* aux2;   // TD_TARGET: done[m]
+  const float* aux3;   // TD_TARGET: q[m] (critic output on (s,a))
+  float* out2;         // TD_TARGET: dq[m] = 2 (q - y) / B
+  float* dbias;        // column sums of B(k,n) over k (bias gradient), written by the m-tile 0 CTAs
+  float alpha;         // TD_TARGET: gamma; SCALE_MASK: scale
+  float inv_batch;     // TD_TARGET: 1/B
+};
+struct GemmBatch { GemmProblem p[4]; int count; };
+
+#define BM 32
+#define BN 32
+#define BK 32
+#define GEMM_THREADS 128
+#define AS_LD (BM + 2)
+#define BS_LD (BN + 4)
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_batch_kernel(const GemmBatch gb) {
+  const GemmProblem& p = gb.p[blockIdx.z];
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;  // M tiles on grid.x (no 65535 limit for large batches)
+  if (m0 >= p.M || n0 >= p.N) return;
+  __shared__ __align__(16) float As[2][BK][AS_LD];
+  __shared__ __align__(16) float Bs[2][BK][BS_LD];
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;  // thread tile: rows ty*2..+1, cols tx*4..+3
+  // global->smem mapping: 8 elements of each operand per thread, walking the contiguous dimension
+  const bool a_kfast = (p.sAk == 1);
+  const bool b_nfast = (p.sBn == 1);
+  float ra[8], rb[8];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = tid + j * GEMM_THREADS;
+      const int kk_a = a_kfast ? (e & 31) : (e >> 5), mm = a_kfast ? (e >> 5) : (e & 31);
+      const int gm = m0 + mm, gk = k0 + kk_a;
+      ra[j] = (gm < p.M && gk < p.K) ? __ldg(p.A + gm * p.sAm + gk * p.sAk) : 0.0f;
+      const int kk_b = b_nfast ? (e >> 5) : (e & 31), nn = b_nfast ? (e & 31) : (e >> 5);
+      const int gn = n0 + nn, gk2 = k0 + kk_b;
+      rb[j] = (gn < p.N && gk2 < p.K) ? __ldg(p.B + gk2 * p.sBk + gn * p.sBn) : 0.0f;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = tid + j * GEMM_THREADS;
+      const int kk_a = a_kfast ? (e & 31) : (e >> 5), mm = a_kfast ? (e >> 5) : (e & 31);
+      As[buf][kk_a][mm] = ra[j];
+      const int kk_b = b_nfast ? (e >> 5) : (e & 31), nn = b_nfast ? (e & 31) : (e >> 5);
+      Bs[buf][kk_b][nn] = rb[j];
+    }
+  };
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float colsum = 0.0f;
+  const bool want_dbias = (p.dbias != nullptr) && (blockIdx.x == 0) && (tid < BN);
+  const int ntiles = (p.K + BK - 1) / BK;
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) load_tiles((t + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float2 a = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+    }
+    if (want_dbias) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) colsum += Bs[buf][kk][tid];
+    }
+    if (t + 1 < ntiles) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+  if (want_dbias && n0 + tid < p.N) p.dbias[n0 + tid] = colsum;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      switch (p.epi) {
+        case EPI_BIAS_RELU: v += p.bias[n]; v = v > 0.0f ? v : 0.0f; break;
+        case EPI_BIAS_TANH: v += p.bias[n]; v = tanhf(v); break;
+        case EPI_BIAS_ID: v += p.bias[n]; break;
+        case EPI_RELU_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v : 0.0f; break;
+        case EPI_SCALE_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v * p.alpha : 0.0f; break;
+        case EPI_TANH_GRAD: { const float y = p.aux[m * p.auxld + n]; v = v * (1.0f - y * y); } break;
+        case EPI_TD_TARGET: {  // y = r + γ(1-done) q'   (DDPG.jl:133);  dq = 2 (q - y) / B  (d mse / d q)
+          const float q2 = v + p.bias[n];
+          const float y = p.aux[m] + (p.alpha * (1.0f - p.aux2[m])) * q2;
+          v = y;
+          p.out2[m] = 2.0f * (p.aux3[m] - y) * p.inv_batch;
+        } break;
+        default: break;
+      }
+      p.C[m * p.ldc + n] = v;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- learner state
+struct LayerDims { int in, out; long long w_off, b_off; };
+struct NetDims { LayerDims l[3]; long long n_params; };
+
+struct DdpgCtrl {  // device-side control block read by the gather kernel (graph replays need no host patching)
+  unsigned long long seed;
+  unsigned update;      // counts updates; Philox counter for minibatch draws
+  int use_idx;          // 1: indices supplied in idx buffer (consumed batch by batch)
+  long long len, head, cap;
+  int idx_cursor;
+  int pad;
+  double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
+};
+
+struct Ddpg {
+  int device;
+  cudaStream_t stream;
+  DdpgParams p;
+  NetDims dims[2];       // 0 actor-shaped, 1 critic-shaped
+  float* net[4];         // flat params
+  float* grad[2];        // flat grads (actor, critic) — contiguous: grad[1] then grad[0] in gradbuf
+  float* gradbuf;
+  float* adam_m[2]; float* adam_v[2];
+  double beta_pow[2][2];
+  long long n_updates;
+  float* norm;           // [18] s_min | s_max
+  // minibatch + activations (B rows)
+  float *xs, *xs2, *xspi, *r, *done;
+  float *t_h1, *t_h2, *c_h1, *c_h2, *a_h1, *a_h2, *tc_h1, *tc_h2, *p_h1, *p_h2;
+  float *q, *y, *dq, *qpi;
+  float *dz2, *dz1, *dzp2, *dzp1, *dza3, *dza2, *dza1;
+  float* loss_scratch;   // [2]
+  DdpgCtrl* ctrl;
+  int32_t* idx_dev; long long idx_cap;
+  // act() scratch (n rows)
+  float *act_x, *act_h1, *act_h2, *act_y; long long act_cap;
+  cudaGraph_t graph; cudaGraphExec_t graph_exec; const ShemsReplay* graph_rp;
+  float* dqpi;     // [B] constant -1/B: d(-mean q)/dq
+  bool ctrl_init;
+};
+
+static void make_dims(NetDims& d, int in, int l1, int l2, int out) {
+  const int ins[3] = {in, l1, l2}, outs[3] = {l1, l2, out};
+  long long off = 0;
+  for (int k = 0; k < 3; ++k) {
+    d.l[k].in = ins[k]; d.l[k].out = outs[k];
+    d.l[k].w_off = off; off += (long long)ins[k] * outs[k];
+    d.l[k].b_off = off; off += outs[k];
+  }
+  d.n_params = off;
+}
+static inline const NetDims& dims_of(const Ddpg* h, int net) { return h->dims[(net == DDPG_NET_CRITIC || net == DDPG_NET_CRITIC_TARGET) ? 1 : 0]; }
+
+extern "C" int32_t ddpg_default_params(DdpgParams* p) {
+  REQUIRE(p, SHEMS_ERR_INVALID, "ddpg_default_params: NULL");
+  memset(p, 0, sizeof(*p));
+  p->state_size = 9; p->action_size = 2; p->l1 = 250; p->l2 = 500; p->batch = 120;  // README.md:68-86
+  p->gamma = 0.99f; p->tau = 1e-3f; p->lr_actor = 1e-4f; p->lr_critic = 1e-3f;
+  p->adam_beta1 = 0.9; p->adam_beta2 = 0.999; p->adam_eps = 1e-8;
+  p->act_lo[0] = p->act_lo[1] = 0.0f; p->act_hi[0] = p->act_hi[1] = 1.0f;
+  p->use_tensor_cores = 0;
+  return SHEMS_OK;
+}
+
+#define DMALLOC(ptr, count)                                                                         \
+  do {                                                                                              \
+    cudaError_t _e = cudaMalloc((void**)&(ptr), sizeof(*(ptr)) * (size_t)(count));                  \
+    if (_e == cudaSuccess) _e = cudaMemset((ptr), 0, sizeof(*(ptr)) * (size_t)(count));             \
+    if (_e != cudaSuccess) { shems_set_error("ddpg: cudaMalloc(%s) -> %s", #ptr, cudaGetErrorString(_e)); ddpg_destroy(h); return SHEMS_ERR_CUDA; } \
+  } while (0)
+
+extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) {
+  REQUIRE(p && out, SHEMS_ERR_INVALID, "ddpg_create: NULL argument");
+  REQUIRE(p->state_size == 9 && p->action_size == 2, SHEMS_ERR_INVALID, "ddpg_create: STATE_SIZE/ACTION_SIZE must be 9/2 (shems_LU1)");
+  REQUIRE(p->l1 >= 1 && p->l2 >= 1 && p->batch >= 1, SHEMS_ERR_INVALID, "ddpg_create: l1=%d l2=%d batch=%d", p->l1, p->l2, p->batch);
+  REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "ddpg_create: no CUDA device (this library has no CPU fallback)");
+  GUARD(device);
+  Ddpg* h = new (std::nothrow) Ddpg();
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_create: out of host memory");
+  memset(h, 0, sizeof(*h));
+  h->device = device; h->p = *p;
+  const int S = p->state_size, A = p->action_size, B = p->batch, l1 = p->l1, l2 = p->l2, C = S + A;
+  make_dims(h->dims[0], S, l1, l2, A);
+  make_dims(h->dims[1], C, l1, l2, 1);
+  for (int n = 0; n < 4; ++n) DMALLOC(h->net[n], dims_of(h, n).n_params);
+  const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
+  DMALLOC(h->gradbuf, na + nc);
+  h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + nc;
+  DMALLOC(h->adam_m[0], na); DMALLOC(h->adam_v[0], na); DMALLOC(h->adam_m[1], nc); DMALLOC(h->adam_v[1], nc);
+  DMALLOC(h->norm, 18);
+  DMALLOC(h->xs, (long long)B * C); DMALLOC(h->xs2, (long long)B * C); DMALLOC(h->xspi, (long long)B * C);
+  DMALLOC(h->r, B); DMALLOC(h->done, B);
+  DMALLOC(h->t_h1, (long long)B * l1); DMALLOC(h->t_h2, (long long)B * l2); DMALLOC(h->c_h1, (long long)B * l1); DMALLOC(h->c_h2, (long long)B * l2);
+  DMALLOC(h->a_h1, (long long)B * l1); DMALLOC(h->a_h2, (long long)B * l2); DMALLOC(h->tc_h1, (long long)B * l1); DMALLOC(h->tc_h2, (long long)B * l2);
+  DMALLOC(h->p_h1, (long long)B * l1); DMALLOC(h->p_h2, (long long)B * l2);
+  DMALLOC(h->q, B); DMALLOC(h->y, B); DMALLOC(h->dq, B); DMALLOC(h->qpi, B);
+  DMALLOC(h->dz2, (long long)B * l2); DMALLOC(h->dz1, (long long)B * l1); DMALLOC(h->dzp2, (long long)B * l2); DMALLOC(h->dzp1, (long long)B * l1);
+  DMALLOC(h->dza3, (long long)B * A); DMALLOC(h->dza2, (long long)B * l2); DMALLOC(h->dza1, (long long)B * l1);
+  DMALLOC(h->loss_scratch, 2);
+  DMALLOC(h->ctrl, 1);
+  DMALLOC(h->dqpi, B);
+  {
+    std::vector<float> c((size_t)B, -1.0f / (float)B);
+    cudaMemcpy(h->dqpi, c.data(), sizeof(float) * (size_t)B, cudaMemcpyHostToDevice);
+    DdpgCtrl ctl; memset(&ctl, 0, sizeof(ctl));
+    for (int n = 0; n < 2; ++n) { ctl.bp[n][0] = p->adam_beta1; ctl.bp[n][1] = p->adam_beta2; }
+    cudaMemcpy(h->ctrl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice);
+  }
+  {
+    float nm[18];
+    for (int k = 0; k < 9; ++k) { nm[k] = 0.0f; nm[9 + k] = 1.0f; }
+    cudaMemcpy(h->norm, nm, sizeof(nm), cudaMemcpyHostToDevice);
+  }
+  for (int n = 0; n < 2; ++n) { h->beta_pow[n][0] = p->adam_beta1; h->beta_pow[n][1] = p->adam_beta2; }
+  *out = h;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_destroy(Ddpg* h) {
+  if (!h) return SHEMS_OK;
+  GUARD(h->device);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->graph) cudaGraphDestroy(h->graph);
+  for (int n = 0; n < 4; ++n) cudaFree(h->net[n]);
+  cudaFree(h->gradbuf);
+  for (int n = 0; n < 2; ++n) { cudaFree(h->adam_m[n]); cudaFree(h->adam_v[n]); }
+  float* bufs[] = {h->norm, h->xs, h->xs2, h->xspi, h->r, h->done, h->t_h1, h->t_h2, h->c_h1, h->c_h2, h->a_h1, h->a_h2, h->tc_h1, h->tc_h2,
+                   h->p_h1, h->p_h2, h->q, h->y, h->dq, h->qpi, h->dz2, h->dz1, h->dzp2, h->dzp1, h->dza3, h->dza2, h->dza1, h->loss_scratch,
+                   h->act_x, h->act_h1, h->act_h2, h->act_y};
+  for (float* b : bufs) cudaFree(b);
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->dqpi);
+  delete h;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_set_stream(Ddpg* h, void* s) {
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_set_stream: NULL handle");
+  h->stream = (cudaStream_t)s;
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_sync(Ddpg* h) {
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_sync: NULL handle");
+  GUARD(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return SHEMS_OK;
+}
+extern "C" int64_t ddpg_num_params(const Ddpg* h, int32_t net) { return (h && net >= 0 && net < 4) ? dims_of(h, net).n_params : 0; }
+
+extern "C" int32_t ddpg_set_layer(Ddpg* h, int32_t net, int32_t layer, const float* w_host, const float* b_host) {
+  REQUIRE(h && net >= 0 && net < 4 && layer >= 0 && layer < 3, SHEMS_ERR_INVALID, "ddpg_set_layer: net=%d layer=%d", net, layer);
+  GUARD(h->device);
+  const LayerDims& L = dims_of(h, net).l[layer];
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (w_host) CUDA_TRY(cudaMemcpy(h->net[net] + L.w_off, w_host, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyHostToDevice));
+  if (b_host) CUDA_TRY(cudaMemcpy(h->net[net] + L.b_off, b_host, sizeof(float) * (size_t)L.out, cudaMemcpyHostToDevice));
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_get_layer(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host) {
+  REQUIRE(h && net >= 0 && net < 4 && layer >= 0 && layer < 3, SHEMS_ERR_INVALID, "ddpg_get_layer: net=%d layer=%d", net, layer);
+  GUARD(h->device);
+  const LayerDims& L = dims_of(h, net).l[layer];
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->net[net] + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
+  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->net[net] + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host) {
+  REQUIRE(h && (net == DDPG_NET_ACTOR || net == DDPG_NET_CRITIC) && layer >= 0 && layer < 3, SHEMS_ERR_INVALID, "ddpg_get_grad: net=%d layer=%d", net, layer);
+  GUARD(h->device);
+  const LayerDims& L = dims_of(h, net).l[layer];
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->grad[net] + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
+  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->grad[net] + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* s_max_host) {
+  REQUIRE(h && s_min_host && s_max_host, SHEMS_ERR_INVALID, "ddpg_set_norm: NULL argument");
+  GUARD(h->device);
+  float nm[18];
+  memcpy(nm, s_min_host, sizeof(float) * 9);
+  memcpy(nm + 9, s_max_host, sizeof(float) * 9);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(h->norm, nm, sizeof(nm), cudaMemcpyHostToDevice));
+  return SHEMS_OK;
+}
+
+// init: glorot_uniform hidden layers / U(-3e-3, 3e-3) last layer / zero bias (DDPG.jl:21-22, 30-46)
+__global__ void ddpg_init_kernel(float* __restrict__ w, long long n, int in, int out, int last, unsigned long long seed, unsigned layer_id) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  uint32_t r[4];
+  philox4x32_10(seed, (uint64_t)e, layer_id, STREAM_INIT, r);
+  const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+  if (!last) w[e] = __fmul_rn(__fsub_rn(u, 0.5f), sqrtf(24.0f / (float)(in + out)));
+  else w[e] = __fsub_rn(__fmul_rn(6e-3f, u), 3e-3f);
+}
+extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_init: NULL handle");
+  GUARD(h->device);
+  for (int n = 0; n < 2; ++n) {
+    const NetDims& d = h->dims[n];
+    CUDA_TRY(cudaMemsetAsync(h->net[n], 0, sizeof(float) * (size_t)d.n_params, h->stream));
+    for (int k = 0; k < 3; ++k) {
+      const long long nw = (long long)d.l[k].in * d.l[k].out;
+      ddpg_init_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(h->net[n] + d.l[k].w_off, nw, d.l[k].in, d.l[k].out, k == 2, seed,
+                                                                            (unsigned)(n * 3 + k));
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h->net[n + 2], h->net[n], sizeof(float) * (size_t)d.n_params, cudaMemcpyDeviceToDevice, h->stream));  // deepcopy :38,:46
+  }
+  return SHEMS_OK;
+}
+
+// ----------------------------------------------------------------------------- minibatch gather + normalize
+// getData() + normalize() (memory_plotting_saving.jl:31-42, 55-57): builds xs = [s_n; a], xs2[:, :9] = s'_n,
+// xspi[:, :9] = s_n, r, done for the B sampled transitions.  src arrays are SoA with leading dim `ld`.
+__global__ void __launch_bounds__(128)
+ddpg_gather_kernel(const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr, const float* __restrict__ rs2,
+                   const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl, const int32_t* __restrict__ idx, int direct,
+                   const float* __restrict__ norm, int B, float* __restrict__ xs, float* __restrict__ xs2, float* __restrict__ xspi,
+                   float* __restrict__ r, float* __restrict__ done) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  long long slot;
+  if (direct) slot = j;
+  else {
+    const long long len = ctrl->len, head = ctrl->head, cap = ctrl->cap;
+    long long li;
+    if (ctrl->use_idx) li = idx[(long long)ctrl->idx_cursor * B + j];
+    else {
+      uint32_t w[4];
+      philox4x32_10(ctrl->seed, (uint64_t)j, ctrl->update, STREAM_SAMPLE, w);
+      li = (long long)(u53(w[0], w[1]) * (double)len);
+      if (li >= len) li = len - 1;
+    }
+    slot = head - len + li;
+    if (slot < 0) slot += cap;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
+    const float sn = __fdiv_rn(__fsub_rn(rs[k * ld + slot], norm[k]), den);
+    const float s2n = __fdiv_rn(__fsub_rn(rs2[k * ld + slot], norm[k]), den);
+    xs[j * 11 + k] = sn; xspi[j * 11 + k] = sn; xs2[j * 11 + k] = s2n;
+  }
+  xs[j * 11 + 9] = ra[slot]; xs[j * 11 + 10] = ra[ld + slot];
+  r[j] = rr[slot];
+  done[j] = rd ? rd[slot] : 0.0f;
+}
+// last node of an update: advance the device-side counters (`βp .= βp .* β` of Flux.ADAM included)
+__global__ void ddpg_ctrl_advance_kernel(DdpgCtrl* ctrl, double b1, double b2) {
+  ctrl->update += 1; ctrl->idx_cursor += 1;
+  for (int n = 0; n < 2; ++n) { ctrl->bp[n][0] *= b1; ctrl->bp[n][1] *= b2; }
+}
+
+// ----------------------------------------------------------------------------- Adam + Polyak
+// Flux.Optimise.ADAM apply! + update! with Float64 β, ϵ (element math in Float64, stored Float32), then
+// soft_update! p_t = (1-τ) p_t + τ p_m for the target of the same net (DDPG.jl:99-108).
+// βp = β^t is read from the device control block so graph replays stay valid.
+__global__ void __launch_bounds__(256)
+adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
+                   double b2, double eps, float eta, const DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
+                   float* __restrict__ target2, const float* __restrict__ model2, long long n2) {
+  const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
+  const float omt = __fsub_rn(1.0f, tau);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const float gj = g[j];
+    const float g2 = __fmul_rn(gj, gj);
+    const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)m[j]), __dmul_rn(1.0 - b1, (double)gj));
+    const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)v[j]), __dmul_rn(1.0 - b2, (double)g2));
+    m[j] = mj; v[j] = vj;
+    const double d = __dmul_rn(__ddiv_rn(__ddiv_rn((double)mj, c1), __dadd_rn(__dsqrt_rn(__ddiv_rn((double)vj, c2)), eps)), (double)eta);
+    const float xn = __fsub_rn(x[j], (float)d);
+    x[j] = xn;
+    if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
+  }
+  // second Polyak pair: the critic target moves together with the actor step (DDPG.jl:142-143)
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
+    target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
+}
+
+// ----------------------------------------------------------------------------- update sequence
+static inline GemmProblem gp_fwd(const float* X, long long ldx, int M, const float* net, const LayerDims& L, float* Y, long long ldy, int epi) {
+  GemmProblem g; memset(&g, 0, sizeof(g));
+  g.A = X; g.sAm = ldx; g.sAk = 1;
+  g.B = net + L.w_off; g.sBk = L.out; g.sBn = 1;  // Wt[in][out]
+  g.C = Y; g.ldc = ldy; g.M = M; g.N = L.out; g.K = L.in; g.epi = epi; g.bias = net + L.b_off;
+  return g;
+}
+// dW[i][o] = sum_b X[b][i] dZ[b][o]   (+ db[o] = sum_b dZ[b][o])
+static inline GemmProblem gp_dw(const float* X, long long ldx, const float* dZ, long long lddz, int B, const LayerDims& L, float* grad) {
+  GemmProblem g; memset(&g, 0, sizeof(g));
+  g.A = X; g.sAm = 1; g.sAk = ldx;
+  g.B = dZ; g.sBk = lddz; g.sBn = 1;
+  g.C = grad + L.w_off; g.ldc = L.out; g.M = L.in; g.N = L.out; g.K = B; g.epi = EPI_NONE; g.dbias = grad + L.b_off;
+  return g;
+}
+// dX[b][i] = sum_o dZ[b][o] Wt[i][o]  (rows i0..i0+ni-1 of Wt), then the epilogue
+static inline GemmProblem gp_dx(const float* dZ, long long lddz, int B, const float* net, const LayerDims& L, int i0, int ni, float* dX, long long lddx,
+                                int epi, const float* aux, long long auxld) {
+  GemmProblem g; memset(&g, 0, sizeof(g));
+  g.A = dZ; g.sAm = lddz; g.sAk = 1;
+  g.B = net + L.w_off + (long long)i0 * L.out; g.sBk = 1; g.sBn = L.out;
+  g.C = dX; g.ldc = lddx; g.M = B; g.N = ni; g.K = L.out; g.epi = epi; g.aux = aux; g.auxld = auxld;
+  return g;
+}
+static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
+  GemmBatch gb; memset(&gb, 0, sizeof(gb));
+  gb.count = count;
+  int gx = 1, gy = 1;
+  for (int i = 0; i < count; ++i) {
+    gb.p[i] = ps[i];
+    gx = max(gx, (ps[i].N + BN - 1) / BN);
+    gy = max(gy, (ps[i].M + BM - 1) / BM);
+  }
+  gemm_batch_kernel<<<dim3(gy, gx, count), GEMM_THREADS, 0, st>>>(gb);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+#define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
+
+// one replay() after the minibatch has been gathered: 20 dependent launches ("DDPG update")
+static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
+  const DdpgParams& p = h->p;
+  const int B = p.batch, l1 = p.l1, l2 = p.l2;
+  const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
+  float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
+  GemmProblem g[4];
+  // P1-P3: actor_target(s'_n) | critic(s_n, a) | actor(s_n)     (DDPG.jl:131, :114, :117)
+  g[0] = gp_fwd(h->xs2, 11, B, actor_t, da.l[0], h->t_h1, l1, EPI_BIAS_RELU);
+  g[1] = gp_fwd(h->xs, 11, B, critic, dc.l[0], h->c_h1, l1, EPI_BIAS_RELU);
+  g[2] = gp_fwd(h->xs, 11, B, actor, da.l[0], h->a_h1, l1, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 3));
+  g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
+  g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);
+  g[2] = gp_fwd(h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 3));
+  g[0] = gp_fwd(h->t_h2, l2, B, actor_t, da.l[2], h->xs2 + 9, 11, EPI_BIAS_TANH);   // a' -> vcat(s'_n, a')
+  g[1] = gp_fwd(h->c_h2, l2, B, critic, dc.l[2], h->q, 1, EPI_BIAS_ID);
+  g[2] = gp_fwd(h->a_h2, l2, B, actor, da.l[2], h->xspi + 9, 11, EPI_BIAS_TANH);    // actor(s_n) -> vcat(s_n, actions)
+  TRY(launch_gemms(st, g, 3));
+  // P4-P6: q' = critic_target(vcat(s'_n, a'));  y = r + γ(1-done) q';  dq = 2(q-y)/B     (:132-133)
+  g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 1));
+  g[0] = gp_fwd(h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 1));
+  g[0] = gp_fwd(h->tc_h2, l2, B, critic_t, dc.l[2], h->y, 1, EPI_TD_TARGET);
+  g[0].aux = h->r; g[0].aux2 = h->done; g[0].aux3 = h->q; g[0].out2 = h->dq; g[0].alpha = p.gamma; g[0].inv_batch = 1.0f / (float)B;
+  TRY(launch_gemms(st, g, 1));
+  // P7-P9: critic backward (:137, :105-108)
+  g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
+  g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
+  TRY(launch_gemms(st, g, 2));
+  g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
+  g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
+  TRY(launch_gemms(st, g, 2));
+  g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
+  TRY(launch_gemms(st, g, 1));
+  // P10: ADAM(η_crit) on the critic
+  adam_polyak_kernel<<<148, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
+                                         p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0);
+  CUDA_TRY(cudaGetLastError());
+  // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
+  g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 1));
+  g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
+  TRY(launch_gemms(st, g, 1));
+  g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);                              // only feeds loss_act
+  g[1] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);          // dX through the critic only
+  TRY(launch_gemms(st, g, 2));
+  // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
+  g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
+  TRY(launch_gemms(st, g, 1));
+  g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
+  TRY(launch_gemms(st, g, 1));
+  // P16-P18: actor backward
+  g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
+  g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
+  TRY(launch_gemms(st, g, 2));
+  g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
+  g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
+  TRY(launch_gemms(st, g, 2));
+  g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
+  g[0].M = 9;  // only the 9 state columns of xs feed the actor
+  TRY(launch_gemms(st, g, 1));
+  // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
+  adam_polyak_kernel<<<148, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
+                                         p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params);
+  CUDA_TRY(cudaGetLastError());
+  // P20: counters
+  ddpg_ctrl_advance_kernel<<<1, 1, 0, st>>>(h->ctrl, p.adam_beta1, p.adam_beta2);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* s, const float* a, const float* r, const float* s2, const float* done, long long ld,
+                          int direct) {
+  const int B = h->p.batch;
+  ddpg_gather_kernel<<<(B + 127) / 128, 128, 0, st>>>(s, a, r, s2, done, ld, h->ctrl, h->idx_dev, direct, h->norm, B, h->xs, h->xs2, h->xspi, h->r, h->done);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+// capture gather(from replay) + body once; replays read everything that changes from the device control block
+static int ensure_graph(Ddpg* h, const ShemsReplay* rp) {
+  if (h->graph_exec && h->graph_rp == rp) return SHEMS_OK;
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  cudaStream_t cs;
+  CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { cudaStreamDestroy(cs); shems_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
+  int st = enqueue_gather(h, cs, rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, 0);
+  if (!st) st = enqueue_update_body(h, cs);
+  e = cudaStreamEndCapture(cs, &h->graph);
+  cudaStreamDestroy(cs);
+  if (st) return st;
+  if (e != cudaSuccess) { shems_set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
+  CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+  h->graph_rp = rp;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed) {
+  REQUIRE(h && rp, SHEMS_ERR_INVALID, "ddpg_update: NULL argument");
+  REQUIRE(n_updates >= 1, SHEMS_ERR_INVALID, "ddpg_update: n_updates=%d", n_updates);
+  REQUIRE(rp->device == h->device, SHEMS_ERR_INVALID, "ddpg_update: replay on device %d, learner on %d", rp->device, h->device);
+  REQUIRE(rp->length > 0, SHEMS_ERR_STATE, "ddpg_update: memory is empty");
+  GUARD(h->device);
+  const int B = h->p.batch;
+  if (idx_host) {
+    const long long need = (long long)n_updates * B;
+    for (long long j = 0; j < need; ++j)
+      REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "ddpg_update: idx[%lld]=%d outside 0..%lld", j, idx_host[j],
+              (long long)rp->length - 1);
+    if (h->idx_cap < need) {
+      cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
+      CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)need));
+      h->idx_cap = need;
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }  // idx pointer is baked into the graph
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)need, cudaMemcpyHostToDevice, h->stream));
+  }
+  // refresh the part of the control block the host owns (seed, ring geometry, index mode); update/bp stay device-owned
+  struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; int pad; } hp;
+  hp.seed = seed; hp.update = (unsigned)h->n_updates; hp.use_idx = idx_host ? 1 : 0; hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
+  hp.idx_cursor = 0; hp.pad = 0;
+  static_assert(sizeof(HostPart) == offsetof(DdpgCtrl, bp), "control block layout");
+  CUDA_TRY(cudaMemcpyAsync(h->ctrl, &hp, sizeof(hp), cudaMemcpyHostToDevice, h->stream));
+  TRY(ensure_graph(h, rp));
+  for (int u = 0; u < n_updates; ++u) CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
+  h->n_updates += n_updates;
+  // asynchronous: the small pageable H2D copies above are staged by the runtime before they return
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev, const float* s2_dev, const float* done_dev) {
+  REQUIRE(h && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "ddpg_update_batch: NULL argument");
+  GUARD(h->device);
+  TRY(enqueue_gather(h, h->stream, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch, 1));
+  TRY(enqueue_update_body(h, h->stream));
+  h->n_updates += 1;
+  return SHEMS_OK;
+}
+
+// loss_crit = mean((q - y)^2) and loss_act = -mean(q_pi) of the last update (DDPG.jl:114-119)
+__global__ void ddpg_loss_kernel(const float* __restrict__ q, const float* __restrict__ y, const float* __restrict__ qpi, int B, float* __restrict__ out) {
+  double lc = 0.0, la = 0.0;
+  for (int j = threadIdx.x; j < B; j += 32) { const float d = q[j] - y[j]; lc += (double)(d * d); la += (double)qpi[j]; }
+  for (int o = 16; o > 0; o >>= 1) { lc += __shfl_xor_sync(0xffffffffu, lc, o); la += __shfl_xor_sync(0xffffffffu, la, o); }
+  if (threadIdx.x == 0) { out[0] = (float)(lc / B); out[1] = (float)(-la / B); }
+}
+extern "C" int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act) {
+  REQUIRE(h && loss_crit && loss_act, SHEMS_ERR_INVALID, "ddpg_get_losses: NULL argument");
+  GUARD(h->device);
+  ddpg_loss_kernel<<<1, 32, 0, h->stream>>>(h->q, h->y, h->qpi, h->p.batch, h->loss_scratch);
+  CUDA_TRY(cudaGetLastError());
+  float out[2];
+  CUDA_TRY(cudaMemcpyAsync(out, h->loss_scratch, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *loss_crit = out[0]; *loss_act = out[1];
+  return SHEMS_OK;
+}
+
+// ----------------------------------------------------------------------------- act
+// normalize (memory_plotting_saving.jl:55-57) of SoA obs [9][n] -> x [n][9]
+__global__ void __launch_bounds__(256)
+ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* __restrict__ norm, float* __restrict__ x) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
+    x[j * 9 + k] = __fdiv_rn(__fsub_rn(obs[k * n + j], norm[k]), den);
+  }
+}
+// clamp(actor + noise, -1, 1) and scale_action (DDPG.jl:172-184); noise: given, or σ·N(0,1) by Box-Muller on Philox
+__global__ void __launch_bounds__(256)
+ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float sigma, unsigned long long seed, long long step,
+                         long long env_id_base, const float* __restrict__ noise, float lo0, float lo1, float hi0, float hi1,
+                         float* __restrict__ a_out, float* __restrict__ scaled_out) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float nz0 = 0.0f, nz1 = 0.0f;
+  if (noise) { nz0 = noise[j]; nz1 = noise[n + j]; }
+  else if (sigma > 0.0f) {
+    uint32_t w[4];
+    philox4x32_10(seed, (uint64_t)(env_id_base + j), (uint32_t)step, STREAM_NOISE, w);
+    const double u1 = 1.0 - u53(w[0], w[1]), u2 = u53(w[2], w[3]);  // u1 in (0,1]
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    nz0 = (float)((double)sigma * (rad * cs));  // Float32.(rand(Normal(μ=0, σ), 2))  (DDPG.jl:57-61)
+    nz1 = (float)((double)sigma * (rad * sn));
+  }
+  float a0 = __fadd_rn(y[j * 2 + 0], nz0), a1 = __fadd_rn(y[j * 2 + 1], nz1);
+  a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
+  a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
+  a_out[j] = a0; a_out[n + j] = a1;
+  if (scaled_out) {  // Float32.(LO .+ (a .+ 1.0) .* 0.5 .* (HI .- LO)) in Float64
+    const double sp0 = (double)__fsub_rn(hi0, lo0), sp1 = (double)__fsub_rn(hi1, lo1);
+    scaled_out[j] = (float)__dadd_rn((double)lo0, __dmul_rn(__dmul_rn(__dadd_rn((double)a0, 1.0), 0.5), sp0));
+    scaled_out[n + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
+  }
+}
+
+extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                            const float* noise_dev, float* a_dev, float* scaled_dev) {
+  REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
+  REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
+  GUARD(h->device);
+  const int l1 = h->p.l1, l2 = h->p.l2;
+  if (h->act_cap < n) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->act_x); cudaFree(h->act_h1); cudaFree(h->act_h2); cudaFree(h->act_y);
+    h->act_x = h->act_h1 = h->act_h2 = h->act_y = nullptr; h->act_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->act_x, sizeof(float) * 9 * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->act_h1, sizeof(float) * (size_t)l1 * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->act_h2, sizeof(float) * (size_t)l2 * (size_t)n));
+    CUDA_TRY(cudaMalloc(&h->act_y, sizeof(float) * 2 * (size_t)n));
+    h->act_cap = n;
+  }
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x);
+  CUDA_TRY(cudaGetLastError());
+  const NetDims& da = h->dims[0];
+  const float* actor = h->net[DDPG_NET_ACTOR];
+  GemmProblem g[1];
+  g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
+  TRY(launch_gemms(h->stream, g, 1));
+  g[0] = gp_fwd(h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, EPI_BIAS_RELU);
+  TRY(launch_gemms(h->stream, g, 1));
+  g[0] = gp_fwd(h->act_h2, l2, (int)n, actor, da.l[2], h->act_y, 2, EPI_BIAS_TANH);
+  TRY(launch_gemms(h->stream, g, 1));
+  ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
+                                                      h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n) {
+  REQUIRE(h && grad_dev && n, SHEMS_ERR_INVALID, "ddpg_grad_buffer: NULL argument");
+  *grad_dev = h->gradbuf;
+  *n = h->dims[0].n_params + h->dims[1].n_params;
+  return SHEMS_OK;
+}

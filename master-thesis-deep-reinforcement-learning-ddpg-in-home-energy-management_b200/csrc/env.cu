@@ -1,0 +1,530 @@
+// env.cu — batched shems_LU1 environment: reset / step / actions / fused rollout kernels and
+// their C-ABI entry points (include/shems_b200.h).  Compiled with -fmad=false (see shems_device.cuh).
+//
+// Data layout in HBM (per handle, N instances):
+//   obs  [9][N] float   structure-of-arrays ShemsState; thread n touches obs[k*N + n] -> every
+//                       access of a warp is one contiguous 128-byte line
+//   idx  [N]    int32   env.idx (1-based row)
+//   series [nrows] x 2 float4 = one 32-byte row per hour:
+//                       (soc_ev, h_countdown, electkwh, PV_generation | p_buy, hour_cos, hour_sin, season)
+//                       read-only, L1/L2 resident (<= 280 KB), fetched with ld.global.nc
+#include <new>
+#include <vector>
+#include <string.h>
+#include <math.h>
+
+#include "common.h"
+#include "philox.cuh"
+#include "shems_device.cuh"
+
+// ----------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+void shems_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* shems_last_error(void) { return g_err; }
+extern "C" int32_t shems_version(void) { return 100; }
+extern "C" int32_t shems_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// ----------------------------------------------------------------------------- params
+extern "C" int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* p) {
+  REQUIRE(p != nullptr, SHEMS_ERR_INVALID, "shems_params_for_charger: out is NULL");
+  // capacities :: Dict{Int, Tuple{Float32, Float32, Float64}}  (shems_LU1.jl:47-59)
+  struct Row { int id; float ev_cap, b_nom; double rate; };
+  static const Row rows[] = {{1, 48.250f, 7.5f, 3.3},  {2, 36.271f, 10.f, 3.3}, {3, 45.508f, 10.f, 3.3}, {4, 78.993f, 11.f, 4.6},
+                             {5, 37.207f, 10.f, 4.6},  {6, 35.816f, 15.f, 4.6}, {7, 36.521f, 12.f, 3.3}, {8, 45.728f, 10.f, 3.3},
+                             {9, 21.935f, 7.5f, 3.3},  {98, 35.816f, 7.5f, 3.3}, {97, 78.993f, 11.f, 4.6}};
+  for (const Row& r : rows) {
+    if (r.id != charger_id) continue;
+    p->pv_eta = 1.0f;
+    p->b_eta = 0.95f;
+    p->b_soc_min = 0.0f;
+    { volatile float nom = r.b_nom, k = 0.9f; volatile float cap = nom * k; p->b_soc_max = cap; }  // `7.5f0 * 0.9f0`: one Float32 rounding
+    p->b_rate_max = r.rate;
+    p->b_loss = 0.00003f;
+    p->ev_soc_min = 0.0f;
+    p->ev_soc_max = r.ev_cap;
+    p->ev_rate_max = 11.0f;
+    p->penalty_weight = 0.1f;
+    p->sell_discount = (double)0.2f;
+    p->discomfort_weight_ev = (double)0.01f;
+    p->disc_pot = 2.0;
+    return SHEMS_OK;
+  }
+  shems_set_error("KeyError: key %d not found in capacities (shems_LU1.jl:47-59)", charger_id);
+  return SHEMS_ERR_KEY;
+}
+
+static DevParams make_dev_params(const ShemsParams& p) {
+  DevParams d;
+  d.pv_eta = p.pv_eta; d.b_eta = p.b_eta; d.smin = p.b_soc_min; d.smax = p.b_soc_max; d.loss = p.b_loss;
+  d.evmin = p.ev_soc_min; d.evmax = p.ev_soc_max; d.evR = p.ev_rate_max; d.pw = p.penalty_weight;
+  volatile float oml = 1.0f - p.b_loss;       // host fp32, rounded once (no x87, no contraction)
+  volatile float omle = oml - 1e-7f;
+  volatile float C = p.ev_soc_max - p.ev_soc_min;
+  volatile float span = p.b_soc_max - p.b_soc_min;
+  d.one_m_l = oml; d.one_m_l_e = omle; d.C = C; d.span = span;
+  d.R_f = (float)p.b_rate_max;
+  d.R = p.b_rate_max; d.sell = p.sell_discount; d.dw = p.discomfort_weight_ev; d.pot = p.disc_pot;
+  d.eta_d = (double)p.b_eta; d.one_m_l_d = (double)d.one_m_l; d.C_d = (double)d.C;
+  d.smax95 = 0.95 * (double)p.b_soc_max;
+  return d;
+}
+
+// ----------------------------------------------------------------------------- series rows
+struct Row8 { float soc_ev, cd, d_e, g_e, p_buy, h_cos, h_sin, season; };
+__device__ __forceinline__ Row8 load_row(const float4* __restrict__ series, int row1 /*1-based*/) {
+  const float4 a = __ldg(series + 2 * (size_t)(row1 - 1));
+  const float4 b = __ldg(series + 2 * (size_t)(row1 - 1) + 1);
+  Row8 r;
+  r.soc_ev = a.x; r.cd = a.y; r.d_e = a.z; r.g_e = a.w; r.p_buy = b.x; r.h_cos = b.y; r.h_sin = b.z; r.season = b.w;
+  return r;
+}
+
+// ----------------------------------------------------------------------------- reset
+// reset!/reset_state! (shems_LU1.jl:206-262).  mode: SHEMS_RESET_*.
+__global__ void __launch_bounds__(256)
+shems_reset_kernel(DevParams P, const float4* __restrict__ series, int nrows, int maxsteps, long long N, int mode,
+                   const int32_t* __restrict__ idx0_in, const float* __restrict__ socb0_in, unsigned long long seed,
+                   long long env_id_base, float* __restrict__ obs, int32_t* __restrict__ idx_out, int32_t* __restrict__ maxidx) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int idx = 1;
+  if (n < N) {
+    const int hi = nrows - maxsteps;
+    float Soc_b;
+    if (mode == SHEMS_RESET_DETERMINISTIC) {  // rng == -1, :220-222
+      Soc_b = (float)(0.5 * (double)(P.smin + P.smax));
+      idx = 1;
+    } else {
+      int idx0;
+      if (mode == SHEMS_RESET_HOST_DRAWS) {
+        idx0 = idx0_in[n];
+        Soc_b = socb0_in[n];
+      } else {  // Philox draws standing in for the two MersenneTwister(rng) draws of :224-225
+        uint32_t r[4];
+        philox4x32_10(seed, (uint64_t)(env_id_base + n), 0u, STREAM_RESET, r);
+        Soc_b = (float)((double)P.smin + (double)P.span * u53(r[0], r[1]));
+        int k = (int)(u53(r[2], r[3]) * (double)hi);
+        idx0 = 1 + (k >= hi ? hi - 1 : k);
+      }
+      idx = idx0;
+      // :227-246 shift the window until it does not end inside a charging session
+      float c_end = __ldg(&reinterpret_cast<const float*>(series)[8 * (size_t)(idx + maxsteps - 1) + 1]);
+      int counter = 0;
+      while (c_end > -1.0f && idx < hi) {
+        idx += (int)(c_end + 1.0f);
+        if (idx > hi) idx = idx0;  // the re-draw at :236 re-seeds MersenneTwister(rng): same index again
+        c_end = __ldg(&reinterpret_cast<const float*>(series)[8 * (size_t)(idx + maxsteps - 1) + 1]);
+        if (++counter > 100) break;  // :242-245
+      }
+    }
+    const Row8 r = load_row(series, idx);  // :251-260
+    obs[0 * N + n] = Soc_b;
+    obs[1 * N + n] = r.soc_ev;
+    obs[2 * N + n] = r.cd;
+    obs[3 * N + n] = r.d_e;
+    obs[4 * N + n] = r.g_e;
+    obs[5 * N + n] = r.p_buy;
+    obs[6 * N + n] = r.h_cos;
+    obs[7 * N + n] = r.h_sin;
+    obs[8 * N + n] = r.season;
+    idx_out[n] = idx;
+  }
+  // max idx of the block -> one atomic (bounds pre-check of the following steps)
+  int m = idx;
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxidx, m);
+}
+
+// ----------------------------------------------------------------------------- step
+// step!(env, s, a; track) for one instance per thread.  FROM_SERIES: the exogenous state fields are
+// taken from series row idx (they equal env.state there after reset!/step!); otherwise from obs
+// (after shems_set_state injected an arbitrary state).
+template <bool FROM_SERIES, bool WANT_TRACE>
+__global__ void __launch_bounds__(256)
+shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
+                  int32_t* __restrict__ idx_arr, const float* __restrict__ act, int track_neg,
+                  float* __restrict__ reward_out, float* __restrict__ obs_out, double* __restrict__ trace) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int idx = idx_arr[n];
+  const float a0 = act[n], a1 = act[N + n];
+  StepIn s;
+  s.Soc_b = obs[0 * N + n];
+  s.Soc_ev = obs[1 * N + n];
+  float cd_here;
+  if (FROM_SERIES) {
+    const Row8 r = load_row(series, idx);
+    s.c_ev = r.cd; s.d_e = r.d_e; s.g_e = r.g_e; s.p_buy = r.p_buy;
+    cd_here = r.cd;
+  } else {
+    s.c_ev = obs[2 * N + n]; s.d_e = obs[3 * N + n]; s.g_e = obs[4 * N + n]; s.p_buy = obs[5 * N + n];
+    cd_here = __ldg(&reinterpret_cast<const float*>(series)[8 * (size_t)(idx - 1) + 1]);  // df[env.idx, :h_countdown] :270
+  }
+  float B, EV, Bt, EVt;
+  if (!track_neg) {  // :346-349
+    Bt = a0; EVt = a1;
+    shems_action_drl(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
+  } else {           // :350-353
+    Bt = 0.0f; EVt = 0.0f; B = a0; EV = a1;
+  }
+  StepTrace tr;
+  const StepOut o = shems_flows<WANT_TRACE>(P, s, B, EV, EVt, track_neg != 0, &tr);
+  // next_state! :264-281
+  const Row8 nx = load_row(series, idx + 1);
+  float Soc_ev_new = o.Soc_ev;
+  if (nx.cd >= 0.0f && cd_here == -1.0f) Soc_ev_new = nx.soc_ev;  // EV newly connected :270-272
+  obs[0 * N + n] = o.Soc_b;
+  obs[1 * N + n] = Soc_ev_new;
+  obs[2 * N + n] = nx.cd;
+  obs[3 * N + n] = nx.d_e;
+  obs[4 * N + n] = nx.g_e;
+  obs[5 * N + n] = nx.p_buy;
+  obs[6 * N + n] = nx.h_cos;
+  obs[7 * N + n] = nx.h_sin;
+  obs[8 * N + n] = nx.season;
+  idx_arr[n] = idx + 1;  // :456
+  if (reward_out) reward_out[n] = (float)o.reward;
+  if (obs_out) {
+    obs_out[0 * N + n] = o.Soc_b; obs_out[1 * N + n] = Soc_ev_new; obs_out[2 * N + n] = nx.cd; obs_out[3 * N + n] = nx.d_e;
+    obs_out[4 * N + n] = nx.g_e; obs_out[5 * N + n] = nx.p_buy; obs_out[6 * N + n] = nx.h_cos; obs_out[7 * N + n] = nx.h_sin;
+    obs_out[8 * N + n] = nx.season;
+  }
+  if (WANT_TRACE) {  // :476-478
+    double* t = trace + n;
+    t[SHEMS_T_INDEX * N] = (double)(idx + 1); t[SHEMS_T_C_EV * N] = (double)s.c_ev; t[SHEMS_T_EV_TARGET * N] = (double)EVt;
+    t[SHEMS_T_EV * N] = tr.EV; t[SHEMS_T_SOC_EV * N] = (double)s.Soc_ev; t[SHEMS_T_REWARD * N] = o.reward;
+    t[SHEMS_T_PROFIT * N] = tr.profit; t[SHEMS_T_DISCOMFORT * N] = tr.discomfort; t[SHEMS_T_PENALTY * N] = tr.penalty;
+    t[SHEMS_T_PV_DE * N] = tr.PV_DE; t[SHEMS_T_B_DE * N] = tr.B_DE; t[SHEMS_T_GR_DE * N] = tr.GR_DE; t[SHEMS_T_PV_B * N] = tr.PV_B;
+    t[SHEMS_T_PV_GR * N] = tr.PV_GR; t[SHEMS_T_PV_EV * N] = tr.PV_EV; t[SHEMS_T_B_EV * N] = tr.B_EV; t[SHEMS_T_GR_EV * N] = tr.GR_EV;
+    t[SHEMS_T_EX_EV * N] = tr.EX_EV; t[SHEMS_T_GR_B * N] = 0.0; t[SHEMS_T_B_GR * N] = 0.0; t[SHEMS_T_B * N] = tr.B;
+    t[SHEMS_T_B_TARGET * N] = (double)Bt; t[SHEMS_T_SOC_B * N] = (double)s.Soc_b;
+  }
+}
+
+// action(env, track) / action(env, a) for all instances
+template <bool RULE>
+__global__ void __launch_bounds__(256)
+shems_action_kernel(DevParams P, long long N, const float* __restrict__ obs, const float* __restrict__ target, float* __restrict__ bev) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float B, EV;
+  if (RULE) shems_action_rule(P, obs[0 * N + n], obs[1 * N + n], obs[3 * N + n], obs[4 * N + n], B, EV);
+  else shems_action_drl(P, obs[0 * N + n], obs[1 * N + n], obs[2 * N + n], obs[3 * N + n], obs[4 * N + n], target[n], target[N + n], B, EV);
+  bev[n] = B;
+  bev[N + n] = EV;
+}
+
+// ----------------------------------------------------------------------------- fused rollout
+// T transitions per instance with the state kept in registers (episode!/populate_memory/inference
+// loops: DDPG.jl:186-242, memory_plotting_saving.jl:9-29, 62-89).  One thread per instance.
+struct RolloutSinks {
+  double* ep_return;   // [N]
+  double* trace;       // [T][23][N]
+  float* obs_traj;     // [T][9][N]
+  float* reward_traj;  // [T][N]
+  // replay ring (SoA, capacity cap, first slot `head`)
+  float* rp_s; float* rp_a; float* rp_r; float* rp_s2; float* rp_done;
+  long long cap, head;
+};
+
+template <int POLICY, bool WANT_TRACE>
+__global__ void __launch_bounds__(256)
+shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
+                     int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
+                     const float* __restrict__ tape, RolloutSinks S) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int idx = idx_arr[n];
+  float st[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) st[k] = obs[k * N + n];
+  float cd_here = __ldg(&reinterpret_cast<const float*>(series)[8 * (size_t)(idx - 1) + 1]);
+  double ret = 0.0;
+  for (int t = 0; t < T; ++t) {
+    StepIn s;
+    s.Soc_b = st[0]; s.Soc_ev = st[1]; s.c_ev = st[2]; s.d_e = st[3]; s.g_e = st[4]; s.p_buy = st[5];
+    float B, EV, Bt, EVt, a_raw0, a_raw1;
+    bool track_neg = false;
+    if (POLICY == SHEMS_POLICY_RULE) {  // DDPG.jl:209-212
+      shems_action_rule(P, s.Soc_b, s.Soc_ev, s.d_e, s.g_e, B, EV);
+      Bt = 0.0f; EVt = 0.0f; a_raw0 = B; a_raw1 = EV; track_neg = true;
+    } else {
+      if (POLICY == SHEMS_POLICY_RANDOM) {  // memory_plotting_saving.jl:14-19
+        uint32_t r[4];
+        philox4x32_10(seed, (uint64_t)(env_id_base + n), (uint32_t)(step0 + t), STREAM_ACTION, r);
+        a_raw0 = (float)(u53(r[0], r[1]) * 2.0 - 1.0);
+        a_raw1 = (float)(u53(r[2], r[3]) * 2.0 - 1.0);
+        // scale_action with bounds (0,0)/(1,1) (DDPG.jl:178-184, input.jl:182-183)
+        Bt = (float)(0.0 + (((double)a_raw0 + 1.0) * 0.5) * 1.0);
+        EVt = (float)(0.0 + (((double)a_raw1 + 1.0) * 0.5) * 1.0);
+      } else {
+        Bt = tape[((size_t)t * 2 + 0) * N + n];
+        EVt = tape[((size_t)t * 2 + 1) * N + n];
+        a_raw0 = Bt; a_raw1 = EVt;
+      }
+      shems_action_drl(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
+    }
+    StepTrace tr;
+    const StepOut o = shems_flows<WANT_TRACE>(P, s, B, EV, EVt, track_neg, &tr);
+    const Row8 nx = load_row(series, idx + 1);
+    float Soc_ev_new = o.Soc_ev;
+    if (nx.cd >= 0.0f && cd_here == -1.0f) Soc_ev_new = nx.soc_ev;
+    if (S.rp_s) {  // remember(s, a, r, s', finished) — memory_plotting_saving.jl:46-47
+      long long slot = S.head + (long long)t * N + n;
+      slot -= (slot / S.cap) * S.cap;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) S.rp_s[k * S.cap + slot] = st[k];
+      S.rp_a[slot] = a_raw0; S.rp_a[S.cap + slot] = a_raw1;
+      S.rp_r[slot] = (float)o.reward;
+      S.rp_s2[0 * S.cap + slot] = o.Soc_b; S.rp_s2[1 * S.cap + slot] = Soc_ev_new; S.rp_s2[2 * S.cap + slot] = nx.cd;
+      S.rp_s2[3 * S.cap + slot] = nx.d_e; S.rp_s2[4 * S.cap + slot] = nx.g_e; S.rp_s2[5 * S.cap + slot] = nx.p_buy;
+      S.rp_s2[6 * S.cap + slot] = nx.h_cos; S.rp_s2[7 * S.cap + slot] = nx.h_sin; S.rp_s2[8 * S.cap + slot] = nx.season;
+      S.rp_done[slot] = 0.0f;  // finished() is always false (shems_LU1.jl:487-502)
+    }
+    if (WANT_TRACE) {
+      double* q = S.trace + (size_t)t * SHEMS_TRACE_COLS * N + n;
+      q[SHEMS_T_INDEX * N] = (double)(idx + 1); q[SHEMS_T_C_EV * N] = (double)s.c_ev; q[SHEMS_T_EV_TARGET * N] = (double)EVt;
+      q[SHEMS_T_EV * N] = tr.EV; q[SHEMS_T_SOC_EV * N] = (double)s.Soc_ev; q[SHEMS_T_REWARD * N] = o.reward;
+      q[SHEMS_T_PROFIT * N] = tr.profit; q[SHEMS_T_DISCOMFORT * N] = tr.discomfort; q[SHEMS_T_PENALTY * N] = tr.penalty;
+      q[SHEMS_T_PV_DE * N] = tr.PV_DE; q[SHEMS_T_B_DE * N] = tr.B_DE; q[SHEMS_T_GR_DE * N] = tr.GR_DE; q[SHEMS_T_PV_B * N] = tr.PV_B;
+      q[SHEMS_T_PV_GR * N] = tr.PV_GR; q[SHEMS_T_PV_EV * N] = tr.PV_EV; q[SHEMS_T_B_EV * N] = tr.B_EV; q[SHEMS_T_GR_EV * N] = tr.GR_EV;
+      q[SHEMS_T_EX_EV * N] = tr.EX_EV; q[SHEMS_T_GR_B * N] = 0.0; q[SHEMS_T_B_GR * N] = 0.0; q[SHEMS_T_B * N] = tr.B;
+      q[SHEMS_T_B_TARGET * N] = (double)Bt; q[SHEMS_T_SOC_B * N] = (double)s.Soc_b;
+    }
+    st[0] = o.Soc_b; st[1] = Soc_ev_new; st[2] = nx.cd; st[3] = nx.d_e; st[4] = nx.g_e; st[5] = nx.p_buy;
+    st[6] = nx.h_cos; st[7] = nx.h_sin; st[8] = nx.season;
+    cd_here = nx.cd;
+    idx += 1;
+    ret += o.reward;  // reward_eps += r (DDPG.jl:223; Float64 accumulation)
+    if (S.obs_traj) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) S.obs_traj[((size_t)t * 9 + k) * N + n] = st[k];
+    }
+    if (S.reward_traj) S.reward_traj[(size_t)t * N + n] = (float)o.reward;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) obs[k * N + n] = st[k];
+  idx_arr[n] = idx;
+  if (S.ep_return) S.ep_return[n] = ret;
+}
+
+// ----------------------------------------------------------------------------- C ABI
+static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+extern "C" int32_t shems_create(const ShemsParams* params, const float* series_host, int32_t nrows, int32_t maxsteps,
+                                int64_t n_envs, int32_t device, ShemsEnv** out) {
+  REQUIRE(params && series_host && out, SHEMS_ERR_INVALID, "shems_create: NULL argument");
+  REQUIRE(nrows >= 2 && maxsteps >= 1 && n_envs >= 1, SHEMS_ERR_INVALID, "shems_create: nrows=%d maxsteps=%d n_envs=%lld", nrows,
+          maxsteps, (long long)n_envs);
+  REQUIRE(nrows - maxsteps >= 1, SHEMS_ERR_INVALID,
+          "shems_create: nrows - maxsteps = %d < 1: rand(1:(nrow-maxsteps)) would be empty (shems_LU1.jl:225)", nrows - maxsteps);
+  REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "shems_create: no CUDA device (this library has no CPU fallback)");
+  GUARD(device);
+  ShemsEnv* e = new (std::nothrow) ShemsEnv();
+  REQUIRE(e, SHEMS_ERR_INVALID, "shems_create: out of host memory");
+  memset(e, 0, sizeof(*e));
+  e->device = device; e->stream = 0; e->params = *params; e->dp = make_dev_params(*params);
+  e->nrows = nrows; e->maxsteps = maxsteps; e->n = n_envs; e->max_idx = 1; e->consistent = true;
+  // interleave the 8 columns into 32-byte rows
+  std::vector<float> rows((size_t)nrows * 8);
+  for (int r = 0; r < nrows; ++r)
+    for (int c = 0; c < 8; ++c) rows[(size_t)r * 8 + c] = series_host[(size_t)c * nrows + r];
+  cudaError_t st = cudaSuccess;
+  if ((st = cudaMalloc(&e->series, sizeof(float) * 8 * (size_t)nrows)) != cudaSuccess ||
+      (st = cudaMalloc(&e->obs, sizeof(float) * 9 * (size_t)n_envs)) != cudaSuccess ||
+      (st = cudaMalloc(&e->idx, sizeof(int32_t) * (size_t)n_envs)) != cudaSuccess ||
+      (st = cudaMalloc(&e->d_maxidx, sizeof(int32_t))) != cudaSuccess ||
+      (st = cudaMemcpy(e->series, rows.data(), sizeof(float) * rows.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (st = cudaMemset(e->obs, 0, sizeof(float) * 9 * (size_t)n_envs)) != cudaSuccess ||
+      (st = cudaMemset(e->idx, 0, sizeof(int32_t) * (size_t)n_envs)) != cudaSuccess) {
+    shems_set_error("shems_create: %s", cudaGetErrorString(st));
+    shems_destroy(e);
+    return SHEMS_ERR_CUDA;
+  }
+  *out = e;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_destroy(ShemsEnv* e) {
+  if (!e) return SHEMS_OK;
+  GUARD(e->device);
+  cudaFree(e->series); cudaFree(e->obs); cudaFree(e->idx); cudaFree(e->d_maxidx); cudaFree(e->scratch_i); cudaFree(e->scratch_f);
+  delete e;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_set_stream(ShemsEnv* e, void* s) {
+  REQUIRE(e, SHEMS_ERR_INVALID, "shems_set_stream: NULL handle");
+  e->stream = (cudaStream_t)s;
+  return SHEMS_OK;
+}
+extern "C" int32_t shems_sync(ShemsEnv* e) {
+  REQUIRE(e, SHEMS_ERR_INVALID, "shems_sync: NULL handle");
+  GUARD(e->device);
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SHEMS_OK;
+}
+extern "C" int64_t shems_num_envs(const ShemsEnv* e) { return e ? e->n : 0; }
+extern "C" int32_t shems_get_step(const ShemsEnv* e, int32_t* step) {
+  REQUIRE(e && step, SHEMS_ERR_INVALID, "shems_get_step: NULL argument");
+  *step = e->step;
+  return SHEMS_OK;
+}
+extern "C" int32_t shems_finished(const ShemsEnv* e, int32_t* out) {
+  REQUIRE(e && out, SHEMS_ERR_INVALID, "shems_finished: NULL argument");
+  *out = 0;  // shems_LU1.jl:487-502 returns false on both paths
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_host, const float* socb0_host, uint64_t seed,
+                               int64_t env_id_base) {
+  REQUIRE(e, SHEMS_ERR_INVALID, "shems_reset: NULL handle");
+  REQUIRE(mode >= 0 && mode <= 2, SHEMS_ERR_INVALID, "shems_reset: unknown mode %d", mode);
+  GUARD(e->device);
+  const int hi = e->nrows - e->maxsteps;
+  if (mode == SHEMS_RESET_HOST_DRAWS) {
+    REQUIRE(idx0_host && socb0_host, SHEMS_ERR_INVALID, "shems_reset: HOST_DRAWS needs idx0_host and socb0_host");
+    for (int64_t i = 0; i < e->n; ++i)
+      REQUIRE(idx0_host[i] >= 1 && idx0_host[i] <= hi, SHEMS_ERR_INVALID, "shems_reset: idx0[%lld]=%d outside 1..%d", (long long)i,
+              idx0_host[i], hi);
+    if (!e->scratch_i) {
+      CUDA_TRY(cudaMalloc(&e->scratch_i, sizeof(int32_t) * (size_t)e->n));
+      CUDA_TRY(cudaMalloc(&e->scratch_f, sizeof(float) * (size_t)e->n));
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->scratch_i, idx0_host, sizeof(int32_t) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->scratch_f, socb0_host, sizeof(float) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+  }
+  CUDA_TRY(cudaMemsetAsync(e->d_maxidx, 0, sizeof(int32_t), e->stream));
+  shems_reset_kernel<<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->series, e->nrows, e->maxsteps, e->n, mode, e->scratch_i,
+                                                                e->scratch_f, seed, env_id_base, e->obs, e->idx, e->d_maxidx);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(&e->max_idx, e->d_maxidx, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->step = 0;          // :210
+  e->was_reset = true;
+  e->consistent = true;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, float* reward_dev, float* obs_dev, double* trace_dev) {
+  REQUIRE(e && act_dev, SHEMS_ERR_INVALID, "shems_step: NULL argument");
+  REQUIRE(e->was_reset, SHEMS_ERR_STATE, "shems_step: reset! (or shems_set_state) must come first");
+  if (e->max_idx + 1 > e->nrows) {
+    shems_set_error("BoundsError: attempt to access %d-row series at row %d (next_state!, shems_LU1.jl:266-268)", e->nrows, e->max_idx + 1);
+    return SHEMS_ERR_BOUNDS;
+  }
+  GUARD(e->device);
+  const unsigned g = grid_for(e->n, 256);
+  const int tn = track < 0 ? 1 : 0;
+#define LAUNCH_STEP(FS, TR) \
+  shems_step_kernel<FS, TR><<<g, 256, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, act_dev, tn, reward_dev, obs_dev, trace_dev)
+  if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
+  else { if (trace_dev) LAUNCH_STEP(false, true); else LAUNCH_STEP(false, false); }
+#undef LAUNCH_STEP
+  CUDA_TRY(cudaGetLastError());
+  e->max_idx += 1;
+  e->step += 1;  // :455
+  e->consistent = true;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_action_rule(ShemsEnv* e, float* bev_dev) {
+  REQUIRE(e && bev_dev, SHEMS_ERR_INVALID, "shems_action_rule: NULL argument");
+  GUARD(e->device);
+  shems_action_kernel<true><<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->n, e->obs, nullptr, bev_dev);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+extern "C" int32_t shems_action_drl(ShemsEnv* e, const float* target_dev, float* bev_dev) {
+  REQUIRE(e && target_dev && bev_dev, SHEMS_ERR_INVALID, "shems_action_drl: NULL argument");
+  GUARD(e->device);
+  shems_action_kernel<false><<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->n, e->obs, target_dev, bev_dev);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_state_ptr(ShemsEnv* e, float** obs_dev, int32_t** idx_dev) {
+  REQUIRE(e, SHEMS_ERR_INVALID, "shems_state_ptr: NULL handle");
+  if (obs_dev) *obs_dev = e->obs;
+  if (idx_dev) *idx_dev = e->idx;
+  return SHEMS_OK;
+}
+extern "C" int32_t shems_get_state(ShemsEnv* e, float* obs_host, int32_t* idx_host) {
+  REQUIRE(e && obs_host, SHEMS_ERR_INVALID, "shems_get_state: NULL argument");
+  GUARD(e->device);
+  CUDA_TRY(cudaMemcpyAsync(obs_host, e->obs, sizeof(float) * 9 * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+  if (idx_host) CUDA_TRY(cudaMemcpyAsync(idx_host, e->idx, sizeof(int32_t) * (size_t)e->n, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return SHEMS_OK;
+}
+extern "C" int32_t shems_set_state(ShemsEnv* e, const float* obs_host, const int32_t* idx_host) {
+  REQUIRE(e && obs_host && idx_host, SHEMS_ERR_INVALID, "shems_set_state: NULL argument");
+  GUARD(e->device);
+  int32_t mx = 1;
+  for (int64_t i = 0; i < e->n; ++i) {
+    REQUIRE(idx_host[i] >= 1 && idx_host[i] <= e->nrows, SHEMS_ERR_INVALID, "shems_set_state: idx[%lld]=%d outside 1..%d", (long long)i,
+            idx_host[i], e->nrows);
+    mx = idx_host[i] > mx ? idx_host[i] : mx;
+  }
+  CUDA_TRY(cudaMemcpyAsync(e->obs, obs_host, sizeof(float) * 9 * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaMemcpyAsync(e->idx, idx_host, sizeof(int32_t) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->max_idx = mx;
+  e->was_reset = true;
+  e->consistent = false;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
+  REQUIRE(e && a, SHEMS_ERR_INVALID, "shems_rollout: NULL argument");
+  REQUIRE(e->was_reset, SHEMS_ERR_STATE, "shems_rollout: reset! must come first");
+  REQUIRE(a->n_steps >= 1, SHEMS_ERR_INVALID, "shems_rollout: n_steps=%d", a->n_steps);
+  REQUIRE(a->policy >= 0 && a->policy <= 2, SHEMS_ERR_INVALID, "shems_rollout: unknown policy %d", a->policy);
+  REQUIRE(a->policy != SHEMS_POLICY_TAPE || a->tape_dev, SHEMS_ERR_INVALID, "shems_rollout: POLICY_TAPE needs tape_dev");
+  if ((int64_t)e->max_idx + a->n_steps > e->nrows) {
+    shems_set_error("BoundsError: rollout of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", a->n_steps,
+                    e->max_idx, e->nrows);
+    return SHEMS_ERR_BOUNDS;
+  }
+  GUARD(e->device);
+  RolloutSinks S;
+  memset(&S, 0, sizeof(S));
+  S.ep_return = a->ep_return_dev; S.trace = a->trace_dev; S.obs_traj = a->obs_traj_dev; S.reward_traj = a->reward_traj_dev;
+  S.cap = 1;
+  const int64_t total = (int64_t)a->n_steps * e->n;
+  if (a->replay) {
+    ShemsReplay* rp = a->replay;
+    REQUIRE(rp->device == e->device, SHEMS_ERR_INVALID, "shems_rollout: replay lives on device %d, env on %d", rp->device, e->device);
+    // a slot must only ever be written by one thread inside a launch: either no wrap onto itself, or
+    // the wrap lands on the same instance (capacity multiple of N)
+    REQUIRE(total <= rp->capacity || rp->capacity % e->n == 0, SHEMS_ERR_INVALID,
+            "shems_rollout: replay capacity %lld must hold n_steps*n_envs=%lld or be a multiple of n_envs=%lld", (long long)rp->capacity,
+            (long long)total, (long long)e->n);
+    S.rp_s = rp->s; S.rp_a = rp->a; S.rp_r = rp->r; S.rp_s2 = rp->s2; S.rp_done = rp->done; S.cap = rp->capacity; S.head = rp->head;
+  }
+  const unsigned g = grid_for(e->n, 256);
+#define LAUNCH_RO(POL, TR)                                                                                                          \
+  shems_rollout_kernel<POL, TR><<<g, 256, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, a->n_steps, e->step, a->seed,     \
+                                                          a->env_id_base, a->tape_dev, S)
+  const bool tr = a->trace_dev != nullptr;
+  switch (a->policy) {
+    case SHEMS_POLICY_RULE: if (tr) LAUNCH_RO(SHEMS_POLICY_RULE, true); else LAUNCH_RO(SHEMS_POLICY_RULE, false); break;
+    case SHEMS_POLICY_RANDOM: if (tr) LAUNCH_RO(SHEMS_POLICY_RANDOM, true); else LAUNCH_RO(SHEMS_POLICY_RANDOM, false); break;
+    default: if (tr) LAUNCH_RO(SHEMS_POLICY_TAPE, true); else LAUNCH_RO(SHEMS_POLICY_TAPE, false); break;
+  }
+#undef LAUNCH_RO
+  CUDA_TRY(cudaGetLastError());
+  e->max_idx += a->n_steps;
+  e->step += a->n_steps;
+  e->consistent = true;
+  if (a->replay) return replay_after_rollout(a->replay, total);
+  return SHEMS_OK;
+}

@@ -1,0 +1,249 @@
+// replay.cu — device-resident replay memory: `memory = CircularBuffer{Any}(MEM_SIZE)` of
+// [s, a, r, s', done] (RL-SHEMS/input.jl:140; src/memory_plotting_saving.jl:31-57) as a
+// structure-of-arrays ring in HBM with on-device sampling.
+//
+// Layout: s[9][cap], a[2][cap], r[cap], s2[9][cap], done[cap] float32 = 88 B per transition.
+// Logical index i (0 = oldest) lives in physical slot (head - length + i) mod cap.
+#include <new>
+#include <vector>
+#include <string.h>
+
+#include "common.h"
+#include "philox.cuh"
+
+extern "C" int32_t replay_create(int64_t capacity, int32_t device, ShemsReplay** out) {
+  REQUIRE(out && capacity >= 1, SHEMS_ERR_INVALID, "replay_create: capacity=%lld", (long long)capacity);
+  REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "replay_create: no CUDA device (this library has no CPU fallback)");
+  GUARD(device);
+  ShemsReplay* rp = new (std::nothrow) ShemsReplay();
+  REQUIRE(rp, SHEMS_ERR_INVALID, "replay_create: out of host memory");
+  memset(rp, 0, sizeof(*rp));
+  rp->device = device; rp->capacity = capacity;
+  const size_t c = (size_t)capacity;
+  cudaError_t st;
+  if ((st = cudaMalloc(&rp->s, sizeof(float) * 9 * c)) != cudaSuccess || (st = cudaMalloc(&rp->a, sizeof(float) * 2 * c)) != cudaSuccess ||
+      (st = cudaMalloc(&rp->r, sizeof(float) * c)) != cudaSuccess || (st = cudaMalloc(&rp->s2, sizeof(float) * 9 * c)) != cudaSuccess ||
+      (st = cudaMalloc(&rp->done, sizeof(float) * c)) != cudaSuccess || (st = cudaMalloc(&rp->minmax_scratch, sizeof(float) * 18)) != cudaSuccess) {
+    shems_set_error("replay_create: %s", cudaGetErrorString(st));
+    replay_destroy(rp);
+    return SHEMS_ERR_CUDA;
+  }
+  *out = rp;
+  return SHEMS_OK;
+}
+extern "C" int32_t replay_destroy(ShemsReplay* rp) {
+  if (!rp) return SHEMS_OK;
+  GUARD(rp->device);
+  cudaFree(rp->s); cudaFree(rp->a); cudaFree(rp->r); cudaFree(rp->s2); cudaFree(rp->done); cudaFree(rp->idx_scratch); cudaFree(rp->minmax_scratch);
+  delete rp;
+  return SHEMS_OK;
+}
+extern "C" int32_t replay_set_stream(ShemsReplay* rp, void* s) {
+  REQUIRE(rp, SHEMS_ERR_INVALID, "replay_set_stream: NULL handle");
+  rp->stream = (cudaStream_t)s;
+  return SHEMS_OK;
+}
+extern "C" int64_t replay_length(const ShemsReplay* rp) { return rp ? rp->length : 0; }
+extern "C" int64_t replay_capacity(const ShemsReplay* rp) { return rp ? rp->capacity : 0; }
+
+int replay_after_rollout(ShemsReplay* rp, int64_t n_written) {
+  rp->head = (rp->head + n_written) % rp->capacity;
+  rp->length = rp->length + n_written > rp->capacity ? rp->capacity : rp->length + n_written;
+  return SHEMS_OK;
+}
+
+// remember() for n transitions: slot = (head + i) mod cap.  When n > cap only the last cap survive.
+__global__ void __launch_bounds__(256)
+replay_push_kernel(float* __restrict__ rs, float* __restrict__ ra, float* __restrict__ rr, float* __restrict__ rs2, float* __restrict__ rd,
+                   long long cap, long long head, const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ r,
+                   const float* __restrict__ s2, const float* __restrict__ done, long long n, long long first) {
+  const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long slot = head + i;
+  slot -= (slot / cap) * cap;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rs[k * cap + slot] = s[k * n + i];
+  ra[slot] = a[i];
+  ra[cap + slot] = a[n + i];
+  rr[slot] = r[i];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rs2[k * cap + slot] = s2[k * n + i];
+  rd[slot] = done ? done[i] : 0.0f;
+}
+
+extern "C" int32_t replay_push(ShemsReplay* rp, const float* s_dev, const float* a_dev, const float* r_dev, const float* s2_dev,
+                               const float* done_dev, int64_t n) {
+  REQUIRE(rp && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "replay_push: NULL argument");
+  REQUIRE(n >= 0, SHEMS_ERR_INVALID, "replay_push: n=%lld", (long long)n);
+  if (n == 0) return SHEMS_OK;
+  GUARD(rp->device);
+  // only the newest `cap` of the n transitions can survive; skipping the rest also keeps slots single-writer
+  const int64_t first = n > rp->capacity ? n - rp->capacity : 0;
+  const int64_t cnt = n - first;
+  replay_push_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, rp->stream>>>(rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, rp->head,
+                                                                           s_dev, a_dev, r_dev, s2_dev, done_dev, n, first);
+  CUDA_TRY(cudaGetLastError());
+  return replay_after_rollout(rp, n);
+}
+
+// getData(): gather B sampled transitions into SoA minibatch arrays [k][B].
+// idx != NULL: logical indices; else Philox(seed, id = draw j, ctr = update) -> floor(u * len).
+__device__ __forceinline__ long long replay_slot(long long logical, long long head, long long len, long long cap) {
+  long long slot = head - len + logical;
+  if (slot < 0) slot += cap;
+  return slot;
+}
+__global__ void __launch_bounds__(128)
+replay_sample_kernel(const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr, const float* __restrict__ rs2,
+                     const float* __restrict__ rd, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
+                     unsigned long long seed, unsigned update, int B, float* __restrict__ s, float* __restrict__ a, float* __restrict__ r,
+                     float* __restrict__ s2, float* __restrict__ done) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= B) return;
+  long long li;
+  if (idx) li = idx[j];
+  else {
+    uint32_t w[4];
+    philox4x32_10(seed, (uint64_t)j, update, STREAM_SAMPLE, w);
+    li = (long long)(u53(w[0], w[1]) * (double)len);
+    if (li >= len) li = len - 1;
+  }
+  const long long slot = replay_slot(li, head, len, cap);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s[k * B + j] = rs[k * cap + slot];
+  a[j] = ra[slot];
+  a[B + j] = ra[cap + slot];
+  r[j] = rr[slot];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) s2[k * B + j] = rs2[k * cap + slot];
+  done[j] = rd[slot];
+}
+
+static int ensure_idx_scratch(ShemsReplay* rp, int64_t n) {
+  if (rp->idx_scratch_n >= n) return SHEMS_OK;
+  cudaFree(rp->idx_scratch);
+  rp->idx_scratch = nullptr; rp->idx_scratch_n = 0;
+  CUDA_TRY(cudaMalloc(&rp->idx_scratch, sizeof(int32_t) * (size_t)n));
+  rp->idx_scratch_n = n;
+  return SHEMS_OK;
+}
+
+extern "C" int32_t replay_sample(ShemsReplay* rp, int32_t batch, const int32_t* idx_host, uint64_t seed, float* s_dev, float* a_dev,
+                                 float* r_dev, float* s2_dev, float* done_dev) {
+  REQUIRE(rp && s_dev && a_dev && r_dev && s2_dev && done_dev, SHEMS_ERR_INVALID, "replay_sample: NULL argument");
+  REQUIRE(batch >= 1, SHEMS_ERR_INVALID, "replay_sample: batch=%d", batch);
+  REQUIRE(rp->length > 0, SHEMS_ERR_STATE, "replay_sample: memory is empty (sample from an empty collection)");
+  GUARD(rp->device);
+  const int32_t* didx = nullptr;
+  if (idx_host) {
+    for (int j = 0; j < batch; ++j)
+      REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "replay_sample: idx[%d]=%d outside 0..%lld", j, idx_host[j],
+              (long long)rp->length - 1);
+    int st = ensure_idx_scratch(rp, batch);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(rp->idx_scratch, idx_host, sizeof(int32_t) * batch, cudaMemcpyHostToDevice, rp->stream));
+    didx = rp->idx_scratch;
+  }
+  replay_sample_kernel<<<(batch + 127) / 128, 128, 0, rp->stream>>>(rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, rp->head, rp->length,
+                                                                   didx, seed, 0u, batch, s_dev, a_dev, r_dev, s2_dev, done_dev);
+  CUDA_TRY(cudaGetLastError());
+  if (idx_host) CUDA_TRY(cudaStreamSynchronize(rp->stream));  // idx_host was staged asynchronously
+  return SHEMS_OK;
+}
+
+// min_max_buffer(): min/max of the 9 state fields over a with-replacement sample of n draws.
+// Float min/max are exact and order-independent -> atomics on the int-ordered bit pattern.
+__device__ __forceinline__ void atomic_minf(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_maxf(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__global__ void __launch_bounds__(256)
+replay_minmax_kernel(const float* __restrict__ rs, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
+                     unsigned long long seed, long long n, float* __restrict__ out /* [0..8]=min, [9..17]=max */) {
+  float mn[9], mx[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    long long li;
+    if (idx) li = idx[j];
+    else {
+      uint32_t w[4];
+      philox4x32_10(seed, (uint64_t)j, 0u, STREAM_SAMPLE, w);
+      li = (long long)(u53(w[0], w[1]) * (double)len);
+      if (li >= len) li = len - 1;
+    }
+    const long long slot = replay_slot(li, head, len, cap);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { const float v = rs[k * cap + slot]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomic_minf(out + k, mn[k]); atomic_maxf(out + 9 + k, mx[k]); }
+  }
+}
+
+extern "C" int32_t replay_minmax(ShemsReplay* rp, int64_t n_samples, const int32_t* idx_host, uint64_t seed, float* s_min_host, float* s_max_host) {
+  REQUIRE(rp && s_min_host && s_max_host, SHEMS_ERR_INVALID, "replay_minmax: NULL argument");
+  REQUIRE(n_samples >= 1, SHEMS_ERR_INVALID, "replay_minmax: n_samples=%lld", (long long)n_samples);
+  REQUIRE(rp->length > 0, SHEMS_ERR_STATE, "replay_minmax: memory is empty");
+  GUARD(rp->device);
+  const int32_t* didx = nullptr;
+  if (idx_host) {
+    for (int64_t j = 0; j < n_samples; ++j)
+      REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "replay_minmax: idx[%lld]=%d outside 0..%lld", (long long)j,
+              idx_host[j], (long long)rp->length - 1);
+    int st = ensure_idx_scratch(rp, n_samples);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(rp->idx_scratch, idx_host, sizeof(int32_t) * (size_t)n_samples, cudaMemcpyHostToDevice, rp->stream));
+    didx = rp->idx_scratch;
+  }
+  float init[18];
+  for (int k = 0; k < 9; ++k) { init[k] = INFINITY; init[9 + k] = -INFINITY; }
+  CUDA_TRY(cudaMemcpyAsync(rp->minmax_scratch, init, sizeof(init), cudaMemcpyHostToDevice, rp->stream));
+  long long blocks = (n_samples + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  replay_minmax_kernel<<<(unsigned)blocks, 256, 0, rp->stream>>>(rp->s, rp->capacity, rp->head, rp->length, didx, seed, n_samples, rp->minmax_scratch);
+  CUDA_TRY(cudaGetLastError());
+  float res[18];
+  CUDA_TRY(cudaMemcpyAsync(res, rp->minmax_scratch, sizeof(res), cudaMemcpyDeviceToHost, rp->stream));
+  CUDA_TRY(cudaStreamSynchronize(rp->stream));
+  memcpy(s_min_host, res, sizeof(float) * 9);
+  memcpy(s_max_host, res + 9, sizeof(float) * 9);
+  return SHEMS_OK;
+}
+
+extern "C" int32_t replay_get(ShemsReplay* rp, float* s_host, float* a_host, float* r_host, float* s2_host, float* done_host) {
+  REQUIRE(rp, SHEMS_ERR_INVALID, "replay_get: NULL handle");
+  GUARD(rp->device);
+  const int64_t len = rp->length, cap = rp->capacity;
+  if (len == 0) return SHEMS_OK;
+  CUDA_TRY(cudaStreamSynchronize(rp->stream));
+  const int64_t start = ((rp->head - len) % cap + cap) % cap;
+  const int64_t n1 = (start + len <= cap) ? len : cap - start;  // first contiguous piece
+  auto copy_field = [&](float* dst, const float* src, int k) -> cudaError_t {
+    if (!dst) return cudaSuccess;
+    for (int f = 0; f < k; ++f) {
+      cudaError_t e1 = cudaMemcpy(dst + (size_t)f * len, src + (size_t)f * cap + start, sizeof(float) * (size_t)n1, cudaMemcpyDeviceToHost);
+      if (e1 != cudaSuccess) return e1;
+      if (n1 < len) {
+        e1 = cudaMemcpy(dst + (size_t)f * len + n1, src + (size_t)f * cap, sizeof(float) * (size_t)(len - n1), cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess) return e1;
+      }
+    }
+    return cudaSuccess;
+  };
+  CUDA_TRY(copy_field(s_host, rp->s, 9));
+  CUDA_TRY(copy_field(a_host, rp->a, 2));
+  CUDA_TRY(copy_field(r_host, rp->r, 1));
+  CUDA_TRY(copy_field(s2_host, rp->s2, 9));
+  CUDA_TRY(copy_field(done_host, rp->done, 1));
+  return SHEMS_OK;
+}

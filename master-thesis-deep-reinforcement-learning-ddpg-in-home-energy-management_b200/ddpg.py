@@ -1,0 +1,289 @@
+"""Host-side mirror of the reference's DDPG globals (RL-SHEMS/algorithms/DDPG.jl and
+src/memory_plotting_saving.jl:1-57) on top of the C ABI.
+
+    reference (Julia global)                  here
+    memory = CircularBuffer{Any}(MEM_SIZE)    Replay(capacity)
+    remember(s, a, r, s′, done)               Replay.push / remember
+    getData(batch; rng_dt)                    Replay.sample
+    min_max_buffer(n; rng_mm)                 Replay.min_max_buffer
+    actor / critic / *_target, opt_*          Learner (ddpg_create / ddpg_init / set_layer)
+    normalize(s)                              fused into Learner.act / Learner.replay
+    act(s_norm; train, rng_act)+scale_action  Learner.act
+    replay(; rng_rpl)                         Learner.replay
+    populate_memory / episode! / run_episodes / inference   Driver.*
+
+Vectorised semantics (stated, because the reference runs 1 env × 1 learner): the N instances
+of a `Shems` handle advance in lock step; one vector step pushes N transitions and is followed
+by `updates_per_step` calls of replay().  With N = 1 and updates_per_step = 1 this is the
+reference loop (DDPG.jl:186-242).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .env import _ptr
+
+
+class Replay:
+    def __init__(self, capacity, device=0):
+        self.lib = L.lib()
+        h = C.c_void_p()
+        L.check(self.lib.replay_create(int(capacity), int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._dev = torch.device("cuda", self.device)
+        self._bind_stream()
+
+    def _bind_stream(self):
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.replay_set_stream(self._h, C.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.replay_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.lib.replay_length(self._h))
+
+    @property
+    def capacity(self):
+        return int(self.lib.replay_capacity(self._h))
+
+    def push(self, s, a, r, s2, done=None):
+        """remember(): s, s2 [9][n]; a [2][n] (UNSCALED action, DDPG.jl:229); r [n]; device float32 tensors."""
+        n = r.numel()
+        L.check(self.lib.replay_push(self._h, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(done), n))
+
+    remember = push
+
+    def sample(self, batch, rng_dt=0, idx=None):
+        """getData(): returns (s [9][B], a [2][B], r [B], s′ [9][B], done [B]) device tensors."""
+        d = self._dev
+        s = torch.empty((9, batch), dtype=torch.float32, device=d)
+        a = torch.empty((2, batch), dtype=torch.float32, device=d)
+        r = torch.empty(batch, dtype=torch.float32, device=d)
+        s2 = torch.empty((9, batch), dtype=torch.float32, device=d)
+        dn = torch.empty(batch, dtype=torch.float32, device=d)
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.int32)
+            ip = idx.ctypes.data_as(L.PI)
+        L.check(self.lib.replay_sample(self._h, int(batch), ip, int(rng_dt) & (2**64 - 1), _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(dn)))
+        return s, a, r, s2, dn
+
+    def min_max_buffer(self, n_samples, rng_mm=0, idx=None):
+        mn = np.empty(9, np.float32)
+        mx = np.empty(9, np.float32)
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.int32)
+            ip = idx.ctypes.data_as(L.PI)
+        L.check(self.lib.replay_minmax(self._h, int(n_samples), ip, int(rng_mm) & (2**64 - 1), mn.ctypes.data_as(L.PF), mx.ctypes.data_as(L.PF)))
+        return mn, mx
+
+    def get(self):
+        n = len(self)
+        s, a, r, s2, d = (np.empty((9, n), np.float32), np.empty((2, n), np.float32), np.empty(n, np.float32),
+                          np.empty((9, n), np.float32), np.empty(n, np.float32))
+        L.check(self.lib.replay_get(self._h, *[x.ctypes.data_as(L.PF) for x in (s, a, r, s2, d)]))
+        return s, a, r, s2, d
+
+
+class Learner:
+    """actor, critic, their targets and both ADAM optimisers (DDPG.jl:30-46, input.jl:126-127)."""
+
+    def __init__(self, params=None, device=0, **kw):
+        self.lib = L.lib()
+        self.p = params if params is not None else L.default_ddpg_params(**kw)
+        h = C.c_void_p()
+        L.check(self.lib.ddpg_create(C.byref(self.p), int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self._dev = torch.device("cuda", self.device)
+        self._bind_stream()
+
+    def _bind_stream(self):
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream().cuda_stream
+        L.check(self.lib.ddpg_set_stream(self._h, C.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ddpg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        L.check(self.lib.ddpg_sync(self._h))
+
+    def layer_shape(self, net, layer):
+        S, A = self.p.state_size, self.p.action_size
+        critic = net in (L.NET_CRITIC, L.NET_CRITIC_TARGET)
+        dims = [(S + A if critic else S), self.p.l1, self.p.l2, (1 if critic else A)]
+        return dims[layer], dims[layer + 1]
+
+    def init(self, seed):
+        L.check(self.lib.ddpg_init(self._h, int(seed) & (2**64 - 1)))
+
+    def set_layer(self, net, layer, w=None, b=None):
+        w = np.ascontiguousarray(w, np.float32) if w is not None else None
+        b = np.ascontiguousarray(b, np.float32) if b is not None else None
+        L.check(self.lib.ddpg_set_layer(self._h, net, layer, w.ctypes.data_as(L.PF) if w is not None else None,
+                                        b.ctypes.data_as(L.PF) if b is not None else None))
+
+    def _get(self, fn, net, layer):
+        i, o = self.layer_shape(net, layer)
+        w, b = np.empty(i * o, np.float32), np.empty(o, np.float32)
+        L.check(fn(self._h, net, layer, w.ctypes.data_as(L.PF), b.ctypes.data_as(L.PF)))
+        return w, b
+
+    def get_layer(self, net, layer):
+        """(weight, bias) in Flux layout: weight[o + out*i] (out×in column-major)."""
+        return self._get(self.lib.ddpg_get_layer, net, layer)
+
+    def get_grad(self, net, layer):
+        return self._get(self.lib.ddpg_get_grad, net, layer)
+
+    def set_norm(self, s_min, s_max):
+        mn, mx = np.ascontiguousarray(s_min, np.float32), np.ascontiguousarray(s_max, np.float32)
+        L.check(self.lib.ddpg_set_norm(self._h, mn.ctypes.data_as(L.PF), mx.ctypes.data_as(L.PF)))
+
+    def act(self, obs, train=True, sigma=0.1, rng_act=0, step=0, env_id_base=0, noise=None):
+        """act(normalize(s); train) + scale_action for obs [9][n] -> (a [2][n] in [-1,1], scaled [2][n])."""
+        n = obs.shape[1]
+        a = torch.empty((2, n), dtype=torch.float32, device=self._dev)
+        sc = torch.empty((2, n), dtype=torch.float32, device=self._dev)
+        sg = float(sigma) if (train and noise is None) else 0.0
+        L.check(self.lib.ddpg_act(self._h, _ptr(obs), n, sg, int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(noise), _ptr(a), _ptr(sc)))
+        return a, sc
+
+    def replay(self, memory, rng_rpl=0, n_updates=1, idx=None):
+        """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back."""
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.int32)
+            assert idx.size == n_updates * self.p.batch
+            ip = idx.ctypes.data_as(L.PI)
+        L.check(self.lib.ddpg_update(self._h, memory._h, int(n_updates), ip, int(rng_rpl) & (2**64 - 1)))
+
+    def update_batch(self, s, a, r, s2, done=None):
+        L.check(self.lib.ddpg_update_batch(self._h, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(done)))
+
+    def losses(self):
+        lc, la = C.c_float(), C.c_float()
+        L.check(self.lib.ddpg_get_losses(self._h, C.byref(lc), C.byref(la)))
+        return lc.value, la.value
+
+    def grad_tensor(self):
+        from .env import _wrap_device
+        p, n = C.c_void_p(), C.c_int64()
+        L.check(self.lib.ddpg_grad_buffer(self._h, C.byref(p), C.byref(n)))
+        return _wrap_device(p.value, (n.value,), torch.float32, self._dev, self)
+
+
+class Driver:
+    """DDPG_reinforce_charger_v1.jl + DDPG.jl loop glue for N lock-stepped instances.
+
+    EP_LENGTH / NUM_EP / MEM_SIZE / noise σ follow input.jl; seeds are integers fed to Philox
+    (Julia's string-concatenated MersenneTwister seeds cannot be reproduced)."""
+
+    def __init__(self, env_train, env_eval=None, learner=None, mem_size=24_000, ep_length=72, sigma=0.1, updates_per_step=1,
+                 rng_run=1231):
+        self.env_train, self.env_eval = env_train, env_eval
+        self.learner = learner if learner is not None else Learner(device=env_train.device)
+        self.memory = Replay(mem_size, device=env_train.device)
+        self.mem_size, self.ep_length, self.sigma = int(mem_size), int(ep_length), float(sigma)
+        self.updates_per_step = int(updates_per_step)
+        self.rng_run = int(rng_run)
+        self.s_min = self.s_max = None
+        self.n_env_steps = 0
+
+    # populate_memory(env; rng) — memory_plotting_saving.jl:9-29 (fused random-policy rollouts)
+    def populate_memory(self, rng=None):
+        rng = self.rng_run if rng is None else rng
+        env = self.env_train
+        while len(self.memory) < self.mem_size:
+            env.reset(rng=rng)
+            env.rollout(L.POLICY_RANDOM, self.ep_length, seed=rng, replay=self.memory, want_return=False)
+            self.n_env_steps += self.ep_length * env.n_envs
+            rng += 1  # `rng += 1` per episode (:26)
+
+    # s_min, s_max = min_max_buffer(MIN_EXP_SIZE; rng_mm) — driver :30
+    def min_max_buffer(self, n=None, rng_mm=None):
+        n = self.mem_size if n is None else n
+        self.s_min, self.s_max = self.memory.min_max_buffer(n, rng_mm=self.rng_run if rng_mm is None else rng_mm)
+        self.learner.set_norm(self.s_min, self.s_max)
+        return self.s_min, self.s_max
+
+    # episode!(env; NUM_STEPS, train, track, rng_ep) — DDPG.jl:186-242
+    def episode(self, env, num_steps=None, train=True, track=0, rng_ep=0):
+        T = self.ep_length if num_steps is None else num_steps
+        env.reset(rng=rng_ep)
+        n = env.n_envs
+        reward_eps = torch.zeros(n, dtype=torch.float64, device=env._torch_dev)
+        noise_eps = 0.0
+        traces = []
+        s_prev = torch.empty((9, n), dtype=torch.float32, device=env._torch_dev)
+        for step in range(1, T + 1):
+            rng_step = (rng_ep * 1000003 + step) & (2**63 - 1)
+            s = env.state_tensor()
+            if track < 0:
+                a = env.action(track)  # DDPG.jl:210
+                r, s2, tr = env.step(a, track=track)
+                traces.append(tr)
+            else:
+                a, scaled = self.learner.act(s, train=train, sigma=self.sigma, rng_act=rng_step, step=step, env_id_base=env.env_id_base)
+                if train:
+                    s_prev.copy_(s)
+                if track == 0:
+                    r, s2 = env.step(scaled)
+                else:
+                    r, s2, tr = env.step(scaled, track=track)
+                    traces.append(tr)
+            reward_eps += r.double()
+            if train:
+                self.memory.push(s_prev, a, r, s2)  # remember(s, a, r, s′, finished) :229
+                self.learner.replay(self.memory, rng_rpl=rng_step, n_updates=self.updates_per_step)  # :231
+                self.n_env_steps += n
+        if track == 0:
+            return reward_eps, T, noise_eps
+        return reward_eps, torch.stack(traces)
+
+    # run_episodes — DDPG.jl:244-298 (periodic evaluation on env_eval every `test_every` episodes)
+    def run_episodes(self, num_ep, test_every=100, test_runs=100, seed_ini=123):
+        total_reward = np.zeros((num_ep, self.env_train.n_envs))
+        score_mean = []
+        for i in range(1, num_ep + 1):
+            rng_ep = self.rng_run * 100003 + i
+            r, _, _ = self.episode(self.env_train, train=True, rng_ep=rng_ep)
+            total_reward[i - 1] = r.cpu().numpy()
+            if self.env_eval is not None and i % test_every == 1:
+                score_all = 0.0
+                for test_ep in range(1, test_runs + 1):
+                    sc, _, _ = self.episode(self.env_eval, train=False, num_steps=self.ep_length, rng_ep=seed_ini * 1000 + test_ep)
+                    score_all += float(sc.mean())
+                score_mean.append(score_all / test_runs)
+        return total_reward, np.array(score_mean)
+
+    # inference(env; track) — memory_plotting_saving.jl:62-89: full-dataset deterministic rollout with the 23-column trace
+    def inference(self, env, num_steps, track=1):
+        if track < 0:
+            env.reset(rng=-1)
+            out = env.rollout(L.POLICY_RULE, num_steps, want_trace=True)
+            return out["ep_return"], out["trace"]
+        return self.episode(env, num_steps=num_steps, train=False, track=track, rng_ep=-1)

@@ -1,0 +1,231 @@
+"""GPU parity tests: replay ring, on-device sampling and the DDPG minibatch update against the CPU oracle.
+
+Tolerances (stated): the oracle accumulates dot products in double and rounds once; the CUDA kernels accumulate in
+fp32 (FMA, tiled order).  Forward outputs / gradients agree to 2e-4 relative (+1e-6·scale absolute); parameters after
+K updates agree to 2% of the distance Adam can move them (lr·K) plus 1e-5 relative — Adam's normalised step
+g/(|g|+ε) amplifies rounding noise of near-zero gradients, which bounds what any fp32 implementation can match.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), device="cuda")
+
+
+def test_ring_push_wrap_and_get(sb):
+    cap, n = 1000, 300
+    mem = sb.Replay(cap)
+    rng = np.random.default_rng(0)
+    allr = []
+    for k in range(5):  # 1500 transitions through a 1000-slot ring
+        s, a, r, s2 = (rng.normal(size=(9, n)).astype(np.float32), rng.normal(size=(2, n)).astype(np.float32),
+                       rng.normal(size=n).astype(np.float32), rng.normal(size=(9, n)).astype(np.float32))
+        mem.push(dev(s), dev(a), dev(r), dev(s2))
+        allr.append((s, a, r, s2))
+        assert len(mem) == min(cap, (k + 1) * n)
+    S = np.concatenate([x[0] for x in allr], 1)[:, -cap:]
+    A = np.concatenate([x[1] for x in allr], 1)[:, -cap:]
+    R = np.concatenate([x[2] for x in allr])[-cap:]
+    S2 = np.concatenate([x[3] for x in allr], 1)[:, -cap:]
+    s, a, r, s2, d = mem.get()  # oldest first, like a CircularBuffer
+    np.testing.assert_array_equal(s, S); np.testing.assert_array_equal(a, A)
+    np.testing.assert_array_equal(r, R); np.testing.assert_array_equal(s2, S2)
+    assert np.all(d == 0)
+    # getData with explicit indices
+    idx = rng.integers(0, cap, 120).astype(np.int32)
+    bs, ba, br, bs2, bd = mem.sample(120, idx=idx)
+    np.testing.assert_array_equal(bs.cpu().numpy(), S[:, idx]); np.testing.assert_array_equal(ba.cpu().numpy(), A[:, idx])
+    np.testing.assert_array_equal(br.cpu().numpy(), R[idx]); np.testing.assert_array_equal(bs2.cpu().numpy(), S2[:, idx])
+    with pytest.raises(sb.ShemsError):
+        mem.sample(4, idx=np.array([0, 1, 2, cap], np.int32))
+    # one push larger than the ring keeps the newest `cap`
+    big = sb.Replay(100)
+    s = rng.normal(size=(9, 250)).astype(np.float32)
+    z2, z1 = np.zeros((2, 250), np.float32), np.arange(250, dtype=np.float32)
+    big.push(dev(s), dev(z2), dev(z1), dev(s))
+    assert len(big) == 100
+    np.testing.assert_array_equal(big.get()[2], z1[-100:])
+
+
+def test_device_sampling_matches_oracle_spec(sb, O):
+    mem = sb.Replay(24000)
+    n = 24000
+    r = np.arange(n, dtype=np.float32)
+    z9, z2 = np.zeros((9, n), np.float32), np.zeros((2, n), np.float32)
+    z9[0] = r
+    mem.push(dev(z9), dev(z2), dev(r), dev(z9))
+    s, a, rr, s2, d = mem.sample(120, rng_dt=12345)
+    want = O.sample_indices(12345, 0, n, 120)  # i.i.d. with replacement (memory_plotting_saving.jl:33)
+    np.testing.assert_array_equal(rr.cpu().numpy().astype(np.int64), want)
+    mn, mx = mem.min_max_buffer(n, rng_mm=7)
+    draws = O.sample_indices(7, 0, n, n)
+    assert mn[0] == draws.min() and mx[0] == draws.max()  # min/max over the SAMPLE, not the buffer (quirk 6)
+    assert len(np.unique(draws)) / n == pytest.approx(0.632, abs=0.01)
+    mn2, mx2 = mem.min_max_buffer(5, idx=np.array([5, 9, 2, 2, 7], np.int32))
+    assert (mn2[0], mx2[0]) == (2, 9)
+    with pytest.raises(sb.ShemsError):
+        sb.Replay(10).sample(4)
+
+
+def _sync_nets(learner, orc):
+    for net in range(4):
+        for k in range(3):
+            w, b = orc.get_layer(net, k)
+            learner.set_layer(net, k, w, b)
+
+
+def _compare_nets(learner, orc, atol_w, rtol=1e-5, nets=range(4)):
+    for net in nets:
+        for k in range(3):
+            w, b = learner.get_layer(net, k)
+            ow, ob = orc.get_layer(net, k)
+            np.testing.assert_allclose(w, ow, rtol=rtol, atol=atol_w[net])
+            np.testing.assert_allclose(b, ob, rtol=rtol, atol=atol_w[net])
+
+
+def test_init_matches_oracle_spec(sb, O):
+    p = sb.default_ddpg_params()
+    le = sb.Learner(params=p)
+    le.init(42)
+    orc = O.OracleDdpg(O.default_ddpg_params())
+    orc.init(42)
+    for net in range(4):
+        for k in range(3):
+            w, b = le.get_layer(net, k)
+            ow, ob = orc.get_layer(net, k)
+            np.testing.assert_array_equal(w, ow)
+            np.testing.assert_array_equal(b, ob)
+    assert le.lib.ddpg_num_params(le._h, 0) == 129_002 and le.lib.ddpg_num_params(le._h, 1) == 129_001
+
+
+@pytest.mark.parametrize("B,l1,l2", [(120, 250, 500), (7, 16, 24), (33, 65, 31)])
+def test_update_parity_vs_oracle(sb, O, B, l1, l2):
+    rng = np.random.default_rng(B)
+    kw = dict(batch=B, l1=l1, l2=l2)
+    orc = O.OracleDdpg(O.default_ddpg_params(**kw))
+    orc.init(5)
+    le = sb.Learner(params=sb.default_ddpg_params(**kw))
+    for net in (0, 1):  # non-zero biases, targets different from the models
+        for k in range(3):
+            w, b = orc.get_layer(net, k)
+            b = rng.normal(0, 0.05, b.shape).astype(np.float32)
+            orc.set_layer(net, k, w, b)
+            orc.set_layer(net + 2, k, w * np.float32(0.9), b * np.float32(1.1))
+    _sync_nets(le, orc)
+    s_min = rng.uniform(-1, 0, 9).astype(np.float32)
+    s_max = (s_min + rng.uniform(0.5, 3, 9)).astype(np.float32)
+    s_max[5] = s_min[5]
+    orc.set_norm(s_min, s_max)
+    le.set_norm(s_min, s_max)
+    K = 5
+    for step in range(K):
+        s = rng.uniform(-1, 3, (9, B)).astype(np.float32)
+        a = rng.uniform(-1, 1, (2, B)).astype(np.float32)
+        r = rng.uniform(-5, 1, B).astype(np.float32)
+        s2 = rng.uniform(-1, 3, (9, B)).astype(np.float32)
+        orc.update_batch(s, a, r, s2)
+        le.update_batch(dev(s), dev(a), dev(r), dev(s2))
+        if step == 0:
+            for net in (0, 1):
+                for k in range(3):
+                    gw, gb = le.get_grad(net, k)
+                    ow, ob = orc.get_grad(net, k)
+                    sc = max(np.abs(ow).max(), 1e-12)
+                    np.testing.assert_allclose(gw, ow, rtol=2e-4, atol=2e-6 * sc)
+                    np.testing.assert_allclose(gb, ob, rtol=2e-4, atol=2e-6 * max(np.abs(ob).max(), 1e-12))
+        lc, la = le.losses()
+        olc, ola = orc.losses()
+        assert lc == pytest.approx(olc, rel=1e-4) and la == pytest.approx(ola, rel=1e-4, abs=1e-6)
+    p = le.p
+    atol = {0: 0.02 * p.lr_actor * K, 1: 0.02 * p.lr_critic * K, 2: 0.02 * p.lr_actor * K * p.tau + 1e-7, 3: 0.02 * p.lr_critic * K * p.tau + 1e-7}
+    _compare_nets(le, orc, atol)
+
+
+def test_update_from_replay_graph_path(sb, O, train_series):
+    """ddpg_update (CUDA-graph path, on-device sampling) == oracle fed with the same transitions and the spec's indices."""
+    n, T, B = 64, 72, 120
+    env = sb.Shems(T, train_series, n_envs=n)
+    mem = sb.Replay(n * T)
+    env.reset(rng=2)
+    env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
+    S, A, R, S2, D = mem.get()
+    le = sb.Learner()
+    le.init(9)
+    orc = O.OracleDdpg(O.default_ddpg_params())
+    orc.init(9)
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
+    le.set_norm(mn, mx)
+    orc.set_norm(mn, mx)
+    K = 4
+    le.replay(mem, rng_rpl=31, n_updates=K)       # Philox indices, counter = update number
+    for u in range(K):
+        idx = O.sample_indices(31, u, len(mem), B)
+        orc.update_batch(S[:, idx], A[:, idx], R[idx], S2[:, idx], D[idx])
+    p = le.p
+    atol = {0: 0.02 * p.lr_actor * K, 1: 0.02 * p.lr_critic * K, 2: 0.02 * p.lr_actor * K * p.tau + 1e-7, 3: 0.02 * p.lr_critic * K * p.tau + 1e-7}
+    _compare_nets(le, orc, atol)
+    lc, la = le.losses()
+    olc, ola = orc.losses()
+    assert lc == pytest.approx(olc, rel=1e-3) and la == pytest.approx(ola, rel=1e-3, abs=1e-6)
+    # explicit host indices drive the same graph
+    le2 = sb.Learner()
+    le2.init(9)
+    le2.set_norm(mn, mx)
+    idx_all = np.stack([O.sample_indices(31, u, len(mem), B) for u in range(K)])
+    le2.replay(mem, n_updates=K, idx=idx_all)
+    for net in range(4):
+        for k in range(3):
+            np.testing.assert_array_equal(le2.get_layer(net, k)[0], le.get_layer(net, k)[0])  # deterministic: bit-identical
+
+
+def test_act_parity_and_noise(sb, O):
+    rng = np.random.default_rng(3)
+    le = sb.Learner()
+    le.init(4)
+    orc = O.OracleDdpg(O.default_ddpg_params())
+    orc.init(4)
+    mn, mx = np.zeros(9, np.float32), rng.uniform(1, 5, 9).astype(np.float32)
+    le.set_norm(mn, mx)
+    orc.set_norm(mn, mx)
+    n = 8192
+    obs = (rng.uniform(0, 1, (9, n)) * mx[:, None]).astype(np.float32)
+    a, sc = le.act(dev(obs), train=False)
+    oa, osc = orc.act(obs)
+    np.testing.assert_allclose(a.cpu().numpy(), oa, rtol=2e-4, atol=2e-6)
+    np.testing.assert_array_equal(sc.cpu().numpy(), ((a.cpu().numpy().astype(np.float64) + 1) * 0.5).astype(np.float32))
+    noise = rng.normal(0, 0.1, (2, n)).astype(np.float32)
+    a2, _ = le.act(dev(obs), noise=dev(noise))
+    oa2, _ = orc.act(obs, noise=noise)
+    np.testing.assert_allclose(a2.cpu().numpy(), oa2, rtol=2e-4, atol=2e-6)
+    # GNoise(σ=0.1) from Philox: N(0, 0.1²), clamped to [-1, 1], reproducible per (seed, step)
+    a3, _ = le.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=1)
+    d = (a3 - a).cpu().numpy()
+    assert abs(d.mean()) < 3e-3 and d.std() == pytest.approx(0.1, rel=0.03) and np.abs(a3.cpu().numpy()).max() <= 1
+    a4, _ = le.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=1)
+    assert torch.equal(a3, a4)
+    a5, _ = le.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=2)
+    assert not torch.equal(a3, a5)
+
+
+def test_driver_short_training_run(sb, train_series):
+    """populate_memory -> min_max_buffer -> a few training episodes -> rule-based and actor inference run end to end."""
+    env = sb.Shems(72, train_series, n_envs=32)
+    ev = sb.Shems(1439, sb.series.synth_charger98(1440, seed=7), n_envs=4)
+    drv = sb.Driver(env, ev, learner=sb.Learner(), mem_size=32 * 72 * 2, ep_length=72, sigma=0.1, rng_run=1231)
+    drv.learner.init(1231)
+    drv.populate_memory()
+    assert len(drv.memory) == 32 * 72 * 2
+    mn, mx = drv.min_max_buffer()
+    assert np.all(mx >= mn) and mx[5] == mn[5] == np.float32(0.4)  # p_buy is constant -> normalises to 0
+    tot, score = drv.run_episodes(2, test_every=2, test_runs=2)
+    assert tot.shape == (2, 32) and np.isfinite(tot).all() and len(score) == 1 and np.isfinite(score).all()
+    ret, trace = drv.inference(ev, 1439, track=-0.5)
+    assert trace.shape == (1439, 23, 4) and torch.isfinite(ret).all()
+    ret2, trace2 = drv.inference(ev, 50, track=1)
+    assert trace2.shape == (50, 23, 4)
+    lc, la = drv.learner.losses()
+    assert np.isfinite(lc) and np.isfinite(la)
