@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                    (the CPU arm: the oracle port on all host cores)
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): shems_LU1 random-action
+rollout, 2^20 instances per GPU x 8760 hourly steps on a synthetic ChargerID98-shaped 8761-row year series,
+every transition (s, a, r, s', done) written into the device-resident replay ring as populate_memory does
+(memory_plotting_saving.jl:9-29).  One bench "step" = one reset + one fused 8760-step rollout of all instances.
+Instances shard across ranks with no collective (global env id keys the RNG), per-GPU work fixed: "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "shems_LU1 env-steps/s (batched)"
+UNIT = "env-steps/s"
+ALG_BYTES_PER_ENV_STEP = 88  # s 36 + a 8 + r 4 + s' 36 + done 4 (rollout writing replay transitions)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--horizon", type=int, default=8760)
+    ap.add_argument("--ring-slots", type=int, default=16, help="replay ring capacity in multiples of envs-per-gpu")
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="0: auto-size the CPU sample to ~15 s")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-ddpg", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_rollout_rate(ser, horizon, n_envs, seed=1):
+    """env-steps/s of the CPU oracle (OpenMP over instances, all host cores) on n_envs x horizon steps."""
+    from oracle import oracle as O
+    P = O.params_for_charger(98)
+    env = O.OracleEnv(P, ser, horizon, n_envs)
+    env.reset(mode=2, seed=seed)
+    t0 = time.perf_counter()
+    env.rollout(1, horizon, seed=seed)
+    dt = time.perf_counter() - t0
+    return n_envs * horizon / dt, dt
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(ser, horizon, sample_envs=0, target_s=15.0):
+    cores = cpu_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if sample_envs <= 0:
+        probe = max(cores * 2, 16)
+        rate, dt = cpu_rollout_rate(ser, horizon, probe)
+        sample_envs = int(max(probe, min(1 << 16, target_s * rate / horizon)))
+        sample_envs = (sample_envs // cores) * cores or cores
+    rate, dt = cpu_rollout_rate(ser, horizon, sample_envs)
+    return dict(value=rate, unit=UNIT, cores=cores, kind="port",
+                sample=f"{sample_envs} instances x {horizon} steps (same series, same Philox actions), OpenMP over instances, {dt:.1f} s; "
+                       "the reference's Julia cannot run here (not installed), this is the repo's C restatement of it"), dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (Julia is not installed)."""
+    if rank != 0:
+        return
+    import shems_b200 as sb
+    ser = sb.series.synth_charger98(args.horizon + 1, seed=98)
+    cores = cpu_cores()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    probe_rate, _ = cpu_rollout_rate(ser, args.horizon, max(cores * 2, 16))
+    per_step_s = min(20.0, 120.0 / max(1, args.steps + args.warmup))
+    n = int(max(cores, per_step_s * probe_rate / args.horizon))
+    n = (n // cores) * cores or cores
+    for _ in range(args.warmup):
+        cpu_rollout_rate(ser, args.horizon, n)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_rollout_rate(ser, args.horizon, n)
+    dt = time.perf_counter() - t0
+    value = args.steps * n * args.horizon / dt
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32/f64 mixed",
+                data="synthetic", impl="reference",
+                config=dict(workload="shems_LU1 random-action rollout, bounded sample on host cores", envs=n, horizon=args.horizon,
+                            series_rows=args.horizon + 1, policy="random (populate_memory)", charger=98),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{n} instances x {args.horizon} steps per step, OpenMP over instances"),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
+    """DDPG updates/s at the reference's tuned config (B=120, MEM=24,000, 250/500) — reported beside the env metric."""
+    env = sb.Shems(72, ser_train, n_envs=1000)
+    mem = sb.Replay(24_000)
+    for ep in range(1):
+        env.reset(rng=ep + 1)
+        env.rollout(sb.POLICY_RANDOM, 24, seed=ep + 1, replay=mem, want_return=False)
+    le = sb.Learner()
+    le.init(1)
+    mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
+    le.set_norm(mn, mx)
+    le.replay(mem, rng_rpl=1, n_updates=50)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    le.replay(mem, rng_rpl=2, n_updates=n_updates)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, batch=120, l1=250, l2=500, mem=24_000,
+                kernels_per_update=21, flops_per_update=3.078e8)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import shems_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, T = args.envs_per_gpu, args.horizon
+    ser = sb.series.synth_charger98(T + 1, seed=98)
+    env = sb.Shems(T, ser, n_envs=n, device=local_rank, env_id_base=rank * n)
+    mem = sb.Replay(n * args.ring_slots, device=local_rank)
+    # e2e inputs: the two reset draws per instance come from pinned HOST memory every step (H2D inside the timed region),
+    # the per-instance episode return is read back to pinned HOST memory every step (D2H inside the timed region)
+    rng = np.random.default_rng(1234 + rank)
+    idx0_pin = torch.ones(n, dtype=torch.int32).pin_memory()          # nrows - maxsteps == 1: the only admissible start row
+    socb0_pin = torch.from_numpy(rng.uniform(0, 6.75, n).astype(np.float32)).pin_memory()
+    ret_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    kernel_ms = []
+
+    def device_step(seed, timed):
+        env.reset(rng=seed)                      # reset kernel (Philox draws on the device)
+        if timed:
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+        out = env.rollout(sb.POLICY_RANDOM, T, seed=seed, replay=mem, want_return=True)
+        if timed:
+            k1.record()
+            kernel_ms.append((k0, k1))
+        return out
+
+    def e2e_step(seed):
+        env.reset(idx0=idx0_pin.numpy(), socb0=socb0_pin.numpy())     # H2D of the host draws + reset kernel
+        out = env.rollout(sb.POLICY_RANDOM, T, seed=seed, replay=mem, want_return=True)
+        ret_pin.copy_(out["ep_return"], non_blocking=True)            # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        return float(ret_pin[0])
+
+    # ---- device-resident throughput (`value`) ----
+    for w in range(args.warmup):
+        device_step(100 + w, False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev[0].record()
+    for k in range(args.steps):
+        device_step(1000 + k, True)
+    ev[1].record()
+    barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    # ---- end-to-end through the public API with host buffers (`e2e`) ----
+    for w in range(max(1, args.warmup // 2)):
+        e2e_step(200 + w)
+    barrier()
+    ev[2].record()
+    for k in range(args.steps):
+        e2e_step(2000 + k)
+    ev[3].record()
+    barrier()
+    ms_e2e = ev[2].elapsed_time(ev[3])
+    clocks = sampler.stop()
+    kern = [a.elapsed_time(b) for a, b in kernel_ms]
+    t = torch.tensor([ms, ms_e2e, float(np.mean(kern))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, kern_ms = (float(x) for x in t.cpu())
+    total_steps = float(world) * n * T * args.steps
+    value = total_steps / (ms * 1e-3)
+    e2e_value = total_steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = ALG_BYTES_PER_ENV_STEP * n * T / (kern_ms * 1e-3) / 1e9
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    kernel="shems_rollout_kernel<POLICY_RANDOM>", kernel_ms=kern_ms,
+                    algorithmic_bytes_per_launch=ALG_BYTES_PER_ENV_STEP * n * T, peak_source=peak_src)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32/f64 mixed (Julia promotion rules)", data="synthetic",
+                config=dict(workload="BASELINE configs[2]: shems_LU1 random-action rollout writing replay transitions",
+                            envs_per_gpu=n, envs_total=n * world, horizon=T, series_rows=T + 1, charger=98,
+                            replay_ring_transitions=n * args.ring_slots, bytes_per_env_step=ALG_BYTES_PER_ENV_STEP,
+                            l2_policy=f"working set per launch {ALG_BYTES_PER_ENV_STEP * n * args.ring_slots / 1e6:.0f} MB of ring >> 126 MB L2 (no flush needed)",
+                            parallelism=f"env-sharded x{world}, no collective"),
+                roofline=roofline, clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(8 * n), d2h_bytes_per_step=int(8 * n),
+                         note="reset draws (idx0, Soc_b0) from pinned host memory and episode returns back to pinned host memory every step"),
+                gpu_launches=int(2 * args.steps * 2))
+    if not args.skip_ddpg:
+        try:
+            line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
+        except Exception as e:  # never lose the env number to the secondary metric
+            line["ddpg"] = dict(error=str(e))
+    if not args.skip_cpu_baseline:
+        cb, _ = cpu_baseline(ser, T, args.cpu_sample_envs)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
