@@ -115,10 +115,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.gpu = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -126,10 +126,10 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
