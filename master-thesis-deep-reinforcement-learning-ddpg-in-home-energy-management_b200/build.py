@@ -19,6 +19,20 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines, verbose=False):
+    """tools/: a differently-tuned copy of the library (extra -D macros) as libshems_b200_<name>.so"""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = os.path.join(HERE, f"libshems_b200_{name}.so")
+    objs = []
+    for src, extra in UNITS:
+        o = os.path.join(CSRC, src.replace(".cu", f".{name}.o"))
+        subprocess.check_call([nvcc] + ARCH + COMMON + extra + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) +
+                              ["-c", os.path.join(CSRC, src), "-o", o])
+        objs.append(o)
+    subprocess.check_call([nvcc] + ARCH + ["-shared", "-o", out] + objs + ["-ccbin", "/usr/bin/g++"])
+    return out
+
+
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]

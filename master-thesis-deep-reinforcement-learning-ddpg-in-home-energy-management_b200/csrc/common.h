@@ -54,17 +54,31 @@ struct DevParams {
   float R_f;         // Float32(b.rate_max) (only where the Float64 min is provably equivalent)
   double R, sell, dw, pot;
   double eta_d, one_m_l_d, C_d, smax95;
+  // division by the constants eta / span / C as multiply + 2 FMA (see fdiv_const / ddiv_const in shems_device.cuh)
+  float r_eta_f, r_span_f;   // Float32(1/eta), Float32(1/span)
+  double r_eta_d, r_C_d;     // 1/Float64(eta), 1/Float64(C)
+  int fast_eta_f, fast_span_f;  // host-verified over all 2^23 significands: the 3-op sequence == IEEE division
+  int fast_d;                   // eta_d and C_d are Float32-valued: the 3-op sequence is provably correctly rounded
 };
+
+// ---- replay ring layout: 22 fields per transition, tiled so that one transition's fields sit at fixed
+// 128-byte strides: element (slot, k) lives at ((slot >> 5) * 22 + k) * 32 + (slot & 31).
+// A warp writing 32 consecutive slots stores one full 128-byte line per field, with the field offset an
+// immediate (no per-field address arithmetic in the rollout kernel).
+#define RING_FIELDS 22
+#define RING_S 0      // s[0..8]
+#define RING_A 9      // a[0..1]
+#define RING_R 11     // r
+#define RING_S2 12    // s'[0..8]
+#define RING_DONE 21  // done
+__host__ __device__ __forceinline__ size_t ring_base(long long slot) { return ((size_t)(slot >> 5) * RING_FIELDS) * 32 + (size_t)(slot & 31); }
+__host__ __device__ __forceinline__ size_t ring_off(long long slot, int k) { return ring_base(slot) + (size_t)k * 32; }
 
 struct ShemsReplay {
   int device;
   cudaStream_t stream;
   int64_t capacity, length, head;  // head = physical slot of the next push
-  float* s;     // [9][cap]
-  float* a;     // [2][cap]
-  float* r;     // [cap]
-  float* s2;    // [9][cap]
-  float* done;  // [cap]
+  float* ring;  // tiled SoA, see ring_off(): ceil(cap/32) tiles x 22 fields x 32 slots
   int32_t* idx_scratch;  // device scratch for sampled indices
   int64_t idx_scratch_n;
   float* minmax_scratch; // [18]

@@ -360,16 +360,16 @@ extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
 // ----------------------------------------------------------------------------- minibatch gather + normalize
 // getData() + normalize() (memory_plotting_saving.jl:31-42, 55-57): builds xs = [s_n; a], xs2[:, :9] = s'_n,
 // xspi[:, :9] = s_n, r, done for the B sampled transitions.  src arrays are SoA with leading dim `ld`.
+// src: either the replay ring (tiled layout, ring != NULL) or caller-supplied SoA arrays with leading dim ld (direct).
 __global__ void __launch_bounds__(128)
-ddpg_gather_kernel(const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr, const float* __restrict__ rs2,
-                   const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl, const int32_t* __restrict__ idx, int direct,
-                   const float* __restrict__ norm, int B, float* __restrict__ xs, float* __restrict__ xs2, float* __restrict__ xspi,
-                   float* __restrict__ r, float* __restrict__ done) {
+ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
+                   const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
+                   const int32_t* __restrict__ idx, const float* __restrict__ norm, int B, float* __restrict__ xs, float* __restrict__ xs2,
+                   float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= B) return;
-  long long slot;
-  if (direct) slot = j;
-  else {
+  float sv[9], s2v[9], a0, a1, rv, dv;
+  if (ring) {
     const long long len = ctrl->len, head = ctrl->head, cap = ctrl->cap;
     long long li;
     if (ctrl->use_idx) li = idx[(long long)ctrl->idx_cursor * B + j];
@@ -379,19 +379,27 @@ ddpg_gather_kernel(const float* __restrict__ rs, const float* __restrict__ ra, c
       li = (long long)(u53(w[0], w[1]) * (double)len);
       if (li >= len) li = len - 1;
     }
-    slot = head - len + li;
+    long long slot = head - len + li;
     if (slot < 0) slot += cap;
+    const float* q = ring + ring_base(slot);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { sv[k] = q[(RING_S + k) * 32]; s2v[k] = q[(RING_S2 + k) * 32]; }
+    a0 = q[(RING_A + 0) * 32]; a1 = q[(RING_A + 1) * 32]; rv = q[RING_R * 32]; dv = q[RING_DONE * 32];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { sv[k] = rs[k * ld + j]; s2v[k] = rs2[k * ld + j]; }
+    a0 = ra[j]; a1 = ra[ld + j]; rv = rr[j]; dv = rd ? rd[j] : 0.0f;
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
-    const float sn = __fdiv_rn(__fsub_rn(rs[k * ld + slot], norm[k]), den);
-    const float s2n = __fdiv_rn(__fsub_rn(rs2[k * ld + slot], norm[k]), den);
+    const float sn = __fdiv_rn(__fsub_rn(sv[k], norm[k]), den);
+    const float s2n = __fdiv_rn(__fsub_rn(s2v[k], norm[k]), den);
     xs[j * 11 + k] = sn; xspi[j * 11 + k] = sn; xs2[j * 11 + k] = s2n;
   }
-  xs[j * 11 + 9] = ra[slot]; xs[j * 11 + 10] = ra[ld + slot];
-  r[j] = rr[slot];
-  done[j] = rd ? rd[slot] : 0.0f;
+  xs[j * 11 + 9] = a0; xs[j * 11 + 10] = a1;
+  r[j] = rv;
+  done[j] = dv;
 }
 // last node of an update: advance the device-side counters (`βp .= βp .* β` of Flux.ADAM included)
 __global__ void ddpg_ctrl_advance_kernel(DdpgCtrl* ctrl, double b1, double b2) {
@@ -540,10 +548,11 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   return SHEMS_OK;
 }
 
-static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* s, const float* a, const float* r, const float* s2, const float* done, long long ld,
-                          int direct) {
+static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* ring, const float* s, const float* a, const float* r, const float* s2,
+                          const float* done, long long ld) {
   const int B = h->p.batch;
-  ddpg_gather_kernel<<<(B + 127) / 128, 128, 0, st>>>(s, a, r, s2, done, ld, h->ctrl, h->idx_dev, direct, h->norm, B, h->xs, h->xs2, h->xspi, h->r, h->done);
+  ddpg_gather_kernel<<<(B + 127) / 128, 128, 0, st>>>(ring, s, a, r, s2, done, ld, h->ctrl, h->idx_dev, h->norm, B, h->xs, h->xs2, h->xspi, h->r,
+                                                      h->done);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -557,7 +566,7 @@ static int ensure_graph(Ddpg* h, const ShemsReplay* rp) {
   CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { cudaStreamDestroy(cs); shems_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
-  int st = enqueue_gather(h, cs, rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, 0);
+  int st = enqueue_gather(h, cs, rp->ring, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   if (!st) st = enqueue_update_body(h, cs);
   e = cudaStreamEndCapture(cs, &h->graph);
   cudaStreamDestroy(cs);
@@ -604,7 +613,7 @@ extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, cons
 extern "C" int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev, const float* s2_dev, const float* done_dev) {
   REQUIRE(h && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "ddpg_update_batch: NULL argument");
   GUARD(h->device);
-  TRY(enqueue_gather(h, h->stream, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch, 1));
+  TRY(enqueue_gather(h, h->stream, nullptr, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch));
   TRY(enqueue_update_body(h, h->stream));
   h->n_updates += 1;
   return SHEMS_OK;

@@ -62,6 +62,29 @@ extern "C" int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* p) 
   return SHEMS_ERR_KEY;
 }
 
+// Exhaustive host check that q = x*r; e = fma(-q, d, x); q' = fma(e, r, q) equals the IEEE quotient x/d for every
+// Float32 significand (the exponent of x only scales the computation while nothing is subnormal — the device falls back
+// to the IEEE division below 2^-60).  ~10 ms per distinct divisor, cached.
+static int verify_fdiv_const(float d) {
+  static float cache_d[8]; static int cache_ok[8]; static int n_cache = 0;
+  for (int i = 0; i < n_cache; ++i) if (memcmp(&cache_d[i], &d, 4) == 0) return cache_ok[i];
+  int ok = (d == d) && d != 0.0f && fabsf(d) > 1e-30f && fabsf(d) < 1e30f;
+  if (ok) {
+    volatile float rv = 1.0f / d;
+    const float r = rv;
+    for (uint32_t m = 0x3f800000u; m < 0x40000000u && ok; ++m) {
+      float x; memcpy(&x, &m, 4);
+      volatile float q = x * r;
+      const float e = fmaf(-q, d, x);
+      const float q2 = fmaf(e, r, q);
+      volatile float ref = x / d;
+      if (q2 != ref) ok = 0;
+    }
+  }
+  if (n_cache < 8) { cache_d[n_cache] = d; cache_ok[n_cache] = ok; ++n_cache; }
+  return ok;
+}
+
 static DevParams make_dev_params(const ShemsParams& p) {
   DevParams d;
   d.pv_eta = p.pv_eta; d.b_eta = p.b_eta; d.smin = p.b_soc_min; d.smax = p.b_soc_max; d.loss = p.b_loss;
@@ -75,6 +98,12 @@ static DevParams make_dev_params(const ShemsParams& p) {
   d.R = p.b_rate_max; d.sell = p.sell_discount; d.dw = p.discomfort_weight_ev; d.pot = p.disc_pot;
   d.eta_d = (double)p.b_eta; d.one_m_l_d = (double)d.one_m_l; d.C_d = (double)d.C;
   d.smax95 = 0.95 * (double)p.b_soc_max;
+  { volatile float r1 = 1.0f / p.b_eta, r2 = 1.0f / d.span; d.r_eta_f = r1; d.r_span_f = r2; }
+  d.r_eta_d = 1.0 / d.eta_d; d.r_C_d = 1.0 / d.C_d;
+  d.fast_eta_f = verify_fdiv_const(p.b_eta);
+  d.fast_span_f = verify_fdiv_const(d.span);
+  // eta_d and C_d are converted Float32 values by construction (<= 24 significant bits): see ddiv_const
+  d.fast_d = ((double)(float)d.eta_d == d.eta_d) && ((double)(float)d.C_d == d.C_d) && d.eta_d != 0.0 && d.C_d != 0.0;
   return d;
 }
 
@@ -230,13 +259,21 @@ struct RolloutSinks {
   double* trace;       // [T][23][N]
   float* obs_traj;     // [T][9][N]
   float* reward_traj;  // [T][N]
-  // replay ring (SoA, capacity cap, first slot `head`)
-  float* rp_s; float* rp_a; float* rp_r; float* rp_s2; float* rp_done;
+  float* ring;         // replay ring (tiled SoA, common.h ring_off), capacity cap, first slot `head`
   long long cap, head;
 };
 
+// Occupancy matters more than anything else here (measured, profiles/r1_rollout_sweep.md): 128 threads x >= 6 blocks/SM
+// caps the kernel at 80 registers -> 24 warps/SM, enough to cover the FP64/XU latencies; at the compiler's
+// unconstrained 115 registers (8 warps/SM) the same code runs at half the speed.
+#ifndef ROLLOUT_THREADS
+#define ROLLOUT_THREADS 128
+#endif
+#ifndef ROLLOUT_MIN_BLOCKS
+#define ROLLOUT_MIN_BLOCKS 6
+#endif
 template <int POLICY, bool WANT_TRACE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ROLLOUT_THREADS, ROLLOUT_MIN_BLOCKS)
 shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                      int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
                      const float* __restrict__ tape, RolloutSinks S) {
@@ -248,6 +285,9 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
   for (int k = 0; k < 9; ++k) st[k] = obs[k * N + n];
   float cd_here = __ldg(&reinterpret_cast<const float*>(series)[8 * (size_t)(idx - 1) + 1]);
   double ret = 0.0;
+  long long slot = 0;
+  if (S.ring) { slot = S.head + n; if (slot >= S.cap) slot -= S.cap; }  // head < cap, n < N <= cap
+  uint32_t rw[4] = {0u, 0u, 0u, 0u};
   for (int t = 0; t < T; ++t) {
     StepIn s;
     s.Soc_b = st[0]; s.Soc_ev = st[1]; s.c_ev = st[2]; s.d_e = st[3]; s.g_e = st[4]; s.p_buy = st[5];
@@ -258,13 +298,18 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
       Bt = 0.0f; EVt = 0.0f; a_raw0 = B; a_raw1 = EV; track_neg = true;
     } else {
       if (POLICY == SHEMS_POLICY_RANDOM) {  // memory_plotting_saving.jl:14-19
-        uint32_t r[4];
-        philox4x32_10(seed, (uint64_t)(env_id_base + n), (uint32_t)(step0 + t), STREAM_ACTION, r);
-        a_raw0 = (float)(u53(r[0], r[1]) * 2.0 - 1.0);
-        a_raw1 = (float)(u53(r[2], r[3]) * 2.0 - 1.0);
-        // scale_action with bounds (0,0)/(1,1) (DDPG.jl:178-184, input.jl:182-183)
-        Bt = (float)(0.0 + (((double)a_raw0 + 1.0) * 0.5) * 1.0);
-        EVt = (float)(0.0 + (((double)a_raw1 + 1.0) * 0.5) * 1.0);
+        // one Philox block per two steps; u = w * 2^-32; a = Float32(2u - 1).  1 + u is assembled in the
+        // significand of a double in [1, 2): 2 (1 + u) - 3 == 2u - 1 exactly.
+        const unsigned st_abs = (unsigned)(step0 + t);
+        if (t == 0 || (st_abs & 1u) == 0u) philox4x32_10(seed, (uint64_t)(env_id_base + n), st_abs >> 1, STREAM_ACTION, rw);
+        const uint32_t w0 = (st_abs & 1u) ? rw[2] : rw[0], w1 = (st_abs & 1u) ? rw[3] : rw[1];
+        a_raw0 = (float)fma(__hiloint2double((int)(0x3ff00000u | (w0 >> 12)), (int)(w0 << 20)), 2.0, -3.0);
+        a_raw1 = (float)fma(__hiloint2double((int)(0x3ff00000u | (w1 >> 12)), (int)(w1 << 20)), 2.0, -3.0);
+        // scale_action with bounds (0,0)/(1,1) (DDPG.jl:178-184, input.jl:182-183): Float32((Float64(a) + 1.0) * 0.5).
+        // a is a multiple of 2^-31, so a + 1.0 and the halving are exact in Float64 and the single final rounding
+        // equals the Float32 add followed by the exact halving.
+        Bt = (a_raw0 + 1.0f) * 0.5f;
+        EVt = (a_raw1 + 1.0f) * 0.5f;
       } else {
         Bt = tape[((size_t)t * 2 + 0) * N + n];
         EVt = tape[((size_t)t * 2 + 1) * N + n];
@@ -277,17 +322,18 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
     const Row8 nx = load_row(series, idx + 1);
     float Soc_ev_new = o.Soc_ev;
     if (nx.cd >= 0.0f && cd_here == -1.0f) Soc_ev_new = nx.soc_ev;
-    if (S.rp_s) {  // remember(s, a, r, s', finished) — memory_plotting_saving.jl:46-47
-      long long slot = S.head + (long long)t * N + n;
-      slot -= (slot / S.cap) * S.cap;
+    if (S.ring) {  // remember(s, a, r, s', finished) — memory_plotting_saving.jl:46-47; 22 stores at fixed 128-byte strides
+      float* q = S.ring + ring_base(slot);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) S.rp_s[k * S.cap + slot] = st[k];
-      S.rp_a[slot] = a_raw0; S.rp_a[S.cap + slot] = a_raw1;
-      S.rp_r[slot] = (float)o.reward;
-      S.rp_s2[0 * S.cap + slot] = o.Soc_b; S.rp_s2[1 * S.cap + slot] = Soc_ev_new; S.rp_s2[2 * S.cap + slot] = nx.cd;
-      S.rp_s2[3 * S.cap + slot] = nx.d_e; S.rp_s2[4 * S.cap + slot] = nx.g_e; S.rp_s2[5 * S.cap + slot] = nx.p_buy;
-      S.rp_s2[6 * S.cap + slot] = nx.h_cos; S.rp_s2[7 * S.cap + slot] = nx.h_sin; S.rp_s2[8 * S.cap + slot] = nx.season;
-      S.rp_done[slot] = 0.0f;  // finished() is always false (shems_LU1.jl:487-502)
+      for (int k = 0; k < 9; ++k) q[(RING_S + k) * 32] = st[k];
+      q[(RING_A + 0) * 32] = a_raw0; q[(RING_A + 1) * 32] = a_raw1;
+      q[RING_R * 32] = (float)o.reward;
+      q[(RING_S2 + 0) * 32] = o.Soc_b; q[(RING_S2 + 1) * 32] = Soc_ev_new; q[(RING_S2 + 2) * 32] = nx.cd;
+      q[(RING_S2 + 3) * 32] = nx.d_e; q[(RING_S2 + 4) * 32] = nx.g_e; q[(RING_S2 + 5) * 32] = nx.p_buy;
+      q[(RING_S2 + 6) * 32] = nx.h_cos; q[(RING_S2 + 7) * 32] = nx.h_sin; q[(RING_S2 + 8) * 32] = nx.season;
+      q[RING_DONE * 32] = 0.0f;  // finished() is always false (shems_LU1.jl:487-502)
+      slot += N;
+      if (slot >= S.cap) slot -= S.cap;
     }
     if (WANT_TRACE) {
       double* q = S.trace + (size_t)t * SHEMS_TRACE_COLS * N + n;
@@ -508,11 +554,12 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
     REQUIRE(total <= rp->capacity || rp->capacity % e->n == 0, SHEMS_ERR_INVALID,
             "shems_rollout: replay capacity %lld must hold n_steps*n_envs=%lld or be a multiple of n_envs=%lld", (long long)rp->capacity,
             (long long)total, (long long)e->n);
-    S.rp_s = rp->s; S.rp_a = rp->a; S.rp_r = rp->r; S.rp_s2 = rp->s2; S.rp_done = rp->done; S.cap = rp->capacity; S.head = rp->head;
+    REQUIRE(e->n <= rp->capacity, SHEMS_ERR_INVALID, "shems_rollout: replay capacity %lld < n_envs %lld", (long long)rp->capacity, (long long)e->n);
+    S.ring = rp->ring; S.cap = rp->capacity; S.head = rp->head;
   }
-  const unsigned g = grid_for(e->n, 256);
+  const unsigned gro = grid_for(e->n, ROLLOUT_THREADS);
 #define LAUNCH_RO(POL, TR)                                                                                                          \
-  shems_rollout_kernel<POL, TR><<<g, 256, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, a->n_steps, e->step, a->seed,     \
+  shems_rollout_kernel<POL, TR><<<gro, ROLLOUT_THREADS, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, a->n_steps, e->step, a->seed,     \
                                                           a->env_id_base, a->tape_dev, S)
   const bool tr = a->trace_dev != nullptr;
   switch (a->policy) {

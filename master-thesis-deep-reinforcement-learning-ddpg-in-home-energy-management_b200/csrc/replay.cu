@@ -2,8 +2,8 @@
 // [s, a, r, s', done] (RL-SHEMS/input.jl:140; src/memory_plotting_saving.jl:31-57) as a
 // structure-of-arrays ring in HBM with on-device sampling.
 //
-// Layout: s[9][cap], a[2][cap], r[cap], s2[9][cap], done[cap] float32 = 88 B per transition.
-// Logical index i (0 = oldest) lives in physical slot (head - length + i) mod cap.
+// Layout: 22 float32 fields per transition (s 9, a 2, r 1, s' 9, done 1 = 88 B) in 32-slot tiles, see
+// ring_off() in common.h.  Logical index i (0 = oldest) lives in physical slot (head - length + i) mod cap.
 #include <new>
 #include <vector>
 #include <string.h>
@@ -19,11 +19,11 @@ extern "C" int32_t replay_create(int64_t capacity, int32_t device, ShemsReplay**
   REQUIRE(rp, SHEMS_ERR_INVALID, "replay_create: out of host memory");
   memset(rp, 0, sizeof(*rp));
   rp->device = device; rp->capacity = capacity;
-  const size_t c = (size_t)capacity;
+  const size_t tiles = ((size_t)capacity + 31) / 32;
   cudaError_t st;
-  if ((st = cudaMalloc(&rp->s, sizeof(float) * 9 * c)) != cudaSuccess || (st = cudaMalloc(&rp->a, sizeof(float) * 2 * c)) != cudaSuccess ||
-      (st = cudaMalloc(&rp->r, sizeof(float) * c)) != cudaSuccess || (st = cudaMalloc(&rp->s2, sizeof(float) * 9 * c)) != cudaSuccess ||
-      (st = cudaMalloc(&rp->done, sizeof(float) * c)) != cudaSuccess || (st = cudaMalloc(&rp->minmax_scratch, sizeof(float) * 18)) != cudaSuccess) {
+  if ((st = cudaMalloc(&rp->ring, sizeof(float) * RING_FIELDS * 32 * tiles)) != cudaSuccess ||
+      (st = cudaMemset(rp->ring, 0, sizeof(float) * RING_FIELDS * 32 * tiles)) != cudaSuccess ||
+      (st = cudaMalloc(&rp->minmax_scratch, sizeof(float) * 18)) != cudaSuccess) {
     shems_set_error("replay_create: %s", cudaGetErrorString(st));
     replay_destroy(rp);
     return SHEMS_ERR_CUDA;
@@ -34,7 +34,7 @@ extern "C" int32_t replay_create(int64_t capacity, int32_t device, ShemsReplay**
 extern "C" int32_t replay_destroy(ShemsReplay* rp) {
   if (!rp) return SHEMS_OK;
   GUARD(rp->device);
-  cudaFree(rp->s); cudaFree(rp->a); cudaFree(rp->r); cudaFree(rp->s2); cudaFree(rp->done); cudaFree(rp->idx_scratch); cudaFree(rp->minmax_scratch);
+  cudaFree(rp->ring); cudaFree(rp->idx_scratch); cudaFree(rp->minmax_scratch);
   delete rp;
   return SHEMS_OK;
 }
@@ -54,21 +54,21 @@ int replay_after_rollout(ShemsReplay* rp, int64_t n_written) {
 
 // remember() for n transitions: slot = (head + i) mod cap.  When n > cap only the last cap survive.
 __global__ void __launch_bounds__(256)
-replay_push_kernel(float* __restrict__ rs, float* __restrict__ ra, float* __restrict__ rr, float* __restrict__ rs2, float* __restrict__ rd,
-                   long long cap, long long head, const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ r,
-                   const float* __restrict__ s2, const float* __restrict__ done, long long n, long long first) {
+replay_push_kernel(float* __restrict__ ring, long long cap, long long head, const float* __restrict__ s, const float* __restrict__ a,
+                   const float* __restrict__ r, const float* __restrict__ s2, const float* __restrict__ done, long long n, long long first) {
   const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   long long slot = head + i;
   slot -= (slot / cap) * cap;
+  float* q = ring + ring_base(slot);
 #pragma unroll
-  for (int k = 0; k < 9; ++k) rs[k * cap + slot] = s[k * n + i];
-  ra[slot] = a[i];
-  ra[cap + slot] = a[n + i];
-  rr[slot] = r[i];
+  for (int k = 0; k < 9; ++k) q[(RING_S + k) * 32] = s[k * n + i];
+  q[(RING_A + 0) * 32] = a[i];
+  q[(RING_A + 1) * 32] = a[n + i];
+  q[RING_R * 32] = r[i];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) rs2[k * cap + slot] = s2[k * n + i];
-  rd[slot] = done ? done[i] : 0.0f;
+  for (int k = 0; k < 9; ++k) q[(RING_S2 + k) * 32] = s2[k * n + i];
+  q[RING_DONE * 32] = done ? done[i] : 0.0f;
 }
 
 extern "C" int32_t replay_push(ShemsReplay* rp, const float* s_dev, const float* a_dev, const float* r_dev, const float* s2_dev,
@@ -80,8 +80,8 @@ extern "C" int32_t replay_push(ShemsReplay* rp, const float* s_dev, const float*
   // only the newest `cap` of the n transitions can survive; skipping the rest also keeps slots single-writer
   const int64_t first = n > rp->capacity ? n - rp->capacity : 0;
   const int64_t cnt = n - first;
-  replay_push_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, rp->stream>>>(rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, rp->head,
-                                                                           s_dev, a_dev, r_dev, s2_dev, done_dev, n, first);
+  replay_push_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, rp->stream>>>(rp->ring, rp->capacity, rp->head, s_dev, a_dev, r_dev, s2_dev,
+                                                                           done_dev, n, first);
   CUDA_TRY(cudaGetLastError());
   return replay_after_rollout(rp, n);
 }
@@ -94,8 +94,7 @@ __device__ __forceinline__ long long replay_slot(long long logical, long long he
   return slot;
 }
 __global__ void __launch_bounds__(128)
-replay_sample_kernel(const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr, const float* __restrict__ rs2,
-                     const float* __restrict__ rd, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
+replay_sample_kernel(const float* __restrict__ ring, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
                      unsigned long long seed, unsigned update, int B, float* __restrict__ s, float* __restrict__ a, float* __restrict__ r,
                      float* __restrict__ s2, float* __restrict__ done) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,15 +107,15 @@ replay_sample_kernel(const float* __restrict__ rs, const float* __restrict__ ra,
     li = (long long)(u53(w[0], w[1]) * (double)len);
     if (li >= len) li = len - 1;
   }
-  const long long slot = replay_slot(li, head, len, cap);
+  const float* q = ring + ring_base(replay_slot(li, head, len, cap));
 #pragma unroll
-  for (int k = 0; k < 9; ++k) s[k * B + j] = rs[k * cap + slot];
-  a[j] = ra[slot];
-  a[B + j] = ra[cap + slot];
-  r[j] = rr[slot];
+  for (int k = 0; k < 9; ++k) s[k * B + j] = q[(RING_S + k) * 32];
+  a[j] = q[(RING_A + 0) * 32];
+  a[B + j] = q[(RING_A + 1) * 32];
+  r[j] = q[RING_R * 32];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) s2[k * B + j] = rs2[k * cap + slot];
-  done[j] = rd[slot];
+  for (int k = 0; k < 9; ++k) s2[k * B + j] = q[(RING_S2 + k) * 32];
+  done[j] = q[RING_DONE * 32];
 }
 
 static int ensure_idx_scratch(ShemsReplay* rp, int64_t n) {
@@ -144,8 +143,8 @@ extern "C" int32_t replay_sample(ShemsReplay* rp, int32_t batch, const int32_t* 
     CUDA_TRY(cudaMemcpyAsync(rp->idx_scratch, idx_host, sizeof(int32_t) * batch, cudaMemcpyHostToDevice, rp->stream));
     didx = rp->idx_scratch;
   }
-  replay_sample_kernel<<<(batch + 127) / 128, 128, 0, rp->stream>>>(rp->s, rp->a, rp->r, rp->s2, rp->done, rp->capacity, rp->head, rp->length,
-                                                                   didx, seed, 0u, batch, s_dev, a_dev, r_dev, s2_dev, done_dev);
+  replay_sample_kernel<<<(batch + 127) / 128, 128, 0, rp->stream>>>(rp->ring, rp->capacity, rp->head, rp->length, didx, seed, 0u, batch,
+                                                                   s_dev, a_dev, r_dev, s2_dev, done_dev);
   CUDA_TRY(cudaGetLastError());
   if (idx_host) CUDA_TRY(cudaStreamSynchronize(rp->stream));  // idx_host was staged asynchronously
   return SHEMS_OK;
@@ -162,7 +161,7 @@ __device__ __forceinline__ void atomic_maxf(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 __global__ void __launch_bounds__(256)
-replay_minmax_kernel(const float* __restrict__ rs, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
+replay_minmax_kernel(const float* __restrict__ ring, long long cap, long long head, long long len, const int32_t* __restrict__ idx,
                      unsigned long long seed, long long n, float* __restrict__ out /* [0..8]=min, [9..17]=max */) {
   float mn[9], mx[9];
 #pragma unroll
@@ -176,9 +175,9 @@ replay_minmax_kernel(const float* __restrict__ rs, long long cap, long long head
       li = (long long)(u53(w[0], w[1]) * (double)len);
       if (li >= len) li = len - 1;
     }
-    const long long slot = replay_slot(li, head, len, cap);
+    const float* q = ring + ring_base(replay_slot(li, head, len, cap));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { const float v = rs[k * cap + slot]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
+    for (int k = 0; k < 9; ++k) { const float v = q[(RING_S + k) * 32]; mn[k] = fminf(mn[k], v); mx[k] = fmaxf(mx[k], v); }
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
@@ -210,7 +209,7 @@ extern "C" int32_t replay_minmax(ShemsReplay* rp, int64_t n_samples, const int32
   CUDA_TRY(cudaMemcpyAsync(rp->minmax_scratch, init, sizeof(init), cudaMemcpyHostToDevice, rp->stream));
   long long blocks = (n_samples + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  replay_minmax_kernel<<<(unsigned)blocks, 256, 0, rp->stream>>>(rp->s, rp->capacity, rp->head, rp->length, didx, seed, n_samples, rp->minmax_scratch);
+  replay_minmax_kernel<<<(unsigned)blocks, 256, 0, rp->stream>>>(rp->ring, rp->capacity, rp->head, rp->length, didx, seed, n_samples, rp->minmax_scratch);
   CUDA_TRY(cudaGetLastError());
   float res[18];
   CUDA_TRY(cudaMemcpyAsync(res, rp->minmax_scratch, sizeof(res), cudaMemcpyDeviceToHost, rp->stream));
@@ -226,24 +225,20 @@ extern "C" int32_t replay_get(ShemsReplay* rp, float* s_host, float* a_host, flo
   const int64_t len = rp->length, cap = rp->capacity;
   if (len == 0) return SHEMS_OK;
   CUDA_TRY(cudaStreamSynchronize(rp->stream));
-  const int64_t start = ((rp->head - len) % cap + cap) % cap;
-  const int64_t n1 = (start + len <= cap) ? len : cap - start;  // first contiguous piece
-  auto copy_field = [&](float* dst, const float* src, int k) -> cudaError_t {
-    if (!dst) return cudaSuccess;
-    for (int f = 0; f < k; ++f) {
-      cudaError_t e1 = cudaMemcpy(dst + (size_t)f * len, src + (size_t)f * cap + start, sizeof(float) * (size_t)n1, cudaMemcpyDeviceToHost);
-      if (e1 != cudaSuccess) return e1;
-      if (n1 < len) {
-        e1 = cudaMemcpy(dst + (size_t)f * len + n1, src + (size_t)f * cap, sizeof(float) * (size_t)(len - n1), cudaMemcpyDeviceToHost);
-        if (e1 != cudaSuccess) return e1;
-      }
+  const size_t tiles = ((size_t)cap + 31) / 32;
+  std::vector<float> host(RING_FIELDS * 32 * tiles);
+  CUDA_TRY(cudaMemcpy(host.data(), rp->ring, sizeof(float) * host.size(), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < len; ++i) {  // logical order, oldest first
+    int64_t slot = rp->head - len + i;
+    if (slot < 0) slot += cap;
+    const float* q = host.data() + ring_base(slot);
+    for (int k = 0; k < 9; ++k) {
+      if (s_host) s_host[(size_t)k * len + i] = q[(RING_S + k) * 32];
+      if (s2_host) s2_host[(size_t)k * len + i] = q[(RING_S2 + k) * 32];
     }
-    return cudaSuccess;
-  };
-  CUDA_TRY(copy_field(s_host, rp->s, 9));
-  CUDA_TRY(copy_field(a_host, rp->a, 2));
-  CUDA_TRY(copy_field(r_host, rp->r, 1));
-  CUDA_TRY(copy_field(s2_host, rp->s2, 9));
-  CUDA_TRY(copy_field(done_host, rp->done, 1));
+    if (a_host) { a_host[i] = q[(RING_A + 0) * 32]; a_host[(size_t)len + i] = q[(RING_A + 1) * 32]; }
+    if (r_host) r_host[i] = q[RING_R * 32];
+    if (done_host) done_host[i] = q[RING_DONE * 32];
+  }
   return SHEMS_OK;
 }

@@ -5,10 +5,11 @@
 //
 // The Julia source is dynamically typed: which intermediates are Float32 and which are Float64
 // depends on the branch (zeros(11) are Float64, b.rate_max is Float64, `pv_ = 0` is an Int ...).
-// Here every flow branch ("leaf") only ASSIGNS values into a canonical set of registers — doubles
-// holding exactly-representable Float32 or genuine Float64 values — and the common tail applies
-// the rounding each leaf implies; the two leaves whose sums stay Float32 in Julia (A2a, B1a) are
-// flagged.  Built with -fmad=false: Julia never contracts a*b+c, so neither may this file.
+// Here the flow branches are evaluated with predicates/selects into a canonical set of registers —
+// doubles holding exactly-representable Float32 or genuine Float64 values — and the common tail
+// applies the rounding each branch implies; the two branches whose partial sums stay Float32 in Julia
+// (A2a: PV_EV + B_EV, B1a: B_DE + B_EV) are flagged.  Built with -fmad=false: Julia never contracts
+// a*b+c, so neither may this file (explicit fma()/fmaf() calls below are the only fused ops).
 #pragma once
 #include "common.h"
 
@@ -20,7 +21,7 @@ struct StepOut {
   double reward;        // env.reward (Float64)
 };
 struct StepTrace {  // the remaining `results` columns (:476-478); all values exact in double
-  double EV_target, EV, profit, discomfort, penalty, PV_DE, B_DE, GR_DE, PV_B, PV_GR, PV_EV, B_EV, GR_EV, EX_EV, B, B_target;
+  double EV, profit, discomfort, penalty, PV_DE, B_DE, GR_DE, PV_B, PV_GR, PV_EV, B_EV, GR_EV, EX_EV, B;
 };
 
 __device__ __forceinline__ float jl_minf(float x, float y) { return (y < x) ? y : x; }     // Base.min(x, y), no NaN
@@ -28,21 +29,38 @@ __device__ __forceinline__ double jl_mind(double x, double y) { return (y < x) ?
 // Base.clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x))
 __device__ __forceinline__ double jl_clampd(double x, double lo, double hi) { return (x > hi) ? hi : ((x < lo) ? lo : x); }
 
+// IEEE-754 correctly rounded x / d for a CONSTANT divisor as q = x*r; e = x - q*d (exact, FMA); q' = q + e*r.
+// Float32: `ok` says the host verified the sequence against x/d for all 2^23 significands of this d
+// (env.cu: verify_fdiv_const); operands so small that the residual would be subnormal take the IEEE path.
+__device__ __forceinline__ float fdiv_const(float x, float d, float r, int ok) {
+  if (!ok || (fabsf(x) < 8.6736174e-19f /* 2^-60 */ && x != 0.0f)) return x / d;
+  const float q = x * r;
+  const float e = fmaf(-q, d, x);
+  return fmaf(e, r, q);
+}
+// Float64 with a divisor that is a converted Float32 (<= 24 significant bits): q + e*r differs from x/d by
+// < 2^-105 relative, while x/d is either exactly representable-or-farther than 2^-77 relative from any
+// rounding midpoint (x - m*d lies on a grid of 2^-76 |x| and cannot vanish for a 54-bit odd m), so
+// RN(q + e*r) == RN(x/d) for every normal x.  `ok` = the divisor really is Float32-valued.
+__device__ __forceinline__ double ddiv_const(double x, double d, double r, int ok) {
+  if (!ok) return x / d;
+  const double q = x * r;
+  const double e = fma(-q, d, x);
+  return fma(e, r, q);
+}
+
 // action(env, a::ShemsAction) :283-316 -> Float32.([B, EV])
 __device__ __forceinline__ void shems_action_drl(const DevParams& P, float Soc_b, float Soc_ev, float c_ev, float d_e,
                                                  float g_e, float Bt, float EVt, float& B, float& EV) {
-  const float perc = (Soc_b - P.smin) / P.span;                                   // :288
-  EV = (c_ev > -1.0f && Soc_ev < EVt) ? jl_minf(P.evR, (EVt - Soc_ev) * P.C) : 0.0f;  // :292-297
-  const float pv = (g_e - d_e) - EV;                                              // :301
-  if (pv > 0.0f && perc < Bt) {                                                   // :304
-    const float Btv = Bt * P.span + P.smin;                                       // :306 (two roundings, fmad off)
-    const double hi = jl_mind(P.R, (double)((Btv - Soc_b) + P.loss));             // :307
-    B = (float)jl_clampd((double)pv, 0.0, hi);
-  } else if (Soc_b > 1e-3f) {                                                     // :309
-    B = (float)(-jl_mind(P.R, (double)(P.one_m_l * Soc_b)));                      // :310
-  } else {
-    B = 0.0f;
-  }
+  const float perc = fdiv_const(Soc_b - P.smin, P.span, P.r_span_f, P.fast_span_f);       // :288
+  EV = (c_ev > -1.0f && Soc_ev < EVt) ? jl_minf(P.evR, (EVt - Soc_ev) * P.C) : 0.0f;      // :292-297
+  const float pv = (g_e - d_e) - EV;                                                      // :301
+  // :304-313 evaluated branch-free: charge request / discharge request / nothing
+  const float Btv = Bt * P.span + P.smin;                                                 // :306 (two roundings, fmad off)
+  const double hi = jl_mind(P.R, (double)((Btv - Soc_b) + P.loss));                       // :307
+  const float Bc = (float)jl_clampd((double)pv, 0.0, hi);
+  const float Bd = (float)(-jl_mind(P.R, (double)(P.one_m_l * Soc_b)));                   // :310
+  B = (pv > 0.0f && perc < Bt) ? Bc : ((Soc_b > 1e-3f) ? Bd : 0.0f);
 }
 
 // action(env, track) rule-based controller :318-340 -> Float32.([B, EV])
@@ -50,106 +68,71 @@ __device__ __forceinline__ void shems_action_rule(const DevParams& P, float Soc_
                                                   float& B, float& EV) {
   EV = jl_minf(P.evR, (1.0f - Soc_ev) * P.C);                                     // :323
   const float pv = (g_e - d_e) - EV;                                              // :327
-  if (pv > 0.0f && (double)Soc_b < P.smax95) {                                    // :330 (0.95 is Float64)
-    const double hi = jl_mind(P.R, (double)((P.smax - Soc_b) + P.loss));          // :331
-    B = (float)jl_clampd((double)pv, 0.0, hi);
-  } else if (Soc_b > 1e-3f) {                                                     // :333
-    B = (float)(-jl_mind(P.R, (double)(P.one_m_l * Soc_b)));                      // :334
-  } else {
-    B = 0.0f;
-  }
+  const double hi = jl_mind(P.R, (double)((P.smax - Soc_b) + P.loss));            // :331
+  const float Bc = (float)jl_clampd((double)pv, 0.0, hi);
+  const float Bd = (float)(-jl_mind(P.R, (double)(P.one_m_l * Soc_b)));           // :334
+  B = (pv > 0.0f && (double)Soc_b < P.smax95) ? Bc : ((Soc_b > 1e-3f) ? Bd : 0.0f);  // :330 (0.95 is Float64), :333
 }
 
-// step! :343-485 given the feasible (B, EV) and the recorded targets (Bt, EVt).
-// TRACK_NEG <=> track < 0 (no penalty in the reward, :466-471).
+// step! :343-485 given the feasible (B, EV) and the recorded EV target.  track_neg <=> track < 0
+// (no penalty in the reward, :466-471).
 template <bool WANT_TRACE>
 __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn& s, float B, float EV, float EVt,
                                                bool track_neg, StepTrace* tr) {
   const float eta = P.b_eta;
   const double eta_d = P.eta_d;
-  // :362-364  battery discharge amount (Float64)
-  double BD = 0.0;
-  if (B < -0.01f) {  // F32 < -0.01 (Float64 literal) <=> F32 < -0.01f0, see tests/test_oracle_env.py
-    BD = jl_clampd((double)(-B), 0.001, jl_mind(P.R, (double)(P.one_m_l_e * s.Soc_b)));
-  }
-  // canonical registers (values exact in double)
-  float PV_DE, PV_EV = 0.0f, pv = 0.0f;  // always Float32 (or a zero)
-  double B_DE = 0.0, B_EV = 0.0, GR_DE = 0.0, GR_EV = 0.0;
-  bool leafA2a = false, leafB1a = false;
-  float f32sum = 0.0f;  // the Float32 partial sum of the flagged leaf
+  // :362-364  battery discharge budget (Float64).  F32 < -0.01 (Float64 literal) <=> F32 < -0.01f0.
+  const double BD0 = (B < -0.01f) ? jl_clampd((double)(-B), 0.001, jl_mind(P.R, (double)(P.one_m_l_e * s.Soc_b))) : 0.0;
+  // :368-409  PV -> demand -> EV, then battery -> demand -> EV, grid takes the slack
   const float ge = s.g_e * P.pv_eta;
-  if (ge > s.d_e) {  // :368 PV covers the demand
-    PV_DE = s.d_e;
-    pv = ge - PV_DE;
-    if (pv > EV) {   // :371
-      PV_EV = EV;
-      pv = pv - PV_EV;
-    } else {         // :374
-      PV_EV = pv;
-      pv = 0.0f;
-      const float rem = EV - PV_EV;
-      const float need = rem / eta;
-      if (BD > (double)need) {  // :377
-        B_EV = (double)rem;
-        BD = BD - (double)need;
-        leafA2a = true;
-        f32sum = PV_EV + rem;   // PV_EV + B_EV is a Float32 add in Julia (:435)
-      } else {                  // :380
-        B_EV = BD * eta_d;
-        BD = 0.0;
-        GR_EV = (double)rem - B_EV;
-      }
-    }
-  } else {           // :388 PV short of the demand
-    PV_DE = ge;
-    const float d = s.d_e - PV_DE;
-    const float dn = d / eta;
-    if (BD > (double)dn) {      // :392
-      B_DE = (double)d;
-      BD = BD - (double)dn;
-      const float en = EV / eta;
-      if (BD > (double)en) {    // :395
-        B_EV = (double)EV;
-        BD = BD - (double)en;
-        leafB1a = true;
-        f32sum = d + EV;        // B_DE + B_EV is a Float32 add in Julia (:432)
-      } else {                  // :398
-        B_EV = BD * eta_d;
-        BD = 0.0;
-        GR_EV = (double)EV - B_EV;
-      }
-    } else {                    // :403
-      B_DE = BD * eta_d;
-      BD = 0.0;
-      GR_DE = (double)d - B_DE;
-      GR_EV = (double)EV;
-    }
-  }
-  // :412-422 battery charging
-  double PV_B = 0.0;        // value of PV_B
-  double X = (double)s.Soc_b;  // Soc_b + PV_B + GR_B with Julia's rounding
-  double pv_d = (double)pv;  // pv_ / PV_GR
-  if (B > 0.01f) {  // F32 > 0.01 (Float64) <=> F32 > 0.01f0
-    const double BC = jl_clampd((double)B, 0.001, jl_mind(P.R, (double)(P.smax - s.Soc_b)));
-    const double thr = BC / eta_d;
-    if (pv_d > thr) {  // :414
-      PV_B = BC;
-      pv_d = pv_d - thr;
-      X = (double)s.Soc_b + BC;
-    } else {           // :417 PV_B = pv_ * b.eta stays Float32 (pv_ is Float32, or the Int 0)
-      const float pvb = pv * eta;
-      PV_B = (double)pvb;
-      pv_d = 0.0;
-      X = (double)(s.Soc_b + pvb);
-    }
+  const bool A = ge > s.d_e;                 // :368 PV covers the demand      (else :388)
+  const float pvr = ge - s.d_e;              // :370 PV left after the demand   (branch A)
+  const float dB = s.d_e - ge;               // :391 demand left after the PV   (branch B)
+  const bool A1 = A && (pvr > EV);           // :371 PV also covers the EV
+  const float PV_DE = A ? s.d_e : ge;        // :369 / :389
+  const float PV_EV = A ? (A1 ? EV : pvr) : 0.0f;   // :372 / :375
+  const float pv = A1 ? (pvr - EV) : 0.0f;   // :373 / :376 / :390  (Float32, or the Int 0)
+  // battery stage 1 (branch B only): the residual demand dB   :392-408
+  const float q1 = fdiv_const(dB, eta, P.r_eta_f, P.fast_eta_f);
+  const bool cover1 = (!A) && (BD0 > (double)q1);
+  const double B_DE = A ? 0.0 : (cover1 ? (double)dB : BD0 * eta_d);              // :393 / :404
+  const double GR_DE = (A || cover1) ? 0.0 : ((double)dB - B_DE);                 // :406
+  const double BD1 = A ? BD0 : (cover1 ? BD0 - (double)q1 : 0.0);                 // :394 / :405
+  // battery stage 2: the EV share not served by PV — x2 = EV - PV_EV (:377-384); in branch B it is EV itself (:395-402)
+  const float x2 = EV - PV_EV;
+  const float q2 = fdiv_const(x2, eta, P.r_eta_f, P.fast_eta_f);
+  const bool act2 = A ? (!A1) : cover1;
+  const bool cover2 = act2 && (BD1 > (double)q2);
+  const double B_EV = cover2 ? (double)x2 : (act2 ? BD1 * eta_d : 0.0);           // :378/:396, :381/:399
+  const double GR_EV = cover2 ? 0.0 : (act2 ? ((double)x2 - B_EV) : (A ? 0.0 : (double)EV));  // :383/:401, :407
+  // Julia keeps these two partial sums in Float32 (both addends are Float32 on exactly these paths)
+  const bool leafA2a = A && cover2;          // PV_EV + B_EV  (:435)
+  const bool leafB1a = (!A) && cover2;       // B_DE + B_EV   (:432)
+  const float f32sum = A ? (PV_EV + x2) : (dB + EV);
+  // :412-422 battery charging.  F32 > 0.01 (Float64) <=> F32 > 0.01f0
+  double PV_B = 0.0, X = (double)s.Soc_b, pv_d = (double)pv;
+  if (B > 0.01f) {
+    const double BC = jl_clampd((double)B, 0.001, jl_mind(P.R, (double)(P.smax - s.Soc_b)));   // :413
+    const double thr = ddiv_const(BC, eta_d, P.r_eta_d, P.fast_d);
+    const bool c1 = pv_d > thr;              // :414
+    const float pvb = pv * eta;              // :418 stays Float32 (pv_ is Float32 or the Int 0)
+    PV_B = c1 ? BC : (double)pvb;
+    X = c1 ? ((double)s.Soc_b + BC) : (double)(s.Soc_b + pvb);
+    pv_d = c1 ? (pv_d - thr) : 0.0;          // :416 / :419
   }
   // :432  (1 - loss) * (Soc_b + PV_B + GR_B - (B_DE + B_EV + B_GR) / eta)
-  const double Y = leafB1a ? (double)(f32sum / eta) : (B_DE + B_EV) / eta_d;
+  double Y = 0.0;
+  if (BD0 > 0.0) {  // without a discharge budget B_DE = B_EV = 0 and the quotient is 0
+    const double Yd = ddiv_const(B_DE + B_EV, eta_d, P.r_eta_d, P.fast_d);
+    const float Yf = fdiv_const(f32sum, eta, P.r_eta_f, P.fast_eta_f);
+    Y = leafB1a ? (double)Yf : Yd;
+  }
   StepOut o;
   o.Soc_b = (float)(P.one_m_l_d * (X - Y));
   // :435  Soc_ev + (PV_EV + B_EV + GR_EV) / (ev.soc_max - ev.soc_min)
   const double T = leafA2a ? (double)f32sum : (((double)PV_EV + B_EV) + GR_EV);
-  float Soc_ev_new = (float)((double)s.Soc_ev + T / P.C_d);
+  float Soc_ev_new = s.Soc_ev;
+  if (T != 0.0) Soc_ev_new = (float)((double)s.Soc_ev + ddiv_const(T, P.C_d, P.r_C_d, P.fast_d));
   // :438-449
   float disc = 0.0f, pen = 0.0f, EX_EV = 0.0f;
   if (s.c_ev == 0.0f && Soc_ev_new < 1.0f) {

@@ -399,12 +399,15 @@ void oracle_reset_draws(const ShemsParams* P, int nrows, int maxsteps, uint64_t 
   *idx0 = 1 + k;
 }
 
-/* random warm-up action a = Float32.(rand(2) .* 2 .- 1) (memory_plotting_saving.jl:17) at (env, step) */
+/* random warm-up action a = Float32.(rand(2) .* 2 .- 1) (memory_plotting_saving.jl:17) at (env, step).
+ * Spec: one Philox block serves two consecutive steps (ctr = step >> 1; words 0,1 for even, 2,3 for odd
+ * steps); u = word * 2^-32 stands in for Julia's Float64 rand(). */
 void oracle_random_action(uint64_t seed, uint64_t env_id, uint32_t step, float* a) {
   uint32_t r[4];
-  oracle_philox(seed, env_id, step, STREAM_ACTION, r);
-  volatile double a0 = oracle_u53(r[0], r[1]) * 2.0; a0 = a0 - 1.0;
-  volatile double a1 = oracle_u53(r[2], r[3]) * 2.0; a1 = a1 - 1.0;
+  oracle_philox(seed, env_id, step >> 1, STREAM_ACTION, r);
+  const uint32_t w0 = r[(step & 1u) * 2u], w1 = r[(step & 1u) * 2u + 1u];
+  volatile double a0 = ((double)w0 * (1.0 / 4294967296.0)) * 2.0; a0 = a0 - 1.0;
+  volatile double a1 = ((double)w1 * (1.0 / 4294967296.0)) * 2.0; a1 = a1 - 1.0;
   a[0] = (float)a0; a[1] = (float)a1;
 }
 
