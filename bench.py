@@ -186,7 +186,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, T = args.envs_per_gpu, args.horizon
     ser = sb.series.synth_charger98(T + 1, seed=98)
-    env = sb.Shems(T, ser, n_envs=n, device=local_rank, env_id_base=rank * n)
+    from shems_b200 import sharding
+    env_base, _ = sharding.weak_range(n, rank)
+    env = sb.Shems(T, ser, n_envs=n, device=local_rank, env_id_base=env_base)
     mem = sb.Replay(n * args.ring_slots, device=local_rank)
     # e2e inputs: the two reset draws per instance come from pinned HOST memory every step (H2D inside the timed region),
     # the per-instance episode return is read back to pinned HOST memory every step (D2H inside the timed region)

@@ -159,6 +159,7 @@ SHEMS_API int32_t shems_get_state(ShemsEnv* env, float* obs_host /* [9][N] */, i
 SHEMS_API int32_t shems_set_state(ShemsEnv* env, const float* obs_host /* [9][N] */, const int32_t* idx_host /* [N] */);
 SHEMS_API int32_t shems_get_step(const ShemsEnv* env, int32_t* step);
 SHEMS_API int64_t shems_num_envs(const ShemsEnv* env);
+SHEMS_API int32_t shems_num_rows(const ShemsEnv* env); /* nrow(df) of the series (shems_LU1.jl:225) */
 
 /* Fused T-step rollout: episode!/populate_memory/inference loops with the policy evaluated
  * on the device (DDPG.jl:186-242, memory_plotting_saving.jl:9-29, 62-89).  State stays in

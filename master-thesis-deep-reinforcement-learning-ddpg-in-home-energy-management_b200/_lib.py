@@ -78,6 +78,7 @@ SIGNATURES = {
     "shems_set_state": (I32, [VP, PF, PI]),
     "shems_get_step": (I32, [VP, PI]),
     "shems_num_envs": (I64, [VP]),
+    "shems_num_rows": (I32, [VP]),
     "shems_rollout": (I32, [VP, C.POINTER(ShemsRolloutArgs)]),
     "replay_create": (I32, [I64, I32, C.POINTER(VP)]),
     "replay_destroy": (I32, [VP]),

@@ -419,6 +419,7 @@ extern "C" int32_t shems_sync(ShemsEnv* e) {
   return SHEMS_OK;
 }
 extern "C" int64_t shems_num_envs(const ShemsEnv* e) { return e ? e->n : 0; }
+extern "C" int32_t shems_num_rows(const ShemsEnv* e) { return e ? e->nrows : 0; }
 extern "C" int32_t shems_get_step(const ShemsEnv* e, int32_t* step) {
   REQUIRE(e && step, SHEMS_ERR_INVALID, "shems_get_step: NULL argument");
   *step = e->step;
