@@ -46,60 +46,123 @@ struct GemmProblem {
 };
 struct GemmBatch { GemmProblem p[4]; int count; };
 
-#define BM 32
-#define BN 32
 #define BK 32
-#define GEMM_THREADS 128
-#define AS_LD (BM + 2)
-#define BS_LD (BN + 4)
+#define GEMM_KGROUPS 4                       // intra-CTA split-K: each k-group owns BK/4 of every k-tile
+#define GEMM_STAGES 3
 
-__global__ void __launch_bounds__(GEMM_THREADS)
+// 4-byte cp.async (LDGSTS) with zero fill when `valid` is false: the tile loads bypass registers and stay in flight
+// across GEMM_STAGES tiles.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// the fused epilogues (see the EPI_* enum)
+__device__ __forceinline__ float gemm_epilogue(const GemmProblem& p, int m, int n, float v) {
+  switch (p.epi) {
+    case EPI_BIAS_RELU: v += p.bias[n]; v = v > 0.0f ? v : 0.0f; break;
+    case EPI_BIAS_TANH: v += p.bias[n]; v = tanhf(v); break;
+    case EPI_BIAS_ID: v += p.bias[n]; break;
+    case EPI_RELU_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v : 0.0f; break;
+    case EPI_SCALE_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v * p.alpha : 0.0f; break;
+    case EPI_TANH_GRAD: { const float y = p.aux[m * p.auxld + n]; v = v * (1.0f - y * y); } break;
+    case EPI_TD_TARGET: {  // y = r + γ(1-done) q'   (DDPG.jl:133);  dq = 2 (q - y) / B  (d mse / d q)
+      const float q2 = v + p.bias[n];
+      const float y = p.aux[m] + (p.alpha * (1.0f - p.aux2[m])) * q2;
+      v = y;
+      p.out2[m] = 2.0f * (p.aux3[m] - y) * p.inv_batch;
+    } break;
+    default: break;
+  }
+  return v;
+}
+
+// C = epilogue(A · B) for up to 4 independent problems (blockIdx.z).  TBM×TBN output tile per CTA, k-tiles of 32 in a
+// 3-stage cp.async ring.  These problems are small (B = 120 rows): the kernel is built for latency, not for peak
+// FLOPs — 4 k-groups × the classic 2×4 register tiling keep the schedulers busy, partial sums meet in shared memory
+// in a fixed order (deterministic), and all threads run the fused epilogue and the coalesced store.  The 16×16
+// variant quadruples the CTA count for launches that would otherwise occupy a fraction of the 148 SMs.
+template <int TBM, int TBN>
+__global__ void __launch_bounds__(TBM * TBN / 2)
 gemm_batch_kernel(const GemmBatch gb) {
+  constexpr int THREADS = TBM * TBN / 2;          // 4 k-groups x (TBM/2 x TBN/4) threads
+  constexpr int GROUP = THREADS / GEMM_KGROUPS;
+  constexpr int TXN = TBN / 4;                    // threads along n inside a k-group
+  constexpr int AS_LD = TBM + 2, BS_LD = TBN + 4, RED_LD = TBN + 1;
+  constexpr int EA = TBM * BK / THREADS, EB = BK * TBN / THREADS;
   const GemmProblem& p = gb.p[blockIdx.z];
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;  // M tiles on grid.x (no 65535 limit for large batches)
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;  // M tiles on grid.x (no 65535 limit for large batches)
   if (m0 >= p.M || n0 >= p.N) return;
-  __shared__ __align__(16) float As[2][BK][AS_LD];
-  __shared__ __align__(16) float Bs[2][BK][BS_LD];
+  __shared__ __align__(16) float As[GEMM_STAGES][BK][AS_LD];
+  __shared__ __align__(16) float Bs[GEMM_STAGES][BK][BS_LD];
+  __shared__ float red[GEMM_KGROUPS][TBM][RED_LD];
+  __shared__ float colred[GEMM_KGROUPS][TBN];
   const int tid = threadIdx.x;
-  const int tx = tid & 7, ty = tid >> 3;  // thread tile: rows ty*2..+1, cols tx*4..+3
-  // global->smem mapping: 8 elements of each operand per thread, walking the contiguous dimension
+  const int kg = tid / GROUP, t = tid % GROUP;
+  const int tx = t % TXN, ty = t / TXN;  // thread tile inside the k-group: rows ty*2..+1, cols tx*4..+3
+  // global->smem mapping, walking the contiguous dimension of each operand
   const bool a_kfast = (p.sAk == 1);
   const bool b_nfast = (p.sBn == 1);
-  float ra[8], rb[8];
-  auto load_tiles = [&](int k0) {
+  const float* a_ptr[EA]; const float* b_ptr[EB];
+  float* a_dst[EA]; float* b_dst[EB];
+  int a_k[EA], b_k[EB]; bool a_ok[EA], b_ok[EB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = tid + j * GEMM_THREADS;
-      const int kk_a = a_kfast ? (e & 31) : (e >> 5), mm = a_kfast ? (e >> 5) : (e & 31);
-      const int gm = m0 + mm, gk = k0 + kk_a;
-      ra[j] = (gm < p.M && gk < p.K) ? __ldg(p.A + gm * p.sAm + gk * p.sAk) : 0.0f;
-      const int kk_b = b_nfast ? (e >> 5) : (e & 31), nn = b_nfast ? (e & 31) : (e >> 5);
-      const int gn = n0 + nn, gk2 = k0 + kk_b;
-      rb[j] = (gn < p.N && gk2 < p.K) ? __ldg(p.B + gk2 * p.sBk + gn * p.sBn) : 0.0f;
+  for (int j = 0; j < EA; ++j) {
+    const int e = tid + j * THREADS;
+    const int kk_a = a_kfast ? (e & 31) : (e / TBM), mm = a_kfast ? (e >> 5) : (e % TBM);
+    a_k[j] = kk_a; a_ok[j] = (m0 + mm) < p.M;
+    a_ptr[j] = p.A + (long long)(m0 + mm) * p.sAm + (long long)kk_a * p.sAk;
+    a_dst[j] = &As[0][kk_a][mm];
+  }
+#pragma unroll
+  for (int j = 0; j < EB; ++j) {
+    const int e = tid + j * THREADS;
+    const int kk_b = b_nfast ? (e / TBN) : (e & 31), nn = b_nfast ? (e % TBN) : (e >> 5);
+    b_k[j] = kk_b; b_ok[j] = (n0 + nn) < p.N;
+    b_ptr[j] = p.B + (long long)kk_b * p.sBk + (long long)(n0 + nn) * p.sBn;
+    b_dst[j] = &Bs[0][kk_b][nn];
+  }
+  const long long a_step = (long long)BK * p.sAk, b_step = (long long)BK * p.sBk;
+  auto issue_tile = [&](int tile, int buf) {
+    const int k0 = tile * BK;
+#pragma unroll
+    for (int j = 0; j < EA; ++j) {
+      const bool va = a_ok[j] && (k0 + a_k[j] < p.K);
+      cp_async4(a_dst[j] + buf * (BK * AS_LD), va ? a_ptr[j] + tile * a_step : p.A, va);
     }
-  };
-  auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int e = tid + j * GEMM_THREADS;
-      const int kk_a = a_kfast ? (e & 31) : (e >> 5), mm = a_kfast ? (e >> 5) : (e & 31);
-      As[buf][kk_a][mm] = ra[j];
-      const int kk_b = b_nfast ? (e >> 5) : (e & 31), nn = b_nfast ? (e & 31) : (e >> 5);
-      Bs[buf][kk_b][nn] = rb[j];
+    for (int j = 0; j < EB; ++j) {
+      const bool vb = b_ok[j] && (k0 + b_k[j] < p.K);
+      cp_async4(b_dst[j] + buf * (BK * BS_LD), vb ? b_ptr[j] + tile * b_step : p.B, vb);
     }
   };
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   float colsum = 0.0f;
-  const bool want_dbias = (p.dbias != nullptr) && (blockIdx.x == 0) && (tid < BN);
+  const bool want_dbias = (p.dbias != nullptr) && (blockIdx.x == 0);
+  const bool col_thread = want_dbias && (tid < GEMM_KGROUPS * TBN);  // thread (col = tid % TBN, k-quarter = tid / TBN)
   const int ntiles = (p.K + BK - 1) / BK;
-  load_tiles(0);
-  store_tiles(0);
-  __syncthreads();
-  for (int t = 0; t < ntiles; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < ntiles) load_tiles((t + 1) * BK);
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < ntiles) issue_tile(s, s);
+    cp_async_commit();
+  }
+  constexpr int KSUB = BK / GEMM_KGROUPS;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    cp_async_wait<GEMM_STAGES - 2>();  // tile `tile` has landed (this thread's copies) ...
+    __syncthreads();                   // ... and everyone's; everyone is also done with tile-1, whose buffer is refilled next
+    {
+      const int tn = tile + GEMM_STAGES - 1;
+      if (tn < ntiles) issue_tile(tn, tn % GEMM_STAGES);
+      cp_async_commit();
+    }
+    const int buf = tile % GEMM_STAGES;
+#pragma unroll
+    for (int kq = 0; kq < KSUB; ++kq) {
+      const int kk = kg * KSUB + kq;
       const float2 a = *reinterpret_cast<const float2*>(&As[buf][kk][ty * 2]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
       acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]);
@@ -107,40 +170,58 @@ gemm_batch_kernel(const GemmBatch gb) {
       acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]);
       acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
     }
-    if (want_dbias) {
+    if (col_thread) {
 #pragma unroll
-      for (int kk = 0; kk < BK; ++kk) colsum += Bs[buf][kk][tid];
+      for (int kq = 0; kq < KSUB; ++kq) colsum += Bs[buf][(tid / TBN) * KSUB + kq][tid % TBN];
     }
-    if (t + 1 < ntiles) store_tiles(buf ^ 1);
-    __syncthreads();
   }
-  if (want_dbias && n0 + tid < p.N) p.dbias[n0 + tid] = colsum;
+  // meet the k-groups' partial sums in shared memory (fixed order: deterministic)
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int m = m0 + ty * 2 + i;
-    if (m >= p.M) continue;
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n >= p.N) continue;
-      float v = acc[i][j];
-      switch (p.epi) {
-        case EPI_BIAS_RELU: v += p.bias[n]; v = v > 0.0f ? v : 0.0f; break;
-        case EPI_BIAS_TANH: v += p.bias[n]; v = tanhf(v); break;
-        case EPI_BIAS_ID: v += p.bias[n]; break;
-        case EPI_RELU_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v : 0.0f; break;
-        case EPI_SCALE_MASK: v = (p.aux[m * p.auxld + n] > 0.0f) ? v * p.alpha : 0.0f; break;
-        case EPI_TANH_GRAD: { const float y = p.aux[m * p.auxld + n]; v = v * (1.0f - y * y); } break;
-        case EPI_TD_TARGET: {  // y = r + γ(1-done) q'   (DDPG.jl:133);  dq = 2 (q - y) / B  (d mse / d q)
-          const float q2 = v + p.bias[n];
-          const float y = p.aux[m] + (p.alpha * (1.0f - p.aux2[m])) * q2;
-          v = y;
-          p.out2[m] = 2.0f * (p.aux3[m] - y) * p.inv_batch;
-        } break;
-        default: break;
-      }
-      p.C[m * p.ldc + n] = v;
+    for (int j = 0; j < 4; ++j) red[kg][ty * 2 + i][tx * 4 + j] = acc[i][j];
+  if (col_thread) colred[tid / TBN][tid % TBN] = colsum;
+  __syncthreads();
+  if (want_dbias && tid < TBN && n0 + tid < p.N) p.dbias[n0 + tid] = ((colred[0][tid] + colred[1][tid]) + colred[2][tid]) + colred[3][tid];
+#pragma unroll
+  for (int o = 0; o < (TBM * TBN) / THREADS; ++o) {
+    const int e = tid + o * THREADS;
+    const int mm = e / TBN, nn = e % TBN;
+    const int m = m0 + mm, n = n0 + nn;
+    if (m >= p.M || n >= p.N) continue;
+    const float v = ((red[0][mm][nn] + red[1][mm][nn]) + red[2][mm][nn]) + red[3][mm][nn];
+    p.C[m * p.ldc + n] = gemm_epilogue(p, m, n, v);
+  }
+}
+
+// Skinny problems (N <= 2: the output layers and the back-prop into the two action inputs): one warp per output row,
+// lanes stride over k, all loads of the row issued before the first use, warp-shuffle reduction.  A must be k-contiguous.
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const GemmBatch gb) {
+  const GemmProblem& p = gb.p[blockIdx.y];
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= p.M) return;
+  float a0 = 0.0f, a1 = 0.0f;
+  const float* arow = p.A + (long long)m * p.sAm;
+  const bool two = p.N > 1;
+  for (int kb = 0; kb < p.K; kb += 512) {  // 16 k-values per lane and pass: all 48 loads are issued before the first FMA
+    float av[16], b0[16], b1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = kb + i * 32 + lane;
+      const bool ok = k < p.K;
+      av[i] = ok ? __ldg(arow + k) : 0.0f;
+      b0[i] = ok ? __ldg(p.B + (long long)k * p.sBk) : 0.0f;
+      b1[i] = (ok && two) ? __ldg(p.B + (long long)k * p.sBk + p.sBn) : 0.0f;
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a0 = fmaf(av[i], b0[i], a0); a1 = fmaf(av[i], b1[i], a1); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); }
+  if (lane == 0) {
+    p.C[m * p.ldc] = gemm_epilogue(p, m, 0, a0);
+    if (two) p.C[m * p.ldc + 1] = gemm_epilogue(p, m, 1, a1);
   }
 }
 
@@ -154,7 +235,7 @@ struct DdpgCtrl {  // device-side control block read by the gather kernel (graph
   int use_idx;          // 1: indices supplied in idx buffer (consumed batch by batch)
   long long len, head, cap;
   int idx_cursor;
-  int pad;
+  unsigned blocks_done; // last-block-done counter of the final kernel of an update (advances the counters below)
   double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
 };
 
@@ -361,14 +442,16 @@ extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
 // getData() + normalize() (memory_plotting_saving.jl:31-42, 55-57): builds xs = [s_n; a], xs2[:, :9] = s'_n,
 // xspi[:, :9] = s_n, r, done for the B sampled transitions.  src arrays are SoA with leading dim `ld`.
 // src: either the replay ring (tiled layout, ring != NULL) or caller-supplied SoA arrays with leading dim ld (direct).
+// One thread per (sample j, state field k): thread k == 0 also moves a, r, done.
 __global__ void __launch_bounds__(128)
 ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
                    const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
                    const int32_t* __restrict__ idx, const float* __restrict__ norm, int B, float* __restrict__ xs, float* __restrict__ xs2,
                    float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = g / 9, k = g - j * 9;
   if (j >= B) return;
-  float sv[9], s2v[9], a0, a1, rv, dv;
+  float sv, s2v, a0 = 0.f, a1 = 0.f, rv = 0.f, dv = 0.f;
   if (ring) {
     const long long len = ctrl->len, head = ctrl->head, cap = ctrl->cap;
     long long li;
@@ -382,29 +465,17 @@ ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs,
     long long slot = head - len + li;
     if (slot < 0) slot += cap;
     const float* q = ring + ring_base(slot);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { sv[k] = q[(RING_S + k) * 32]; s2v[k] = q[(RING_S2 + k) * 32]; }
-    a0 = q[(RING_A + 0) * 32]; a1 = q[(RING_A + 1) * 32]; rv = q[RING_R * 32]; dv = q[RING_DONE * 32];
+    sv = q[(RING_S + k) * 32]; s2v = q[(RING_S2 + k) * 32];
+    if (k == 0) { a0 = q[(RING_A + 0) * 32]; a1 = q[(RING_A + 1) * 32]; rv = q[RING_R * 32]; dv = q[RING_DONE * 32]; }
   } else {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { sv[k] = rs[k * ld + j]; s2v[k] = rs2[k * ld + j]; }
-    a0 = ra[j]; a1 = ra[ld + j]; rv = rr[j]; dv = rd ? rd[j] : 0.0f;
+    sv = rs[k * ld + j]; s2v = rs2[k * ld + j];
+    if (k == 0) { a0 = ra[j]; a1 = ra[ld + j]; rv = rr[j]; dv = rd ? rd[j] : 0.0f; }
   }
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
-    const float sn = __fdiv_rn(__fsub_rn(sv[k], norm[k]), den);
-    const float s2n = __fdiv_rn(__fsub_rn(s2v[k], norm[k]), den);
-    xs[j * 11 + k] = sn; xspi[j * 11 + k] = sn; xs2[j * 11 + k] = s2n;
-  }
-  xs[j * 11 + 9] = a0; xs[j * 11 + 10] = a1;
-  r[j] = rv;
-  done[j] = dv;
-}
-// last node of an update: advance the device-side counters (`βp .= βp .* β` of Flux.ADAM included)
-__global__ void ddpg_ctrl_advance_kernel(DdpgCtrl* ctrl, double b1, double b2) {
-  ctrl->update += 1; ctrl->idx_cursor += 1;
-  for (int n = 0; n < 2; ++n) { ctrl->bp[n][0] *= b1; ctrl->bp[n][1] *= b2; }
+  const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
+  const float sn = __fdiv_rn(__fsub_rn(sv, norm[k]), den);
+  const float s2n = __fdiv_rn(__fsub_rn(s2v, norm[k]), den);
+  xs[j * 11 + k] = sn; xspi[j * 11 + k] = sn; xs2[j * 11 + k] = s2n;
+  if (k == 0) { xs[j * 11 + 9] = a0; xs[j * 11 + 10] = a1; r[j] = rv; done[j] = dv; }
 }
 
 // ----------------------------------------------------------------------------- Adam + Polyak
@@ -413,8 +484,8 @@ __global__ void ddpg_ctrl_advance_kernel(DdpgCtrl* ctrl, double b1, double b2) {
 // βp = β^t is read from the device control block so graph replays stay valid.
 __global__ void __launch_bounds__(256)
 adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
-                   double b2, double eps, float eta, const DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
-                   float* __restrict__ target2, const float* __restrict__ model2, long long n2) {
+                   double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
+                   float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance) {
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -432,6 +503,20 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
   // second Polyak pair: the critic target moves together with the actor step (DDPG.jl:142-143)
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
     target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
+  // the last block to finish the final kernel of an update advances the device-side counters
+  // (`βp .= βp .* β` of Flux.ADAM for both optimisers, the Philox update counter, the host-index cursor)
+  if (advance) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned done = atomicAdd(&ctrl->blocks_done, 1u);
+      if (done == gridDim.x - 1) {
+        ctrl->blocks_done = 0;
+        ctrl->update += 1; ctrl->idx_cursor += 1;
+        for (int o = 0; o < 2; ++o) { ctrl->bp[o][0] *= b1; ctrl->bp[o][1] *= b2; }
+      }
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------- update sequence
@@ -462,19 +547,28 @@ static inline GemmProblem gp_dx(const float* dZ, long long lddz, int B, const fl
 static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
   GemmBatch gb; memset(&gb, 0, sizeof(gb));
   gb.count = count;
-  int gx = 1, gy = 1;
+  bool skinny = true;
+  int maxM = 1, maxN = 1;
+  long long ctas32 = 0;
   for (int i = 0; i < count; ++i) {
     gb.p[i] = ps[i];
-    gx = max(gx, (ps[i].N + BN - 1) / BN);
-    gy = max(gy, (ps[i].M + BM - 1) / BM);
+    skinny = skinny && ps[i].N <= 2 && ps[i].sAk == 1 && ps[i].dbias == nullptr && ps[i].K >= 32;
+    maxM = max(maxM, ps[i].M); maxN = max(maxN, ps[i].N);
+    ctas32 += (long long)((ps[i].M + 31) / 32) * ((ps[i].N + 31) / 32);
   }
-  gemm_batch_kernel<<<dim3(gy, gx, count), GEMM_THREADS, 0, st>>>(gb);
+  if (skinny) {
+    gemm_skinny_kernel<<<dim3((maxM + 7) / 8, count), 256, 0, st>>>(gb);
+  } else if (ctas32 < 296) {  // fewer than two CTAs per SM with 32x32 tiles: use 16x16 tiles (4x the CTAs, 1/4 of the serial work each)
+    gemm_batch_kernel<16, 16><<<dim3((maxM + 15) / 16, (maxN + 15) / 16, count), 128, 0, st>>>(gb);
+  } else {
+    gemm_batch_kernel<32, 32><<<dim3((maxM + 31) / 32, (maxN + 31) / 32, count), 512, 0, st>>>(gb);
+  }
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 #define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
 
-// one replay() after the minibatch has been gathered: 20 dependent launches ("DDPG update")
+// one replay() after the minibatch has been gathered: 19 dependent launches ("DDPG update")
 static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = p.l1, l2 = p.l2;
@@ -512,17 +606,17 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
   TRY(launch_gemms(st, g, 1));
   // P10: ADAM(η_crit) on the critic
-  adam_polyak_kernel<<<148, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
-                                         p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0);
+  const unsigned adam_grid = (unsigned)((dc.n_params + 255) / 256);  // one element per thread: the Float64 div/sqrt chains need TLP
+  adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
+                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
   TRY(launch_gemms(st, g, 1));
   g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
   TRY(launch_gemms(st, g, 1));
-  g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);                              // only feeds loss_act
-  g[1] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);          // dX through the critic only
-  TRY(launch_gemms(st, g, 2));
+  g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);          // dX through the critic only
+  TRY(launch_gemms(st, g, 1));
   // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
   g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
   TRY(launch_gemms(st, g, 1));
@@ -538,12 +632,12 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
   g[0].M = 9;  // only the 9 state columns of xs feed the actor
   TRY(launch_gemms(st, g, 1));
+  // q(s, actor(s)) itself only feeds loss_act (reporting): off the critical path, skinny kernel
+  g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
+  TRY(launch_gemms(st, g, 1));
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
-  adam_polyak_kernel<<<148, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
-                                         p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params);
-  CUDA_TRY(cudaGetLastError());
-  // P20: counters
-  ddpg_ctrl_advance_kernel<<<1, 1, 0, st>>>(h->ctrl, p.adam_beta1, p.adam_beta2);
+  adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -551,7 +645,7 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
 static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* ring, const float* s, const float* a, const float* r, const float* s2,
                           const float* done, long long ld) {
   const int B = h->p.batch;
-  ddpg_gather_kernel<<<(B + 127) / 128, 128, 0, st>>>(ring, s, a, r, s2, done, ld, h->ctrl, h->idx_dev, h->norm, B, h->xs, h->xs2, h->xspi, h->r,
+  ddpg_gather_kernel<<<(B * 9 + 127) / 128, 128, 0, st>>>(ring, s, a, r, s2, done, ld, h->ctrl, h->idx_dev, h->norm, B, h->xs, h->xs2, h->xspi, h->r,
                                                       h->done);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
@@ -598,9 +692,9 @@ extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, cons
     CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)need, cudaMemcpyHostToDevice, h->stream));
   }
   // refresh the part of the control block the host owns (seed, ring geometry, index mode); update/bp stay device-owned
-  struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; int pad; } hp;
+  struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; unsigned blocks_done; } hp;
   hp.seed = seed; hp.update = (unsigned)h->n_updates; hp.use_idx = idx_host ? 1 : 0; hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
-  hp.idx_cursor = 0; hp.pad = 0;
+  hp.idx_cursor = 0; hp.blocks_done = 0;
   static_assert(sizeof(HostPart) == offsetof(DdpgCtrl, bp), "control block layout");
   CUDA_TRY(cudaMemcpyAsync(h->ctrl, &hp, sizeof(hp), cudaMemcpyHostToDevice, h->stream));
   TRY(ensure_graph(h, rp));
