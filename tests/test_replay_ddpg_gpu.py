@@ -229,3 +229,58 @@ def test_driver_short_training_run(sb, train_series):
     assert trace2.shape == (50, 23, 4)
     lc, la = drv.learner.losses()
     assert np.isfinite(lc) and np.isfinite(la)
+
+
+def test_closed_loop_episode_parity(sb, O, train_series):
+    """episode!(train=true) end to end — act(normalize(s)) + noise -> scale_action -> step! -> remember -> replay() every step —
+    on CUDA vs the CPU oracle with identical init weights, injected noise and the spec's minibatch indices (DDPG.jl:186-242)."""
+    rng = np.random.default_rng(11)
+    n, T, B = 8, 40, 32
+    kw = dict(batch=B, l1=48, l2=64)
+    P = O.params_for_charger(98)
+    env = sb.Shems(72, train_series, n_envs=n)
+    ref = O.OracleEnv(P, train_series, 72, n)
+    mem = sb.Replay(4096)
+    # warm-up transitions (random policy) so that replay() has something to sample from
+    env.reset(rng=5)
+    env.rollout(sb.POLICY_RANDOM, 16, seed=5, replay=mem, want_return=False)
+    S, A, R, S2, D = [x.copy() for x in mem.get()]
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=3)
+    le = sb.Learner(params=sb.default_ddpg_params(**kw))
+    le.init(77)
+    orc = O.OracleDdpg(O.default_ddpg_params(**kw))
+    orc.init(77)
+    le.set_norm(mn, mx)
+    orc.set_norm(mn, mx)
+    env.reset(rng=6)
+    ref.reset(mode=2, seed=6)
+    ret_gpu = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ret_ref = np.zeros(n)
+    for step in range(T):
+        noise = rng.normal(0, 0.1, (2, n)).astype(np.float32)
+        s_gpu = env.state_tensor().clone()
+        a, scaled = le.act(s_gpu, noise=dev(noise))
+        r, s2 = env.step(scaled)
+        ret_gpu += r.double()
+        mem.push(s_gpu, a, r, s2)
+        le.replay(mem, rng_rpl=1000 + step, n_updates=1)
+        # oracle side
+        s_ref = ref.obs.copy()
+        oa, osc = orc.act(s_ref, noise=noise)
+        r_ref, s2_ref, _ = ref.step(osc)
+        ret_ref += r_ref
+        S = np.concatenate([S, s_ref], 1); A = np.concatenate([A, oa], 1); R = np.concatenate([R, r_ref.astype(np.float32)])
+        S2 = np.concatenate([S2, s2_ref], 1); D = np.concatenate([D, np.zeros(n, np.float32)])
+        idx = O.sample_indices(1000 + step, 0, S.shape[1], B)
+        orc.update_batch(S[:, idx], A[:, idx], R[idx], S2[:, idx], D[idx])
+        # the two learners drift apart slowly (fp32 summation order, amplified by Adam's normalised step): stated tolerances
+        # 5e-4 on actions in [-1,1], 5e-3 on states (kWh / fractions), 1e-2 relative on the 40-step episode return
+        np.testing.assert_allclose(a.cpu().numpy(), oa, rtol=0, atol=(5e-5 if step < 5 else 5e-4))
+        np.testing.assert_allclose(s2.cpu().numpy(), s2_ref, rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(ret_gpu.cpu().numpy(), ret_ref, rtol=1e-2, atol=1e-2)
+    p = le.p
+    for net, lr in ((0, p.lr_actor), (1, p.lr_critic)):
+        for k in range(3):
+            w, b = le.get_layer(net, k)
+            ow, ob = orc.get_layer(net, k)
+            np.testing.assert_allclose(w, ow, rtol=1e-4, atol=0.05 * lr * T)
