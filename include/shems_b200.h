@@ -259,6 +259,11 @@ SHEMS_API int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const
 /* the same update on a caller-supplied minibatch (device, [9][B],[2][B],[B],[9][B],[B]) */
 SHEMS_API int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev,
                                     const float* s2_dev, const float* done_dev);
+/* Data-parallel learner (one process per GPU): the same replay() in three calls.  After phase 0 the critic part of the
+ * flat gradient buffer (ddpg_grad_buffer, first ddpg_num_params(CRITIC) floats) is final on this rank, after phase 1 the
+ * actor part; the caller all-reduces (sum) each part over the ranks (NCCL) and passes grad_scale = 1/world_size to the
+ * next phase, which applies ADAM to the averaged gradient.  grad_scale is ignored by phase 0. */
+SHEMS_API int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, const int32_t* idx_host, uint64_t seed, float grad_scale);
 /* last update's loss_crit / loss_act values (DDPG.jl:114-119) */
 SHEMS_API int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act);
 /* gradients of the last update (Flux layout, like ddpg_get_layer); net = ACTOR or CRITIC */

@@ -102,6 +102,7 @@ SIGNATURES = {
     "ddpg_set_norm": (I32, [VP, PF, PF]),
     "ddpg_act": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
+    "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),
     "ddpg_update_batch": (I32, [VP, VP, VP, VP, VP, VP]),
     "ddpg_get_losses": (I32, [VP, PF, PF]),
     "ddpg_grad_buffer": (I32, [VP, C.POINTER(VP), C.POINTER(I64)]),

@@ -485,12 +485,12 @@ ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs,
 __global__ void __launch_bounds__(256)
 adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
                    double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
-                   float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance) {
+                   float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance, float gscale) {
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const float gj = g[j];
+    const float gj = (gscale == 1.0f) ? g[j] : __fmul_rn(g[j], gscale);  // data-parallel: mean of the ranks' summed gradients
     const float g2 = __fmul_rn(gj, gj);
     const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)m[j]), __dmul_rn(1.0 - b1, (double)gj));
     const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)v[j]), __dmul_rn(1.0 - b2, (double)g2));
@@ -568,8 +568,12 @@ static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
 }
 #define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
 
-// one replay() after the minibatch has been gathered: 19 dependent launches ("DDPG update")
-static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
+// one replay() after the minibatch has been gathered ("DDPG update"), in three phases so that a data-parallel
+// learner can all-reduce the flat gradient buffer between them:
+//   phase 0: targets, TD target, critic forward/backward            -> grad[critic]
+//   phase 1: ADAM(critic), actor-loss forward/backward through the UPDATED critic -> grad[actor]
+//   phase 2: ADAM(actor), soft_update! of both targets, counters
+static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = p.l1, l2 = p.l2;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
@@ -605,10 +609,19 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   TRY(launch_gemms(st, g, 2));
   g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
   TRY(launch_gemms(st, g, 1));
+  return SHEMS_OK;
+}
+
+static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
+  const DdpgParams& p = h->p;
+  const int B = p.batch, l1 = p.l1, l2 = p.l2;
+  const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
+  float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
+  GemmProblem g[4];
   // P10: ADAM(η_crit) on the critic
   const unsigned adam_grid = (unsigned)((dc.n_params + 255) / 256);  // one element per thread: the Float64 div/sqrt chains need TLP
   adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
@@ -635,11 +648,26 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   // q(s, actor(s)) itself only feeds loss_act (reporting): off the critical path, skinny kernel
   g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
   TRY(launch_gemms(st, g, 1));
+  return SHEMS_OK;
+}
+
+static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale) {
+  const DdpgParams& p = h->p;
+  const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
+  float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
+  const unsigned adam_grid = (unsigned)((dc.n_params + 255) / 256);
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
   adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
+                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
+}
+
+static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
+  int s0 = enqueue_phase0(h, st);
+  if (!s0) s0 = enqueue_phase1(h, st, 1.0f);
+  if (!s0) s0 = enqueue_phase2(h, st, 1.0f);
+  return s0;
 }
 
 static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* ring, const float* s, const float* a, const float* r, const float* s2,
@@ -701,6 +729,40 @@ extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, cons
   for (int u = 0; u < n_updates; ++u) CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
   h->n_updates += n_updates;
   // asynchronous: the small pageable H2D copies above are staged by the runtime before they return
+  return SHEMS_OK;
+}
+
+// Data-parallel learner: one replay() in three calls; between them the caller all-reduces (sum) the gradient buffer
+// (ddpg_grad_buffer: critic part after phase 0, actor part after phase 1) and passes grad_scale = 1/world_size.
+extern "C" int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, const int32_t* idx_host, uint64_t seed, float grad_scale) {
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_update_phase: NULL handle");
+  REQUIRE(phase >= 0 && phase <= 2, SHEMS_ERR_INVALID, "ddpg_update_phase: phase=%d", phase);
+  GUARD(h->device);
+  if (phase == 0) {
+    REQUIRE(rp && rp->device == h->device && rp->length > 0, SHEMS_ERR_STATE, "ddpg_update_phase: replay missing, empty or on another device");
+    const int B = h->p.batch;
+    if (idx_host) {
+      for (int j = 0; j < B; ++j)
+        REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "ddpg_update_phase: idx[%d]=%d outside 0..%lld", j, idx_host[j],
+                (long long)rp->length - 1);
+      if (h->idx_cap < B) {
+        cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
+        CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)B));
+        h->idx_cap = B;
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+      }
+      CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
+    }
+    struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; unsigned blocks_done; } hp;
+    hp.seed = seed; hp.update = (unsigned)h->n_updates; hp.use_idx = idx_host ? 1 : 0; hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
+    hp.idx_cursor = 0; hp.blocks_done = 0;
+    CUDA_TRY(cudaMemcpyAsync(h->ctrl, &hp, sizeof(hp), cudaMemcpyHostToDevice, h->stream));
+    TRY(enqueue_gather(h, h->stream, rp->ring, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
+    return enqueue_phase0(h, h->stream);
+  }
+  if (phase == 1) return enqueue_phase1(h, h->stream, grad_scale);
+  TRY(enqueue_phase2(h, h->stream, grad_scale));
+  h->n_updates += 1;
   return SHEMS_OK;
 }
 

@@ -181,6 +181,25 @@ class Learner:
             ip = idx.ctypes.data_as(L.PI)
         L.check(self.lib.ddpg_update(self._h, memory._h, int(n_updates), ip, int(rng_rpl) & (2**64 - 1)))
 
+    def replay_dp(self, memory, rng_rpl=0, dist=None, idx=None):
+        """replay() for a data-parallel learner: every rank samples its own replay shard, the critic and actor gradients are
+        averaged over the ranks with two NCCL all-reduces (1.03 MB in total), every rank applies the identical ADAM step."""
+        world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.int32)
+            ip = idx.ctypes.data_as(L.PI)
+        g = self.grad_tensor()
+        nc = int(self.lib.ddpg_num_params(self._h, L.NET_CRITIC))
+        seed = int(rng_rpl) & (2**64 - 1)
+        L.check(self.lib.ddpg_update_phase(self._h, memory._h, 0, ip, seed, 1.0))
+        if world > 1:
+            dist.all_reduce(g[:nc])
+        L.check(self.lib.ddpg_update_phase(self._h, memory._h, 1, None, seed, 1.0 / world))
+        if world > 1:
+            dist.all_reduce(g[nc:])
+        L.check(self.lib.ddpg_update_phase(self._h, memory._h, 2, None, seed, 1.0 / world))
+
     def update_batch(self, s, a, r, s2, done=None):
         L.check(self.lib.ddpg_update_batch(self._h, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(done)))
 

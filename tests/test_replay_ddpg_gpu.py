@@ -284,3 +284,46 @@ def test_closed_loop_episode_parity(sb, O, train_series):
             w, b = le.get_layer(net, k)
             ow, ob = orc.get_layer(net, k)
             np.testing.assert_allclose(w, ow, rtol=1e-4, atol=0.05 * lr * T)
+
+
+def test_data_parallel_phases_equal_full_batch(sb, O, train_series):
+    """Two emulated ranks (two learner handles on one GPU) each take half of a minibatch through ddpg_update_phase; summing
+    their gradient buffers (what the NCCL all-reduce does) and applying ADAM with grad_scale = 1/2 must equal one learner
+    on the full minibatch: mean over 2B samples == mean of the two B-sample means."""
+    n, T, B = 64, 72, 64
+    env = sb.Shems(T, train_series, n_envs=n)
+    mem = sb.Replay(n * T)
+    env.reset(rng=2)
+    env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
+    idx = np.random.default_rng(0).integers(0, len(mem), 2 * B).astype(np.int32)
+    full = sb.Learner(params=sb.default_ddpg_params(batch=2 * B))
+    halves = [sb.Learner(params=sb.default_ddpg_params(batch=B)) for _ in range(2)]
+    for le in [full] + halves:
+        le.init(3)
+        le.set_norm(mn, mx)
+    K = 3
+    for u in range(K):
+        idx_u = np.roll(idx, 7 * u)
+        full.replay(mem, n_updates=1, idx=idx_u)
+        nc = int(full.lib.ddpg_num_params(full._h, sb._lib.NET_CRITIC))
+        g = [le.grad_tensor() for le in halves]
+        for r, le in enumerate(halves):
+            sb._lib.check(le.lib.ddpg_update_phase(le._h, mem._h, 0, idx_u[r * B:(r + 1) * B].ctypes.data_as(sb._lib.PI), 0, 1.0))
+        tot = g[0][:nc] + g[1][:nc]            # all_reduce(sum) of the critic part
+        g[0][:nc] = tot; g[1][:nc] = tot
+        for le in halves:
+            sb._lib.check(le.lib.ddpg_update_phase(le._h, mem._h, 1, None, 0, 0.5))
+        tot = g[0][nc:] + g[1][nc:]            # all_reduce(sum) of the actor part
+        g[0][nc:] = tot; g[1][nc:] = tot
+        for le in halves:
+            sb._lib.check(le.lib.ddpg_update_phase(le._h, mem._h, 2, None, 0, 0.5))
+    p = full.p
+    for net, lr in ((0, p.lr_actor), (1, p.lr_critic), (2, p.lr_actor * p.tau), (3, p.lr_critic * p.tau)):
+        for k in range(3):
+            w0, b0 = halves[0].get_layer(net, k)
+            w1, b1 = halves[1].get_layer(net, k)
+            np.testing.assert_array_equal(w0, w1)      # the ranks stay bit-identical replicas
+            wf, bf = full.get_layer(net, k)
+            np.testing.assert_allclose(w0, wf, rtol=1e-5, atol=0.02 * lr * K + 1e-7)
+            np.testing.assert_allclose(b0, bf, rtol=1e-5, atol=0.02 * lr * K + 1e-7)
