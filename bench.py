@@ -165,6 +165,38 @@ def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
                 kernels_per_update=21, flops_per_update=3.078e8)
 
 
+def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
+    """Data-parallel learner: every rank samples its own replay shard (B=120 each), two NCCL gradient all-reduces per update."""
+    env = sb.Shems(72, ser_train, n_envs=1000, device=torch.cuda.current_device(), env_id_base=rank * 1000)
+    mem = sb.Replay(24_000, device=torch.cuda.current_device())
+    env.reset(rng=1)
+    env.rollout(sb.POLICY_RANDOM, 24, seed=1, replay=mem, want_return=False)
+    le = sb.Learner(device=torch.cuda.current_device())
+    le.init(1)                                   # identical replicas on every rank
+    mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
+    le.set_norm(mn, mx)
+    for u in range(20):
+        le.replay_dp(mem, rng_rpl=100 + rank, dist=dist)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for u in range(n_updates):
+        le.replay_dp(mem, rng_rpl=1000 + rank, dist=dist)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    w0 = torch.from_numpy(le.get_layer(0, 1)[0]).cuda()
+    ref = w0.clone()
+    dist.broadcast(ref, 0)
+    in_sync = torch.tensor([float(torch.equal(w0, ref))], device="cuda")
+    dist.all_reduce(in_sync, op=dist.ReduceOp.MIN)
+    ms = float(t.item())
+    return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, global_batch=120 * dist.get_world_size(),
+                allreduce_bytes_per_update=4 * int(le.grad_tensor().numel()), replicas_bit_identical=bool(in_sync.item() == 1.0))
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -256,6 +288,12 @@ def main():
     value = total_steps / (ms * 1e-3)
     e2e_value = total_steps / (ms_e2e * 1e-3)
 
+    ddpg_dp = None
+    if dist is not None and not args.skip_ddpg:
+        try:
+            ddpg_dp = ddpg_dp_updates_per_s(sb, torch, dist, rank, sb.series.synth_charger98(4320, seed=98))
+        except Exception as e:
+            ddpg_dp = dict(error=str(e))
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -293,6 +331,8 @@ def main():
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:  # never lose the env number to the secondary metric
             line["ddpg"] = dict(error=str(e))
+    if ddpg_dp is not None:
+        line["ddpg_data_parallel"] = ddpg_dp
     if not args.skip_cpu_baseline:
         cb, _ = cpu_baseline(ser, T, args.cpu_sample_envs)
         line["cpu_baseline"] = cb
