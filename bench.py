@@ -47,6 +47,7 @@ def parse():
 def cpu_rollout_rate(ser, horizon, n_envs, seed=1):
     """env-steps/s of the CPU oracle (OpenMP over instances, all host cores) on n_envs x horizon steps."""
     from oracle import oracle as O
+    O.set_threads(cpu_cores())
     P = O.params_for_charger(98)
     env = O.OracleEnv(P, ser, horizon, n_envs)
     env.reset(mode=2, seed=seed)

@@ -72,6 +72,7 @@ def lib():
         L = C.CDLL(so)
         PF, PD, PI = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int32)
         PP = C.POINTER(ShemsParams)
+        L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_params_for_charger.argtypes = [C.c_int, PP]
         L.oracle_action_drl.argtypes = [PP, PF, C.c_float, C.c_float, PF]
         L.oracle_action_drl.restype = None
@@ -116,6 +117,10 @@ def lib():
         L.oracle_sample_indices.restype = None
         _LIB = L
     return _LIB
+
+
+def set_threads(n):
+    return lib().oracle_set_threads(int(n))
 
 
 def params_for_charger(cid=98):

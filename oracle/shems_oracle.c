@@ -30,6 +30,19 @@
 
 #include "../include/shems_b200.h"
 #include "oracle.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* torchrun exports OMP_NUM_THREADS=1: the CPU baseline sets its thread count explicitly */
+int oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 
 /* --------------------------------------------------------------- jl values */
 typedef enum { K_INT = 0, K_F32 = 1, K_F64 = 2 } jkind;
