@@ -220,3 +220,25 @@ def test_full_size_properties_config3(sb, O, P98, cuda_ok):
     sh.reset(rng=1)
     o2 = sh.rollout(sb.POLICY_RANDOM, 200, seed=5)
     assert torch.equal(o2["ep_return"], out["ep_return"][(1 << 19):(1 << 19) + 1024])
+
+
+def test_tracker_csv_and_checkpoint_roundtrip(sb, charger98_test_series, cuda_ok, tmp_path):
+    """f1: the 23-column tracker CSV of write_to_results_file (memory_plotting_saving.jl:167-190); f3: checkpoint round trip."""
+    env = sb.Shems(2998, charger98_test_series, n_envs=1)
+    env.reset(rng=-1)
+    out = env.rollout(sb.POLICY_RULE, 2998, want_trace=True)
+    sums = sb.tracker.write_results_csv(tmp_path / "rule.csv", out["trace"])
+    lines = open(tmp_path / "rule.csv").read().splitlines()
+    assert lines[0].split(",") == sb.tracker.TRACE_HEADER and len(lines) == 2999
+    back = np.loadtxt(tmp_path / "rule.csv", delimiter=",", skiprows=1)
+    np.testing.assert_array_equal(back, out["trace"][:, :, 0].cpu().numpy())          # repr() round-trips Float64 exactly
+    assert sums["rewards"] == pytest.approx(float(out["ep_return"][0]), rel=1e-12)
+    le = sb.Learner()
+    le.init(3)
+    sb.tracker.save_checkpoint(tmp_path / "ck.npz", le, s_min=np.zeros(9), s_max=np.ones(9), best_run=7)
+    le2 = sb.Learner()
+    z = sb.tracker.load_checkpoint(tmp_path / "ck.npz", le2)
+    assert int(z["best_run"]) == 7 and z["actor_W2"].shape == (500, 250)
+    for net in range(4):
+        for k in range(3):
+            np.testing.assert_array_equal(le.get_layer(net, k)[0], le2.get_layer(net, k)[0])
