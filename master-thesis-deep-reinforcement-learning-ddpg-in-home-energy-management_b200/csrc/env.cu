@@ -176,8 +176,15 @@ shems_reset_kernel(DevParams P, const float4* __restrict__ series, int nrows, in
 // step!(env, s, a; track) for one instance per thread.  FROM_SERIES: the exogenous state fields are
 // taken from series row idx (they equal env.state there after reset!/step!); otherwise from obs
 // (after shems_set_state injected an arbitrary state).
+// measured (profiles/r1_step_kernel.md): 128 threads x 12 blocks/SM (40 registers) is the fastest of the sweep
+#ifndef STEP_THREADS
+#define STEP_THREADS 128
+#endif
+#ifndef STEP_MIN_BLOCKS
+#define STEP_MIN_BLOCKS 12
+#endif
 template <bool FROM_SERIES, bool WANT_TRACE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                   int32_t* __restrict__ idx_arr, const float* __restrict__ act, int track_neg,
                   float* __restrict__ reward_out, float* __restrict__ obs_out, double* __restrict__ trace) {
@@ -469,10 +476,10 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
     return SHEMS_ERR_BOUNDS;
   }
   GUARD(e->device);
-  const unsigned g = grid_for(e->n, 256);
+  const unsigned g = grid_for(e->n, STEP_THREADS);
   const int tn = track < 0 ? 1 : 0;
 #define LAUNCH_STEP(FS, TR) \
-  shems_step_kernel<FS, TR><<<g, 256, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, act_dev, tn, reward_dev, obs_dev, trace_dev)
+  shems_step_kernel<FS, TR><<<g, STEP_THREADS, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, act_dev, tn, reward_dev, obs_dev, trace_dev)
   if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
   else { if (trace_dev) LAUNCH_STEP(false, true); else LAUNCH_STEP(false, false); }
 #undef LAUNCH_STEP
