@@ -105,6 +105,7 @@ SIGNATURES = {
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),
     "ddpg_update_batch": (I32, [VP, VP, VP, VP, VP, VP]),
     "ddpg_get_losses": (I32, [VP, PF, PF]),
+    "shems_tc_gemm": (I32, [VP, I64, I32, VP, I64, I32, VP, I64, I32, I32, I32, I32, VP, VP, I64, I32, VP, VP]),
     "ddpg_grad_buffer": (I32, [VP, C.POINTER(VP), C.POINTER(I64)]),
 }
 

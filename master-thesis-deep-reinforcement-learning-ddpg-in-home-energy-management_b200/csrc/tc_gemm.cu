@@ -1,0 +1,326 @@
+// tc_gemm.cu — TF32 tensor-core GEMM for the large-batch DDPG update (B >= 1024): sm_100a tcgen05 + TMEM + TMA.
+//
+//   D[M×N] = epilogue( A · B^T-or-B ),  fp32 in HBM, TF32 multiply, fp32 accumulate in TMEM.
+//
+// Each operand is described the way it already sits in HBM (no transposed copies):
+//   K-major  : element (row, k) at  ptr[row*ld + k]   (k contiguous)   — activations as the M operand of forward / dX
+//   MN-major : element (row, k) at  ptr[k*ld + row]   (row contiguous) — Flux weights Wt[in][out] as the N operand of the
+//              forward pass, and both operands of dW = X^T · dZ
+// One CTA computes one 128×128 output tile (optionally one K-split of it).  Warp roles (192 threads):
+//   warp 0   : TMA producer — cp.async.bulk.tensor into a 3-stage ring of 128B-swizzled tiles, mbarrier expect_tx
+//   warp 1   : TMEM allocator + MMA issuer — one elected lane issues 4 tcgen05.mma.kind::tf32 (K = 8 each) per 32-wide
+//              k-block, tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5: epilogue — tcgen05.ld (32 lanes × 32 columns per instruction) TMEM -> registers -> fused epilogue -> HBM
+// Descriptor encodings follow cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor) of CUTLASS 3.9.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "common.h"
+#include "tc_gemm.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32, UMMA_K = 8, STAGES = 3;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
+constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB per operand and stage
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024;   // + alignment slack
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+// layout_type [61,64): SWIZZLE_128B = 2 (K-major tiles), SWIZZLE_128B_BASE32B = 1 (the only layout for MN-major tf32)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 2)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N, split = blockIdx.z;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (kb_total + p.splits - 1) / p.splits;
+  const int kb_begin = split * kb_per;
+  const int kb_end = min(kb_total, kb_begin + kb_per);
+  const int num_kb = max(0, kb_end - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns × 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+        uint8_t* sa = smem + s * 2 * TILE_BYTES;
+        uint8_t* sb = sa + TILE_BYTES;
+        const int k0 = (kb_begin + i) * BLOCK_K;
+        if (A_MN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0);  // box {32 rows(MN), 32 k}
+        } else {
+          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);                                                   // box {32 k, 128 rows}
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0);
+        } else {
+          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // InstrDescriptor: c_format F32 (1) [4,6), a/b_format TF32 (2) [7,10)/[10,13), a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                           ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    if (elect_one()) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES, ph = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * 2 * TILE_BYTES), sb = sa + TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          // K-major, SWIZZLE_128B: rows of 128 B (32 k), 8-row groups 1024 B apart (SBO); one UMMA_K = 32 B further along the row.
+          // MN-major, SWIZZLE_128B_BASE32B: k-rows of 128 B (32 MN elements); the swizzle atom is 4 k-rows (512 B, 32-byte
+          //   chunks XOR row%4), so one UMMA_K = 8 spans two atoms 512 B apart (SBO); 32-wide MN chunks are 4096 B apart (LBO).
+          const uint64_t ad = A_MN ? make_smem_desc(sa + kk * 1024, 4096, 512, 1) : make_smem_desc(sa + kk * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? make_smem_desc(sb + kk * 1024, 4096, 512, 1) : make_smem_desc(sb + kk * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, ad, bd, idesc, (i | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
+      }
+      umma_commit(&tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ===== epilogue (warps 2-5): TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(&tmem_full_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+    float* Dp = p.D + (long long)split * p.split_stride;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;
+      }
+      if (m < p.M) {
+        // each thread owns 32 consecutive columns of its row: 8 full 16-byte stores (whole sectors) when aligned
+        const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dp) & 15) == 0);
+        const float* auxrow = (p.epi == TC_EPI_RELU_MASK) ? p.aux + (long long)m * p.auxld : nullptr;
+        float* drow = Dp + (long long)m * p.ldd;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = n0 + c * 32 + j4 * 4;
+          float x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            x[u] = __uint_as_float(v[j4 * 4 + u]);
+            if (n + u < p.N) {
+              if (p.epi == TC_EPI_BIAS_RELU) { x[u] += p.bias[n + u]; x[u] = x[u] > 0.0f ? x[u] : 0.0f; }
+              else if (p.epi == TC_EPI_RELU_MASK) { x[u] = (auxrow[n + u] > 0.0f) ? x[u] : 0.0f; }
+            }
+          }
+          if (vec && n + 3 < p.N) *reinterpret_cast<float4*>(drow + n) = make_float4(x[0], x[1], x[2], x[3]);
+          else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (n + u < p.N) drow[n + u] = x[u];
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// deterministic second pass of a split-K GEMM: D[m][n] = sum_s W[s][m][n] (fixed order)
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, float* __restrict__ D, long long n_elems) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_elems) return;
+  float acc = ws[i];
+  for (int s = 1; s < splits; ++s) acc += ws[(long long)s * split_stride + i];
+  D[i] = acc;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 = contiguous dimension (n0 elements), dim1 = strided dimension (n1 rows, `ld` floats apart)
+int make_tmap(CUtensorMap* tm, const float* ptr, long long n0, long long n1, long long ld, int box0, int box1, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  REQUIRE(enc, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
+  REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, SHEMS_ERR_INVALID, "tc_gemm: operand needs a 16-byte aligned base and row stride (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)n0, (cuuint64_t)n1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SHEMS_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmArgs& a) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.splits);
+  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+}  // namespace
+
+// D = epi(A·B): see tc_gemm.h.  With splits > 1, `workspace` must hold splits*M*N floats; the partial tiles are summed in a
+// fixed order by a second kernel (deterministic, unlike atomics).
+int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
+            const float* bias, const float* aux, long long auxld, int splits, float* workspace) {
+  REQUIRE(M >= 1 && N >= 1 && K >= 1 && splits >= 1, SHEMS_ERR_INVALID, "tc_gemm: M=%d N=%d K=%d splits=%d", M, N, K, splits);
+  REQUIRE(splits == 1 || (workspace && epi == TC_EPI_NONE && ldd == N), SHEMS_ERR_INVALID, "tc_gemm: split-K needs a workspace, no epilogue and ldd == N");
+  CUtensorMap ta, tb;
+  int s;
+  // K-major: dim0 = K, dim1 = rows, box {32 k, 128 rows}; MN-major: dim0 = rows, dim1 = K, box {32 rows, 32 k}
+  if ((s = A.mn_major ? make_tmap(&ta, A.ptr, M, K, A.ld, 32, BLOCK_K, true) : make_tmap(&ta, A.ptr, K, M, A.ld, BLOCK_K, BLOCK_M, false))) return s;
+  if ((s = B.mn_major ? make_tmap(&tb, B.ptr, N, K, B.ld, 32, BLOCK_K, true) : make_tmap(&tb, B.ptr, K, N, B.ld, BLOCK_K, BLOCK_N, false))) return s;
+  TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.bias = bias; a.aux = aux; a.auxld = auxld;
+  if (splits == 1) { a.D = D; a.ldd = ldd; a.split_stride = 0; }
+  else { a.D = workspace; a.ldd = N; a.split_stride = (long long)M * N; }
+  if (A.mn_major && B.mn_major) s = launch_variant<true, true>(st, ta, tb, a);
+  else if (A.mn_major) s = launch_variant<true, false>(st, ta, tb, a);
+  else if (B.mn_major) s = launch_variant<false, true>(st, ta, tb, a);
+  else s = launch_variant<false, false>(st, ta, tb, a);
+  if (s) return s;
+  if (splits > 1) {
+    const long long ne = (long long)M * N;
+    tc_splitk_reduce_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(workspace, a.split_stride, splits, D, ne);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return SHEMS_OK;
+}
+
+// test / benchmark entry point (device pointers): D[M×N] = A·B with the stated major-ness
+extern "C" int32_t shems_tc_gemm(const float* a_dev, int64_t lda, int32_t a_mn, const float* b_dev, int64_t ldb, int32_t b_mn, float* d_dev,
+                                 int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t epi, const float* bias_dev, const float* aux_dev,
+                                 int64_t auxld, int32_t splits, float* workspace_dev, void* cuda_stream) {
+  REQUIRE(a_dev && b_dev && d_dev, SHEMS_ERR_INVALID, "shems_tc_gemm: NULL argument");
+  TcOperand A{a_dev, lda, a_mn != 0}, B{b_dev, ldb, b_mn != 0};
+  return tc_gemm((cudaStream_t)cuda_stream, A, B, d_dev, ldd, M, N, K, epi, bias_dev, aux_dev, auxld, splits, workspace_dev);
+}

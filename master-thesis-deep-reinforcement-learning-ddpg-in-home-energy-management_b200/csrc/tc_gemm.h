@@ -1,0 +1,20 @@
+// tc_gemm.h — TF32 tcgen05 GEMM used by the large-batch DDPG update (csrc/tc_gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum { TC_EPI_NONE = 0, TC_EPI_BIAS_RELU = 1, TC_EPI_RELU_MASK = 2 };
+
+struct TcOperand {
+  const float* ptr;
+  long long ld;      // floats between consecutive rows (K-major) or consecutive k (MN-major)
+  bool mn_major;     // false: (row, k) at ptr[row*ld + k]; true: (row, k) at ptr[k*ld + row]
+};
+struct TcGemmArgs {
+  int M, N, K, splits, epi;
+  float* D; long long ldd, split_stride;
+  const float* bias; const float* aux; long long auxld;
+};
+// D[M×N] (row-major, ldd) = epilogue(sum_k A(m,k) · B(n,k))
+int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
+            const float* bias, const float* aux, long long auxld, int splits, float* workspace);
