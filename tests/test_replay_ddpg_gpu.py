@@ -256,6 +256,7 @@ def test_closed_loop_episode_parity(sb, O, train_series):
     ref.reset(mode=2, seed=6)
     ret_gpu = torch.zeros(n, dtype=torch.float64, device="cuda")
     ret_ref = np.zeros(n)
+    worst = 0.0
     for step in range(T):
         noise = rng.normal(0, 0.1, (2, n)).astype(np.float32)
         s_gpu = env.state_tensor().clone()
@@ -271,25 +272,24 @@ def test_closed_loop_episode_parity(sb, O, train_series):
         ret_ref += r_ref
         S = np.concatenate([S, s_ref], 1); A = np.concatenate([A, oa], 1); R = np.concatenate([R, r_ref.astype(np.float32)])
         S2 = np.concatenate([S2, s2_ref], 1); D = np.concatenate([D, np.zeros(n, np.float32)])
-        idx = O.sample_indices(1000 + step, 0, S.shape[1], B)
+        idx = O.sample_indices(1000 + step, step, S.shape[1], B)   # Philox counter = the learner's cumulative update number
         orc.update_batch(S[:, idx], A[:, idx], R[idx], S2[:, idx], D[idx])
-        # the two learners drift apart slowly (fp32 summation order, amplified by Adam's normalised step) and a single
-        # instance can take a different flow branch once its action differs in the last bits, so the closed loop is
-        # compared statistically — stated tolerances: first 5 steps every action within 5e-5; the median action difference
-        # may grow by 1e-4 per update (each ADAM step moves a weight by up to lr and amplifies rounding noise of near-zero
-        # gradients) and >= 80 % of the actions stay within 1e-2; 40-step episode returns: median relative difference < 2e-2
+        # Stated tolerances.  The CPU oracle itself is insensitive to rounding here (1-ulp perturbations of its initial weights
+        # move its actions by < 2e-8 over these 40 steps), so the loop is compared directly: the fp32 summation order of the
+        # CUDA GEMMs differs from the oracle's double accumulation, which ADAM's normalised step turns into weight
+        # differences of a few percent of lr per update -> actions within 1e-6 + 1e-6 * step.
         da = np.abs(a.cpu().numpy() - oa)
-        if step < 5:
-            assert da.max() < 5e-5, (step, da.max())
-        assert np.median(da) < 1e-4 + 1e-4 * step and (da < 1e-2).mean() >= 0.8, (step, np.median(da), da.max())
+        worst = max(worst, da.max() / (1e-6 + 1e-6 * step))
+        assert da.max() < 1e-6 + 1e-6 * step, (step, da.max())
+    print("closed loop: worst action difference / tolerance = %.3f" % worst)
     rel = np.abs(ret_gpu.cpu().numpy() - ret_ref) / np.maximum(1e-9, np.abs(ret_ref))
-    assert np.median(rel) < 2e-2, rel
+    assert rel.max() < 1e-4, rel
     p = le.p
     for net, lr in ((0, p.lr_actor), (1, p.lr_critic)):
         for k in range(3):
             w, b = le.get_layer(net, k)
             ow, ob = orc.get_layer(net, k)
-            assert np.median(np.abs(w - ow)) < 0.05 * lr * T
+            assert np.abs(w - ow).max() < 0.05 * lr * T, (net, k, np.abs(w - ow).max() / (lr * T))
 
 
 def test_data_parallel_phases_equal_full_batch(sb, O, train_series):
