@@ -24,6 +24,7 @@
 
 #include "common.h"
 #include "philox.cuh"
+#include "tc_gemm.h"
 
 // ----------------------------------------------------------------------------- GEMM
 enum { EPI_NONE = 0, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_ID, EPI_RELU_MASK, EPI_TD_TARGET, EPI_TANH_GRAD, EPI_SCALE_MASK };
@@ -44,7 +45,12 @@ struct GemmProblem {
   float alpha;         // TD_TARGET: gamma; SCALE_MASK: scale
   float inv_batch;     // TD_TARGET: 1/B
 };
-struct GemmBatch { GemmProblem p[4]; int count; };
+struct GemmBatch {
+  GemmProblem p[4]; int count;
+  // split-K (count == 1, dW-type problems with K = batch >= 1024): blockIdx.z is the K-split; split s writes its partial
+  // [M*N | N] (tile sums | bias-gradient column sums) at C + s*split_stride; splitk_reduce_kernel adds them in a fixed order
+  int ksplit; long long split_stride;
+};
 
 #define BK 32
 #define GEMM_KGROUPS 4                       // intra-CTA split-K: each k-group owns BK/4 of every k-tile
@@ -94,7 +100,9 @@ gemm_batch_kernel(const GemmBatch gb) {
   constexpr int TXN = TBN / 4;                    // threads along n inside a k-group
   constexpr int AS_LD = TBM + 2, BS_LD = TBN + 4, RED_LD = TBN + 1;
   constexpr int EA = TBM * BK / THREADS, EB = BK * TBN / THREADS;
-  const GemmProblem& p = gb.p[blockIdx.z];
+  const bool splitk = gb.ksplit > 1;
+  const GemmProblem& p = gb.p[splitk ? 0 : blockIdx.z];
+  const int split = splitk ? blockIdx.z : 0;
   const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;  // M tiles on grid.x (no 65535 limit for large batches)
   if (m0 >= p.M || n0 >= p.N) return;
   __shared__ __align__(16) float As[GEMM_STAGES][BK][AS_LD];
@@ -144,10 +152,13 @@ gemm_batch_kernel(const GemmBatch gb) {
   float colsum = 0.0f;
   const bool want_dbias = (p.dbias != nullptr) && (blockIdx.x == 0);
   const bool col_thread = want_dbias && (tid < GEMM_KGROUPS * TBN);  // thread (col = tid % TBN, k-quarter = tid / TBN)
-  const int ntiles = (p.K + BK - 1) / BK;
+  const int ntiles_all = (p.K + BK - 1) / BK;
+  const int tiles_per = splitk ? (ntiles_all + gb.ksplit - 1) / gb.ksplit : ntiles_all;
+  const int t_begin = split * tiles_per;
+  const int ntiles = max(0, min(ntiles_all, t_begin + tiles_per) - t_begin);  // this CTA's k-tiles: t_begin .. t_begin+ntiles-1
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-    if (s < ntiles) issue_tile(s, s);
+    if (s < ntiles) issue_tile(t_begin + s, s);
     cp_async_commit();
   }
   constexpr int KSUB = BK / GEMM_KGROUPS;
@@ -156,7 +167,7 @@ gemm_batch_kernel(const GemmBatch gb) {
     __syncthreads();                   // ... and everyone's; everyone is also done with tile-1, whose buffer is refilled next
     {
       const int tn = tile + GEMM_STAGES - 1;
-      if (tn < ntiles) issue_tile(tn, tn % GEMM_STAGES);
+      if (tn < ntiles) issue_tile(t_begin + tn, tn % GEMM_STAGES);
       cp_async_commit();
     }
     const int buf = tile % GEMM_STAGES;
@@ -182,7 +193,9 @@ gemm_batch_kernel(const GemmBatch gb) {
     for (int j = 0; j < 4; ++j) red[kg][ty * 2 + i][tx * 4 + j] = acc[i][j];
   if (col_thread) colred[tid / TBN][tid % TBN] = colsum;
   __syncthreads();
-  if (want_dbias && tid < TBN && n0 + tid < p.N) p.dbias[n0 + tid] = ((colred[0][tid] + colred[1][tid]) + colred[2][tid]) + colred[3][tid];
+  const long long soff = (long long)split * gb.split_stride;
+  if (want_dbias && tid < TBN && n0 + tid < p.N)
+    p.dbias[soff + n0 + tid] = ((colred[0][tid] + colred[1][tid]) + colred[2][tid]) + colred[3][tid];
 #pragma unroll
   for (int o = 0; o < (TBM * TBN) / THREADS; ++o) {
     const int e = tid + o * THREADS;
@@ -190,7 +203,7 @@ gemm_batch_kernel(const GemmBatch gb) {
     const int m = m0 + mm, n = n0 + nn;
     if (m >= p.M || n >= p.N) continue;
     const float v = ((red[0][mm][nn] + red[1][mm][nn]) + red[2][mm][nn]) + red[3][mm][nn];
-    p.C[m * p.ldc + n] = gemm_epilogue(p, m, n, v);
+    p.C[soff + m * p.ldc + n] = splitk ? v : gemm_epilogue(p, m, n, v);
   }
 }
 
@@ -222,6 +235,156 @@ gemm_skinny_kernel(const GemmBatch gb) {
   if (lane == 0) {
     p.C[m * p.ldc] = gemm_epilogue(p, m, 0, a0);
     if (two) p.C[m * p.ldc + 1] = gemm_epilogue(p, m, 1, a1);
+  }
+}
+
+// second pass of every split-K product: out[i] = sum_s ws[s*stride + i], fixed order (deterministic, unlike atomics)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, long long stride, int splits, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = ws[i];
+  for (int s = 1; s < splits; ++s) acc += ws[(long long)s * stride + i];
+  out[i] = acc;
+}
+// ---- large-batch helpers (B >= SPLITK_MIN_BATCH): the thin products around the 250x500 contractions are streaming
+// passes over [B][width] activations, so they get streaming kernels instead of tiled GEMMs.
+
+// Weighted column sums over a slab of rows: J == 0: ws[slab][n] = sum_b Z[b][n]          (bias gradient beside a tensor-core dW)
+//                                           J >= 1: ws[slab][n*J + j] = sum_b Z[b][n] w[b][j]   (dW of an output layer, Flux layout
+//                                                   [in][out=J]) followed by ws[slab][N*J + j] = sum_b w[b][j] (its bias gradient)
+// Block = 32 columns x 8 row lanes; the row lanes meet in shared memory in a fixed order.
+template <int J>
+__global__ void __launch_bounds__(256)
+wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, const float* __restrict__ w, int rows_per, long long stride,
+                       float* __restrict__ ws) {
+  constexpr int JJ = J > 0 ? J : 1;
+  __shared__ float red[8][32][JJ];
+  const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
+  const int r0 = blockIdx.y * rows_per, r1 = min(B, r0 + rows_per);
+  float acc[JJ];
+#pragma unroll
+  for (int j = 0; j < JJ; ++j) acc[j] = 0.0f;
+  if (n < N) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const float z = Z[(long long)r * ld + n];
+      if (J == 0) acc[0] += z;
+      else {
+#pragma unroll
+        for (int j = 0; j < JJ; ++j) acc[j] = fmaf(z, w[(long long)r * J + j], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < JJ; ++j) red[rl][c][j] = acc[j];
+  __syncthreads();
+  float* out = ws + (long long)blockIdx.y * stride;
+  if (rl == 0 && n < N) {
+#pragma unroll
+    for (int j = 0; j < JJ; ++j) {
+      float t = red[0][c][j];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) t += red[q][c][j];
+      out[(long long)n * JJ + j] = t;
+    }
+  }
+  if (J > 0 && blockIdx.x == 0) {  // bias gradient of the output layer: sum_b w[b][j]
+    __syncthreads();
+    float t = 0.0f;
+    if (c < J) for (int r = r0 + rl; r < r1; r += 8) t += w[(long long)r * J + c];
+    red[rl][c][0] = t;
+    __syncthreads();
+    if (rl == 0 && c < J) {
+      float u = red[0][c][0];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) u += red[q][c][0];
+      out[(long long)N * J + c] = u;
+    }
+  }
+}
+
+// First layer for many rows (K = 9 or 11 inputs): Y[m][n] = relu(b[n] + sum_k X[m][k] W[k][n]), up to 3 problems per launch.
+// A thread keeps its 4 weight columns in registers and walks 16 rows; stores are 16-byte, coalesced along n.
+struct L1Batch { const float* X[3]; const float* W[3]; const float* bias[3]; float* Y[3]; int K[3]; int M, N, ldx, ldy; };
+__global__ void __launch_bounds__(256)
+l1_fwd_kernel(const L1Batch a) {
+  const int z = blockIdx.z, K = a.K[z];
+  const float* __restrict__ X = a.X[z]; const float* __restrict__ W = a.W[z]; const float* __restrict__ bias = a.bias[z];
+  float* __restrict__ Y = a.Y[z];
+  __shared__ float xs[64][12];
+  const int m0 = blockIdx.x * 64;
+  for (int e = threadIdx.x; e < 64 * 12; e += 256) {
+    const int r = e / 12, k = e - r * 12;
+    xs[r][k] = (m0 + r < a.M && k < K) ? X[(long long)(m0 + r) * a.ldx + k] : 0.0f;
+  }
+  const int n = (blockIdx.y * 64 + (threadIdx.x & 63)) * 4, rg = threadIdx.x >> 6;
+  float w[12][4], bv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    bv[u] = (n + u < a.N) ? bias[n + u] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) w[k][u] = (k < K && n + u < a.N) ? W[(long long)k * a.N + n + u] : 0.0f;
+  }
+  __syncthreads();
+  if (n >= a.N) return;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int r = rg * 16 + i, m = m0 + r;
+    if (m >= a.M) break;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float x = xs[r][k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) o[u] = fmaf(x, w[k][u], o[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { o[u] += bv[u]; o[u] = o[u] > 0.0f ? o[u] : 0.0f; }
+    float* y = Y + (long long)m * a.ldy + n;
+    if (n + 3 < a.N) *reinterpret_cast<float4*>(y) = make_float4(o[0], o[1], o[2], o[3]);
+    else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (n + u < a.N) y[u] = o[u];
+    }
+  }
+}
+
+// Back-propagation through an output layer with J <= 2 outputs: dX[b][n] = relu'(H[b][n]) * sum_j dZ[b][j] W[n][j]
+// (Flux weight Wt[in=n][out=j]).  One thread per 4 columns; H and dX share the leading dimension ld (multiple of 4).
+template <int J>
+__global__ void __launch_bounds__(256)
+outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const float* __restrict__ H, long long ld, int B, int N,
+                  float* __restrict__ dX) {
+  const int n4 = (N + 3) / 4;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)B * n4) return;
+  const int b = (int)(e / n4), n = (int)(e - (long long)b * n4) * 4;
+  float dz[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) dz[j] = dZ[(long long)b * J + j];
+  float o[4], hv[4];
+  const float* hrow = H + (long long)b * ld + n;
+  if (n + 3 < N) { const float4 t = *reinterpret_cast<const float4*>(hrow); hv[0] = t.x; hv[1] = t.y; hv[2] = t.z; hv[3] = t.w; }
+  else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hv[u] = (n + u < N) ? hrow[u] : 0.0f;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    float v = 0.0f;
+    if (n + u < N) {
+#pragma unroll
+      for (int j = 0; j < J; ++j) v = fmaf(dz[j], W[(long long)(n + u) * J + j], v);
+    }
+    o[u] = hv[u] > 0.0f ? v : 0.0f;
+  }
+  float* x = dX + (long long)b * ld + n;
+  if (n + 3 < N) *reinterpret_cast<float4*>(x) = make_float4(o[0], o[1], o[2], o[3]);
+  else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (n + u < N) x[u] = o[u];
   }
 }
 
@@ -264,7 +427,15 @@ struct Ddpg {
   cudaGraph_t graph; cudaGraphExec_t graph_exec; const ShemsReplay* graph_rp;
   float* dqpi;     // [B] constant -1/B: d(-mean q)/dq
   bool ctrl_init;
+  int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 4 floats: TMA rows)
+  bool tc;         // layer-2 contractions on TF32 tensor cores (use_tensor_cores, batch >= 256, operands 16-byte aligned)
+  float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
+  long long ws_floats;
 };
+static inline int round4(int x) { return (x + 3) & ~3; }
+#define TC_MIN_ROWS 256
+#define SPLITK_MIN_BATCH 1024
+#define SPLITK_MAX 32
 
 static void make_dims(NetDims& d, int in, int l1, int l2, int out) {
   const int ins[3] = {in, l1, l2}, outs[3] = {l1, l2, out};
@@ -306,9 +477,16 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_create: out of host memory");
   memset(h, 0, sizeof(*h));
   h->device = device; h->p = *p;
-  const int S = p->state_size, A = p->action_size, B = p->batch, l1 = p->l1, l2 = p->l2, C = S + A;
-  make_dims(h->dims[0], S, l1, l2, A);
-  make_dims(h->dims[1], C, l1, l2, 1);
+  const int S = p->state_size, A = p->action_size, B = p->batch, C = S + A;
+  make_dims(h->dims[0], S, p->l1, p->l2, A);
+  make_dims(h->dims[1], C, p->l1, p->l2, 1);
+  h->ld1 = round4(p->l1); h->ld2 = round4(p->l2);
+  const int l1 = h->ld1, l2 = h->ld2;  // allocation strides
+  // W2 of both nets must start on a 16-byte boundary and have 16-byte rows for the TMA descriptors
+  h->tc = p->use_tensor_cores && (p->l2 % 4 == 0) && (h->dims[0].l[1].w_off % 4 == 0) && (h->dims[1].l[1].w_off % 4 == 0);
+  h->ws_floats = (long long)SPLITK_MAX * ((long long)p->l1 * p->l2 + p->l2 + (long long)C * p->l1 + p->l1 + (long long)p->l2 * A + A);
+  DMALLOC(h->ws, h->ws_floats);
+  if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   for (int n = 0; n < 4; ++n) DMALLOC(h->net[n], dims_of(h, n).n_params);
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
   DMALLOC(h->gradbuf, na + nc);
@@ -355,7 +533,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
                    h->p_h1, h->p_h2, h->q, h->y, h->dq, h->qpi, h->dz2, h->dz1, h->dzp2, h->dzp1, h->dza3, h->dza2, h->dza1, h->loss_scratch,
                    h->act_x, h->act_h1, h->act_h2, h->act_y};
   for (float* b : bufs) cudaFree(b);
-  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->dqpi);
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->dqpi); cudaFree(h->ws);
   delete h;
   return SHEMS_OK;
 }
@@ -546,7 +724,7 @@ static inline GemmProblem gp_dx(const float* dZ, long long lddz, int B, const fl
 }
 static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
   GemmBatch gb; memset(&gb, 0, sizeof(gb));
-  gb.count = count;
+  gb.count = count; gb.ksplit = 1;
   bool skinny = true;
   int maxM = 1, maxN = 1;
   long long ctas32 = 0;
@@ -568,53 +746,165 @@ static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
 }
 #define TRY(x) do { int _s = (x); if (_s) return _s; } while (0)
 
+// dW-type product (K = batch) with its bias gradient.  From SPLITK_MIN_BATCH rows on the batch dimension is split over
+// blockIdx.z: every split writes [tile sums | column sums] into the workspace, splitk_reduce_kernel adds them in order.
+static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g) {
+  const int B = g.K;
+  if (B < SPLITK_MIN_BATCH) return launch_gemms(st, &g, 1);
+  const long long mn = (long long)g.M * g.N, stride = mn + g.N;
+  REQUIRE(g.ldc == g.N && g.dbias == g.C + mn && g.epi == EPI_NONE, SHEMS_ERR_INVALID, "launch_dw: not a contiguous [W|b] gradient block");
+  const int ksplit = min(SPLITK_MAX, B / 256);
+  REQUIRE(stride * ksplit <= h->ws_floats, SHEMS_ERR_INVALID, "launch_dw: workspace too small");
+  GemmBatch gb; memset(&gb, 0, sizeof(gb));
+  gb.count = 1; gb.ksplit = ksplit; gb.split_stride = stride;
+  gb.p[0] = g; gb.p[0].C = h->ws; gb.p[0].dbias = h->ws + mn;
+  const long long ctas32 = (long long)((g.M + 31) / 32) * ((g.N + 31) / 32) * ksplit;
+  if (ctas32 < 296) gemm_batch_kernel<16, 16><<<dim3((g.M + 15) / 16, (g.N + 15) / 16, ksplit), 128, 0, st>>>(gb);
+  else gemm_batch_kernel<32, 32><<<dim3((g.M + 31) / 32, (g.N + 31) / 32, ksplit), 512, 0, st>>>(gb);
+  CUDA_TRY(cudaGetLastError());
+  splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, ksplit, g.C, stride);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+// ---- layer-2 contractions on TF32 tensor cores (csrc/tc_gemm.cu); operands are used where they lie in HBM
+// Y = relu(X · W + b):  X [M][ldx] K-major, Flux weight Wt[in][out] MN-major
+static int tc_fwd(cudaStream_t st, const float* X, int ldx, int M, const float* net, const LayerDims& L, float* Y, int ldy) {
+  TcOperand A{X, ldx, false}, Bo{net + L.w_off, L.out, true};
+  return tc_gemm(st, A, Bo, Y, ldy, M, L.out, L.in, TC_EPI_BIAS_RELU, net + L.b_off, nullptr, 0, 1, nullptr);
+}
+// dX = (dZ · W^T) masked by relu'(H):  dZ [M][lddz] K-major, Wt[in][out] K-major (k = out)
+static int tc_dx(cudaStream_t st, const float* dZ, int lddz, int M, const float* net, const LayerDims& L, float* dX, int lddx, const float* H, int ldh) {
+  TcOperand A{dZ, lddz, false}, Bo{net + L.w_off, L.out, false};
+  return tc_gemm(st, A, Bo, dX, lddx, M, L.in, L.out, TC_EPI_RELU_MASK, nullptr, H, ldh, 1, nullptr);
+}
+// dW = X^T · dZ (both MN-major, K = batch, split-K), db = column sums of dZ
+static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float* dZ, int lddz, int B, const LayerDims& L, float* grad) {
+  const int tiles = ((L.in + 127) / 128) * ((L.out + 127) / 128), kb = (B + 31) / 32;
+  const int splits = max(1, min(min(kb / 4, (148 + tiles - 1) / tiles), SPLITK_MAX));
+  TcOperand A{X, ldx, true}, Bo{dZ, lddz, true};
+  TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? h->ws : nullptr));
+  const int slabs = max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
+  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws);
+  CUDA_TRY(cudaGetLastError());
+  splitk_reduce_kernel<<<(L.out + 255) / 256, 256, 0, st>>>(h->ws, L.out, slabs, grad + L.b_off, L.out);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+// large-batch first layer (up to 3 problems): see l1_fwd_kernel
+static int big_l1(cudaStream_t st, int count, const float* const* X, int ldx, int M, const float* const* net, const LayerDims* const* L,
+                  float* const* Y, int ldy) {
+  L1Batch a; memset(&a, 0, sizeof(a));
+  for (int i = 0; i < count; ++i) {
+    a.X[i] = X[i]; a.W[i] = net[i] + L[i]->w_off; a.bias[i] = net[i] + L[i]->b_off; a.Y[i] = Y[i]; a.K[i] = L[i]->in;
+    REQUIRE(L[i]->in <= 12 && L[i]->out == L[0]->out, SHEMS_ERR_INVALID, "big_l1: unsupported first-layer shape");
+  }
+  a.M = M; a.N = L[0]->out; a.ldx = ldx; a.ldy = ldy;
+  l1_fwd_kernel<<<dim3((M + 63) / 64, (a.N + 255) / 256, count), 256, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+// large-batch output layer backward: dW3 (+db3) by weighted column sums, dX by the masked outer product
+static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const float* dZ, int J, int B, const float* net, const LayerDims& L,
+                       float* grad, float* dX) {
+  REQUIRE(J == L.out && (J == 1 || J == 2), SHEMS_ERR_INVALID, "big_out_bwd: output layer must have 1 or 2 units");
+  const int N = L.in, slabs = max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
+  const long long stride = (long long)N * J + J;
+  const dim3 grid((N + 31) / 32, slabs);
+  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws);
+  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws);
+  CUDA_TRY(cudaGetLastError());
+  splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, slabs, grad + L.w_off, stride);
+  CUDA_TRY(cudaGetLastError());
+  const long long ne = (long long)B * ((N + 3) / 4);
+  if (J == 1) outer_mask_kernel<1><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dZ, net + L.w_off, H, ldh, B, N, dX);
+  else outer_mask_kernel<2><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dZ, net + L.w_off, H, ldh, B, N, dX);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows >= TC_MIN_ROWS; }
+
 // one replay() after the minibatch has been gathered ("DDPG update"), in three phases so that a data-parallel
 // learner can all-reduce the flat gradient buffer between them:
 //   phase 0: targets, TD target, critic forward/backward            -> grad[critic]
 //   phase 1: ADAM(critic), actor-loss forward/backward through the UPDATED critic -> grad[actor]
 //   phase 2: ADAM(actor), soft_update! of both targets, counters
+// Small batches (the reference's B = 120) are latency bound: independent problems share launches (up to 4 per kernel).
+// Large batches run one problem per launch; the 250x500 contractions go to the TF32 tensor-core kernel when enabled and
+// every product whose K is the batch is split over the batch.
 static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   const DdpgParams& p = h->p;
-  const int B = p.batch, l1 = p.l1, l2 = p.l2;
+  const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
+  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   GemmProblem g[4];
   // P1-P3: actor_target(s'_n) | critic(s_n, a) | actor(s_n)     (DDPG.jl:131, :114, :117)
-  g[0] = gp_fwd(h->xs2, 11, B, actor_t, da.l[0], h->t_h1, l1, EPI_BIAS_RELU);
-  g[1] = gp_fwd(h->xs, 11, B, critic, dc.l[0], h->c_h1, l1, EPI_BIAS_RELU);
-  g[2] = gp_fwd(h->xs, 11, B, actor, da.l[0], h->a_h1, l1, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 3));
-  g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
-  g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);
-  g[2] = gp_fwd(h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 3));
+  if (big) {
+    const float* X[3] = {h->xs2, h->xs, h->xs}; const float* nets[3] = {actor_t, critic, actor};
+    const LayerDims* Ls[3] = {&da.l[0], &dc.l[0], &da.l[0]}; float* Y[3] = {h->t_h1, h->c_h1, h->a_h1};
+    TRY(big_l1(st, 3, X, 11, B, nets, Ls, Y, l1));
+  } else {
+    g[0] = gp_fwd(h->xs2, 11, B, actor_t, da.l[0], h->t_h1, l1, EPI_BIAS_RELU);
+    g[1] = gp_fwd(h->xs, 11, B, critic, dc.l[0], h->c_h1, l1, EPI_BIAS_RELU);
+    g[2] = gp_fwd(h->xs, 11, B, actor, da.l[0], h->a_h1, l1, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 3));
+  }
+  if (tc) {
+    TRY(tc_fwd(st, h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2));
+    TRY(tc_fwd(st, h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2));
+    TRY(tc_fwd(st, h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2));
+  } else {
+    g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
+    g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);
+    g[2] = gp_fwd(h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 3));
+  }
   g[0] = gp_fwd(h->t_h2, l2, B, actor_t, da.l[2], h->xs2 + 9, 11, EPI_BIAS_TANH);   // a' -> vcat(s'_n, a')
   g[1] = gp_fwd(h->c_h2, l2, B, critic, dc.l[2], h->q, 1, EPI_BIAS_ID);
   g[2] = gp_fwd(h->a_h2, l2, B, actor, da.l[2], h->xspi + 9, 11, EPI_BIAS_TANH);    // actor(s_n) -> vcat(s_n, actions)
   TRY(launch_gemms(st, g, 3));
   // P4-P6: q' = critic_target(vcat(s'_n, a'));  y = r + γ(1-done) q';  dq = 2(q-y)/B     (:132-133)
-  g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 1));
-  g[0] = gp_fwd(h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 1));
+  if (big) {
+    const float* X[1] = {h->xs2}; const float* nets[1] = {critic_t}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->tc_h1};
+    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
+  } else {
+    g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 1));
+  }
+  if (tc) TRY(tc_fwd(st, h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2));
+  else {
+    g[0] = gp_fwd(h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 1));
+  }
   g[0] = gp_fwd(h->tc_h2, l2, B, critic_t, dc.l[2], h->y, 1, EPI_TD_TARGET);
   g[0].aux = h->r; g[0].aux2 = h->done; g[0].aux3 = h->q; g[0].out2 = h->dq; g[0].alpha = p.gamma; g[0].inv_batch = 1.0f / (float)B;
   TRY(launch_gemms(st, g, 1));
   // P7-P9: critic backward (:137, :105-108)
-  g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
-  g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
-  TRY(launch_gemms(st, g, 2));
-  g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
-  g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
-  TRY(launch_gemms(st, g, 2));
+  if (big) TRY(big_out_bwd(h, st, h->c_h2, l2, h->dq, 1, B, critic, dc.l[2], h->grad[1], h->dz2));
+  else {
+    g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
+    g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, p.l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
+    TRY(launch_gemms(st, g, 2));
+  }
+  if (tc) {
+    TRY(tc_dw(h, st, h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]));
+    TRY(tc_dx(st, h->dz2, l2, B, critic, dc.l[1], h->dz1, l1, h->c_h1, l1));
+  } else {
+    g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
+    g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
+    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1)); }
+    else TRY(launch_gemms(st, g, 2));
+  }
   g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
-  TRY(launch_gemms(st, g, 1));
+  TRY(launch_dw(h, st, g[0]));
   return SHEMS_OK;
 }
 
 static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   const DdpgParams& p = h->p;
-  const int B = p.batch, l1 = p.l1, l2 = p.l2;
+  const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
+  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
   GemmProblem g[4];
@@ -624,27 +914,53 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
                                                p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
-  g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 1));
-  g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
-  TRY(launch_gemms(st, g, 1));
-  g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);          // dX through the critic only
-  TRY(launch_gemms(st, g, 1));
+  if (big) {
+    const float* X[1] = {h->xspi}; const float* nets[1] = {critic}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->p_h1};
+    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
+  } else {
+    g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 1));
+  }
+  if (tc) TRY(tc_fwd(st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2));
+  else {
+    g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
+    TRY(launch_gemms(st, g, 1));
+  }
+  if (big) {                                                                                               // dX through the critic only
+    const long long ne = (long long)B * ((p.l2 + 3) / 4);
+    outer_mask_kernel<1><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->dqpi, critic + dc.l[2].w_off, h->p_h2, l2, B, p.l2, h->dzp2);
+    CUDA_TRY(cudaGetLastError());
+  } else {
+    g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, p.l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);
+    TRY(launch_gemms(st, g, 1));
+  }
   // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
-  g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
-  TRY(launch_gemms(st, g, 1));
+  if (tc) TRY(tc_dx(st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
+  else {
+    g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, p.l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
+    TRY(launch_gemms(st, g, 1));
+  }
   g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
   TRY(launch_gemms(st, g, 1));
   // P16-P18: actor backward
-  g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
-  g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
-  TRY(launch_gemms(st, g, 2));
-  g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
-  g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
-  TRY(launch_gemms(st, g, 2));
+  if (big) TRY(big_out_bwd(h, st, h->a_h2, l2, h->dza3, 2, B, actor, da.l[2], h->grad[0], h->dza2));
+  else {
+    g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
+    g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, p.l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
+    TRY(launch_gemms(st, g, 2));
+  }
+  if (tc) {
+    TRY(tc_dw(h, st, h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]));
+    TRY(tc_dx(st, h->dza2, l2, B, actor, da.l[1], h->dza1, l1, h->a_h1, l1));
+  } else {
+    g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
+    g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
+    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1)); }
+    else TRY(launch_gemms(st, g, 2));
+  }
   g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
   g[0].M = 9;  // only the 9 state columns of xs feed the actor
-  TRY(launch_gemms(st, g, 1));
+  TRY(launch_dw(h, st, g[0]));
   // q(s, actor(s)) itself only feeds loss_act (reporting): off the critical path, skinny kernel
   g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
   TRY(launch_gemms(st, g, 1));
@@ -841,7 +1157,7 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
   REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
   GUARD(h->device);
-  const int l1 = h->p.l1, l2 = h->p.l2;
+  const int l1 = h->ld1, l2 = h->ld2;
   if (h->act_cap < n) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->act_x); cudaFree(h->act_h1); cudaFree(h->act_h2); cudaFree(h->act_y);
@@ -858,10 +1174,18 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
   const NetDims& da = h->dims[0];
   const float* actor = h->net[DDPG_NET_ACTOR];
   GemmProblem g[1];
-  g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
-  TRY(launch_gemms(h->stream, g, 1));
-  g[0] = gp_fwd(h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, EPI_BIAS_RELU);
-  TRY(launch_gemms(h->stream, g, 1));
+  if (n >= SPLITK_MIN_BATCH) {
+    const float* X[1] = {h->act_x}; const float* nets[1] = {actor}; const LayerDims* Ls[1] = {&da.l[0]}; float* Y[1] = {h->act_h1};
+    TRY(big_l1(h->stream, 1, X, 9, (int)n, nets, Ls, Y, l1));
+  } else {
+    g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
+    TRY(launch_gemms(h->stream, g, 1));
+  }
+  if (use_tc(h, n)) TRY(tc_fwd(h->stream, h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2));
+  else {
+    g[0] = gp_fwd(h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, EPI_BIAS_RELU);
+    TRY(launch_gemms(h->stream, g, 1));
+  }
   g[0] = gp_fwd(h->act_h2, l2, (int)n, actor, da.l[2], h->act_y, 2, EPI_BIAS_TANH);
   TRY(launch_gemms(h->stream, g, 1));
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],

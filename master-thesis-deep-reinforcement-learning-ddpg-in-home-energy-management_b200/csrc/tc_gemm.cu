@@ -273,10 +273,15 @@ int make_tmap(CUtensorMap* tm, const float* ptr, long long n0, long long n1, lon
 }
 
 template <bool A_MN, bool B_MN>
+int set_smem_attr() {
+  CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return SHEMS_OK;
+}
+template <bool A_MN, bool B_MN>
 int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmArgs& a) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (int s = set_smem_attr<A_MN, B_MN>()) return s;
     attr_set = true;
   }
   dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.splits);
@@ -286,6 +291,17 @@ int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb
 }
 
 }  // namespace
+
+// opt every variant into its dynamic shared memory on the current device (call once per device, outside stream capture)
+int tc_gemm_prepare() {
+  int s;
+  if ((s = set_smem_attr<false, false>())) return s;
+  if ((s = set_smem_attr<false, true>())) return s;
+  if ((s = set_smem_attr<true, false>())) return s;
+  if ((s = set_smem_attr<true, true>())) return s;
+  REQUIRE(get_encode(), SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
+  return SHEMS_OK;
+}
 
 // D = epi(A·B): see tc_gemm.h.  With splits > 1, `workspace` must hold splits*M*N floats; the partial tiles are summed in a
 // fixed order by a second kernel (deterministic, unlike atomics).

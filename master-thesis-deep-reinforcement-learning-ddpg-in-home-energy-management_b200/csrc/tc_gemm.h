@@ -18,3 +18,5 @@ struct TcGemmArgs {
 // D[M×N] (row-major, ldd) = epilogue(sum_k A(m,k) · B(n,k))
 int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
             const float* bias, const float* aux, long long auxld, int splits, float* workspace);
+// sets the kernels' shared-memory attribute on the current device; call once per device before capturing launches in a graph
+int tc_gemm_prepare();

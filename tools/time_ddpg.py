@@ -1,4 +1,4 @@
-"""Times ddpg_update (CUDA-graph path) at the reference's tuned config.  usage: python tools/time_ddpg.py [batch] [n_updates]"""
+"""Times ddpg_update (CUDA-graph path) at the reference's tuned config.  usage: python tools/time_ddpg.py [batch] [n_updates] [use_tensor_cores]"""
 import json
 import os
 import sys
@@ -10,12 +10,13 @@ import shems_b200 as sb  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 n_updates = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+tc = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 ser = sb.series.synth_charger98(4320, seed=98)
 env = sb.Shems(72, ser, n_envs=1000)
 mem = sb.Replay(max(24_000, B))
 env.reset(rng=1)
 env.rollout(sb.POLICY_RANDOM, 24, seed=1, replay=mem, want_return=False)
-le = sb.Learner(params=sb.default_ddpg_params(batch=B))
+le = sb.Learner(params=sb.default_ddpg_params(batch=B, use_tensor_cores=tc))
 le.init(1)
 mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
 le.set_norm(mn, mx)
@@ -32,5 +33,5 @@ for rep in range(3):
 ms = sorted(res)[1]
 lc, la = le.losses()
 flops = 10 * 256_500 * B
-print(json.dumps(dict(batch=B, n_updates=n_updates, us_per_update=1e3 * ms / n_updates, updates_per_s=n_updates / ms * 1e3,
+print(json.dumps(dict(batch=B, tensor_cores=tc, n_updates=n_updates, us_per_update=1e3 * ms / n_updates, updates_per_s=n_updates / ms * 1e3,
                       tflops=flops * n_updates / ms / 1e9, loss_crit=lc, loss_act=la)))
