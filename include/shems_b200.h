@@ -275,7 +275,8 @@ SHEMS_API int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n);
  * The TF32 tcgen05 kernel behind the large-batch DDPG update, exposed for unit tests and roofline measurements:
  * D[M x N] (row-major, ldd) = epi(sum_k A(m,k) B(n,k)); *_mn = 0: operand is K-major ((row,k) at p[row*ld+k]),
  * 1: MN-major ((row,k) at p[k*ld+row]).  epi: 0 none, 1 bias+ReLU, 2 ReLU-mask by aux.  splits > 1: split-K through
- * workspace_dev (splits*M*N floats), reduced in a fixed order.  All pointers are device pointers, 16-byte aligned. */
+ * workspace_dev (splits*M*N floats), reduced in a fixed order.  All pointers are device pointers, 16-byte aligned.  When ldd > N the
+ * padding floats N .. roundup(N,4)-1 of a row may be overwritten with zeros (the tile store clips at 16 bytes); nothing beyond them. */
 SHEMS_API int32_t shems_tc_gemm(const float* a_dev, int64_t lda, int32_t a_mn, const float* b_dev, int64_t ldb, int32_t b_mn,
                                 float* d_dev, int64_t ldd, int32_t M, int32_t N, int32_t K, int32_t epi, const float* bias_dev,
                                 const float* aux_dev, int64_t auxld, int32_t splits, float* workspace_dev, void* cuda_stream);

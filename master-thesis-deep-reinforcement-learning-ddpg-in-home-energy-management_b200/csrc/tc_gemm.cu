@@ -54,6 +54,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// smem -> global tile store (3-D map {N, M, splits}); completion is tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(tm), "r"(smem_u32(smem_src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -104,11 +110,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 2)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcGemmArgs p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+               const TcGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float bias_s[BLOCK_N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N, split = blockIdx.z;
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -123,6 +131,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmD) : "memory");
+  }
+  if (threadIdx.x >= 64) {  // the epilogue warps stage this tile's bias slice
+    const int j = threadIdx.x - 64;
+    bias_s[j] = (p.epi == TC_EPI_BIAS_RELU && n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
   }
   if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns × 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
@@ -183,46 +196,85 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ===== epilogue (warps 2-5): TMEM lane quarter = warp % 4 =====
+    // A thread owns one accumulator row; tcgen05.ld hands it 32 consecutive columns at a time.  With a TMA-storable D
+    // (16-byte rows) the warp writes its 32x32 chunk into 128B-swizzled shared memory (the k-loop's stage buffers are
+    // free once tmem_full fires) and one lane issues a bulk tensor store: full 128-byte lines, clipped at M / N by the
+    // tensor map.  Otherwise every thread stores its row segment directly.
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
+    const bool mask = (p.epi == TC_EPI_RELU_MASK);
+    const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    const float* auxrow = mask ? p.aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
     if (num_kb > 0) {
       mbar_wait(&tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
     float* Dp = p.D + (long long)split * p.split_stride;
+    uint8_t* stage = smem + q * (4 * 4096);  // this warp's four 32x32 fp32 chunk buffers (4 KB each, 1024-byte aligned)
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
+      const int nc = n0 + c * 32;
+      if (nc >= p.N) break;
+      float4 hx[8];
+      if (mask) {  // relu'(H): this row's 32 mask values, requested before the accumulator is read
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int n = nc + j4 * 4;
+          if (aux_vec && n + 3 < p.N) hx[j4] = *reinterpret_cast<const float4*>(auxrow + n);
+          else {
+            hx[j4].x = (n + 0 < p.N) ? auxrow[n + 0] : 0.0f; hx[j4].y = (n + 1 < p.N) ? auxrow[n + 1] : 0.0f;
+            hx[j4].z = (n + 2 < p.N) ? auxrow[n + 2] : 0.0f; hx[j4].w = (n + 3 < p.N) ? auxrow[n + 3] : 0.0f;
+          }
+        }
+      }
       uint32_t v[32];
       if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
       else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      if (m < p.M) {
-        // each thread owns 32 consecutive columns of its row: 8 full 16-byte stores (whole sectors) when aligned
+      float4 o[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = __uint_as_float(v[j4 * 4 + u]);
+        if (p.epi == TC_EPI_BIAS_RELU) {
+          const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c * 32 + j4 * 4]);
+          x[0] = fmaxf(x[0] + bv.x, 0.0f); x[1] = fmaxf(x[1] + bv.y, 0.0f); x[2] = fmaxf(x[2] + bv.z, 0.0f); x[3] = fmaxf(x[3] + bv.w, 0.0f);
+        } else if (mask) {
+          x[0] = hx[j4].x > 0.0f ? x[0] : 0.0f; x[1] = hx[j4].y > 0.0f ? x[1] : 0.0f;
+          x[2] = hx[j4].z > 0.0f ? x[2] : 0.0f; x[3] = hx[j4].w > 0.0f ? x[3] : 0.0f;
+        }
+        o[j4] = make_float4(x[0], x[1], x[2], x[3]);
+      }
+      if (p.tma_store) {
+        uint8_t* buf = stage + c * 4096;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)  // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmD, buf, nc, m0 + q * 32, split);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      } else if (m < p.M) {
         const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dp) & 15) == 0);
-        const float* auxrow = (p.epi == TC_EPI_RELU_MASK) ? p.aux + (long long)m * p.auxld : nullptr;
         float* drow = Dp + (long long)m * p.ldd;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = n0 + c * 32 + j4 * 4;
-          float x[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            x[u] = __uint_as_float(v[j4 * 4 + u]);
-            if (n + u < p.N) {
-              if (p.epi == TC_EPI_BIAS_RELU) { x[u] += p.bias[n + u]; x[u] = x[u] > 0.0f ? x[u] : 0.0f; }
-              else if (p.epi == TC_EPI_RELU_MASK) { x[u] = (auxrow[n + u] > 0.0f) ? x[u] : 0.0f; }
-            }
-          }
-          if (vec && n + 3 < p.N) *reinterpret_cast<float4*>(drow + n) = make_float4(x[0], x[1], x[2], x[3]);
+          const int n = nc + j4 * 4;
+          if (vec && n + 3 < p.N) *reinterpret_cast<float4*>(drow + n) = o[j4];
           else {
+            const float x[4] = {o[j4].x, o[j4].y, o[j4].z, o[j4].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (n + u < p.N) drow[n + u] = x[u];
           }
         }
       }
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem must outlive the reads
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
   __syncthreads();
@@ -277,15 +329,29 @@ int set_smem_attr() {
   CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return SHEMS_OK;
 }
+// 3-D fp32 map of the output {N, M, splits} (rows ldd floats apart, splits split_stride floats apart), box 32 x 32 x 1, 128B swizzle
+int make_tmap_out(CUtensorMap* tm, float* ptr, long long N, long long M, long long splits, long long ldd, long long split_stride) {
+  EncodeTiledFn enc = get_encode();
+  REQUIRE(enc, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  cuuint64_t strides[2] = {(cuuint64_t)ldd * 4, (cuuint64_t)(splits > 1 ? split_stride : ldd * M) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled(D) failed (%d)", (int)r);
+  return SHEMS_OK;
+}
+
 template <bool A_MN, bool B_MN>
-int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const TcGemmArgs& a) {
+int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const TcGemmArgs& a) {
   static bool attr_set = false;
   if (!attr_set) {
     if (int s = set_smem_attr<A_MN, B_MN>()) return s;
     attr_set = true;
   }
   dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.splits);
-  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, a);
+  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, td, a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -319,10 +385,15 @@ int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, l
   a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.bias = bias; a.aux = aux; a.auxld = auxld;
   if (splits == 1) { a.D = D; a.ldd = ldd; a.split_stride = 0; }
   else { a.D = workspace; a.ldd = N; a.split_stride = (long long)M * N; }
-  if (A.mn_major && B.mn_major) s = launch_variant<true, true>(st, ta, tb, a);
-  else if (A.mn_major) s = launch_variant<true, false>(st, ta, tb, a);
-  else if (B.mn_major) s = launch_variant<false, true>(st, ta, tb, a);
-  else s = launch_variant<false, false>(st, ta, tb, a);
+  // TMA store of the output tile when D's rows are 16-byte aligned (activations with padded ld, gradients, the split-K workspace)
+  CUtensorMap td;
+  memset(&td, 0, sizeof(td));
+  a.tma_store = (((uintptr_t)a.D & 15) == 0 && (a.ldd % 4) == 0 && (a.split_stride % 4) == 0) ? 1 : 0;
+  if (a.tma_store && (s = make_tmap_out(&td, a.D, N, M, splits, a.ldd, a.split_stride))) return s;
+  if (A.mn_major && B.mn_major) s = launch_variant<true, true>(st, ta, tb, td, a);
+  else if (A.mn_major) s = launch_variant<true, false>(st, ta, tb, td, a);
+  else if (B.mn_major) s = launch_variant<false, true>(st, ta, tb, td, a);
+  else s = launch_variant<false, false>(st, ta, tb, td, a);
   if (s) return s;
   if (splits > 1) {
     const long long ne = (long long)M * N;

@@ -11,7 +11,7 @@ struct TcOperand {
   bool mn_major;     // false: (row, k) at ptr[row*ld + k]; true: (row, k) at ptr[k*ld + row]
 };
 struct TcGemmArgs {
-  int M, N, K, splits, epi;
+  int M, N, K, splits, epi, tma_store;
   float* D; long long ldd, split_stride;
   const float* bias; const float* aux; long long auxld;
 };
