@@ -226,6 +226,9 @@ typedef struct DdpgParams {
   float act_lo[2];      /* ACTION_BOUND_LO input.jl:183 */
   float act_hi[2];      /* ACTION_BOUND_HI input.jl:182 */
   int32_t use_tensor_cores; /* 0: fp32 SIMT GEMMs (parity path); 1: TF32 tensor cores where the batch allows */
+  int32_t population;       /* 0/1: the reference's single learner; P > 1: P independent learners (own nets, optimisers, replay
+                             * memory, seeds) advanced by the same launches — BASELINE configs[4], the reference's one-process-per-seed
+                             * parallelism (RL-SHEMS_bs_scheduler_*.sh:73-81) folded into one handle */
 } DdpgParams;
 
 enum { DDPG_NET_ACTOR = 0, DDPG_NET_CRITIC = 1, DDPG_NET_ACTOR_TARGET = 2, DDPG_NET_CRITIC_TARGET = 3 };
@@ -264,6 +267,14 @@ SHEMS_API int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_
  * actor part; the caller all-reduces (sum) each part over the ranks (NCCL) and passes grad_scale = 1/world_size to the
  * next phase, which applies ADAM to the averaged gradient.  grad_scale is ignored by phase 0. */
 SHEMS_API int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, const int32_t* idx_host, uint64_t seed, float grad_scale);
+/* Population handles (DdpgParams.population = P > 1).  Batched arrays gain a leading [P] dimension: ddpg_act takes
+ * obs_dev [P][9][n], noise_dev [P][2][n] and fills a_dev / scaled_dev [P][2][n]; ddpg_init seeds learner l with seed + l;
+ * get/set_layer, get_grad, set_norm and get_losses address the learner chosen by ddpg_select_learner (default 0).
+ * ddpg_update_population: replay() n_updates times for every learner, learner l sampling rps[l] with Philox(seeds[l]) or
+ * idx_host [P][n_updates][batch].  Also valid for P == 1 (ddpg_update is that case). */
+SHEMS_API int32_t ddpg_select_learner(Ddpg* h, int32_t learner);
+SHEMS_API int32_t ddpg_population(const Ddpg* h);
+SHEMS_API int32_t ddpg_update_population(Ddpg* h, ShemsReplay* const* rps, int32_t n_updates, const int32_t* idx_host, const uint64_t* seeds);
 /* last update's loss_crit / loss_act values (DDPG.jl:114-119) */
 SHEMS_API int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act);
 /* gradients of the last update (Flux layout, like ddpg_get_layer); net = ACTOR or CRITIC */

@@ -50,7 +50,19 @@ struct GemmBatch {
   // split-K (count == 1, dW-type problems with K = batch >= 1024): blockIdx.z is the K-split; split s writes its partial
   // [M*N | N] (tile sums | bias-gradient column sums) at C + s*split_stride; splitk_reduce_kernel adds them in a fixed order
   int ksplit; long long split_stride;
+  // population of independent learners (ksplit == 1): blockIdx.z = learner * count + problem; learner l reads its weights
+  // (B, bias) ls_w floats and everything else (A, C, aux*, out2, dbias) ls_x floats behind learner 0's pointers
+  int pop; long long ls_w, ls_x;
 };
+__device__ __forceinline__ void gemm_shift(GemmProblem& p, long long ow, long long ox) {
+  p.A += ox; p.B += ow; p.C += ox;
+  if (p.bias) p.bias += ow;
+  if (p.aux) p.aux += ox;
+  if (p.aux2) p.aux2 += ox;
+  if (p.aux3) p.aux3 += ox;
+  if (p.out2) p.out2 += ox;
+  if (p.dbias) p.dbias += ox;
+}
 
 #define BK 32
 #define GEMM_KGROUPS 4                       // intra-CTA split-K: each k-group owns BK/4 of every k-tile
@@ -101,7 +113,9 @@ gemm_batch_kernel(const GemmBatch gb) {
   constexpr int AS_LD = TBM + 2, BS_LD = TBN + 4, RED_LD = TBN + 1;
   constexpr int EA = TBM * BK / THREADS, EB = BK * TBN / THREADS;
   const bool splitk = gb.ksplit > 1;
-  const GemmProblem& p = gb.p[splitk ? 0 : blockIdx.z];
+  const int learner = splitk ? 0 : blockIdx.z / gb.count;
+  GemmProblem p = gb.p[splitk ? 0 : blockIdx.z - learner * gb.count];
+  if (learner) gemm_shift(p, learner * gb.ls_w, learner * gb.ls_x);
   const int split = splitk ? blockIdx.z : 0;
   const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;  // M tiles on grid.x (no 65535 limit for large batches)
   if (m0 >= p.M || n0 >= p.N) return;
@@ -211,7 +225,8 @@ gemm_batch_kernel(const GemmBatch gb) {
 // lanes stride over k, all loads of the row issued before the first use, warp-shuffle reduction.  A must be k-contiguous.
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const GemmBatch gb) {
-  const GemmProblem& p = gb.p[blockIdx.y];
+  GemmProblem p = gb.p[blockIdx.y];
+  if (blockIdx.z) gemm_shift(p, blockIdx.z * gb.ls_w, blockIdx.z * gb.ls_x);
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= p.M) return;
   float a0 = 0.0f, a1 = 0.0f;
@@ -424,13 +439,21 @@ struct Ddpg {
   int32_t* idx_dev; long long idx_cap;
   // act() scratch (n rows)
   float *act_x, *act_h1, *act_h2, *act_y; long long act_cap;
-  cudaGraph_t graph; cudaGraphExec_t graph_exec; const ShemsReplay* graph_rp;
+  cudaGraph_t graph; cudaGraphExec_t graph_exec; 
   float* dqpi;     // [B] constant -1/B: d(-mean q)/dq
   bool ctrl_init;
   int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 4 floats: TMA rows)
   bool tc;         // layer-2 contractions on TF32 tensor cores (use_tensor_cores, batch >= 256, operands 16-byte aligned)
   float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
   long long ws_floats;
+  // population: `pop` independent learners in one handle.  Every float buffer above lives in one slab per learner
+  // (learner l's copy is l*pop_stride floats behind learner 0's), so a launch covers all learners through blockIdx.
+  int pop, sel;            // sel: the learner get/set/init/losses address (ddpg_select_learner)
+  long long pop_stride;
+  float* slab;
+  const float** rings_dev; // [pop] replay ring of every learner (device array)
+  long long idx_stride;    // ints between consecutive learners' host-supplied minibatch indices
+  long long act_stride;    // floats between consecutive learners' act() scratch blocks
 };
 static inline int round4(int x) { return (x + 3) & ~3; }
 #define TC_MIN_ROWS 256
@@ -471,12 +494,16 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   REQUIRE(p && out, SHEMS_ERR_INVALID, "ddpg_create: NULL argument");
   REQUIRE(p->state_size == 9 && p->action_size == 2, SHEMS_ERR_INVALID, "ddpg_create: STATE_SIZE/ACTION_SIZE must be 9/2 (shems_LU1)");
   REQUIRE(p->l1 >= 1 && p->l2 >= 1 && p->batch >= 1, SHEMS_ERR_INVALID, "ddpg_create: l1=%d l2=%d batch=%d", p->l1, p->l2, p->batch);
+  REQUIRE(p->population >= 0 && p->population <= 4096, SHEMS_ERR_INVALID, "ddpg_create: population=%d", p->population);
+  const int pop = p->population > 1 ? p->population : 1;
+  REQUIRE(pop == 1 || (p->batch < SPLITK_MIN_BATCH && !p->use_tensor_cores), SHEMS_ERR_INVALID,
+          "ddpg_create: a population of learners runs the small-batch path (batch < %d, use_tensor_cores = 0)", SPLITK_MIN_BATCH);
   REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "ddpg_create: no CUDA device (this library has no CPU fallback)");
   GUARD(device);
   Ddpg* h = new (std::nothrow) Ddpg();
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_create: out of host memory");
   memset(h, 0, sizeof(*h));
-  h->device = device; h->p = *p;
+  h->device = device; h->p = *p; h->pop = pop; h->p.population = pop;
   const int S = p->state_size, A = p->action_size, B = p->batch, C = S + A;
   make_dims(h->dims[0], S, p->l1, p->l2, A);
   make_dims(h->dims[1], C, p->l1, p->l2, 1);
@@ -487,34 +514,39 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   h->ws_floats = (long long)SPLITK_MAX * ((long long)p->l1 * p->l2 + p->l2 + (long long)C * p->l1 + p->l1 + (long long)p->l2 * A + A);
   DMALLOC(h->ws, h->ws_floats);
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
-  for (int n = 0; n < 4; ++n) DMALLOC(h->net[n], dims_of(h, n).n_params);
+  // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
-  DMALLOC(h->gradbuf, na + nc);
+  struct Carve { float** ptr; long long count; };
+  const Carve plan[] = {
+      {&h->net[0], na}, {&h->net[1], nc}, {&h->net[2], na}, {&h->net[3], nc}, {&h->gradbuf, na + nc},
+      {&h->adam_m[0], na}, {&h->adam_v[0], na}, {&h->adam_m[1], nc}, {&h->adam_v[1], nc}, {&h->norm, 18},
+      {&h->xs, (long long)B * C}, {&h->xs2, (long long)B * C}, {&h->xspi, (long long)B * C}, {&h->r, B}, {&h->done, B},
+      {&h->t_h1, (long long)B * l1}, {&h->t_h2, (long long)B * l2}, {&h->c_h1, (long long)B * l1}, {&h->c_h2, (long long)B * l2},
+      {&h->a_h1, (long long)B * l1}, {&h->a_h2, (long long)B * l2}, {&h->tc_h1, (long long)B * l1}, {&h->tc_h2, (long long)B * l2},
+      {&h->p_h1, (long long)B * l1}, {&h->p_h2, (long long)B * l2}, {&h->q, B}, {&h->y, B}, {&h->dq, B}, {&h->qpi, B},
+      {&h->dz2, (long long)B * l2}, {&h->dz1, (long long)B * l1}, {&h->dzp2, (long long)B * l2}, {&h->dzp1, (long long)B * l1},
+      {&h->dza3, (long long)B * A}, {&h->dza2, (long long)B * l2}, {&h->dza1, (long long)B * l1}, {&h->loss_scratch, 2}, {&h->dqpi, B}};
+  long long off = 0;
+  for (const Carve& c : plan) off += (c.count + 63) & ~63ll;
+  h->pop_stride = off;
+  DMALLOC(h->slab, off * pop);
+  off = 0;
+  for (const Carve& c : plan) { *c.ptr = h->slab + off; off += (c.count + 63) & ~63ll; }
   h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + nc;
-  DMALLOC(h->adam_m[0], na); DMALLOC(h->adam_v[0], na); DMALLOC(h->adam_m[1], nc); DMALLOC(h->adam_v[1], nc);
-  DMALLOC(h->norm, 18);
-  DMALLOC(h->xs, (long long)B * C); DMALLOC(h->xs2, (long long)B * C); DMALLOC(h->xspi, (long long)B * C);
-  DMALLOC(h->r, B); DMALLOC(h->done, B);
-  DMALLOC(h->t_h1, (long long)B * l1); DMALLOC(h->t_h2, (long long)B * l2); DMALLOC(h->c_h1, (long long)B * l1); DMALLOC(h->c_h2, (long long)B * l2);
-  DMALLOC(h->a_h1, (long long)B * l1); DMALLOC(h->a_h2, (long long)B * l2); DMALLOC(h->tc_h1, (long long)B * l1); DMALLOC(h->tc_h2, (long long)B * l2);
-  DMALLOC(h->p_h1, (long long)B * l1); DMALLOC(h->p_h2, (long long)B * l2);
-  DMALLOC(h->q, B); DMALLOC(h->y, B); DMALLOC(h->dq, B); DMALLOC(h->qpi, B);
-  DMALLOC(h->dz2, (long long)B * l2); DMALLOC(h->dz1, (long long)B * l1); DMALLOC(h->dzp2, (long long)B * l2); DMALLOC(h->dzp1, (long long)B * l1);
-  DMALLOC(h->dza3, (long long)B * A); DMALLOC(h->dza2, (long long)B * l2); DMALLOC(h->dza1, (long long)B * l1);
-  DMALLOC(h->loss_scratch, 2);
-  DMALLOC(h->ctrl, 1);
-  DMALLOC(h->dqpi, B);
+  DMALLOC(h->ctrl, pop);
+  DMALLOC(h->rings_dev, pop);
   {
     std::vector<float> c((size_t)B, -1.0f / (float)B);
-    cudaMemcpy(h->dqpi, c.data(), sizeof(float) * (size_t)B, cudaMemcpyHostToDevice);
-    DdpgCtrl ctl; memset(&ctl, 0, sizeof(ctl));
-    for (int n = 0; n < 2; ++n) { ctl.bp[n][0] = p->adam_beta1; ctl.bp[n][1] = p->adam_beta2; }
-    cudaMemcpy(h->ctrl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice);
-  }
-  {
     float nm[18];
     for (int k = 0; k < 9; ++k) { nm[k] = 0.0f; nm[9 + k] = 1.0f; }
-    cudaMemcpy(h->norm, nm, sizeof(nm), cudaMemcpyHostToDevice);
+    std::vector<DdpgCtrl> ctl((size_t)pop);
+    memset(ctl.data(), 0, sizeof(DdpgCtrl) * (size_t)pop);
+    for (int l = 0; l < pop; ++l) {
+      cudaMemcpy(h->dqpi + l * h->pop_stride, c.data(), sizeof(float) * (size_t)B, cudaMemcpyHostToDevice);
+      cudaMemcpy(h->norm + l * h->pop_stride, nm, sizeof(nm), cudaMemcpyHostToDevice);
+      for (int n = 0; n < 2; ++n) { ctl[l].bp[n][0] = p->adam_beta1; ctl[l].bp[n][1] = p->adam_beta2; }
+    }
+    cudaMemcpy(h->ctrl, ctl.data(), sizeof(DdpgCtrl) * (size_t)pop, cudaMemcpyHostToDevice);
   }
   for (int n = 0; n < 2; ++n) { h->beta_pow[n][0] = p->adam_beta1; h->beta_pow[n][1] = p->adam_beta2; }
   *out = h;
@@ -526,17 +558,21 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   GUARD(h->device);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->graph) cudaGraphDestroy(h->graph);
-  for (int n = 0; n < 4; ++n) cudaFree(h->net[n]);
-  cudaFree(h->gradbuf);
-  for (int n = 0; n < 2; ++n) { cudaFree(h->adam_m[n]); cudaFree(h->adam_v[n]); }
-  float* bufs[] = {h->norm, h->xs, h->xs2, h->xspi, h->r, h->done, h->t_h1, h->t_h2, h->c_h1, h->c_h2, h->a_h1, h->a_h2, h->tc_h1, h->tc_h2,
-                   h->p_h1, h->p_h2, h->q, h->y, h->dq, h->qpi, h->dz2, h->dz1, h->dzp2, h->dzp1, h->dza3, h->dza2, h->dza1, h->loss_scratch,
-                   h->act_x, h->act_h1, h->act_h2, h->act_y};
-  for (float* b : bufs) cudaFree(b);
-  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->dqpi); cudaFree(h->ws);
+  cudaFree(h->slab);
+  cudaFree(h->act_x);  // act() scratch: one allocation (x | h1 | h2 | y per learner)
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev);
   delete h;
   return SHEMS_OK;
 }
+
+// get/set/init-style calls address one learner of a population (default 0)
+extern "C" int32_t ddpg_select_learner(Ddpg* h, int32_t learner) {
+  REQUIRE(h && learner >= 0 && learner < h->pop, SHEMS_ERR_INVALID, "ddpg_select_learner: learner=%d outside 0..%d", learner, h ? h->pop - 1 : -1);
+  h->sel = learner;
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_population(const Ddpg* h) { return h ? h->pop : 0; }
+static inline long long sel_off(const Ddpg* h) { return (long long)h->sel * h->pop_stride; }
 
 extern "C" int32_t ddpg_set_stream(Ddpg* h, void* s) {
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_set_stream: NULL handle");
@@ -556,8 +592,8 @@ extern "C" int32_t ddpg_set_layer(Ddpg* h, int32_t net, int32_t layer, const flo
   GUARD(h->device);
   const LayerDims& L = dims_of(h, net).l[layer];
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (w_host) CUDA_TRY(cudaMemcpy(h->net[net] + L.w_off, w_host, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyHostToDevice));
-  if (b_host) CUDA_TRY(cudaMemcpy(h->net[net] + L.b_off, b_host, sizeof(float) * (size_t)L.out, cudaMemcpyHostToDevice));
+  if (w_host) CUDA_TRY(cudaMemcpy(h->net[net] + sel_off(h) + L.w_off, w_host, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyHostToDevice));
+  if (b_host) CUDA_TRY(cudaMemcpy(h->net[net] + sel_off(h) + L.b_off, b_host, sizeof(float) * (size_t)L.out, cudaMemcpyHostToDevice));
   return SHEMS_OK;
 }
 extern "C" int32_t ddpg_get_layer(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host) {
@@ -565,8 +601,8 @@ extern "C" int32_t ddpg_get_layer(Ddpg* h, int32_t net, int32_t layer, float* w_
   GUARD(h->device);
   const LayerDims& L = dims_of(h, net).l[layer];
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->net[net] + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
-  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->net[net] + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
+  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->net[net] + sel_off(h) + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
+  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->net[net] + sel_off(h) + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
   return SHEMS_OK;
 }
 extern "C" int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host) {
@@ -574,8 +610,8 @@ extern "C" int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_h
   GUARD(h->device);
   const LayerDims& L = dims_of(h, net).l[layer];
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->grad[net] + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
-  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->grad[net] + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
+  if (w_host) CUDA_TRY(cudaMemcpy(w_host, h->grad[net] + sel_off(h) + L.w_off, sizeof(float) * (size_t)L.in * L.out, cudaMemcpyDeviceToHost));
+  if (b_host) CUDA_TRY(cudaMemcpy(b_host, h->grad[net] + sel_off(h) + L.b_off, sizeof(float) * (size_t)L.out, cudaMemcpyDeviceToHost));
   return SHEMS_OK;
 }
 extern "C" int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* s_max_host) {
@@ -585,7 +621,7 @@ extern "C" int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* 
   memcpy(nm, s_min_host, sizeof(float) * 9);
   memcpy(nm + 9, s_max_host, sizeof(float) * 9);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  CUDA_TRY(cudaMemcpy(h->norm, nm, sizeof(nm), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->norm + sel_off(h), nm, sizeof(nm), cudaMemcpyHostToDevice));
   return SHEMS_OK;
 }
 
@@ -602,16 +638,19 @@ __global__ void ddpg_init_kernel(float* __restrict__ w, long long n, int in, int
 extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_init: NULL handle");
   GUARD(h->device);
-  for (int n = 0; n < 2; ++n) {
-    const NetDims& d = h->dims[n];
-    CUDA_TRY(cudaMemsetAsync(h->net[n], 0, sizeof(float) * (size_t)d.n_params, h->stream));
-    for (int k = 0; k < 3; ++k) {
-      const long long nw = (long long)d.l[k].in * d.l[k].out;
-      ddpg_init_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(h->net[n] + d.l[k].w_off, nw, d.l[k].in, d.l[k].out, k == 2, seed,
-                                                                            (unsigned)(n * 3 + k));
+  for (int l = 0; l < h->pop; ++l) {  // learner l of a population draws from Philox(seed + l): independent seeds
+    const long long lo = (long long)l * h->pop_stride;
+    for (int n = 0; n < 2; ++n) {
+      const NetDims& d = h->dims[n];
+      CUDA_TRY(cudaMemsetAsync(h->net[n] + lo, 0, sizeof(float) * (size_t)d.n_params, h->stream));
+      for (int k = 0; k < 3; ++k) {
+        const long long nw = (long long)d.l[k].in * d.l[k].out;
+        ddpg_init_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, h->stream>>>(h->net[n] + lo + d.l[k].w_off, nw, d.l[k].in, d.l[k].out, k == 2,
+                                                                              seed + (uint64_t)l, (unsigned)(n * 3 + k));
+      }
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(h->net[n + 2] + lo, h->net[n] + lo, sizeof(float) * (size_t)d.n_params, cudaMemcpyDeviceToDevice, h->stream));  // deepcopy :38,:46
     }
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h->net[n + 2], h->net[n], sizeof(float) * (size_t)d.n_params, cudaMemcpyDeviceToDevice, h->stream));  // deepcopy :38,:46
   }
   return SHEMS_OK;
 }
@@ -622,13 +661,19 @@ extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
 // src: either the replay ring (tiled layout, ring != NULL) or caller-supplied SoA arrays with leading dim ld (direct).
 // One thread per (sample j, state field k): thread k == 0 also moves a, r, done.
 __global__ void __launch_bounds__(128)
-ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
+ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restrict__ rs, const float* __restrict__ ra, const float* __restrict__ rr,
                    const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
-                   const int32_t* __restrict__ idx, const float* __restrict__ norm, int B, float* __restrict__ xs, float* __restrict__ xs2,
-                   float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done) {
+                   const int32_t* __restrict__ idx, long long idx_stride, const float* __restrict__ norm, int B, float* __restrict__ xs,
+                   float* __restrict__ xs2, float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done, long long pop_stride) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = g / 9, k = g - j * 9;
   if (j >= B) return;
+  {  // blockIdx.y = learner of a population: own ring, control block, indices and slab
+    const long long lo = (long long)blockIdx.y * pop_stride;
+    ctrl += blockIdx.y; idx += (long long)blockIdx.y * idx_stride;
+    norm += lo; xs += lo; xs2 += lo; xspi += lo; r += lo; done += lo;
+  }
+  const float* ring = rings ? rings[blockIdx.y] : nullptr;
   float sv, s2v, a0 = 0.f, a1 = 0.f, rv = 0.f, dv = 0.f;
   if (ring) {
     const long long len = ctrl->len, head = ctrl->head, cap = ctrl->cap;
@@ -663,7 +708,13 @@ ddpg_gather_kernel(const float* __restrict__ ring, const float* __restrict__ rs,
 __global__ void __launch_bounds__(256)
 adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
                    double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
-                   float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance, float gscale) {
+                   float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance, float gscale, long long pop_stride) {
+  {  // blockIdx.y = learner of a population
+    const long long lo = (long long)blockIdx.y * pop_stride;
+    x += lo; g += lo; m += lo; v += lo; ctrl += blockIdx.y;
+    if (target) target += lo;
+    if (target2) { target2 += lo; model2 += lo; }
+  }
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -722,9 +773,9 @@ static inline GemmProblem gp_dx(const float* dZ, long long lddz, int B, const fl
   g.C = dX; g.ldc = lddx; g.M = B; g.N = ni; g.K = L.out; g.epi = epi; g.aux = aux; g.auxld = auxld;
   return g;
 }
-static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
+static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count, int pop = 1, long long ls_w = 0, long long ls_x = 0) {
   GemmBatch gb; memset(&gb, 0, sizeof(gb));
-  gb.count = count; gb.ksplit = 1;
+  gb.count = count; gb.ksplit = 1; gb.pop = pop; gb.ls_w = ls_w; gb.ls_x = ls_x;
   bool skinny = true;
   int maxM = 1, maxN = 1;
   long long ctas32 = 0;
@@ -735,11 +786,11 @@ static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
     ctas32 += (long long)((ps[i].M + 31) / 32) * ((ps[i].N + 31) / 32);
   }
   if (skinny) {
-    gemm_skinny_kernel<<<dim3((maxM + 7) / 8, count), 256, 0, st>>>(gb);
-  } else if (ctas32 < 296) {  // fewer than two CTAs per SM with 32x32 tiles: use 16x16 tiles (4x the CTAs, 1/4 of the serial work each)
-    gemm_batch_kernel<16, 16><<<dim3((maxM + 15) / 16, (maxN + 15) / 16, count), 128, 0, st>>>(gb);
+    gemm_skinny_kernel<<<dim3((maxM + 7) / 8, count, pop), 256, 0, st>>>(gb);
+  } else if (ctas32 * pop < 296) {  // fewer than two CTAs per SM with 32x32 tiles: use 16x16 tiles (4x the CTAs, 1/4 of the serial work each)
+    gemm_batch_kernel<16, 16><<<dim3((maxM + 15) / 16, (maxN + 15) / 16, count * pop), 128, 0, st>>>(gb);
   } else {
-    gemm_batch_kernel<32, 32><<<dim3((maxM + 31) / 32, (maxN + 31) / 32, count), 512, 0, st>>>(gb);
+    gemm_batch_kernel<32, 32><<<dim3((maxM + 31) / 32, (maxN + 31) / 32, count * pop), 512, 0, st>>>(gb);
   }
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
@@ -750,7 +801,7 @@ static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count) {
 // blockIdx.z: every split writes [tile sums | column sums] into the workspace, splitk_reduce_kernel adds them in order.
 static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g) {
   const int B = g.K;
-  if (B < SPLITK_MIN_BATCH) return launch_gemms(st, &g, 1);
+  if (B < SPLITK_MIN_BATCH) return launch_gemms(st, &g, 1, h->pop, h->pop_stride, h->pop_stride);
   const long long mn = (long long)g.M * g.N, stride = mn + g.N;
   REQUIRE(g.ldc == g.N && g.dbias == g.C + mn && g.epi == EPI_NONE, SHEMS_ERR_INVALID, "launch_dw: not a contiguous [W|b] gradient block");
   const int ksplit = min(SPLITK_MAX, B / 256);
@@ -848,7 +899,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     g[0] = gp_fwd(h->xs2, 11, B, actor_t, da.l[0], h->t_h1, l1, EPI_BIAS_RELU);
     g[1] = gp_fwd(h->xs, 11, B, critic, dc.l[0], h->c_h1, l1, EPI_BIAS_RELU);
     g[2] = gp_fwd(h->xs, 11, B, actor, da.l[0], h->a_h1, l1, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 3));
+    TRY(launch_gemms(st, g, 3, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) {
     TRY(tc_fwd(st, h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2));
@@ -858,34 +909,34 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
     g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);
     g[2] = gp_fwd(h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 3));
+    TRY(launch_gemms(st, g, 3, h->pop, h->pop_stride, h->pop_stride));
   }
   g[0] = gp_fwd(h->t_h2, l2, B, actor_t, da.l[2], h->xs2 + 9, 11, EPI_BIAS_TANH);   // a' -> vcat(s'_n, a')
   g[1] = gp_fwd(h->c_h2, l2, B, critic, dc.l[2], h->q, 1, EPI_BIAS_ID);
   g[2] = gp_fwd(h->a_h2, l2, B, actor, da.l[2], h->xspi + 9, 11, EPI_BIAS_TANH);    // actor(s_n) -> vcat(s_n, actions)
-  TRY(launch_gemms(st, g, 3));
+  TRY(launch_gemms(st, g, 3, h->pop, h->pop_stride, h->pop_stride));
   // P4-P6: q' = critic_target(vcat(s'_n, a'));  y = r + γ(1-done) q';  dq = 2(q-y)/B     (:132-133)
   if (big) {
     const float* X[1] = {h->xs2}; const float* nets[1] = {critic_t}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->tc_h1};
     TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
   } else {
     g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) TRY(tc_fwd(st, h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2));
   else {
     g[0] = gp_fwd(h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   g[0] = gp_fwd(h->tc_h2, l2, B, critic_t, dc.l[2], h->y, 1, EPI_TD_TARGET);
   g[0].aux = h->r; g[0].aux2 = h->done; g[0].aux3 = h->q; g[0].out2 = h->dq; g[0].alpha = p.gamma; g[0].inv_batch = 1.0f / (float)B;
-  TRY(launch_gemms(st, g, 1));
+  TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   // P7-P9: critic backward (:137, :105-108)
   if (big) TRY(big_out_bwd(h, st, h->c_h2, l2, h->dq, 1, B, critic, dc.l[2], h->grad[1], h->dz2));
   else {
     g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
     g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, p.l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
-    TRY(launch_gemms(st, g, 2));
+    TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) {
     TRY(tc_dw(h, st, h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]));
@@ -893,8 +944,8 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   } else {
     g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
     g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
-    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1)); }
-    else TRY(launch_gemms(st, g, 2));
+    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride)); }
+    else TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   }
   g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
   TRY(launch_dw(h, st, g[0]));
@@ -909,9 +960,9 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
   GemmProblem g[4];
   // P10: ADAM(η_crit) on the critic
-  const unsigned adam_grid = (unsigned)((dc.n_params + 255) / 256);  // one element per thread: the Float64 div/sqrt chains need TLP
+  const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);  // one element per thread: the Float64 div/sqrt chains need TLP
   adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale);
+                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   if (big) {
@@ -919,12 +970,12 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
     TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
   } else {
     g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) TRY(tc_fwd(st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2));
   else {
     g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   if (big) {                                                                                               // dX through the critic only
     const long long ne = (long long)B * ((p.l2 + 3) / 4);
@@ -932,22 +983,22 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
     CUDA_TRY(cudaGetLastError());
   } else {
     g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, p.l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
   if (tc) TRY(tc_dx(st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
   else {
     g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, p.l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
-    TRY(launch_gemms(st, g, 1));
+    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
-  TRY(launch_gemms(st, g, 1));
+  TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   // P16-P18: actor backward
   if (big) TRY(big_out_bwd(h, st, h->a_h2, l2, h->dza3, 2, B, actor, da.l[2], h->grad[0], h->dza2));
   else {
     g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
     g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, p.l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
-    TRY(launch_gemms(st, g, 2));
+    TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) {
     TRY(tc_dw(h, st, h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]));
@@ -955,15 +1006,15 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   } else {
     g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
     g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
-    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1)); }
-    else TRY(launch_gemms(st, g, 2));
+    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride)); }
+    else TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   }
   g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
   g[0].M = 9;  // only the 9 state columns of xs feed the actor
   TRY(launch_dw(h, st, g[0]));
   // q(s, actor(s)) itself only feeds loss_act (reporting): off the critical path, skinny kernel
   g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
-  TRY(launch_gemms(st, g, 1));
+  TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   return SHEMS_OK;
 }
 
@@ -971,10 +1022,10 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale) {
   const DdpgParams& p = h->p;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
-  const unsigned adam_grid = (unsigned)((dc.n_params + 255) / 256);
+  const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
   adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale);
+                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -986,66 +1037,92 @@ static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
   return s0;
 }
 
-static int enqueue_gather(Ddpg* h, cudaStream_t st, const float* ring, const float* s, const float* a, const float* r, const float* s2,
+// from_rings: every learner samples its own replay ring (h->rings_dev); else one caller-supplied minibatch (single learner)
+static int enqueue_gather(Ddpg* h, cudaStream_t st, bool from_rings, const float* s, const float* a, const float* r, const float* s2,
                           const float* done, long long ld) {
   const int B = h->p.batch;
-  ddpg_gather_kernel<<<(B * 9 + 127) / 128, 128, 0, st>>>(ring, s, a, r, s2, done, ld, h->ctrl, h->idx_dev, h->norm, B, h->xs, h->xs2, h->xspi, h->r,
-                                                      h->done);
+  ddpg_gather_kernel<<<dim3((B * 9 + 127) / 128, from_rings ? h->pop : 1), 128, 0, st>>>(from_rings ? h->rings_dev : nullptr, s, a, r, s2, done, ld,
+                                                                                     h->ctrl, h->idx_dev, h->idx_stride, h->norm, B, h->xs,
+                                                                                     h->xs2, h->xspi, h->r, h->done, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 
-// capture gather(from replay) + body once; replays read everything that changes from the device control block
-static int ensure_graph(Ddpg* h, const ShemsReplay* rp) {
-  if (h->graph_exec && h->graph_rp == rp) return SHEMS_OK;
-  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+// capture gather(from the replay rings) + body once; replays read everything that changes from the device control blocks
+static int ensure_graph(Ddpg* h) {
+  if (h->graph_exec) return SHEMS_OK;
   if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
   cudaStream_t cs;
   CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { cudaStreamDestroy(cs); shems_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
-  int st = enqueue_gather(h, cs, rp->ring, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  int st = enqueue_gather(h, cs, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   if (!st) st = enqueue_update_body(h, cs);
   e = cudaStreamEndCapture(cs, &h->graph);
   cudaStreamDestroy(cs);
   if (st) return st;
   if (e != cudaSuccess) { shems_set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
   CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
-  h->graph_rp = rp;
   return SHEMS_OK;
 }
 
-extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed) {
-  REQUIRE(h && rp, SHEMS_ERR_INVALID, "ddpg_update: NULL argument");
-  REQUIRE(n_updates >= 1, SHEMS_ERR_INVALID, "ddpg_update: n_updates=%d", n_updates);
-  REQUIRE(rp->device == h->device, SHEMS_ERR_INVALID, "ddpg_update: replay on device %d, learner on %d", rp->device, h->device);
-  REQUIRE(rp->length > 0, SHEMS_ERR_STATE, "ddpg_update: memory is empty");
-  GUARD(h->device);
-  const int B = h->p.batch;
+struct CtrlHostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; unsigned blocks_done; };
+static_assert(sizeof(CtrlHostPart) == offsetof(DdpgCtrl, bp), "control block layout");
+
+// host-owned part of every learner's control block (seed, ring geometry, index mode) + ring pointers + optional indices;
+// update/bp stay device-owned.  rps[l], seeds[l]: learner l's replay memory and Philox seed; idx_host [pop][per_learner] or NULL.
+static int stage_update_inputs(Ddpg* h, ShemsReplay* const* rps, const uint64_t* seeds, const int32_t* idx_host, long long per_learner) {
+  const int pop = h->pop;
+  std::vector<CtrlHostPart> hp((size_t)pop);
+  std::vector<const float*> rings((size_t)pop);
+  for (int l = 0; l < pop; ++l) {
+    ShemsReplay* rp = rps[l];
+    REQUIRE(rp, SHEMS_ERR_INVALID, "ddpg_update: learner %d has no replay memory", l);
+    REQUIRE(rp->device == h->device, SHEMS_ERR_INVALID, "ddpg_update: replay on device %d, learner on %d", rp->device, h->device);
+    REQUIRE(rp->length > 0, SHEMS_ERR_STATE, "ddpg_update: memory is empty");
+    if (idx_host)
+      for (long long j = 0; j < per_learner; ++j) {
+        const int32_t v = idx_host[(long long)l * per_learner + j];
+        REQUIRE(v >= 0 && v < rp->length, SHEMS_ERR_INVALID, "ddpg_update: idx[%d][%lld]=%d outside 0..%lld", l, j, v, (long long)rp->length - 1);
+      }
+    hp[l].seed = seeds[l]; hp[l].update = (unsigned)h->n_updates; hp[l].use_idx = idx_host ? 1 : 0;
+    hp[l].len = rp->length; hp[l].head = rp->head; hp[l].cap = rp->capacity; hp[l].idx_cursor = 0; hp[l].blocks_done = 0;
+    rings[l] = rp->ring;
+  }
   if (idx_host) {
-    const long long need = (long long)n_updates * B;
-    for (long long j = 0; j < need; ++j)
-      REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "ddpg_update: idx[%lld]=%d outside 0..%lld", j, idx_host[j],
-              (long long)rp->length - 1);
+    const long long need = (long long)pop * per_learner;
     if (h->idx_cap < need) {
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
       cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
       CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)need));
       h->idx_cap = need;
       if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }  // idx pointer is baked into the graph
     }
+    if (h->idx_stride != per_learner && h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    h->idx_stride = per_learner;
     CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)need, cudaMemcpyHostToDevice, h->stream));
   }
-  // refresh the part of the control block the host owns (seed, ring geometry, index mode); update/bp stay device-owned
-  struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; unsigned blocks_done; } hp;
-  hp.seed = seed; hp.update = (unsigned)h->n_updates; hp.use_idx = idx_host ? 1 : 0; hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
-  hp.idx_cursor = 0; hp.blocks_done = 0;
-  static_assert(sizeof(HostPart) == offsetof(DdpgCtrl, bp), "control block layout");
-  CUDA_TRY(cudaMemcpyAsync(h->ctrl, &hp, sizeof(hp), cudaMemcpyHostToDevice, h->stream));
-  TRY(ensure_graph(h, rp));
+  // pageable sources: the runtime stages these small copies before returning, so the vectors may go out of scope
+  CUDA_TRY(cudaMemcpy2DAsync(h->ctrl, sizeof(DdpgCtrl), hp.data(), sizeof(CtrlHostPart), sizeof(CtrlHostPart), (size_t)pop, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync((void*)h->rings_dev, rings.data(), sizeof(const float*) * (size_t)pop, cudaMemcpyHostToDevice, h->stream));
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_update_population(Ddpg* h, ShemsReplay* const* rps, int32_t n_updates, const int32_t* idx_host, const uint64_t* seeds) {
+  REQUIRE(h && rps && seeds, SHEMS_ERR_INVALID, "ddpg_update_population: NULL argument");
+  REQUIRE(n_updates >= 1, SHEMS_ERR_INVALID, "ddpg_update_population: n_updates=%d", n_updates);
+  GUARD(h->device);
+  TRY(stage_update_inputs(h, rps, seeds, idx_host, (long long)n_updates * h->p.batch));
+  TRY(ensure_graph(h));
   for (int u = 0; u < n_updates; ++u) CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
   h->n_updates += n_updates;
-  // asynchronous: the small pageable H2D copies above are staged by the runtime before they return
   return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed) {
+  REQUIRE(h && rp, SHEMS_ERR_INVALID, "ddpg_update: NULL argument");
+  REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_update: this handle holds %d learners, use ddpg_update_population", h->pop);
+  return ddpg_update_population(h, &rp, n_updates, idx_host, &seed);
 }
 
 // Data-parallel learner: one replay() in three calls; between them the caller all-reduces (sum) the gradient buffer
@@ -1053,27 +1130,12 @@ extern "C" int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, cons
 extern "C" int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, const int32_t* idx_host, uint64_t seed, float grad_scale) {
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_update_phase: NULL handle");
   REQUIRE(phase >= 0 && phase <= 2, SHEMS_ERR_INVALID, "ddpg_update_phase: phase=%d", phase);
+  REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_update_phase: not available for a population handle");
   GUARD(h->device);
   if (phase == 0) {
-    REQUIRE(rp && rp->device == h->device && rp->length > 0, SHEMS_ERR_STATE, "ddpg_update_phase: replay missing, empty or on another device");
-    const int B = h->p.batch;
-    if (idx_host) {
-      for (int j = 0; j < B; ++j)
-        REQUIRE(idx_host[j] >= 0 && idx_host[j] < rp->length, SHEMS_ERR_INVALID, "ddpg_update_phase: idx[%d]=%d outside 0..%lld", j, idx_host[j],
-                (long long)rp->length - 1);
-      if (h->idx_cap < B) {
-        cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
-        CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)B));
-        h->idx_cap = B;
-        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-      }
-      CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, h->stream));
-    }
-    struct HostPart { unsigned long long seed; unsigned update; int use_idx; long long len, head, cap; int idx_cursor; unsigned blocks_done; } hp;
-    hp.seed = seed; hp.update = (unsigned)h->n_updates; hp.use_idx = idx_host ? 1 : 0; hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
-    hp.idx_cursor = 0; hp.blocks_done = 0;
-    CUDA_TRY(cudaMemcpyAsync(h->ctrl, &hp, sizeof(hp), cudaMemcpyHostToDevice, h->stream));
-    TRY(enqueue_gather(h, h->stream, rp->ring, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
+    REQUIRE(rp, SHEMS_ERR_STATE, "ddpg_update_phase: replay missing");
+    TRY(stage_update_inputs(h, &rp, &seed, idx_host, h->p.batch));
+    TRY(enqueue_gather(h, h->stream, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0));
     return enqueue_phase0(h, h->stream);
   }
   if (phase == 1) return enqueue_phase1(h, h->stream, grad_scale);
@@ -1084,8 +1146,9 @@ extern "C" int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, co
 
 extern "C" int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev, const float* s2_dev, const float* done_dev) {
   REQUIRE(h && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "ddpg_update_batch: NULL argument");
+  REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_update_batch: not available for a population handle");
   GUARD(h->device);
-  TRY(enqueue_gather(h, h->stream, nullptr, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch));
+  TRY(enqueue_gather(h, h->stream, false, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch));
   TRY(enqueue_update_body(h, h->stream));
   h->n_updates += 1;
   return SHEMS_OK;
@@ -1101,7 +1164,7 @@ __global__ void ddpg_loss_kernel(const float* __restrict__ q, const float* __res
 extern "C" int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act) {
   REQUIRE(h && loss_crit && loss_act, SHEMS_ERR_INVALID, "ddpg_get_losses: NULL argument");
   GUARD(h->device);
-  ddpg_loss_kernel<<<1, 32, 0, h->stream>>>(h->q, h->y, h->qpi, h->p.batch, h->loss_scratch);
+  ddpg_loss_kernel<<<1, 32, 0, h->stream>>>(h->q + sel_off(h), h->y + sel_off(h), h->qpi + sel_off(h), h->p.batch, h->loss_scratch);
   CUDA_TRY(cudaGetLastError());
   float out[2];
   CUDA_TRY(cudaMemcpyAsync(out, h->loss_scratch, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
@@ -1113,9 +1176,11 @@ extern "C" int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act) {
 // ----------------------------------------------------------------------------- act
 // normalize (memory_plotting_saving.jl:55-57) of SoA obs [9][n] -> x [n][9]
 __global__ void __launch_bounds__(256)
-ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* __restrict__ norm, float* __restrict__ x) {
+ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* __restrict__ norm, float* __restrict__ x, long long pop_stride,
+                      long long act_stride) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  obs += (long long)blockIdx.y * 9 * n; norm += (long long)blockIdx.y * pop_stride; x += (long long)blockIdx.y * act_stride;  // learner
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
@@ -1126,9 +1191,15 @@ ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* _
 __global__ void __launch_bounds__(256)
 ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float sigma, unsigned long long seed, long long step,
                          long long env_id_base, const float* __restrict__ noise, float lo0, float lo1, float hi0, float hi1,
-                         float* __restrict__ a_out, float* __restrict__ scaled_out) {
+                         float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  {  // blockIdx.y = learner of a population: arrays carry a leading [pop] dimension, noise streams are keyed by the global env id
+    const long long l = blockIdx.y;
+    y += l * act_stride; a_out += l * 2 * n; env_id_base += l * n;
+    if (noise) noise += l * 2 * n;
+    if (scaled_out) scaled_out += l * 2 * n;
+  }
   float nz0 = 0.0f, nz1 = 0.0f;
   if (noise) { nz0 = noise[j]; nz1 = noise[n + j]; }
   else if (sigma > 0.0f) {
@@ -1157,39 +1228,39 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
   REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
   GUARD(h->device);
-  const int l1 = h->ld1, l2 = h->ld2;
-  if (h->act_cap < n) {
+  const int l1 = h->ld1, l2 = h->ld2, pop = h->pop;
+  if (h->act_cap < n) {  // scratch: per learner [x n*9 | h1 n*ld1 | h2 n*ld2 | y n*2], each part at a 256-byte boundary
     CUDA_TRY(cudaStreamSynchronize(h->stream));
-    cudaFree(h->act_x); cudaFree(h->act_h1); cudaFree(h->act_h2); cudaFree(h->act_y);
+    cudaFree(h->act_x);
     h->act_x = h->act_h1 = h->act_h2 = h->act_y = nullptr; h->act_cap = 0;
-    CUDA_TRY(cudaMalloc(&h->act_x, sizeof(float) * 9 * (size_t)n));
-    CUDA_TRY(cudaMalloc(&h->act_h1, sizeof(float) * (size_t)l1 * (size_t)n));
-    CUDA_TRY(cudaMalloc(&h->act_h2, sizeof(float) * (size_t)l2 * (size_t)n));
-    CUDA_TRY(cudaMalloc(&h->act_y, sizeof(float) * 2 * (size_t)n));
+    const long long o1 = (9 * n + 63) & ~63ll, o2 = o1 + (((long long)l1 * n + 63) & ~63ll), o3 = o2 + (((long long)l2 * n + 63) & ~63ll);
+    h->act_stride = o3 + ((2 * n + 63) & ~63ll);
+    CUDA_TRY(cudaMalloc(&h->act_x, sizeof(float) * (size_t)h->act_stride * (size_t)pop));
+    h->act_h1 = h->act_x + o1; h->act_h2 = h->act_x + o2; h->act_y = h->act_x + o3;
     h->act_cap = n;
   }
-  const unsigned gn = (unsigned)((n + 255) / 256);
-  ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x);
+  const dim3 gn((unsigned)((n + 255) / 256), pop);
+  ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x, h->pop_stride, h->act_stride);
   CUDA_TRY(cudaGetLastError());
   const NetDims& da = h->dims[0];
   const float* actor = h->net[DDPG_NET_ACTOR];
   GemmProblem g[1];
-  if (n >= SPLITK_MIN_BATCH) {
+  if (pop == 1 && n >= SPLITK_MIN_BATCH) {
     const float* X[1] = {h->act_x}; const float* nets[1] = {actor}; const LayerDims* Ls[1] = {&da.l[0]}; float* Y[1] = {h->act_h1};
     TRY(big_l1(h->stream, 1, X, 9, (int)n, nets, Ls, Y, l1));
   } else {
     g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
-    TRY(launch_gemms(h->stream, g, 1));
+    TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
   }
-  if (use_tc(h, n)) TRY(tc_fwd(h->stream, h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2));
+  if (pop == 1 && use_tc(h, n)) TRY(tc_fwd(h->stream, h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2));
   else {
     g[0] = gp_fwd(h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, EPI_BIAS_RELU);
-    TRY(launch_gemms(h->stream, g, 1));
+    TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
   }
   g[0] = gp_fwd(h->act_h2, l2, (int)n, actor, da.l[2], h->act_y, 2, EPI_BIAS_TANH);
-  TRY(launch_gemms(h->stream, g, 1));
+  TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
-                                                      h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev);
+                                                      h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev, h->act_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }

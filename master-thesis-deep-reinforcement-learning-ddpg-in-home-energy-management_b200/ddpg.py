@@ -103,11 +103,15 @@ class Learner:
     """actor, critic, their targets and both ADAM optimisers (DDPG.jl:30-46, input.jl:126-127)."""
 
     def __init__(self, params=None, device=0, **kw):
+        """population=P (keyword or params.population) builds P independent learners in one handle (BASELINE configs[4]: the
+        reference's one-process-per-seed parallelism): `select(l)` picks the learner that get/set/losses address, batched
+        arrays of act() gain a leading [P] dimension, replay() takes one Replay per learner."""
         self.lib = L.lib()
         self.p = params if params is not None else L.default_ddpg_params(**kw)
         h = C.c_void_p()
         L.check(self.lib.ddpg_create(C.byref(self.p), int(device), C.byref(h)))
         self._h = h
+        self.population = int(self.lib.ddpg_population(h))
         self.device = int(device)
         self._dev = torch.device("cuda", self.device)
         self._bind_stream()
@@ -130,6 +134,11 @@ class Learner:
 
     def sync(self):
         L.check(self.lib.ddpg_sync(self._h))
+
+    def select(self, learner):
+        """ddpg_select_learner: the learner of a population that set/get_layer, get_grad, set_norm and losses address."""
+        L.check(self.lib.ddpg_select_learner(self._h, int(learner)))
+        return self
 
     def layer_shape(self, net, layer):
         S, A = self.p.state_size, self.p.action_size
@@ -165,21 +174,32 @@ class Learner:
 
     def act(self, obs, train=True, sigma=0.1, rng_act=0, step=0, env_id_base=0, noise=None):
         """act(normalize(s); train) + scale_action for obs [9][n] -> (a [2][n] in [-1,1], scaled [2][n])."""
-        n = obs.shape[1]
-        a = torch.empty((2, n), dtype=torch.float32, device=self._dev)
-        sc = torch.empty((2, n), dtype=torch.float32, device=self._dev)
+        n = obs.shape[-1]
+        shape = (2, n) if self.population == 1 else (self.population, 2, n)   # population: obs [P][9][n] -> [P][2][n]
+        assert obs.numel() == 9 * n * self.population
+        a = torch.empty(shape, dtype=torch.float32, device=self._dev)
+        sc = torch.empty(shape, dtype=torch.float32, device=self._dev)
         sg = float(sigma) if (train and noise is None) else 0.0
         L.check(self.lib.ddpg_act(self._h, _ptr(obs), n, sg, int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(noise), _ptr(a), _ptr(sc)))
         return a, sc
 
     def replay(self, memory, rng_rpl=0, n_updates=1, idx=None):
-        """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back."""
+        """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back.  Population handles: `memory` is the list of the
+        learners' Replay objects, rng_rpl an int (learner l uses rng_rpl + l) or one seed per learner, idx [P][n_updates][batch]."""
         ip = None
         if idx is not None:
             idx = np.ascontiguousarray(idx, np.int32)
-            assert idx.size == n_updates * self.p.batch
+            assert idx.size == n_updates * self.p.batch * self.population
             ip = idx.ctypes.data_as(L.PI)
-        L.check(self.lib.ddpg_update(self._h, memory._h, int(n_updates), ip, int(rng_rpl) & (2**64 - 1)))
+        if self.population == 1 and not isinstance(memory, (list, tuple)):
+            L.check(self.lib.ddpg_update(self._h, memory._h, int(n_updates), ip, int(rng_rpl) & (2**64 - 1)))
+            return
+        mems = list(memory)
+        assert len(mems) == self.population
+        seeds = [int(rng_rpl) + l for l in range(self.population)] if np.isscalar(rng_rpl) else [int(x) for x in rng_rpl]
+        hs = (C.c_void_p * self.population)(*[m._h for m in mems])
+        sd = (C.c_uint64 * self.population)(*[x & (2**64 - 1) for x in seeds])
+        L.check(self.lib.ddpg_update_population(self._h, hs, int(n_updates), ip, sd))
 
     def replay_dp(self, memory, rng_rpl=0, dist=None, idx=None):
         """replay() for a data-parallel learner: every rank samples its own replay shard, the critic and actor gradients are

@@ -353,3 +353,70 @@ def test_data_parallel_phases_equal_full_batch(sb, O, train_series):
             wf, bf = full.get_layer(net, k)
             np.testing.assert_allclose(w0, wf, rtol=1e-5, atol=0.02 * lr * K + 1e-7)
             np.testing.assert_allclose(b0, bf, rtol=1e-5, atol=0.02 * lr * K + 1e-7)
+
+
+def test_population_equals_independent_learners(sb, O, train_series):
+    """A population handle (P learners advanced by the same launches, BASELINE configs[4]) must do exactly what P separate
+    single-learner handles do: same init (seed + l), own replay memory, own minibatch stream, own normalisation constants.
+    The batched launches pick other tile shapes than a lone learner, so sums are re-associated: weights within 2 % of
+    lr·K, actions within 1e-5."""
+    P, n, T, B, K = 3, 32, 40, 64, 4
+    kw = dict(batch=B, l1=48, l2=64)
+    mems, singles = [], []
+    for l in range(P):
+        env = sb.Shems(72, train_series, n_envs=n, env_id_base=1000 * l)
+        mem = sb.Replay(n * T)
+        env.reset(rng=20 + l)
+        env.rollout(sb.POLICY_RANDOM, T, seed=20 + l, replay=mem, want_return=False)
+        mems.append(mem)
+    pop = sb.Learner(params=sb.default_ddpg_params(population=P, **kw))
+    assert pop.population == P
+    pop.init(50)
+    norms = []
+    for l in range(P):
+        le = sb.Learner(params=sb.default_ddpg_params(**kw))
+        le.init(50 + l)
+        mn, mx = mems[l].min_max_buffer(n * T, rng_mm=l)
+        le.set_norm(mn, mx)
+        pop.select(l).set_norm(mn, mx)
+        norms.append((mn, mx))
+        singles.append(le)
+        for net in range(4):   # identical initial weights: Philox(seed + l)
+            for k in range(3):
+                np.testing.assert_array_equal(pop.get_layer(net, k)[0], le.get_layer(net, k)[0])
+    idx = np.stack([np.random.default_rng(l).integers(0, n * T, (K, B)) for l in range(P)]).astype(np.int32)
+    pop.replay(mems, n_updates=K, idx=idx)
+    for l in range(P):
+        singles[l].replay(mems[l], n_updates=K, idx=idx[l])
+    p = pop.p
+    for l in range(P):
+        pop.select(l)
+        for net, lr in ((0, p.lr_actor), (1, p.lr_critic), (2, p.lr_actor * p.tau), (3, p.lr_critic * p.tau)):
+            for k in range(3):
+                for x, y in zip(pop.get_layer(net, k), singles[l].get_layer(net, k)):
+                    np.testing.assert_allclose(x, y, rtol=1e-5, atol=0.02 * lr * K + 1e-7)
+        lc, la = pop.losses()
+        slc, sla = singles[l].losses()
+        assert lc == pytest.approx(slc, rel=1e-4) and la == pytest.approx(sla, rel=1e-4, abs=1e-6)
+    # Philox-sampled minibatches: learner l draws from seed + l, exactly like a lone learner with that seed
+    pop.replay(mems, rng_rpl=900, n_updates=2)
+    for l in range(P):
+        singles[l].replay(mems[l], rng_rpl=900 + l, n_updates=2)
+        pop.select(l)
+        for x, y in zip(pop.get_layer(1, 1), singles[l].get_layer(1, 1)):
+            np.testing.assert_allclose(x, y, rtol=1e-5, atol=0.02 * p.lr_critic * (K + 2))
+    # act(): obs [P][9][m] -> a [P][2][m]
+    m = 40
+    obs = torch.stack([torch.as_tensor(mems[l].get()[0][:, :m], device="cuda") for l in range(P)]).contiguous()
+    noise = torch.as_tensor(np.random.default_rng(3).normal(0, 0.1, (P, 2, m)).astype(np.float32), device="cuda")
+    a, sc = pop.act(obs, noise=noise)
+    assert a.shape == (P, 2, m)
+    for l in range(P):
+        a1, sc1 = singles[l].act(obs[l].contiguous(), noise=noise[l].contiguous())
+        np.testing.assert_allclose(a[l].cpu().numpy(), a1.cpu().numpy(), rtol=0, atol=1e-5)
+        np.testing.assert_allclose(sc[l].cpu().numpy(), sc1.cpu().numpy(), rtol=0, atol=1e-5)
+    # guards
+    with pytest.raises(sb.ShemsError):
+        pop.replay(mems[0], n_updates=1) if False else sb._lib.check(pop.lib.ddpg_update(pop._h, mems[0]._h, 1, None, 0))
+    with pytest.raises(sb.ShemsError):
+        sb.Learner(params=sb.default_ddpg_params(population=2, batch=2048))
