@@ -272,8 +272,10 @@ splitk_reduce_kernel(const float* __restrict__ ws, long long stride, int splits,
 template <int J>
 __global__ void __launch_bounds__(256)
 wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, const float* __restrict__ w, int rows_per, long long stride,
-                       float* __restrict__ ws) {
+                       float* __restrict__ ws, long long pop_stride) {
   constexpr int JJ = J > 0 ? J : 1;
+  Z += (long long)blockIdx.z * pop_stride; ws += (long long)blockIdx.z * pop_stride;  // learner of a population (one slab: writes the gradient itself)
+  if (J > 0) w += (long long)blockIdx.z * pop_stride;
   __shared__ float red[8][32][JJ];
   const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + c;
@@ -496,8 +498,8 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   REQUIRE(p->l1 >= 1 && p->l2 >= 1 && p->batch >= 1, SHEMS_ERR_INVALID, "ddpg_create: l1=%d l2=%d batch=%d", p->l1, p->l2, p->batch);
   REQUIRE(p->population >= 0 && p->population <= 4096, SHEMS_ERR_INVALID, "ddpg_create: population=%d", p->population);
   const int pop = p->population > 1 ? p->population : 1;
-  REQUIRE(pop == 1 || (p->batch < SPLITK_MIN_BATCH && !p->use_tensor_cores), SHEMS_ERR_INVALID,
-          "ddpg_create: a population of learners runs the small-batch path (batch < %d, use_tensor_cores = 0)", SPLITK_MIN_BATCH);
+  REQUIRE(pop == 1 || p->batch < SPLITK_MIN_BATCH, SHEMS_ERR_INVALID,
+          "ddpg_create: a population of learners runs the small-batch path (batch < %d)", SPLITK_MIN_BATCH);
   REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "ddpg_create: no CUDA device (this library has no CPU fallback)");
   GUARD(device);
   Ddpg* h = new (std::nothrow) Ddpg();
@@ -818,25 +820,35 @@ static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g) {
   return SHEMS_OK;
 }
 
-// ---- layer-2 contractions on TF32 tensor cores (csrc/tc_gemm.cu); operands are used where they lie in HBM
+// ---- layer-2 contractions on TF32 tensor cores (csrc/tc_gemm.cu); operands are used where they lie in HBM.  A population
+// handle runs all learners' products in one launch (grid.z = learner): weights/gradients/activations of learner l sit
+// l*pop_stride floats behind learner 0's; act() scratch uses its own stride (xs).
 // Y = relu(X · W + b):  X [M][ldx] K-major, Flux weight Wt[in][out] MN-major
-static int tc_fwd(cudaStream_t st, const float* X, int ldx, int M, const float* net, const LayerDims& L, float* Y, int ldy) {
+static int tc_fwd(const Ddpg* h, cudaStream_t st, const float* X, int ldx, int M, const float* net, const LayerDims& L, float* Y, int ldy, long long xstride) {
   TcOperand A{X, ldx, false}, Bo{net + L.w_off, L.out, true};
-  return tc_gemm(st, A, Bo, Y, ldy, M, L.out, L.in, TC_EPI_BIAS_RELU, net + L.b_off, nullptr, 0, 1, nullptr);
+  TcBatch bt; bt.count = h->pop; bt.sA = xstride; bt.sB = h->pop_stride; bt.sD = xstride; bt.sBias = h->pop_stride;
+  return tc_gemm(st, A, Bo, Y, ldy, M, L.out, L.in, TC_EPI_BIAS_RELU, net + L.b_off, nullptr, 0, 1, nullptr, bt);
 }
 // dX = (dZ · W^T) masked by relu'(H):  dZ [M][lddz] K-major, Wt[in][out] K-major (k = out)
-static int tc_dx(cudaStream_t st, const float* dZ, int lddz, int M, const float* net, const LayerDims& L, float* dX, int lddx, const float* H, int ldh) {
+static int tc_dx(const Ddpg* h, cudaStream_t st, const float* dZ, int lddz, int M, const float* net, const LayerDims& L, float* dX, int lddx, const float* H, int ldh) {
   TcOperand A{dZ, lddz, false}, Bo{net + L.w_off, L.out, false};
-  return tc_gemm(st, A, Bo, dX, lddx, M, L.in, L.out, TC_EPI_RELU_MASK, nullptr, H, ldh, 1, nullptr);
+  TcBatch bt; bt.count = h->pop; bt.sA = bt.sB = bt.sD = bt.sAux = h->pop_stride;
+  return tc_gemm(st, A, Bo, dX, lddx, M, L.in, L.out, TC_EPI_RELU_MASK, nullptr, H, ldh, 1, nullptr, bt);
 }
-// dW = X^T · dZ (both MN-major, K = batch, split-K), db = column sums of dZ
+// dW = X^T · dZ (both MN-major, K = batch, split-K for one large-batch learner), db = column sums of dZ
 static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float* dZ, int lddz, int B, const LayerDims& L, float* grad) {
   const int tiles = ((L.in + 127) / 128) * ((L.out + 127) / 128), kb = (B + 31) / 32;
-  const int splits = max(1, min(min(kb / 4, (148 + tiles - 1) / tiles), SPLITK_MAX));
+  const int splits = h->pop > 1 ? 1 : max(1, min(min(kb / 4, (148 + tiles - 1) / tiles), SPLITK_MAX));
   TcOperand A{X, ldx, true}, Bo{dZ, lddz, true};
-  TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? h->ws : nullptr));
-  const int slabs = max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
-  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws);
+  TcBatch bt; bt.count = h->pop; bt.sA = bt.sB = bt.sD = h->pop_stride;
+  TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? h->ws : nullptr, bt));
+  const int slabs = h->pop > 1 ? 1 : max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
+  if (slabs == 1) {  // small batch: the column sums are the bias gradient (every learner of a population in one launch)
+    wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, 1, h->pop), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, grad + L.b_off, h->pop_stride);
+    CUDA_TRY(cudaGetLastError());
+    return SHEMS_OK;
+  }
+  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws, 0);
   CUDA_TRY(cudaGetLastError());
   splitk_reduce_kernel<<<(L.out + 255) / 256, 256, 0, st>>>(h->ws, L.out, slabs, grad + L.b_off, L.out);
   CUDA_TRY(cudaGetLastError());
@@ -862,8 +874,8 @@ static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const 
   const int N = L.in, slabs = max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
   const long long stride = (long long)N * J + J;
   const dim3 grid((N + 31) / 32, slabs);
-  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws);
-  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws);
+  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws, 0);
+  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws, 0);
   CUDA_TRY(cudaGetLastError());
   splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, slabs, grad + L.w_off, stride);
   CUDA_TRY(cudaGetLastError());
@@ -873,7 +885,7 @@ static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const 
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
-static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows >= TC_MIN_ROWS; }
+static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows * h->pop >= TC_MIN_ROWS; }
 
 // one replay() after the minibatch has been gathered ("DDPG update"), in three phases so that a data-parallel
 // learner can all-reduce the flat gradient buffer between them:
@@ -886,7 +898,7 @@ static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows 
 static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
-  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH;
+  const bool tc = use_tc(h, B), big = h->pop == 1 && (tc || B >= SPLITK_MIN_BATCH);
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   GemmProblem g[4];
@@ -902,9 +914,9 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     TRY(launch_gemms(st, g, 3, h->pop, h->pop_stride, h->pop_stride));
   }
   if (tc) {
-    TRY(tc_fwd(st, h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2));
-    TRY(tc_fwd(st, h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2));
-    TRY(tc_fwd(st, h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2));
+    TRY(tc_fwd(h, st, h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, h->pop_stride));
+    TRY(tc_fwd(h, st, h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, h->pop_stride));
+    TRY(tc_fwd(h, st, h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, h->pop_stride));
   } else {
     g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
     g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);
@@ -923,7 +935,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
-  if (tc) TRY(tc_fwd(st, h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2));
+  if (tc) TRY(tc_fwd(h, st, h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, h->pop_stride));
   else {
     g[0] = gp_fwd(h->tc_h1, l1, B, critic_t, dc.l[1], h->tc_h2, l2, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -940,7 +952,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   }
   if (tc) {
     TRY(tc_dw(h, st, h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]));
-    TRY(tc_dx(st, h->dz2, l2, B, critic, dc.l[1], h->dz1, l1, h->c_h1, l1));
+    TRY(tc_dx(h, st, h->dz2, l2, B, critic, dc.l[1], h->dz1, l1, h->c_h1, l1));
   } else {
     g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
     g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
@@ -955,7 +967,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
 static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
-  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH;
+  const bool tc = use_tc(h, B), big = h->pop == 1 && (tc || B >= SPLITK_MIN_BATCH);
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
   GemmProblem g[4];
@@ -972,7 +984,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
     g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
-  if (tc) TRY(tc_fwd(st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2));
+  if (tc) TRY(tc_fwd(h, st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, h->pop_stride));
   else {
     g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -986,7 +998,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
-  if (tc) TRY(tc_dx(st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
+  if (tc) TRY(tc_dx(h, st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
   else {
     g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, p.l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -1002,7 +1014,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   }
   if (tc) {
     TRY(tc_dw(h, st, h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]));
-    TRY(tc_dx(st, h->dza2, l2, B, actor, da.l[1], h->dza1, l1, h->a_h1, l1));
+    TRY(tc_dx(h, st, h->dza2, l2, B, actor, da.l[1], h->dza1, l1, h->a_h1, l1));
   } else {
     g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
     g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
@@ -1252,7 +1264,7 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
     g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
   }
-  if (pop == 1 && use_tc(h, n)) TRY(tc_fwd(h->stream, h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2));
+  if (use_tc(h, n)) TRY(tc_fwd(h, h->stream, h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, h->act_stride));
   else {
     g[0] = gp_fwd(h->act_h1, l1, (int)n, actor, da.l[1], h->act_h2, l2, EPI_BIAS_RELU);
     TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));

@@ -48,10 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+// operand tile load; the third coordinate is the batch entry (a learner of a population), 0 otherwise
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
                    smem_u32(smem_dst)),
-               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 // smem -> global tile store (3-D map {N, M, splits}); completion is tracked by the bulk async-group of the issuing thread
@@ -118,7 +119,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float bias_s[BLOCK_N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N, split = blockIdx.z;
+  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+  const int split = p.batch > 1 ? 0 : blockIdx.z, bz = p.batch > 1 ? blockIdx.z : 0;  // grid.z: K-split or batch entry
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
   const int kb_begin = split * kb_per;
@@ -135,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (threadIdx.x >= 64) {  // the epilogue warps stage this tile's bias slice
     const int j = threadIdx.x - 64;
-    bias_s[j] = (p.epi == TC_EPI_BIAS_RELU && n0 + j < p.N) ? p.bias[n0 + j] : 0.0f;
+    bias_s[j] = (p.epi == TC_EPI_BIAS_RELU && n0 + j < p.N) ? p.bias[(long long)bz * p.bs_bias + n0 + j] : 0.0f;
   }
   if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns × 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
@@ -158,15 +160,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int k0 = (kb_begin + i) * BLOCK_K;
         if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_2d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0);  // box {32 rows(MN), 32 k}
+          for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0, bz);  // box {32 rows(MN), 32 k}
         } else {
-          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);                                                   // box {32 k, 128 rows}
+          tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, bz);                                               // box {32 k, 128 rows}
         }
         if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0);
+          for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0, bz);
         } else {
-          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+          tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, bz);
         }
       }
     }
@@ -204,12 +206,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int m = m0 + q * 32 + lane;
     const bool mask = (p.epi == TC_EPI_RELU_MASK);
     const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
-    const float* auxrow = mask ? p.aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
+    const float* auxrow = mask ? p.aux + (long long)bz * p.bs_aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
     if (num_kb > 0) {
       mbar_wait(&tmem_full_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     }
-    float* Dp = p.D + (long long)split * p.split_stride;
+    float* Dp = p.D + (long long)(split + bz) * p.split_stride;  // split_stride doubles as the batch stride of D
     uint8_t* stage = smem + q * (4 * 4096);  // this warp's four 32x32 fp32 chunk buffers (4 KB each, 1024-byte aligned)
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -256,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmD, buf, nc, m0 + q * 32, split);
+          tma_store_3d(&tmD, buf, nc, m0 + q * 32, split + bz);
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       } else if (m < p.M) {
@@ -308,16 +310,19 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor map: dim0 = contiguous dimension (n0 elements), dim1 = strided dimension (n1 rows, `ld` floats apart)
-int make_tmap(CUtensorMap* tm, const float* ptr, long long n0, long long n1, long long ld, int box0, int box1, bool mn_major) {
+// fp32 operand map: dim0 = contiguous dimension (n0 elements), dim1 = strided dimension (n1 rows, `ld` floats apart),
+// dim2 = batch entries `bstride` floats apart (1 entry for a plain GEMM)
+int make_tmap(CUtensorMap* tm, const float* ptr, long long n0, long long n1, long long ld, int box0, int box1, bool mn_major, int batch,
+              long long bstride) {
   EncodeTiledFn enc = get_encode();
   REQUIRE(enc, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
-  REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0, SHEMS_ERR_INVALID, "tc_gemm: operand needs a 16-byte aligned base and row stride (ld=%lld)", ld);
-  cuuint64_t dims[2] = {(cuuint64_t)n0, (cuuint64_t)n1};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld * 4) % 16 == 0 && (bstride * 4) % 16 == 0, SHEMS_ERR_INVALID,
+          "tc_gemm: operand needs a 16-byte aligned base, row stride and batch stride (ld=%lld, batch stride=%lld)", ld, bstride);
+  cuuint64_t dims[3] = {(cuuint64_t)n0, (cuuint64_t)n1, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(batch > 1 ? bstride : ld * n1) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   REQUIRE(r == CUDA_SUCCESS, SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -350,7 +355,7 @@ int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb
     if (int s = set_smem_attr<A_MN, B_MN>()) return s;
     attr_set = true;
   }
-  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.splits);
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.batch > 1 ? a.batch : a.splits);
   tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, td, a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
@@ -370,26 +375,30 @@ int tc_gemm_prepare() {
 }
 
 // D = epi(A·B): see tc_gemm.h.  With splits > 1, `workspace` must hold splits*M*N floats; the partial tiles are summed in a
-// fixed order by a second kernel (deterministic, unlike atomics).
+// fixed order by a second kernel (deterministic, unlike atomics).  bt.count > 1: that many independent products of the
+// same shape in one launch (grid.z), operand i found bt.s* floats behind operand i-1 (no split-K then).
 int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
-            const float* bias, const float* aux, long long auxld, int splits, float* workspace) {
-  REQUIRE(M >= 1 && N >= 1 && K >= 1 && splits >= 1, SHEMS_ERR_INVALID, "tc_gemm: M=%d N=%d K=%d splits=%d", M, N, K, splits);
-  REQUIRE(splits == 1 || (workspace && epi == TC_EPI_NONE && ldd == N), SHEMS_ERR_INVALID, "tc_gemm: split-K needs a workspace, no epilogue and ldd == N");
+            const float* bias, const float* aux, long long auxld, int splits, float* workspace, const TcBatch& bt) {
+  REQUIRE(M >= 1 && N >= 1 && K >= 1 && splits >= 1 && bt.count >= 1, SHEMS_ERR_INVALID, "tc_gemm: M=%d N=%d K=%d splits=%d batch=%d", M, N, K, splits, bt.count);
+  REQUIRE(splits == 1 || (workspace && epi == TC_EPI_NONE && ldd == N && bt.count == 1), SHEMS_ERR_INVALID,
+          "tc_gemm: split-K needs a workspace, no epilogue, ldd == N and a single product");
   CUtensorMap ta, tb;
   int s;
   // K-major: dim0 = K, dim1 = rows, box {32 k, 128 rows}; MN-major: dim0 = rows, dim1 = K, box {32 rows, 32 k}
-  if ((s = A.mn_major ? make_tmap(&ta, A.ptr, M, K, A.ld, 32, BLOCK_K, true) : make_tmap(&ta, A.ptr, K, M, A.ld, BLOCK_K, BLOCK_M, false))) return s;
-  if ((s = B.mn_major ? make_tmap(&tb, B.ptr, N, K, B.ld, 32, BLOCK_K, true) : make_tmap(&tb, B.ptr, K, N, B.ld, BLOCK_K, BLOCK_N, false))) return s;
+  if ((s = A.mn_major ? make_tmap(&ta, A.ptr, M, K, A.ld, 32, BLOCK_K, true, bt.count, bt.sA) : make_tmap(&ta, A.ptr, K, M, A.ld, BLOCK_K, BLOCK_M, false, bt.count, bt.sA))) return s;
+  if ((s = B.mn_major ? make_tmap(&tb, B.ptr, N, K, B.ld, 32, BLOCK_K, true, bt.count, bt.sB) : make_tmap(&tb, B.ptr, K, N, B.ld, BLOCK_K, BLOCK_N, false, bt.count, bt.sB))) return s;
   TcGemmArgs a;
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.bias = bias; a.aux = aux; a.auxld = auxld;
-  if (splits == 1) { a.D = D; a.ldd = ldd; a.split_stride = 0; }
+  a.batch = bt.count; a.bs_bias = bt.sBias; a.bs_aux = bt.sAux;
+  if (splits == 1) { a.D = D; a.ldd = ldd; a.split_stride = bt.count > 1 ? bt.sD : 0; }
   else { a.D = workspace; a.ldd = N; a.split_stride = (long long)M * N; }
   // TMA store of the output tile when D's rows are 16-byte aligned (activations with padded ld, gradients, the split-K workspace)
   CUtensorMap td;
   memset(&td, 0, sizeof(td));
   a.tma_store = (((uintptr_t)a.D & 15) == 0 && (a.ldd % 4) == 0 && (a.split_stride % 4) == 0) ? 1 : 0;
-  if (a.tma_store && (s = make_tmap_out(&td, a.D, N, M, splits, a.ldd, a.split_stride))) return s;
+  const int nz = bt.count > 1 ? bt.count : splits;
+  if (a.tma_store && (s = make_tmap_out(&td, a.D, N, M, nz, a.ldd, a.split_stride))) return s;
   if (A.mn_major && B.mn_major) s = launch_variant<true, true>(st, ta, tb, td, a);
   else if (A.mn_major) s = launch_variant<true, false>(st, ta, tb, td, a);
   else if (B.mn_major) s = launch_variant<false, true>(st, ta, tb, td, a);
@@ -409,5 +418,5 @@ extern "C" int32_t shems_tc_gemm(const float* a_dev, int64_t lda, int32_t a_mn, 
                                  int64_t auxld, int32_t splits, float* workspace_dev, void* cuda_stream) {
   REQUIRE(a_dev && b_dev && d_dev, SHEMS_ERR_INVALID, "shems_tc_gemm: NULL argument");
   TcOperand A{a_dev, lda, a_mn != 0}, B{b_dev, ldb, b_mn != 0};
-  return tc_gemm((cudaStream_t)cuda_stream, A, B, d_dev, ldd, M, N, K, epi, bias_dev, aux_dev, auxld, splits, workspace_dev);
+  return tc_gemm((cudaStream_t)cuda_stream, A, B, d_dev, ldd, M, N, K, epi, bias_dev, aux_dev, auxld, splits, workspace_dev, TcBatch());
 }

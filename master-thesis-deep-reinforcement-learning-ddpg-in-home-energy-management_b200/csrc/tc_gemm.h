@@ -11,12 +11,17 @@ struct TcOperand {
   bool mn_major;     // false: (row, k) at ptr[row*ld + k]; true: (row, k) at ptr[k*ld + row]
 };
 struct TcGemmArgs {
-  int M, N, K, splits, epi, tma_store;
+  int M, N, K, splits, epi, tma_store, batch;
   float* D; long long ldd, split_stride;
-  const float* bias; const float* aux; long long auxld;
+  const float* bias; const float* aux; long long auxld, bs_bias, bs_aux;
+};
+// `count` independent products of one shape in a launch (a population of learners): strides in floats between entries
+struct TcBatch {
+  int count = 1;
+  long long sA = 0, sB = 0, sD = 0, sBias = 0, sAux = 0;
 };
 // D[M×N] (row-major, ldd) = epilogue(sum_k A(m,k) · B(n,k))
 int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
-            const float* bias, const float* aux, long long auxld, int splits, float* workspace);
+            const float* bias, const float* aux, long long auxld, int splits, float* workspace, const TcBatch& batch = TcBatch());
 // sets the kernels' shared-memory attribute on the current device; call once per device before capturing launches in a graph
 int tc_gemm_prepare();

@@ -1,5 +1,5 @@
 """Times a population of independent DDPG learners (BASELINE configs[4]) advanced by one launch sequence.
-usage: python tools/time_population.py [P] [n_updates] [batch]"""
+usage: python tools/time_population.py [P] [n_updates] [batch] [use_tensor_cores]"""
 import json
 import os
 import sys
@@ -12,6 +12,7 @@ import shems_b200 as sb  # noqa: E402
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 80
 n_updates = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 120
+tc = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 ser = sb.series.synth_charger98(4320, seed=98)
 mems = []
 for l in range(P):
@@ -20,7 +21,7 @@ for l in range(P):
     env.reset(rng=1 + l)
     env.rollout(sb.POLICY_RANDOM, 48, seed=1 + l, replay=mem, want_return=False)
     mems.append(mem)
-le = sb.Learner(params=sb.default_ddpg_params(batch=B, population=P))
+le = sb.Learner(params=sb.default_ddpg_params(batch=B, population=P, use_tensor_cores=tc))
 le.init(1)
 for l in range(P):
     mn, mx = mems[l].min_max_buffer(24_000, rng_mm=l)
@@ -37,6 +38,6 @@ for rep in range(3):
     res.append(e0.elapsed_time(e1))
 ms = sorted(res)[1]
 lc, la = le.select(P - 1).losses()
-print(json.dumps(dict(population=P, batch=B, n_updates=n_updates, us_per_population_update=1e3 * ms / n_updates,
+print(json.dumps(dict(population=P, batch=B, tensor_cores=tc, n_updates=n_updates, us_per_population_update=1e3 * ms / n_updates,
                       learner_updates_per_s=P * n_updates / ms * 1e3, tflops=10 * 256_500 * B * P * n_updates / ms / 1e9,
                       loss_crit_last=lc, loss_act_last=la)))
