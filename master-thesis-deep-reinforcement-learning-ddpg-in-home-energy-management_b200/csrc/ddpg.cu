@@ -324,12 +324,13 @@ wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, 
 
 // First layer for many rows (K = 9 or 11 inputs): Y[m][n] = relu(b[n] + sum_k X[m][k] W[k][n]), up to 3 problems per launch.
 // A thread keeps its 4 weight columns in registers and walks 16 rows; stores are 16-byte, coalesced along n.
-struct L1Batch { const float* X[3]; const float* W[3]; const float* bias[3]; float* Y[3]; int K[3]; int M, N, ldx, ldy; };
+struct L1Batch { const float* X[3]; const float* W[3]; const float* bias[3]; float* Y[3]; int K[3]; int M, N, ldx, ldy, count; long long ls_w, ls_x; };
 __global__ void __launch_bounds__(256)
 l1_fwd_kernel(const L1Batch a) {
-  const int z = blockIdx.z, K = a.K[z];
-  const float* __restrict__ X = a.X[z]; const float* __restrict__ W = a.W[z]; const float* __restrict__ bias = a.bias[z];
-  float* __restrict__ Y = a.Y[z];
+  const int learner = blockIdx.z / a.count, z = blockIdx.z - learner * a.count, K = a.K[z];  // grid.z = learner * count + problem
+  const float* __restrict__ X = a.X[z] + learner * a.ls_x; const float* __restrict__ W = a.W[z] + learner * a.ls_w;
+  const float* __restrict__ bias = a.bias[z] + learner * a.ls_w;
+  float* __restrict__ Y = a.Y[z] + learner * a.ls_x;
   __shared__ float xs[64][12];
   const int m0 = blockIdx.x * 64;
   for (int e = threadIdx.x; e < 64 * 12; e += 256) {
@@ -373,7 +374,11 @@ l1_fwd_kernel(const L1Batch a) {
 template <int J>
 __global__ void __launch_bounds__(256)
 outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const float* __restrict__ H, long long ld, int B, int N,
-                  float* __restrict__ dX) {
+                  float* __restrict__ dX, long long pop_stride) {
+  {  // blockIdx.y = learner of a population
+    const long long lo = (long long)blockIdx.y * pop_stride;
+    dZ += lo; W += lo; H += lo; dX += lo;
+  }
   const int n4 = (N + 3) / 4;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (long long)B * n4) return;
@@ -417,6 +422,7 @@ struct DdpgCtrl {  // device-side control block read by the gather kernel (graph
   int idx_cursor;
   unsigned blocks_done; // last-block-done counter of the final kernel of an update (advances the counters below)
   double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
+  double rc[2][2];      // 1 / (1 - βp): correctly rounded reciprocals of the two bias-correction divisors
 };
 
 struct Ddpg {
@@ -546,7 +552,10 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
     for (int l = 0; l < pop; ++l) {
       cudaMemcpy(h->dqpi + l * h->pop_stride, c.data(), sizeof(float) * (size_t)B, cudaMemcpyHostToDevice);
       cudaMemcpy(h->norm + l * h->pop_stride, nm, sizeof(nm), cudaMemcpyHostToDevice);
-      for (int n = 0; n < 2; ++n) { ctl[l].bp[n][0] = p->adam_beta1; ctl[l].bp[n][1] = p->adam_beta2; }
+      for (int n = 0; n < 2; ++n) {
+        ctl[l].bp[n][0] = p->adam_beta1; ctl[l].bp[n][1] = p->adam_beta2;
+        ctl[l].rc[n][0] = 1.0 / (1.0 - p->adam_beta1); ctl[l].rc[n][1] = 1.0 / (1.0 - p->adam_beta2);
+      }
     }
     cudaMemcpy(h->ctrl, ctl.data(), sizeof(DdpgCtrl) * (size_t)pop, cudaMemcpyHostToDevice);
   }
@@ -717,7 +726,10 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
     if (target) target += lo;
     if (target2) { target2 += lo; model2 += lo; }
   }
+  // mt / (1 - βp[1]) and vt / (1 - βp[2]) divide every element by the same two numbers: with r = RN(1/c) the sequence
+  // q = a*r; e = fma(-q, c, a); q' = fma(e, r, q) is the correctly rounded quotient (Markstein), at 3 DFMA instead of a DDIV
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
+  const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
@@ -726,7 +738,9 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
     const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)m[j]), __dmul_rn(1.0 - b1, (double)gj));
     const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)v[j]), __dmul_rn(1.0 - b2, (double)g2));
     m[j] = mj; v[j] = vj;
-    const double d = __dmul_rn(__ddiv_rn(__ddiv_rn((double)mj, c1), __dadd_rn(__dsqrt_rn(__ddiv_rn((double)vj, c2)), eps)), (double)eta);
+    double qm = __dmul_rn((double)mj, r1); qm = __fma_rn(__fma_rn(-qm, c1, (double)mj), r1, qm);   // mt / (1 - βp[1])
+    double qv = __dmul_rn((double)vj, r2); qv = __fma_rn(__fma_rn(-qv, c2, (double)vj), r2, qv);   // vt / (1 - βp[2])
+    const double d = __dmul_rn(__ddiv_rn(qm, __dadd_rn(__dsqrt_rn(qv), eps)), (double)eta);
     const float xn = __fsub_rn(x[j], (float)d);
     x[j] = xn;
     if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
@@ -744,7 +758,10 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
       if (done == gridDim.x - 1) {
         ctrl->blocks_done = 0;
         ctrl->update += 1; ctrl->idx_cursor += 1;
-        for (int o = 0; o < 2; ++o) { ctrl->bp[o][0] *= b1; ctrl->bp[o][1] *= b2; }
+        for (int o = 0; o < 2; ++o) {
+          ctrl->bp[o][0] *= b1; ctrl->bp[o][1] *= b2;
+          ctrl->rc[o][0] = 1.0 / (1.0 - ctrl->bp[o][0]); ctrl->rc[o][1] = 1.0 / (1.0 - ctrl->bp[o][1]);
+        }
       }
     }
   }
@@ -856,34 +873,42 @@ static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float*
 }
 // large-batch first layer (up to 3 problems): see l1_fwd_kernel
 static int big_l1(cudaStream_t st, int count, const float* const* X, int ldx, int M, const float* const* net, const LayerDims* const* L,
-                  float* const* Y, int ldy) {
+                  float* const* Y, int ldy, int pop = 1, long long ls_w = 0, long long ls_x = 0) {
   L1Batch a; memset(&a, 0, sizeof(a));
+  a.count = count; a.ls_w = ls_w; a.ls_x = ls_x;
   for (int i = 0; i < count; ++i) {
     a.X[i] = X[i]; a.W[i] = net[i] + L[i]->w_off; a.bias[i] = net[i] + L[i]->b_off; a.Y[i] = Y[i]; a.K[i] = L[i]->in;
     REQUIRE(L[i]->in <= 12 && L[i]->out == L[0]->out, SHEMS_ERR_INVALID, "big_l1: unsupported first-layer shape");
   }
   a.M = M; a.N = L[0]->out; a.ldx = ldx; a.ldy = ldy;
-  l1_fwd_kernel<<<dim3((M + 63) / 64, (a.N + 255) / 256, count), 256, 0, st>>>(a);
+  l1_fwd_kernel<<<dim3((M + 63) / 64, (a.N + 255) / 256, count * pop), 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
-// large-batch output layer backward: dW3 (+db3) by weighted column sums, dX by the masked outer product
+// output layer backward: dW3 (+db3) by weighted column sums, dX by the masked outer product (large batches and populations)
+static int launch_outer_mask(Ddpg* h, cudaStream_t st, const float* dZ, int J, const float* W, const float* H, int ld, int B, int N, float* dX) {
+  const long long ne = (long long)B * ((N + 3) / 4);
+  const dim3 grid((unsigned)((ne + 255) / 256), h->pop);
+  if (J == 1) outer_mask_kernel<1><<<grid, 256, 0, st>>>(dZ, W, H, ld, B, N, dX, h->pop_stride);
+  else outer_mask_kernel<2><<<grid, 256, 0, st>>>(dZ, W, H, ld, B, N, dX, h->pop_stride);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
 static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const float* dZ, int J, int B, const float* net, const LayerDims& L,
                        float* grad, float* dX) {
   REQUIRE(J == L.out && (J == 1 || J == 2), SHEMS_ERR_INVALID, "big_out_bwd: output layer must have 1 or 2 units");
-  const int N = L.in, slabs = max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
+  const int N = L.in, slabs = h->pop > 1 ? 1 : max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
   const long long stride = (long long)N * J + J;
-  const dim3 grid((N + 31) / 32, slabs);
-  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws, 0);
-  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, h->ws, 0);
+  const dim3 grid((N + 31) / 32, slabs, h->pop);
+  float* out = slabs == 1 ? grad + L.w_off : h->ws;  // a single slab is the gradient block [W3 | b3] itself
+  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride);
+  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
-  splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, slabs, grad + L.w_off, stride);
-  CUDA_TRY(cudaGetLastError());
-  const long long ne = (long long)B * ((N + 3) / 4);
-  if (J == 1) outer_mask_kernel<1><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dZ, net + L.w_off, H, ldh, B, N, dX);
-  else outer_mask_kernel<2><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(dZ, net + L.w_off, H, ldh, B, N, dX);
-  CUDA_TRY(cudaGetLastError());
-  return SHEMS_OK;
+  if (slabs > 1) {
+    splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, slabs, grad + L.w_off, stride);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return launch_outer_mask(h, st, dZ, J, net + L.w_off, H, ldh, B, N, dX);
 }
 static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows * h->pop >= TC_MIN_ROWS; }
 
@@ -898,7 +923,7 @@ static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows 
 static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
-  const bool tc = use_tc(h, B), big = h->pop == 1 && (tc || B >= SPLITK_MIN_BATCH);
+  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH || h->pop > 1;  // streaming kernels for the thin products
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   GemmProblem g[4];
@@ -906,7 +931,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   if (big) {
     const float* X[3] = {h->xs2, h->xs, h->xs}; const float* nets[3] = {actor_t, critic, actor};
     const LayerDims* Ls[3] = {&da.l[0], &dc.l[0], &da.l[0]}; float* Y[3] = {h->t_h1, h->c_h1, h->a_h1};
-    TRY(big_l1(st, 3, X, 11, B, nets, Ls, Y, l1));
+    TRY(big_l1(st, 3, X, 11, B, nets, Ls, Y, l1, h->pop, h->pop_stride, h->pop_stride));
   } else {
     g[0] = gp_fwd(h->xs2, 11, B, actor_t, da.l[0], h->t_h1, l1, EPI_BIAS_RELU);
     g[1] = gp_fwd(h->xs, 11, B, critic, dc.l[0], h->c_h1, l1, EPI_BIAS_RELU);
@@ -930,7 +955,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   // P4-P6: q' = critic_target(vcat(s'_n, a'));  y = r + γ(1-done) q';  dq = 2(q-y)/B     (:132-133)
   if (big) {
     const float* X[1] = {h->xs2}; const float* nets[1] = {critic_t}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->tc_h1};
-    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
+    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1, h->pop, h->pop_stride, h->pop_stride));
   } else {
     g[0] = gp_fwd(h->xs2, 11, B, critic_t, dc.l[0], h->tc_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -967,7 +992,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
 static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
-  const bool tc = use_tc(h, B), big = h->pop == 1 && (tc || B >= SPLITK_MIN_BATCH);
+  const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH || h->pop > 1;  // streaming kernels for the thin products
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
   GemmProblem g[4];
@@ -979,7 +1004,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   if (big) {
     const float* X[1] = {h->xspi}; const float* nets[1] = {critic}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->p_h1};
-    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1));
+    TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1, h->pop, h->pop_stride, h->pop_stride));
   } else {
     g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -990,9 +1015,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
   if (big) {                                                                                               // dX through the critic only
-    const long long ne = (long long)B * ((p.l2 + 3) / 4);
-    outer_mask_kernel<1><<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(h->dqpi, critic + dc.l[2].w_off, h->p_h2, l2, B, p.l2, h->dzp2);
-    CUDA_TRY(cudaGetLastError());
+    TRY(launch_outer_mask(h, st, h->dqpi, 1, critic + dc.l[2].w_off, h->p_h2, l2, B, p.l2, h->dzp2));
   } else {
     g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, p.l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -1257,9 +1280,9 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
   const NetDims& da = h->dims[0];
   const float* actor = h->net[DDPG_NET_ACTOR];
   GemmProblem g[1];
-  if (pop == 1 && n >= SPLITK_MIN_BATCH) {
+  if (n * pop >= SPLITK_MIN_BATCH) {
     const float* X[1] = {h->act_x}; const float* nets[1] = {actor}; const LayerDims* Ls[1] = {&da.l[0]}; float* Y[1] = {h->act_h1};
-    TRY(big_l1(h->stream, 1, X, 9, (int)n, nets, Ls, Y, l1));
+    TRY(big_l1(h->stream, 1, X, 9, (int)n, nets, Ls, Y, l1, pop, h->pop_stride, h->act_stride));
   } else {
     g[0] = gp_fwd(h->act_x, 9, (int)n, actor, da.l[0], h->act_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
