@@ -70,7 +70,7 @@ def cpu_baseline(ser, horizon, sample_envs=0, target_s=15.0):
     if sample_envs <= 0:
         probe = max(cores * 2, 16)
         rate, dt = cpu_rollout_rate(ser, horizon, probe)
-        sample_envs = int(max(probe, min(1 << 16, target_s * rate / horizon)))
+        sample_envs = int(max(probe, min(1 << 20, target_s * rate / horizon)))
         sample_envs = (sample_envs // cores) * cores or cores
     rate, dt = cpu_rollout_rate(ser, horizon, sample_envs)
     return dict(value=rate, unit=UNIT, cores=cores, kind="port",
@@ -164,6 +164,77 @@ def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
     ms = e0.elapsed_time(e1)
     return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, batch=120, l1=250, l2=500, mem=24_000,
                 kernels_per_update=21, flops_per_update=3.078e8)
+
+
+def ddpg_large_batch(sb, torch, ser_train, batch=8192, n_updates=100):
+    """DDPG updates/s where batch x width is a dense contraction (BASELINE configs[3], 8192 parallel instances): the 250x500
+    products run on the TF32 tcgen05 kernel; tensor-pipe evidence in profiles/."""
+    env = sb.Shems(72, ser_train, n_envs=8192)
+    mem = sb.Replay(1 << 20)
+    env.reset(rng=1)
+    env.rollout(sb.POLICY_RANDOM, 72, seed=1, replay=mem, want_return=False)
+    out = {}
+    for name, tc in (("tf32_tcgen05", 1), ("fp32_simt", 0)):
+        le = sb.Learner(params=sb.default_ddpg_params(batch=batch, use_tensor_cores=tc))
+        le.init(1)
+        mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
+        le.set_norm(mn, mx)
+        le.replay(mem, rng_rpl=1, n_updates=10)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        le.replay(mem, rng_rpl=2, n_updates=n_updates)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[name] = dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, samples_per_s=batch * n_updates / (ms * 1e-3),
+                         tflops=10 * 256_500 * batch * n_updates / (ms * 1e-3) / 1e12)
+        le.close()
+    out.update(batch=batch, l1=250, l2=500, flops_per_update=10 * 256_500 * batch)
+    return out
+
+
+POP_CHARGERS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)  # capacities of shems_LU1.jl:47-59; 10 chargers x 64 seeds = 640 learners on 8 GPUs
+
+
+def ddpg_population(sb, torch, dist, rank, world, ser_train, per_gpu=80, n_updates=40, tc=1):
+    """BASELINE configs[4]: independent-seed learners (the reference's one-process-per-seed parallelism), per_gpu of them per
+    rank advanced by the same launches; learner g = rank*per_gpu + l trains charger POP_CHARGERS[(g // 64) % 10] with seed g.
+    No collective during training; rank 0 gathers the rates."""
+    dev = torch.cuda.current_device()
+    mems = []
+    for l in range(per_gpu):
+        g = rank * per_gpu + l
+        env = sb.Shems(72, ser_train, n_envs=500, charger_id=POP_CHARGERS[(g // 64) % len(POP_CHARGERS)], device=dev, env_id_base=500 * g)
+        mem = sb.Replay(24_000, device=dev)
+        env.reset(rng=1 + g)
+        env.rollout(sb.POLICY_RANDOM, 48, seed=1 + g, replay=mem, want_return=False)
+        mems.append(mem)
+        env.close()
+    le = sb.Learner(params=sb.default_ddpg_params(population=per_gpu, use_tensor_cores=tc), device=dev)
+    le.init(1 + rank * per_gpu)
+    for l in range(per_gpu):
+        mn, mx = mems[l].min_max_buffer(24_000, rng_mm=l)
+        le.select(l).set_norm(mn, mx)
+    le.replay(mems, rng_rpl=7, n_updates=5)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    le.replay(mems, rng_rpl=11, n_updates=n_updates)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    lc, la = le.select(0).losses()
+    return dict(learners=per_gpu * world, learners_per_gpu=per_gpu, chargers=sorted({POP_CHARGERS[(g // 64) % 10] for g in range(per_gpu * world)}),
+                batch=120, l1=250, l2=500, precision="tf32 products, fp32 accumulate" if tc else "fp32",
+                learner_updates_per_s=per_gpu * world * n_updates / (ms * 1e-3), us_per_population_update=1e3 * ms / n_updates,
+                tflops=10 * 256_500 * 120 * per_gpu * world * n_updates / (ms * 1e-3) / 1e12, collective="none (independent seeds)",
+                loss_crit_learner0=lc, loss_act_learner0=la)
 
 
 def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
@@ -289,12 +360,20 @@ def main():
     value = total_steps / (ms * 1e-3)
     e2e_value = total_steps / (ms_e2e * 1e-3)
 
-    ddpg_dp = None
-    if dist is not None and not args.skip_ddpg:
+    ddpg_dp = ddpg_pop = None
+    if not args.skip_ddpg:
+        mem.close()                       # the 1.5 GB ring is no longer needed
+        env.close()
+        ser_train = sb.series.synth_charger98(4320, seed=98)
+        if dist is not None:
+            try:
+                ddpg_dp = ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train)
+            except Exception as e:
+                ddpg_dp = dict(error=str(e))
         try:
-            ddpg_dp = ddpg_dp_updates_per_s(sb, torch, dist, rank, sb.series.synth_charger98(4320, seed=98))
+            ddpg_pop = ddpg_population(sb, torch, dist, rank, world, ser_train)
         except Exception as e:
-            ddpg_dp = dict(error=str(e))
+            ddpg_pop = dict(error=str(e))
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -332,8 +411,14 @@ def main():
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:  # never lose the env number to the secondary metric
             line["ddpg"] = dict(error=str(e))
+        try:
+            line["ddpg_large_batch"] = ddpg_large_batch(sb, torch, sb.series.synth_charger98(4320, seed=98))
+        except Exception as e:
+            line["ddpg_large_batch"] = dict(error=str(e))
     if ddpg_dp is not None:
         line["ddpg_data_parallel"] = ddpg_dp
+    if ddpg_pop is not None:
+        line["ddpg_population"] = ddpg_pop
     if not args.skip_cpu_baseline:
         cb, _ = cpu_baseline(ser, T, args.cpu_sample_envs)
         line["cpu_baseline"] = cb
