@@ -256,6 +256,12 @@ SHEMS_API int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* s
  *   when sigma > 0 (GNoise, DDPG.jl:57-61), no noise when sigma == 0 (train == false). */
 SHEMS_API int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step,
                            int64_t env_id_base, const float* noise_dev, float* a_dev, float* scaled_dev);
+/* act() with Ornstein-Uhlenbeck exploration noise (noise_type == "ou": sample_noise(ou::OUNoise) DDPG.jl:49-55, :157-158;
+ * OUNoise(μ, σ, θ, dt, X) input.jl:190-234).  ou_x_dev [2][n] is OUNoise.X of every instance, read and advanced in place
+ * (the reference never resets it, not even between episodes); z_dev [2][n]: the standard normal draws randn(2) (Float64)
+ * or NULL -> Philox(seed, global env id, step) + Box-Muller.  Population handles: arrays gain a leading [P] dimension. */
+SHEMS_API int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
+                              uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev);
 /* replay() (DDPG.jl:121-145) n_updates times: sample -> TD target -> critic step -> actor step
  * -> Polyak.  idx_host ([n_updates][batch], 0-based logical indices) or NULL -> Philox(seed, update counter). */
 SHEMS_API int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed);

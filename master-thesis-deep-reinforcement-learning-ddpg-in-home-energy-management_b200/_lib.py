@@ -101,6 +101,7 @@ SIGNATURES = {
     "ddpg_num_params": (I64, [VP, I32]),
     "ddpg_set_norm": (I32, [VP, PF, PF]),
     "ddpg_act": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
+    "ddpg_act_ou": (I32, [VP, VP, I64, F32, F32, F32, F32, VP, U64, I64, I64, VP, VP, VP]),
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),
     "ddpg_update_batch": (I32, [VP, VP, VP, VP, VP, VP]),

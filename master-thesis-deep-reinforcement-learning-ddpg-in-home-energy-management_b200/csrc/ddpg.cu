@@ -1258,11 +1258,57 @@ ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, fl
   }
 }
 
-extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
-                            const float* noise_dev, float* a_dev, float* scaled_dev) {
-  REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
-  REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
-  GUARD(h->device);
+// OUNoise (DDPG.jl:49-55, input.jl:190-234) with Julia's types: θ, μ, σ, dt and X are Float32, randn is Float64:
+//   dx = θ .* (μ .- X) .* dt              (Float32)
+//   dx .+= σ .* sqrt(dt) .* randn(2)      (Float32(σ·√dt) · z in Float64, added in Float64, stored Float32)
+//   X .+= dx;  noise = Float32.(X)        (X persists across steps AND episodes: the reference never resets it)
+// Every instance carries its own X (ou_x [2][n]); z: caller-supplied standard normal draws or Philox + Box-Muller.
+__global__ void __launch_bounds__(256)
+ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float theta, float mu, float sigma, float dt, float* __restrict__ ou_x,
+                            unsigned long long seed, long long step, long long env_id_base, const double* __restrict__ z, float lo0, float lo1,
+                            float hi0, float hi1, float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  {
+    const long long l = blockIdx.y;
+    y += l * act_stride; a_out += l * 2 * n; ou_x += l * 2 * n; env_id_base += l * n;
+    if (z) z += l * 2 * n;
+    if (scaled_out) scaled_out += l * 2 * n;
+  }
+  double z0, z1;
+  if (z) { z0 = z[j]; z1 = z[n + j]; }
+  else {
+    uint32_t w[4];
+    philox4x32_10(seed, (uint64_t)(env_id_base + j), (uint32_t)step, STREAM_NOISE, w);
+    const double u1 = 1.0 - u53(w[0], w[1]), u2 = u53(w[2], w[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs; z1 = rad * sn;
+  }
+  const float ssd = __fmul_rn(sigma, __fsqrt_rn(dt));
+  float nz[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float x = ou_x[k * n + j];
+    float dx = __fmul_rn(__fmul_rn(theta, __fsub_rn(mu, x)), dt);
+    dx = (float)__dadd_rn((double)dx, __dmul_rn((double)ssd, k == 0 ? z0 : z1));
+    nz[k] = __fadd_rn(x, dx);
+    ou_x[k * n + j] = nz[k];
+  }
+  float a0 = __fadd_rn(y[j * 2 + 0], nz[0]), a1 = __fadd_rn(y[j * 2 + 1], nz[1]);
+  a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
+  a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
+  a_out[j] = a0; a_out[n + j] = a1;
+  if (scaled_out) {
+    const double sp0 = (double)__fsub_rn(hi0, lo0), sp1 = (double)__fsub_rn(hi1, lo1);
+    scaled_out[j] = (float)__dadd_rn((double)lo0, __dmul_rn(__dmul_rn(__dadd_rn((double)a0, 1.0), 0.5), sp0));
+    scaled_out[n + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
+  }
+}
+
+// actor(normalize(s)) for n states per learner -> h->act_y [n][2] (pre-noise); shared by the noise variants of act()
+static int act_forward(Ddpg* h, const float* obs_dev, int64_t n) {
   const int l1 = h->ld1, l2 = h->ld2, pop = h->pop;
   if (h->act_cap < n) {  // scratch: per learner [x n*9 | h1 n*ld1 | h2 n*ld2 | y n*2], each part at a 256-byte boundary
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1294,8 +1340,33 @@ extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigm
   }
   g[0] = gp_fwd(h->act_h2, l2, (int)n, actor, da.l[2], h->act_y, 2, EPI_BIAS_TANH);
   TRY(launch_gemms(h->stream, g, 1, pop, h->pop_stride, h->act_stride));
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                            const float* noise_dev, float* a_dev, float* scaled_dev) {
+  REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
+  REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
+  GUARD(h->device);
+  TRY(act_forward(h, obs_dev, n));
+  const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
                                                       h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev, h->act_stride);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
+                               uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev) {
+  REQUIRE(h && obs_dev && a_dev && ou_x_dev, SHEMS_ERR_INVALID, "ddpg_act_ou: NULL argument");
+  REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act_ou: n=%lld", (long long)n);
+  REQUIRE(dt >= 0.0f, SHEMS_ERR_INVALID, "ddpg_act_ou: dt=%g (sqrt(dt) raises DomainError in the reference)", (double)dt);
+  GUARD(h->device);
+  TRY(act_forward(h, obs_dev, n));
+  const dim3 gn((unsigned)((n + 255) / 256), h->pop);
+  ddpg_act_ou_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, theta, mu, sigma, dt, ou_x_dev, seed, step, env_id_base, z_dev,
+                                                         h->p.act_lo[0], h->p.act_lo[1], h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev,
+                                                         h->act_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }

@@ -183,6 +183,17 @@ class Learner:
         L.check(self.lib.ddpg_act(self._h, _ptr(obs), n, sg, int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(noise), _ptr(a), _ptr(sc)))
         return a, sc
 
+    def act_ou(self, obs, ou_x, theta=0.15, mu=0.0, sigma=0.1, dt=1e-2, rng_act=0, step=0, env_id_base=0, z=None):
+        """act() with noise_type == "ou" (DDPG.jl:49-55, :157-158): ou_x [2][n] float32 is OUNoise.X per instance, advanced in
+        place; z [2][n] float64 standard normal draws or None -> Philox."""
+        n = obs.shape[-1]
+        shape = (2, n) if self.population == 1 else (self.population, 2, n)
+        a = torch.empty(shape, dtype=torch.float32, device=self._dev)
+        sc = torch.empty(shape, dtype=torch.float32, device=self._dev)
+        L.check(self.lib.ddpg_act_ou(self._h, _ptr(obs), n, float(theta), float(mu), float(sigma), float(dt), _ptr(ou_x),
+                                     int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(z), _ptr(a), _ptr(sc)))
+        return a, sc
+
     def replay(self, memory, rng_rpl=0, n_updates=1, idx=None):
         """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back.  Population handles: `memory` is the list of the
         learners' Replay objects, rng_rpl an int (learner l uses rng_rpl + l) or one seed per learner, idx [P][n_updates][batch]."""
@@ -242,7 +253,7 @@ class Driver:
     (Julia's string-concatenated MersenneTwister seeds cannot be reproduced)."""
 
     def __init__(self, env_train, env_eval=None, learner=None, mem_size=24_000, ep_length=72, sigma=0.1, updates_per_step=1,
-                 rng_run=1231):
+                 rng_run=1231, noise_type="gn", theta=0.15, ou_dt=1e-2):
         self.env_train, self.env_eval = env_train, env_eval
         self.learner = learner if learner is not None else Learner(device=env_train.device)
         self.memory = Replay(mem_size, device=env_train.device)
@@ -251,6 +262,9 @@ class Driver:
         self.rng_run = int(rng_run)
         self.s_min = self.s_max = None
         self.n_env_steps = 0
+        assert noise_type in ("gn", "ou"), "parameter noise (pn) and epsilon noise (en) are out of scope (SURVEY §2)"
+        self.noise_type, self.theta, self.ou_dt = noise_type, float(theta), float(ou_dt)
+        self._ou_x = None  # OUNoise.X per training instance; like the reference's global `ou` it is never reset (input.jl:234)
 
     # populate_memory(env; rng) — memory_plotting_saving.jl:9-29 (fused random-policy rollouts)
     def populate_memory(self, rng=None):
@@ -286,7 +300,13 @@ class Driver:
                 r, s2, tr = env.step(a, track=track)
                 traces.append(tr)
             else:
-                a, scaled = self.learner.act(s, train=train, sigma=self.sigma, rng_act=rng_step, step=step, env_id_base=env.env_id_base)
+                if train and self.noise_type == "ou":
+                    if self._ou_x is None or self._ou_x.shape[-1] != n:
+                        self._ou_x = torch.zeros((2, n), dtype=torch.float32, device=env._torch_dev)
+                    a, scaled = self.learner.act_ou(s, self._ou_x, theta=self.theta, mu=0.0, sigma=self.sigma, dt=self.ou_dt,
+                                                    rng_act=rng_step, step=step, env_id_base=env.env_id_base)
+                else:
+                    a, scaled = self.learner.act(s, train=train, sigma=self.sigma, rng_act=rng_step, step=step, env_id_base=env.env_id_base)
                 if train:
                     s_prev.copy_(s)
                 if track == 0:

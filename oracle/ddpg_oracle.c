@@ -251,6 +251,25 @@ void oracle_ddpg_act(OracleDdpg* h, const float* obs /*[S][n]*/, int n, const fl
   free(x); free(h1); free(h2); free(y);
 }
 
+/* sample_noise(ou::OUNoise, rng) (DDPG.jl:49-55) for n instances, each with its own X (ou_x [A][n], advanced in place) and
+ * its standard normal draws z [A][n] (Julia: randn(length(ou.X)), Float64).  OUNoise(μ, σ, θ, dt, X) holds Float32 values
+ * (input.jl:216-234):  dx = θ .* (μ .- X) .* dt  is Float32;  dx .+= σ .* sqrt(dt) .* randn  evaluates
+ * Float64(dx) + Float64(Float32(σ*√dt)) * z and stores Float32;  X .+= dx in Float32;  returns Float32.(X). */
+void oracle_ou_noise(float theta, float mu, float sigma, float dt, float* ou_x, const double* z, int n, int A, float* noise_out) {
+  volatile float ssd = sigma * sqrtf(dt);
+  for (int k = 0; k < A; ++k)
+    for (int b = 0; b < n; ++b) {
+      const size_t e = (size_t)k * n + b;
+      volatile float d0 = mu - ou_x[e];
+      volatile float d1 = theta * d0;
+      volatile float dx = d1 * dt;
+      volatile float dx2 = (float)((double)dx + (double)ssd * z[e]);
+      volatile float xn = ou_x[e] + dx2;
+      ou_x[e] = xn;
+      noise_out[e] = xn;
+    }
+}
+
 /* replay() body on a given minibatch (DDPG.jl:131-143). Arrays are SoA [k][B]. */
 void oracle_ddpg_update_batch(OracleDdpg* h, const float* s, const float* a, const float* r, const float* s2, const float* done) {
   const int S = h->p.state_size, A = h->p.action_size, l1 = h->p.l1, l2 = h->p.l2, B = h->p.batch, C = S + A;

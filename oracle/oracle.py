@@ -111,6 +111,8 @@ def lib():
         L.oracle_ddpg_init.restype = None
         L.oracle_ddpg_act.argtypes = [C.c_void_p, PF, C.c_int, PF, PF, PF]
         L.oracle_ddpg_act.restype = None
+        L.oracle_ou_noise.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, PF, C.POINTER(C.c_double), C.c_int, C.c_int, PF]
+        L.oracle_ou_noise.restype = None
         L.oracle_ddpg_update_batch.argtypes = [C.c_void_p, PF, PF, PF, PF, PF]
         L.oracle_ddpg_update_batch.restype = None
         L.oracle_sample_indices.argtypes = [C.c_uint64, C.c_uint32, C.c_longlong, C.c_int, PI]
@@ -268,6 +270,17 @@ class OracleDdpg:
         lc, la = C.c_float(0), C.c_float(0)
         lib().oracle_ddpg_get_losses(self.h, C.byref(lc), C.byref(la))
         return lc.value, la.value
+
+
+def ou_noise(theta, mu, sigma, dt, ou_x, z):
+    """sample_noise(ou::OUNoise) (DDPG.jl:49-55) per instance: advances ou_x [2][n] float32 in place with the standard normal
+    draws z [2][n] float64, returns the noise Float32.(X)."""
+    assert ou_x.dtype == np.float32 and ou_x.flags.c_contiguous
+    z = np.ascontiguousarray(z, np.float64)
+    A, n = ou_x.shape
+    out = np.zeros((A, n), np.float32)
+    lib().oracle_ou_noise(theta, mu, sigma, dt, _fp(ou_x), _dp(z), n, A, _fp(out))
+    return out
 
 
 def sample_indices(seed, update, length, batch):

@@ -143,3 +143,22 @@ def test_sample_indices(O):
     assert idx.min() >= 0 and idx.max() < 24000 and len(np.unique(idx)) > 100
     np.testing.assert_array_equal(idx, O.sample_indices(9, 3, 24000, 120))
     assert not np.array_equal(idx, O.sample_indices(9, 4, 24000, 120))
+
+
+def test_oracle_ou_noise_matches_numpy_typed_restatement(O):
+    """sample_noise(ou::OUNoise) (DDPG.jl:49-55): Float32 drift term, Float64 diffusion term, Float32 stores — restated with numpy
+    scalar types as a second opinion on the C oracle (no reference output exists for it)."""
+    rng = np.random.default_rng(1)
+    th, mu, sg, dt = np.float32(0.15), np.float32(0.0), np.float32(0.2), np.float32(1e-2)
+    x = np.zeros((2, 50), np.float32)
+    xn = x.copy()
+    for step in range(30):
+        z = rng.standard_normal((2, 50))
+        out = O.ou_noise(th, mu, sg, dt, x, z)
+        dx = (th * (mu - xn)) * dt                                    # Float32 .* Float32
+        assert dx.dtype == np.float32
+        dx = (dx.astype(np.float64) + np.float64(np.float32(sg * np.sqrt(dt))) * z).astype(np.float32)
+        xn = (xn + dx).astype(np.float32)
+        np.testing.assert_array_equal(x, xn)
+        np.testing.assert_array_equal(out, xn)
+    assert np.abs(x).max() < 1.0 and x.std() > 0.01

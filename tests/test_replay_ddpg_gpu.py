@@ -431,3 +431,38 @@ def test_population_equals_independent_learners(sb, O, train_series, tc):
         sb._lib.check(pop.lib.ddpg_update(pop._h, mems[0]._h, 1, None, 0))
     with pytest.raises(sb.ShemsError):
         sb.Learner(params=sb.default_ddpg_params(population=2, batch=2048))
+
+
+def test_act_ou_noise_parity(sb, O):
+    """noise_type == "ou" (DDPG.jl:49-55, :157-158): the per-instance OUNoise.X recursion with Julia's Float32/Float64 mix is
+    bit-exact against the oracle for injected standard normal draws over 20 steps; Philox draws are N(0,1)-distributed."""
+    rng = np.random.default_rng(8)
+    le = sb.Learner()
+    le.init(4)
+    orc = O.OracleDdpg(O.default_ddpg_params())
+    orc.init(4)
+    mn, mx = np.zeros(9, np.float32), rng.uniform(1, 5, 9).astype(np.float32)
+    le.set_norm(mn, mx)
+    orc.set_norm(mn, mx)
+    n = 512
+    theta, mu, sigma, dt = np.float32(0.15), np.float32(0.0), np.float32(0.1), np.float32(1e-2)
+    x_gpu = torch.zeros((2, n), dtype=torch.float32, device="cuda")
+    x_ref = np.zeros((2, n), np.float32)
+    for step in range(20):
+        obs = (rng.uniform(0, 1, (9, n)) * mx[:, None]).astype(np.float32)
+        z = rng.standard_normal((2, n))
+        a, sc = le.act_ou(dev(obs), x_gpu, theta, mu, sigma, dt, z=dev(z))
+        noise = O.ou_noise(theta, mu, sigma, dt, x_ref, z)
+        np.testing.assert_array_equal(x_gpu.cpu().numpy(), x_ref)          # the OU state itself: bit-exact
+        oa, osc = orc.act(obs, noise=noise)
+        np.testing.assert_allclose(a.cpu().numpy(), oa, rtol=2e-4, atol=2e-6)
+        np.testing.assert_allclose(sc.cpu().numpy(), osc, rtol=2e-4, atol=2e-6)
+    # device-side draws: X after one step from X = 0 is sigma*sqrt(dt)*z with z ~ N(0, 1)
+    x2 = torch.zeros((2, 8192), dtype=torch.float32, device="cuda")
+    obs = (rng.uniform(0, 1, (9, 8192)) * mx[:, None]).astype(np.float32)
+    le.act_ou(dev(obs), x2, theta, mu, sigma, dt, rng_act=9, step=3)
+    zz = x2.cpu().numpy() / (sigma * np.sqrt(dt))
+    assert abs(zz.mean()) < 0.03 and abs(zz.std() - 1.0) < 0.03
+    x3 = torch.zeros((2, 8192), dtype=torch.float32, device="cuda")
+    le.act_ou(dev(obs), x3, theta, mu, sigma, dt, rng_act=9, step=3)
+    assert torch.equal(x2, x3)                                                # reproducible per (seed, step)
