@@ -281,6 +281,18 @@ SHEMS_API int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, con
 SHEMS_API int32_t ddpg_select_learner(Ddpg* h, int32_t learner);
 SHEMS_API int32_t ddpg_population(const Ddpg* h);
 SHEMS_API int32_t ddpg_update_population(Ddpg* h, ShemsReplay* const* rps, int32_t n_updates, const int32_t* idx_host, const uint64_t* seeds);
+/* Data-parallel learner with the gradient all-reduce fused into the optimiser kernels over NVLink peer memory (one process per
+ * GPU).  Each rank exports DDPG_DP_HANDLE_BYTES (CUDA IPC handles of its gradient buffer and flag array), the caller gathers the
+ * ranks' blobs in rank order (any transport: torch.distributed, MPI, a file) and hands them to ddpg_dp_connect.  ddpg_update_dp is
+ * replay() with both exchanges done in-kernel: no NCCL call, no host synchronisation; all ranks must issue the same calls.
+ * A peer that does not arrive within 4 s makes the kernel give up (ddpg_dp_status reports 1) instead of hanging the GPU. */
+#define DDPG_DP_HANDLE_BYTES 192
+SHEMS_API int32_t ddpg_dp_export(Ddpg* h, void* handle_out /* [DDPG_DP_HANDLE_BYTES] */);
+SHEMS_API int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const void* handles /* [world][DDPG_DP_HANDLE_BYTES] */);
+/* optional: allocate/instantiate up front what ddpg_update_dp needs (idx_ints = n_updates*batch host indices per call, 0 if none) */
+SHEMS_API int32_t ddpg_dp_prepare(Ddpg* h, int64_t idx_ints);
+SHEMS_API int32_t ddpg_update_dp(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed);
+SHEMS_API int32_t ddpg_dp_status(Ddpg* h, int32_t* error_out);
 /* last update's loss_crit / loss_act values (DDPG.jl:114-119) */
 SHEMS_API int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act);
 /* gradients of the last update (Flux layout, like ddpg_get_layer); net = ACTOR or CRITIC */

@@ -13,6 +13,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_BOUNDS, ERR_KEY, ERR_STATE, ERR_NCCL = 0, -1, -2,
 RESET_DETERMINISTIC, RESET_HOST_DRAWS, RESET_DEVICE_PHILOX = 0, 1, 2
 POLICY_RULE, POLICY_RANDOM, POLICY_TAPE = 0, 1, 2
 NET_ACTOR, NET_CRITIC, NET_ACTOR_TARGET, NET_CRITIC_TARGET = 0, 1, 2, 3
+DP_HANDLE_BYTES = 192
 
 
 class ShemsParams(C.Structure):
@@ -105,6 +106,11 @@ SIGNATURES = {
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),
     "ddpg_update_batch": (I32, [VP, VP, VP, VP, VP, VP]),
+    "ddpg_dp_export": (I32, [VP, VP]),
+    "ddpg_dp_connect": (I32, [VP, I32, I32, VP]),
+    "ddpg_dp_prepare": (I32, [VP, I64]),
+    "ddpg_update_dp": (I32, [VP, VP, I32, PI, U64]),
+    "ddpg_dp_status": (I32, [VP, PI]),
     "ddpg_get_losses": (I32, [VP, PF, PF]),
     "ddpg_select_learner": (I32, [VP, I32]),
     "ddpg_population": (I32, [VP]),

@@ -21,6 +21,7 @@
 #include <string.h>
 #include <stddef.h>
 #include <math.h>
+#include <unistd.h>
 
 #include "common.h"
 #include "philox.cuh"
@@ -423,7 +424,14 @@ struct DdpgCtrl {  // device-side control block read by the gather kernel (graph
   unsigned blocks_done; // last-block-done counter of the final kernel of an update (advances the counters below)
   double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
   double rc[2][2];      // 1 / (1 - βp): correctly rounded reciprocals of the two bias-correction divisors
+  unsigned dp_epoch;    // data-parallel learner: number of gradient exchanges completed (two per update)
+  unsigned dp_blocks_done;
+  int dp_error;         // set when a peer's signal did not arrive within DP_TIMEOUT_NS
 };
+#define DP_MAX_WORLD 16
+#define DP_TIMEOUT_NS 4000000000ull
+// peers of a data-parallel learner: rank r's flat gradient buffer and flag array, mapped into this process (CUDA IPC over NVLink)
+struct DpPeers { const float* grad[DP_MAX_WORLD]; unsigned* flags[DP_MAX_WORLD]; int world, rank; };
 
 struct Ddpg {
   int device;
@@ -462,6 +470,12 @@ struct Ddpg {
   const float** rings_dev; // [pop] replay ring of every learner (device array)
   long long idx_stride;    // ints between consecutive learners' host-supplied minibatch indices
   long long act_stride;    // floats between consecutive learners' act() scratch blocks
+  // data-parallel learner over NVLink peer memory (ddpg_dp_export / ddpg_dp_connect / ddpg_update_dp)
+  DpPeers dp;
+  bool dp_on;
+  unsigned* dp_flags;      // [DP_MAX_WORLD] exchange numbers published by the ranks (written by the peers)
+  void* dp_opened[2 * DP_MAX_WORLD]; int dp_n_opened;
+  cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
 };
 static inline int round4(int x) { return (x + 3) & ~3; }
 #define TC_MIN_ROWS 256
@@ -543,6 +557,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + nc;
   DMALLOC(h->ctrl, pop);
   DMALLOC(h->rings_dev, pop);
+  DMALLOC(h->dp_flags, DP_MAX_WORLD);
   {
     std::vector<float> c((size_t)B, -1.0f / (float)B);
     float nm[18];
@@ -571,7 +586,10 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph) cudaGraphDestroy(h->graph);
   cudaFree(h->slab);
   cudaFree(h->act_x);  // act() scratch: one allocation (x | h1 | h2 | y per learner)
-  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev);
+  if (h->graph_dp_exec) cudaGraphExecDestroy(h->graph_dp_exec);
+  if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
+  for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_flags);
   delete h;
   return SHEMS_OK;
 }
@@ -716,6 +734,34 @@ ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restri
 // Flux.Optimise.ADAM apply! + update! with Float64 β, ϵ (element math in Float64, stored Float32), then
 // soft_update! p_t = (1-τ) p_t + τ p_m for the target of the same net (DDPG.jl:99-108).
 // βp = β^t is read from the device control block so graph replays stay valid.
+__device__ __forceinline__ float adam_element(float x, float gj, float* __restrict__ m, float* __restrict__ v, double b1, double b2, double eps, float eta,
+                                              double c1, double c2, double r1, double r2) {
+  const float g2 = __fmul_rn(gj, gj);
+  const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)*m), __dmul_rn(1.0 - b1, (double)gj));
+  const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)*v), __dmul_rn(1.0 - b2, (double)g2));
+  *m = mj; *v = vj;
+  double qm = __dmul_rn((double)mj, r1); qm = __fma_rn(__fma_rn(-qm, c1, (double)mj), r1, qm);   // mt / (1 - βp[1])
+  double qv = __dmul_rn((double)vj, r2); qv = __fma_rn(__fma_rn(-qv, c2, (double)vj), r2, qv);   // vt / (1 - βp[2])
+  const double d = __dmul_rn(__ddiv_rn(qm, __dadd_rn(__dsqrt_rn(qv), eps)), (double)eta);
+  return __fsub_rn(x, (float)d);
+}
+// the last block to finish the final kernel of an update advances the device-side counters
+// (`βp .= βp .* β` of Flux.ADAM for both optimisers, the Philox update counter, the host-index cursor)
+__device__ __forceinline__ void adam_advance(DdpgCtrl* ctrl, double b1, double b2) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(&ctrl->blocks_done, 1u);
+    if (done == gridDim.x - 1) {
+      ctrl->blocks_done = 0;
+      ctrl->update += 1; ctrl->idx_cursor += 1;
+      for (int o = 0; o < 2; ++o) {
+        ctrl->bp[o][0] *= b1; ctrl->bp[o][1] *= b2;
+        ctrl->rc[o][0] = 1.0 / (1.0 - ctrl->bp[o][0]); ctrl->rc[o][1] = 1.0 / (1.0 - ctrl->bp[o][1]);
+      }
+    }
+  }
+}
 __global__ void __launch_bounds__(256)
 adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
                    double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
@@ -734,37 +780,84 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
     const float gj = (gscale == 1.0f) ? g[j] : __fmul_rn(g[j], gscale);  // data-parallel: mean of the ranks' summed gradients
-    const float g2 = __fmul_rn(gj, gj);
-    const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)m[j]), __dmul_rn(1.0 - b1, (double)gj));
-    const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)v[j]), __dmul_rn(1.0 - b2, (double)g2));
-    m[j] = mj; v[j] = vj;
-    double qm = __dmul_rn((double)mj, r1); qm = __fma_rn(__fma_rn(-qm, c1, (double)mj), r1, qm);   // mt / (1 - βp[1])
-    double qv = __dmul_rn((double)vj, r2); qv = __fma_rn(__fma_rn(-qv, c2, (double)vj), r2, qv);   // vt / (1 - βp[2])
-    const double d = __dmul_rn(__ddiv_rn(qm, __dadd_rn(__dsqrt_rn(qv), eps)), (double)eta);
-    const float xn = __fsub_rn(x[j], (float)d);
+    const float xn = adam_element(x[j], gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
     x[j] = xn;
     if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
   }
   // second Polyak pair: the critic target moves together with the actor step (DDPG.jl:142-143)
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
     target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
-  // the last block to finish the final kernel of an update advances the device-side counters
-  // (`βp .= βp .* β` of Flux.ADAM for both optimisers, the Philox update counter, the host-index cursor)
-  if (advance) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned done = atomicAdd(&ctrl->blocks_done, 1u);
-      if (done == gridDim.x - 1) {
-        ctrl->blocks_done = 0;
-        ctrl->update += 1; ctrl->idx_cursor += 1;
-        for (int o = 0; o < 2; ++o) {
-          ctrl->bp[o][0] *= b1; ctrl->bp[o][1] *= b2;
-          ctrl->rc[o][0] = 1.0 / (1.0 - ctrl->bp[o][0]); ctrl->rc[o][1] = 1.0 / (1.0 - ctrl->bp[o][1]);
-        }
-      }
+  if (advance) adam_advance(ctrl, b1, b2);
+}
+
+// Data-parallel learner: gradient all-reduce FUSED into the optimiser step, over NVLink peer memory (no NCCL call, no
+// reduced-gradient round trip through HBM).  Every rank runs this kernel at the same point of its stream:
+//   1. block 0 publishes "my gradient segment is final" by writing the exchange number into every peer's flag array
+//      (st.release.sys after a system fence; the gradient itself was written by earlier kernels of the stream);
+//   2. every block waits until all ranks have published that number (ld.acquire.sys on its own flag array, bounded spin);
+//   3. element j: g = (sum over ranks r = 0..W-1 of peer_grad[r][j]) / W, read straight from the peers' buffers in rank order
+//      (same order everywhere -> bit-identical replicas), then ADAM (+ Polyak) as in adam_polyak_kernel.
+// A rank may overwrite a gradient segment only after the NEXT exchange (critic and actor segments alternate), which every peer
+// signals after it finished reading this one — so no second barrier is needed.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float ld_peer(const float* p) {  // never served from a stale local cache line
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256)
+adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
+                      double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
+                      float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance) {
+  __shared__ int ok_s;
+  const unsigned epoch = ctrl->dp_epoch + 1u;
+  const int W = peers.world;
+  if (blockIdx.x == 0 && threadIdx.x < W) {
+    __threadfence_system();
+    st_release_sys(peers.flags[threadIdx.x] + peers.rank, epoch);
+  }
+  if (threadIdx.x == 0) ok_s = 1;
+  __syncthreads();
+  if (threadIdx.x < W) {
+    const unsigned* f = peers.flags[peers.rank] + threadIdx.x;
+    unsigned long long t0 = 0, t = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+      if (t - t0 > DP_TIMEOUT_NS) { ok_s = 0; ctrl->dp_error = 1; break; }
+      __nanosleep(100);
     }
   }
+  __syncthreads();
+  const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
+  const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
+  const float omt = __fsub_rn(1.0f, tau), inv_w = 1.0f / (float)W;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (ok_s) {
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+      float gs = ld_peer(peers.grad[0] + seg_off + j);
+      for (int r = 1; r < W; ++r) gs = __fadd_rn(gs, ld_peer(peers.grad[r] + seg_off + j));
+      const float xn = adam_element(x[j], __fmul_rn(gs, inv_w), m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+      x[j] = xn;
+      if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
+    }
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
+      target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {  // the last block closes this exchange
+    __threadfence();
+    const unsigned done = atomicAdd(&ctrl->dp_blocks_done, 1u);
+    if (done == gridDim.x - 1) { ctrl->dp_blocks_done = 0; ctrl->dp_epoch = epoch; }
+  }
+  if (advance) adam_advance(ctrl, b1, b2);
 }
 
 // ----------------------------------------------------------------------------- update sequence
@@ -989,7 +1082,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   return SHEMS_OK;
 }
 
-static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
+static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = false) {
   const DdpgParams& p = h->p;
   const int B = p.batch, l1 = h->ld1, l2 = h->ld2;
   const bool tc = use_tc(h, B), big = tc || B >= SPLITK_MIN_BATCH || h->pop > 1;  // streaming kernels for the thin products
@@ -998,8 +1091,12 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   GemmProblem g[4];
   // P10: ADAM(η_crit) on the critic
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);  // one element per thread: the Float64 div/sqrt chains need TLP
-  adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
+  if (dp)  // gradient exchange over NVLink fused into the optimiser step (critic segment = first nc floats of the flat buffer)
+    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
+                                                      p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  else
+    adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
+                                                 p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   if (big) {
@@ -1053,22 +1150,26 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale) {
   return SHEMS_OK;
 }
 
-static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale) {
+static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = false) {
   const DdpgParams& p = h->p;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
-  adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                               p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
+  if (dp)
+    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, dc.n_params, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                                      p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
+  else
+    adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                                 p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 
-static int enqueue_update_body(Ddpg* h, cudaStream_t st) {
+static int enqueue_update_body(Ddpg* h, cudaStream_t st, bool dp = false) {
   int s0 = enqueue_phase0(h, st);
-  if (!s0) s0 = enqueue_phase1(h, st, 1.0f);
-  if (!s0) s0 = enqueue_phase2(h, st, 1.0f);
+  if (!s0) s0 = enqueue_phase1(h, st, 1.0f, dp);
+  if (!s0) s0 = enqueue_phase2(h, st, 1.0f, dp);
   return s0;
 }
 
@@ -1084,20 +1185,22 @@ static int enqueue_gather(Ddpg* h, cudaStream_t st, bool from_rings, const float
 }
 
 // capture gather(from the replay rings) + body once; replays read everything that changes from the device control blocks
-static int ensure_graph(Ddpg* h) {
-  if (h->graph_exec) return SHEMS_OK;
-  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+static int ensure_graph(Ddpg* h, bool dp = false) {
+  cudaGraph_t& graph = dp ? h->graph_dp : h->graph;
+  cudaGraphExec_t& graph_exec = dp ? h->graph_dp_exec : h->graph_exec;
+  if (graph_exec) return SHEMS_OK;
+  if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
   cudaStream_t cs;
   CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { cudaStreamDestroy(cs); shems_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
   int st = enqueue_gather(h, cs, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-  if (!st) st = enqueue_update_body(h, cs);
-  e = cudaStreamEndCapture(cs, &h->graph);
+  if (!st) st = enqueue_update_body(h, cs, dp);
+  e = cudaStreamEndCapture(cs, &graph);
   cudaStreamDestroy(cs);
   if (st) return st;
   if (e != cudaSuccess) { shems_set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
-  CUDA_TRY(cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+  CUDA_TRY(cudaGraphInstantiate(&graph_exec, graph, 0));
   return SHEMS_OK;
 }
 
@@ -1131,9 +1234,13 @@ static int stage_update_inputs(Ddpg* h, ShemsReplay* const* rps, const uint64_t*
       cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
       CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)need));
       h->idx_cap = need;
-      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }  // idx pointer is baked into the graph
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }  // idx pointer is baked into the graphs
+      if (h->graph_dp_exec) { cudaGraphExecDestroy(h->graph_dp_exec); h->graph_dp_exec = nullptr; }
     }
-    if (h->idx_stride != per_learner && h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->idx_stride != per_learner && h->pop > 1) {  // the stride between learners' index blocks is baked in as well
+      if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+      if (h->graph_dp_exec) { cudaGraphExecDestroy(h->graph_dp_exec); h->graph_dp_exec = nullptr; }
+    }
     h->idx_stride = per_learner;
     CUDA_TRY(cudaMemcpyAsync(h->idx_dev, idx_host, sizeof(int32_t) * (size_t)need, cudaMemcpyHostToDevice, h->stream));
   }
@@ -1176,6 +1283,108 @@ extern "C" int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, co
   if (phase == 1) return enqueue_phase1(h, h->stream, grad_scale);
   TRY(enqueue_phase2(h, h->stream, grad_scale));
   h->n_updates += 1;
+  return SHEMS_OK;
+}
+
+// ---- data-parallel learner over NVLink peer memory
+struct DpExport {  // what one rank tells the others (ddpg_dp_export), DDPG_DP_HANDLE_BYTES bytes
+  cudaIpcMemHandle_t slab, flags;
+  long long grad_off;              // floats from the slab base to the flat gradient buffer
+  unsigned long long raw_grad, raw_flags;  // the same addresses for peers living in THIS process (tests: two handles, one process)
+  int pid, device;
+};
+static_assert(sizeof(DpExport) <= DDPG_DP_HANDLE_BYTES, "DDPG_DP_HANDLE_BYTES too small");
+
+extern "C" int32_t ddpg_dp_export(Ddpg* h, void* handle_out) {
+  REQUIRE(h && handle_out, SHEMS_ERR_INVALID, "ddpg_dp_export: NULL argument");
+  REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_dp_export: not available for a population handle");
+  GUARD(h->device);
+  DpExport e; memset(&e, 0, sizeof(e));
+  CUDA_TRY(cudaIpcGetMemHandle(&e.slab, h->slab));
+  CUDA_TRY(cudaIpcGetMemHandle(&e.flags, h->dp_flags));
+  e.grad_off = h->gradbuf - h->slab;
+  e.raw_grad = (unsigned long long)(uintptr_t)h->gradbuf; e.raw_flags = (unsigned long long)(uintptr_t)h->dp_flags;
+  e.pid = (int)getpid(); e.device = h->device;
+  memset(handle_out, 0, DDPG_DP_HANDLE_BYTES);
+  memcpy(handle_out, &e, sizeof(e));
+  return SHEMS_OK;
+}
+
+extern "C" int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const void* handles) {
+  REQUIRE(h && handles, SHEMS_ERR_INVALID, "ddpg_dp_connect: NULL argument");
+  REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, SHEMS_ERR_INVALID, "ddpg_dp_connect: rank=%d world=%d (max %d)", rank, world, DP_MAX_WORLD);
+  REQUIRE(h->pop == 1 && !h->dp_on, SHEMS_ERR_STATE, "ddpg_dp_connect: population handle, or already connected");
+  GUARD(h->device);
+  memset(&h->dp, 0, sizeof(h->dp));
+  h->dp.world = world; h->dp.rank = rank;
+  for (int r = 0; r < world; ++r) {
+    DpExport e;
+    memcpy(&e, (const char*)handles + (size_t)r * DDPG_DP_HANDLE_BYTES, sizeof(e));
+    if (r == rank) { h->dp.grad[r] = h->gradbuf; h->dp.flags[r] = h->dp_flags; continue; }
+    if (e.pid == (int)getpid()) {  // same process: plain pointers (peer access between the two devices if they differ)
+      if (e.device != h->device) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, h->device, e.device));
+        REQUIRE(can, SHEMS_ERR_CUDA, "ddpg_dp_connect: device %d cannot access device %d", h->device, e.device);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(e.device, 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(pe);
+        cudaGetLastError();
+      }
+      h->dp.grad[r] = (const float*)(uintptr_t)e.raw_grad; h->dp.flags[r] = (unsigned*)(uintptr_t)e.raw_flags;
+      continue;
+    }
+    void *ps = nullptr, *pf = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&ps, e.slab, cudaIpcMemLazyEnablePeerAccess));
+    h->dp_opened[h->dp_n_opened++] = ps;
+    CUDA_TRY(cudaIpcOpenMemHandle(&pf, e.flags, cudaIpcMemLazyEnablePeerAccess));
+    h->dp_opened[h->dp_n_opened++] = pf;
+    h->dp.grad[r] = (const float*)ps + e.grad_off; h->dp.flags[r] = (unsigned*)pf;
+  }
+  h->dp_on = true;
+  return SHEMS_OK;
+}
+
+// Everything ddpg_update_dp may have to allocate or instantiate (index staging for idx_ints host-supplied indices per call, the
+// captured graph), done up front: cudaMalloc / graph instantiation can synchronise the device, which must not happen while a
+// peer that shares this GPU (two ranks in one process) already spins in its exchange kernel.
+extern "C" int32_t ddpg_dp_prepare(Ddpg* h, int64_t idx_ints) {
+  REQUIRE(h && h->dp_on, SHEMS_ERR_STATE, "ddpg_dp_prepare: call ddpg_dp_connect first");
+  GUARD(h->device);
+  if (idx_ints > h->idx_cap) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->idx_dev); h->idx_dev = nullptr; h->idx_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->idx_dev, sizeof(int32_t) * (size_t)idx_ints));
+    h->idx_cap = idx_ints;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph_dp_exec) { cudaGraphExecDestroy(h->graph_dp_exec); h->graph_dp_exec = nullptr; }
+  }
+  TRY(ensure_graph(h, true));
+  CUDA_TRY(cudaGraphUpload(h->graph_dp_exec, h->stream));  // the first launch would otherwise upload (and may synchronise)
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return SHEMS_OK;
+}
+
+// replay() n_updates times on a connected data-parallel learner: every rank samples its own replay shard, the two gradient
+// exchanges run inside the optimiser kernels over NVLink (adam_polyak_dp_kernel); every rank must make the same calls.
+extern "C" int32_t ddpg_update_dp(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed) {
+  REQUIRE(h && rp, SHEMS_ERR_INVALID, "ddpg_update_dp: NULL argument");
+  REQUIRE(h->dp_on, SHEMS_ERR_STATE, "ddpg_update_dp: call ddpg_dp_connect first");
+  REQUIRE(n_updates >= 1, SHEMS_ERR_INVALID, "ddpg_update_dp: n_updates=%d", n_updates);
+  GUARD(h->device);
+  TRY(stage_update_inputs(h, &rp, &seed, idx_host, (long long)n_updates * h->p.batch));
+  TRY(ensure_graph(h, true));
+  for (int u = 0; u < n_updates; ++u) CUDA_TRY(cudaGraphLaunch(h->graph_dp_exec, h->stream));
+  h->n_updates += n_updates;
+  return SHEMS_OK;
+}
+// 0 while every gradient exchange completed; 1 after a peer failed to arrive within the spin limit (the update was skipped)
+extern "C" int32_t ddpg_dp_status(Ddpg* h, int32_t* error_out) {
+  REQUIRE(h && error_out, SHEMS_ERR_INVALID, "ddpg_dp_status: NULL argument");
+  GUARD(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  int e = 0;
+  CUDA_TRY(cudaMemcpy(&e, &h->ctrl->dp_error, sizeof(int), cudaMemcpyDeviceToHost));
+  *error_out = e;
   return SHEMS_OK;
 }
 

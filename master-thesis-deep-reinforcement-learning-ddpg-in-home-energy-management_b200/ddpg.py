@@ -231,6 +231,41 @@ class Learner:
             dist.all_reduce(g[nc:])
         L.check(self.lib.ddpg_update_phase(self._h, memory._h, 2, None, seed, 1.0 / world))
 
+    # ---- data-parallel learner with the gradient exchange fused into the optimiser kernels (NVLink peer memory, no NCCL call)
+    def dp_export(self):
+        buf = C.create_string_buffer(L.DP_HANDLE_BYTES)
+        L.check(self.lib.ddpg_dp_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def dp_connect(self, rank, world, blobs):
+        """blobs: the ranks' dp_export() results in rank order."""
+        assert len(blobs) == world and all(len(b) == L.DP_HANDLE_BYTES for b in blobs)
+        L.check(self.lib.ddpg_dp_connect(self._h, int(rank), int(world), C.c_char_p(b"".join(blobs))))
+
+    def dp_connect_dist(self, dist):
+        """one process per GPU: gathers the IPC handles of all ranks through torch.distributed and connects."""
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, self.dp_export())
+        self.dp_connect(dist.get_rank(), dist.get_world_size(), blobs)
+        self.dp_prepare()
+
+    def dp_prepare(self, idx_ints=0):
+        L.check(self.lib.ddpg_dp_prepare(self._h, int(idx_ints)))
+
+    def replay_fused_dp(self, memory, rng_rpl=0, n_updates=1, idx=None):
+        """replay() on a connected data-parallel learner (ddpg_update_dp): every rank calls it with its own replay shard."""
+        ip = None
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, np.int32)
+            assert idx.size == n_updates * self.p.batch
+            ip = idx.ctypes.data_as(L.PI)
+        L.check(self.lib.ddpg_update_dp(self._h, memory._h, int(n_updates), ip, int(rng_rpl) & (2**64 - 1)))
+
+    def dp_status(self):
+        e = C.c_int32()
+        L.check(self.lib.ddpg_dp_status(self._h, C.byref(e)))
+        return e.value
+
     def update_batch(self, s, a, r, s2, done=None):
         L.check(self.lib.ddpg_update_batch(self._h, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(done)))
 

@@ -466,3 +466,44 @@ def test_act_ou_noise_parity(sb, O):
     x3 = torch.zeros((2, 8192), dtype=torch.float32, device="cuda")
     le.act_ou(dev(obs), x3, theta, mu, sigma, dt, rng_act=9, step=3)
     assert torch.equal(x2, x3)                                                # reproducible per (seed, step)
+
+
+def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series):
+    """ddpg_update_dp with a world of one rank (flags, exchange numbers, captured graph, in-kernel gradient read through the peer
+    table) must be bit-identical to the plain update."""
+    n, T, B, K = 64, 72, 64, 4
+    env = sb.Shems(T, train_series, n_envs=n)
+    mem = sb.Replay(n * T)
+    env.reset(rng=2)
+    env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
+    plain, fused = (sb.Learner(params=sb.default_ddpg_params(batch=B)) for _ in range(2))
+    for le in (plain, fused):
+        le.init(3)
+        le.set_norm(mn, mx)
+    with pytest.raises(sb.ShemsError):
+        fused.replay_fused_dp(mem, n_updates=1)          # not connected yet
+    fused.dp_connect(0, 1, [fused.dp_export()])
+    fused.dp_prepare()
+    plain.replay(mem, rng_rpl=5, n_updates=K)
+    fused.replay_fused_dp(mem, rng_rpl=5, n_updates=K)
+    assert fused.dp_status() == 0
+    for net in range(4):
+        for k in range(3):
+            for x, y in zip(plain.get_layer(net, k), fused.get_layer(net, k)):
+                np.testing.assert_array_equal(x, y)
+
+
+def test_fused_peer_allreduce_two_processes():
+    """Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
+    bit-identical and equal to one learner on the full minibatch — checked inside tests/dp_worker.py.  On a one-GPU box both
+    ranks share the device (time-sliced contexts): the same IPC code path, just slower."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "dp_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0 and "DP_OK world=2" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
