@@ -238,35 +238,61 @@ def ddpg_population(sb, torch, dist, rank, world, ser_train, per_gpu=80, n_updat
 
 
 def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
-    """Data-parallel learner: every rank samples its own replay shard (B=120 each), two NCCL gradient all-reduces per update."""
-    env = sb.Shems(72, ser_train, n_envs=1000, device=torch.cuda.current_device(), env_id_base=rank * 1000)
-    mem = sb.Replay(24_000, device=torch.cuda.current_device())
+    """Data-parallel learner: every rank samples its own replay shard (B=120 each); the critic and actor gradients are averaged
+    over the ranks twice per update.  Two implementations are timed: `nccl` (ddpg_update_phase + two NCCL all-reduces issued
+    from the host) and `fused_peer` (ddpg_update_dp: the exchange runs inside the ADAM kernels over NVLink peer memory, the
+    whole update is one captured graph)."""
+    dev = torch.cuda.current_device()
+    env = sb.Shems(72, ser_train, n_envs=1000, device=dev, env_id_base=rank * 1000)
+    mem = sb.Replay(24_000, device=dev)
     env.reset(rng=1)
     env.rollout(sb.POLICY_RANDOM, 24, seed=1, replay=mem, want_return=False)
-    le = sb.Learner(device=torch.cuda.current_device())
-    le.init(1)                                   # identical replicas on every rank
     mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
+    out = dict(global_batch=120 * dist.get_world_size())
+
+    def in_sync(le):
+        w0 = torch.from_numpy(le.get_layer(0, 1)[0]).cuda()
+        ref = w0.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([float(torch.equal(w0, ref))], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return bool(ok.item() == 1.0)
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    le = sb.Learner(device=dev)
+    le.init(1)                                   # identical replicas on every rank
     le.set_norm(mn, mx)
     for u in range(20):
         le.replay_dp(mem, rng_rpl=100 + rank, dist=dist)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for u in range(n_updates):
-        le.replay_dp(mem, rng_rpl=1000 + rank, dist=dist)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    w0 = torch.from_numpy(le.get_layer(0, 1)[0]).cuda()
-    ref = w0.clone()
-    dist.broadcast(ref, 0)
-    in_sync = torch.tensor([float(torch.equal(w0, ref))], device="cuda")
-    dist.all_reduce(in_sync, op=dist.ReduceOp.MIN)
-    ms = float(t.item())
-    return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, global_batch=120 * dist.get_world_size(),
-                allreduce_bytes_per_update=4 * int(le.grad_tensor().numel()), replicas_bit_identical=bool(in_sync.item() == 1.0))
+    ms = timed(lambda: [le.replay_dp(mem, rng_rpl=1000 + rank, dist=dist) for _ in range(n_updates)])
+    out["nccl"] = dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates,
+                       allreduce_bytes_per_update=4 * int(le.grad_tensor().numel()), replicas_bit_identical=in_sync(le))
+    le.close()
+    try:
+        lf = sb.Learner(device=dev)
+        lf.init(1)
+        lf.set_norm(mn, mx)
+        lf.dp_connect_dist(dist)
+        dist.barrier()
+        lf.replay_fused_dp(mem, rng_rpl=100 + rank, n_updates=20)
+        ms = timed(lambda: lf.replay_fused_dp(mem, rng_rpl=1000 + rank, n_updates=n_updates))
+        out["fused_peer"] = dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, exchange_status=lf.dp_status(),
+                                 peer_bytes_read_per_update=4 * int(lf.grad_tensor().numel()) * dist.get_world_size(),
+                                 replicas_bit_identical=in_sync(lf))
+    except Exception as e:
+        out["fused_peer"] = dict(error=str(e))
+    return out
 
 
 def main():
