@@ -297,7 +297,8 @@ SHEMS_API int32_t ddpg_dp_status(Ddpg* h, int32_t* error_out);
 SHEMS_API int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act);
 /* gradients of the last update (Flux layout, like ddpg_get_layer); net = ACTOR or CRITIC */
 SHEMS_API int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_host, float* b_host);
-/* flat fp32 gradient buffer on the device (critic params then actor params) */
+/* flat fp32 gradient buffer on the device: critic gradient at [0, nc), actor gradient at [roundup(nc, 64), roundup(nc, 64) + na),
+ * zero padding between them; *n = roundup(nc, 64) + na (nc, na = ddpg_num_params of critic / actor) */
 SHEMS_API int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n);
 
 /* ------------------------------------------------ tensor-core GEMM (test / benchmark entry point)

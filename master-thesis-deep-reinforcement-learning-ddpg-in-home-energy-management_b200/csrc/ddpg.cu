@@ -540,7 +540,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
   struct Carve { float** ptr; long long count; };
   const Carve plan[] = {
-      {&h->net[0], na}, {&h->net[1], nc}, {&h->net[2], na}, {&h->net[3], nc}, {&h->gradbuf, na + nc},
+      {&h->net[0], na}, {&h->net[1], nc}, {&h->net[2], na}, {&h->net[3], nc}, {&h->gradbuf, ((nc + 63) & ~63ll) + na},
       {&h->adam_m[0], na}, {&h->adam_v[0], na}, {&h->adam_m[1], nc}, {&h->adam_v[1], nc}, {&h->norm, 18},
       {&h->xs, (long long)B * C}, {&h->xs2, (long long)B * C}, {&h->xspi, (long long)B * C}, {&h->r, B}, {&h->done, B},
       {&h->t_h1, (long long)B * l1}, {&h->t_h2, (long long)B * l2}, {&h->c_h1, (long long)B * l1}, {&h->c_h2, (long long)B * l2},
@@ -554,7 +554,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   DMALLOC(h->slab, off * pop);
   off = 0;
   for (const Carve& c : plan) { *c.ptr = h->slab + off; off += (c.count + 63) & ~63ll; }
-  h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + nc;
+  h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + ((nc + 63) & ~63ll);  // the actor part starts on a 256-byte boundary (TMA stores of dW)
   DMALLOC(h->ctrl, pop);
   DMALLOC(h->rings_dev, pop);
   DMALLOC(h->dp_flags, DP_MAX_WORLD);
@@ -734,9 +734,18 @@ ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restri
 // Flux.Optimise.ADAM apply! + update! with Float64 β, ϵ (element math in Float64, stored Float32), then
 // soft_update! p_t = (1-τ) p_t + τ p_m for the target of the same net (DDPG.jl:99-108).
 // βp = β^t is read from the device control block so graph replays stay valid.
+template <bool FAST>
 __device__ __forceinline__ float adam_element(float x, float gj, float* __restrict__ m, float* __restrict__ v, double b1, double b2, double eps, float eta,
                                               double c1, double c2, double r1, double r2) {
   const float g2 = __fmul_rn(gj, gj);
+  if (FAST) {  // tensor-core mode: the gradients carry TF32 noise (1e-3 relative), so the whole step is evaluated in IEEE fp32
+               // (no DDIV / DSQRT, no Float32<->Float64 conversions on the XU pipe)
+    const float mj = __fmaf_rn((float)b1, *m, __fmul_rn((float)(1.0 - b1), gj));
+    const float vj = __fmaf_rn((float)b2, *v, __fmul_rn((float)(1.0 - b2), g2));
+    *m = mj; *v = vj;
+    const float qm = __fmul_rn(mj, (float)r1), qv = __fmul_rn(vj, (float)r2);
+    return __fsub_rn(x, __fmul_rn(__fdiv_rn(qm, __fadd_rn(__fsqrt_rn(qv), (float)eps)), eta));
+  }
   const float mj = (float)__dadd_rn(__dmul_rn(b1, (double)*m), __dmul_rn(1.0 - b1, (double)gj));
   const float vj = (float)__dadd_rn(__dmul_rn(b2, (double)*v), __dmul_rn(1.0 - b2, (double)g2));
   *m = mj; *v = vj;
@@ -762,6 +771,7 @@ __device__ __forceinline__ void adam_advance(DdpgCtrl* ctrl, double b1, double b
     }
   }
 }
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
                    double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
@@ -778,14 +788,47 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
   const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long j0 = 0, k0 = 0;  // scalar loops start here (FAST: after the float4 body)
+  if (FAST) {  // memory-bound fp32 variant: 16-byte accesses (every slab buffer starts on a 256-byte boundary)
+    const long long n4 = n >> 2;
+    for (long long q = tid; q < n4; q += stride) {
+      float4 xv = reinterpret_cast<float4*>(x)[q], mv = reinterpret_cast<float4*>(m)[q], vv = reinterpret_cast<float4*>(v)[q];
+      const float4 gv = reinterpret_cast<const float4*>(g)[q];
+      float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w}, vs[4] = {vv.x, vv.y, vv.z, vv.w};
+      const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        xs[u] = adam_element<true>(xs[u], (gscale == 1.0f) ? gs[u] : __fmul_rn(gs[u], gscale), &ms[u], &vs[u], b1, b2, eps, eta, c1, c2, r1, r2);
+      reinterpret_cast<float4*>(x)[q] = make_float4(xs[0], xs[1], xs[2], xs[3]);
+      reinterpret_cast<float4*>(m)[q] = make_float4(ms[0], ms[1], ms[2], ms[3]);
+      reinterpret_cast<float4*>(v)[q] = make_float4(vs[0], vs[1], vs[2], vs[3]);
+      if (target) {
+        float4 t = reinterpret_cast<float4*>(target)[q];
+        t.x = __fadd_rn(__fmul_rn(omt, t.x), __fmul_rn(tau, xs[0])); t.y = __fadd_rn(__fmul_rn(omt, t.y), __fmul_rn(tau, xs[1]));
+        t.z = __fadd_rn(__fmul_rn(omt, t.z), __fmul_rn(tau, xs[2])); t.w = __fadd_rn(__fmul_rn(omt, t.w), __fmul_rn(tau, xs[3]));
+        reinterpret_cast<float4*>(target)[q] = t;
+      }
+    }
+    j0 = n4 << 2;
+    const long long m4 = n2 >> 2;
+    for (long long q = tid; q < m4; q += stride) {
+      float4 t = reinterpret_cast<float4*>(target2)[q];
+      const float4 w = reinterpret_cast<const float4*>(model2)[q];
+      t.x = __fadd_rn(__fmul_rn(omt, t.x), __fmul_rn(tau, w.x)); t.y = __fadd_rn(__fmul_rn(omt, t.y), __fmul_rn(tau, w.y));
+      t.z = __fadd_rn(__fmul_rn(omt, t.z), __fmul_rn(tau, w.z)); t.w = __fadd_rn(__fmul_rn(omt, t.w), __fmul_rn(tau, w.w));
+      reinterpret_cast<float4*>(target2)[q] = t;
+    }
+    k0 = m4 << 2;
+  }
+  for (long long j = j0 + tid; j < n; j += stride) {
     const float gj = (gscale == 1.0f) ? g[j] : __fmul_rn(g[j], gscale);  // data-parallel: mean of the ranks' summed gradients
-    const float xn = adam_element(x[j], gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+    const float xn = adam_element<FAST>(x[j], gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
     x[j] = xn;
     if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
   }
   // second Polyak pair: the critic target moves together with the actor step (DDPG.jl:142-143)
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
+  for (long long j = k0 + tid; j < n2; j += stride)
     target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
   if (advance) adam_advance(ctrl, b1, b2);
 }
@@ -844,7 +887,7 @@ adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, float* __restrict_
     for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
       float gs = ld_peer(peers.grad[0] + seg_off + j);
       for (int r = 1; r < W; ++r) gs = __fadd_rn(gs, ld_peer(peers.grad[r] + seg_off + j));
-      const float xn = adam_element(x[j], __fmul_rn(gs, inv_w), m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+      const float xn = adam_element<false>(x[j], __fmul_rn(gs, inv_w), m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
       x[j] = xn;
       if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
     }
@@ -1094,9 +1137,12 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   if (dp)  // gradient exchange over NVLink fused into the optimiser step (critic segment = first nc floats of the flat buffer)
     adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
                                                       p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  else if (h->tc)
+    adam_polyak_kernel<true><<<dim3((adam_grid.x + 3) / 4, h->pop), 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
+                                                       p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   else
-    adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
-                                                 p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
+    adam_polyak_kernel<false><<<adam_grid, 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
+                                                        p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
   if (big) {
@@ -1157,11 +1203,14 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
   if (dp)
-    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, dc.n_params, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, h->grad[0] - h->gradbuf, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
                                                       p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
+  else if (h->tc)
+    adam_polyak_kernel<true><<<dim3((adam_grid.x + 3) / 4, h->pop), 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                                       p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
   else
-    adam_polyak_kernel<<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                                 p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
+    adam_polyak_kernel<false><<<adam_grid, 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                                        p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1583,6 +1632,6 @@ extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float t
 extern "C" int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n) {
   REQUIRE(h && grad_dev && n, SHEMS_ERR_INVALID, "ddpg_grad_buffer: NULL argument");
   *grad_dev = h->gradbuf;
-  *n = h->dims[0].n_params + h->dims[1].n_params;
+  *n = (h->grad[0] - h->gradbuf) + h->dims[0].n_params;
   return SHEMS_OK;
 }
