@@ -458,7 +458,7 @@ struct Ddpg {
   cudaGraph_t graph; cudaGraphExec_t graph_exec; 
   float* dqpi;     // [B] constant -1/B: d(-mean q)/dq
   bool ctrl_init;
-  int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 4 floats: TMA rows)
+  int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 32 floats = 128 bytes)
   bool tc;         // layer-2 contractions on TF32 tensor cores (use_tensor_cores, batch >= 256, operands 16-byte aligned)
   float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
   long long ws_floats;
@@ -477,8 +477,10 @@ struct Ddpg {
   void* dp_opened[2 * DP_MAX_WORLD]; int dp_n_opened;
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
 };
-static inline int round4(int x) { return (x + 3) & ~3; }
+static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows start on 128-byte lines: one L2 request per TMA box row
+#ifndef TC_MIN_ROWS
 #define TC_MIN_ROWS 256
+#endif
 #define SPLITK_MIN_BATCH 1024
 #define SPLITK_MAX 32
 
@@ -529,7 +531,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   const int S = p->state_size, A = p->action_size, B = p->batch, C = S + A;
   make_dims(h->dims[0], S, p->l1, p->l2, A);
   make_dims(h->dims[1], C, p->l1, p->l2, 1);
-  h->ld1 = round4(p->l1); h->ld2 = round4(p->l2);
+  h->ld1 = round_ld(p->l1); h->ld2 = round_ld(p->l2);
   const int l1 = h->ld1, l2 = h->ld2;  // allocation strides
   // W2 of both nets must start on a 16-byte boundary and have 16-byte rows for the TMA descriptors
   h->tc = p->use_tensor_cores && (p->l2 % 4 == 0) && (h->dims[0].l[1].w_off % 4 == 0) && (h->dims[1].l[1].w_off % 4 == 0);

@@ -22,10 +22,13 @@
 
 namespace {
 
-constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32, UMMA_K = 8, STAGES = 3;  // 3 x 32 KB: two CTAs per SM, one's epilogue overlaps the other's main loop
+constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32, UMMA_K = 8;
+constexpr int STAGES = 5;                                    // 5 x 32 KB operand ring: one persistent CTA per SM keeps it full across tiles
 constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB per operand and stage
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024;   // + alignment slack
-constexpr int TMEM_COLS = 128;
+constexpr int STAGING_BYTES = 4 * 2 * 4096;                  // epilogue: 4 warps x 2 chunk buffers of 32x32 fp32
+constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + STAGING_BYTES + 1024;   // + alignment slack
+constexpr int ACC_STAGES = 2;                                // double-buffered accumulator: epilogue of tile i overlaps the k-loop of tile i+1
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;              // 256 fp32 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -109,37 +112,43 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent, warp-specialised GEMM: grid = min(#tiles, #SMs) CTAs of 192 threads, CTA c works on tiles c, c + grid, ...
+// (tile = (m-tile, n-tile, z) with z the K-split or the batch entry).  The three roles run the same tile sequence but are coupled
+// only through mbarriers, so the TMA producer streams the operands of tile i+1 while the MMA lane still issues tile i and the
+// epilogue warps drain tile i-1 from the other half of TMEM:
+//   warp 0   : TMA producer          full[s] / empty[s]          5-stage operand ring, running across tile boundaries
+//   warp 1   : tcgen05.mma issuer    acc_full[a] / acc_empty[a]  two 128-column accumulators in TMEM
+//   warps 2-5: epilogue              tcgen05.ld -> fused epilogue -> swizzled smem chunk (double-buffered) -> bulk tensor store
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                const TcGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
-  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+  uint8_t* staging = smem + STAGES * 2 * TILE_BYTES;
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full_bar[ACC_STAGES], acc_empty_bar[ACC_STAGES];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ __align__(16) float bias_s[BLOCK_N];
+  __shared__ __align__(16) float bias_s[2][BLOCK_N];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
-  const int split = p.batch > 1 ? 0 : blockIdx.z, bz = p.batch > 1 ? blockIdx.z : 0;  // grid.z: K-split or batch entry
+  const int mt = (p.M + BLOCK_M - 1) / BLOCK_M, nt = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int nz = p.batch > 1 ? p.batch : p.splits;
+  const int total_tiles = mt * nt * nz;
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
-  const int kb_begin = split * kb_per;
-  const int kb_end = min(kb_total, kb_begin + kb_per);
-  const int num_kb = max(0, kb_end - kb_begin);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full_bar[a], 1); mbar_init(&acc_empty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmD) : "memory");
   }
-  if (threadIdx.x >= 64) {  // the epilogue warps stage this tile's bias slice
-    const int j = threadIdx.x - 64;
-    bias_s[j] = (p.epi == TC_EPI_BIAS_RELU && n0 + j < p.N) ? p.bias[(long long)bz * p.bs_bias + n0 + j] : 0.0f;
-  }
-  if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns × 128 lanes
+  if (warp == 1) {  // TMEM allocation: 2 x 128 fp32 accumulator columns × 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
@@ -148,27 +157,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
 
+// tile -> (m0, n0, split, bz, first k-block, number of k-blocks); m-tiles vary fastest so that concurrently running CTAs share B tiles in L2
+#define TILE_COORDS(tile)                                                               \
+  const int z_ = (tile) / (mt * nt), r_ = (tile) - z_ * (mt * nt);                      \
+  const int m0 = (r_ % mt) * BLOCK_M, n0 = (r_ / mt) * BLOCK_N;                         \
+  const int split = p.batch > 1 ? 0 : z_, bz = p.batch > 1 ? z_ : 0;                    \
+  const int kb_begin = split * kb_per;                                                  \
+  const int num_kb = max(0, min(kb_total, kb_begin + kb_per) - kb_begin);
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-        uint8_t* sa = smem + s * 2 * TILE_BYTES;
-        uint8_t* sb = sa + TILE_BYTES;
-        const int k0 = (kb_begin + i) * BLOCK_K;
-        if (A_MN) {
+      int g = 0;  // k-blocks issued so far (ring position carries over tile boundaries)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TILE_COORDS(tile)
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % STAGES, ph = (g / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+          uint8_t* sa = smem + s * 2 * TILE_BYTES;
+          uint8_t* sb = sa + TILE_BYTES;
+          const int k0 = (kb_begin + i) * BLOCK_K;
+          if (A_MN) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0, bz);  // box {32 rows(MN), 32 k}
-        } else {
-          tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, bz);                                               // box {32 k, 128 rows}
-        }
-        if (B_MN) {
+            for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0, bz);  // box {32 rows(MN), 32 k}
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, bz);                                               // box {32 k, 128 rows}
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0, bz);
-        } else {
-          tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, bz);
+            for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0, bz);
+          } else {
+            tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, bz);
+          }
         }
       }
     }
@@ -178,107 +199,131 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     if (elect_one()) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        TILE_COORDS(tile)
+        (void)m0; (void)n0; (void)bz;
+        const int acc = it & 1, use = it >> 1;
+        mbar_wait(&acc_empty_bar[acc], (use & 1) ^ 1);  // the epilogue has drained this accumulator (passes at once on first use)
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * 2 * TILE_BYTES), sb = sa + TILE_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int i = 0; i < num_kb; ++i, ++g) {
+          const int s = g % STAGES, ph = (g / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * 2 * TILE_BYTES), sb = sa + TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-          // K-major, SWIZZLE_128B: rows of 128 B (32 k), 8-row groups 1024 B apart (SBO); one UMMA_K = 32 B further along the row.
-          // MN-major, SWIZZLE_128B_BASE32B: k-rows of 128 B (32 MN elements); the swizzle atom is 4 k-rows (512 B, 32-byte
-          //   chunks XOR row%4), so one UMMA_K = 8 spans two atoms 512 B apart (SBO); 32-wide MN chunks are 4096 B apart (LBO).
-          const uint64_t ad = A_MN ? make_smem_desc(sa + kk * 1024, 4096, 512, 1) : make_smem_desc(sa + kk * 32, 16, 1024, 2);
-          const uint64_t bd = B_MN ? make_smem_desc(sb + kk * 1024, 4096, 512, 1) : make_smem_desc(sb + kk * 32, 16, 1024, 2);
-          umma_tf32(tmem_base, ad, bd, idesc, (i | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // K-major, SWIZZLE_128B: rows of 128 B (32 k), 8-row groups 1024 B apart (SBO); one UMMA_K = 32 B further along the row.
+            // MN-major, SWIZZLE_128B_BASE32B: k-rows of 128 B (32 MN elements); the swizzle atom is 4 k-rows (512 B, 32-byte
+            //   chunks XOR row%4), so one UMMA_K = 8 spans two atoms 512 B apart (SBO); 32-wide MN chunks are 4096 B apart (LBO).
+            const uint64_t ad = A_MN ? make_smem_desc(sa + kk * 1024, 4096, 512, 1) : make_smem_desc(sa + kk * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? make_smem_desc(sb + kk * 1024, 4096, 512, 1) : make_smem_desc(sb + kk * 32, 16, 1024, 2);
+            umma_tf32(tmem_d, ad, bd, idesc, (i | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
+        umma_commit(&acc_full_bar[acc]);   // accumulator complete (arrives at once for an empty k-range)
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
     // ===== epilogue (warps 2-5): TMEM lane quarter = warp % 4 =====
     // A thread owns one accumulator row; tcgen05.ld hands it 32 consecutive columns at a time.  With a TMA-storable D
-    // (16-byte rows) the warp writes its 32x32 chunk into 128B-swizzled shared memory (the k-loop's stage buffers are
-    // free once tmem_full fires) and one lane issues a bulk tensor store: full 128-byte lines, clipped at M / N by the
-    // tensor map.  Otherwise every thread stores its row segment directly.
+    // (16-byte rows) the warp writes its 32x32 chunk into 128B-swizzled shared memory and one lane issues a bulk tensor
+    // store: full 128-byte lines, clipped at M / N by the tensor map.  Otherwise every thread stores its row segment directly.
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
     const bool mask = (p.epi == TC_EPI_RELU_MASK);
-    const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
-    const float* auxrow = mask ? p.aux + (long long)bz * p.bs_aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
-    if (num_kb > 0) {
-      mbar_wait(&tmem_full_bar, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    }
-    float* Dp = p.D + (long long)(split + bz) * p.split_stride;  // split_stride doubles as the batch stride of D
-    uint8_t* stage = smem + q * (4 * 4096);  // this warp's four 32x32 fp32 chunk buffers (4 KB each, 1024-byte aligned)
+    const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((p.bs_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    uint8_t* stage = staging + q * (2 * 4096);  // this warp's two 32x32 fp32 chunk buffers (4 KB each, 1024-byte aligned)
+    int it = 0, chunk_no = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      TILE_COORDS(tile)
+      const int acc = it & 1, use = it >> 1;
+      const int m = m0 + q * 32 + lane;
+      // this tile's bias slice (double-buffered: the named barrier of tile it+1 proves everyone is done with tile it-1's slice)
+      bias_s[it & 1][threadIdx.x - 64] = (p.epi == TC_EPI_BIAS_RELU && n0 + (int)threadIdx.x - 64 < p.N) ? p.bias[(long long)bz * p.bs_bias + n0 + threadIdx.x - 64] : 0.0f;
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      const float* auxrow = mask ? p.aux + (long long)bz * p.bs_aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
+      if (num_kb > 0) {
+        mbar_wait(&acc_full_bar[acc], use & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      }
+      float* Dp = p.D + (long long)(split + bz) * p.split_stride;  // split_stride doubles as the batch stride of D
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      const int nc = n0 + c * 32;
-      if (nc >= p.N) break;
-      float4 hx[8];
-      if (mask) {  // relu'(H): this row's 32 mask values, requested before the accumulator is read
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int nc = n0 + c * 32;
+        if (nc >= p.N) break;
+        float4 hx[8];
+        if (mask) {  // relu'(H): this row's 32 mask values, requested before the accumulator is read
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int n = nc + j4 * 4;
+            if (aux_vec && n + 3 < p.N) hx[j4] = *reinterpret_cast<const float4*>(auxrow + n);
+            else {
+              hx[j4].x = (n + 0 < p.N) ? auxrow[n + 0] : 0.0f; hx[j4].y = (n + 1 < p.N) ? auxrow[n + 1] : 0.0f;
+              hx[j4].z = (n + 2 < p.N) ? auxrow[n + 2] : 0.0f; hx[j4].w = (n + 3 < p.N) ? auxrow[n + 3] : 0.0f;
+            }
+          }
+        }
+        uint32_t v[32];
+        if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c * 32), v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        float4 o[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nc + j4 * 4;
-          if (aux_vec && n + 3 < p.N) hx[j4] = *reinterpret_cast<const float4*>(auxrow + n);
-          else {
-            hx[j4].x = (n + 0 < p.N) ? auxrow[n + 0] : 0.0f; hx[j4].y = (n + 1 < p.N) ? auxrow[n + 1] : 0.0f;
-            hx[j4].z = (n + 2 < p.N) ? auxrow[n + 2] : 0.0f; hx[j4].w = (n + 3 < p.N) ? auxrow[n + 3] : 0.0f;
+          float x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = __uint_as_float(v[j4 * 4 + u]);
+          if (p.epi == TC_EPI_BIAS_RELU) {
+            const float4 bv = *reinterpret_cast<const float4*>(&bias_s[it & 1][c * 32 + j4 * 4]);
+            x[0] = fmaxf(x[0] + bv.x, 0.0f); x[1] = fmaxf(x[1] + bv.y, 0.0f); x[2] = fmaxf(x[2] + bv.z, 0.0f); x[3] = fmaxf(x[3] + bv.w, 0.0f);
+          } else if (mask) {
+            x[0] = hx[j4].x > 0.0f ? x[0] : 0.0f; x[1] = hx[j4].y > 0.0f ? x[1] : 0.0f;
+            x[2] = hx[j4].z > 0.0f ? x[2] : 0.0f; x[3] = hx[j4].w > 0.0f ? x[3] : 0.0f;
+          }
+          o[j4] = make_float4(x[0], x[1], x[2], x[3]);
+        }
+        if (p.tma_store) {
+          uint8_t* buf = stage + (chunk_no & 1) * 4096;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");  // the store issued two chunks ago has read this buffer
+          __syncwarp();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)  // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmD, buf, nc, m0 + q * 32, split + bz);
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+          ++chunk_no;
+        } else if (m < p.M) {
+          const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dp) & 15) == 0);
+          float* drow = Dp + (long long)m * p.ldd;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int n = nc + j4 * 4;
+            if (vec && n + 3 < p.N) *reinterpret_cast<float4*>(drow + n) = o[j4];
+            else {
+              const float x[4] = {o[j4].x, o[j4].y, o[j4].z, o[j4].w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (n + u < p.N) drow[n + u] = x[u];
+            }
           }
         }
       }
-      uint32_t v[32];
-      if (num_kb > 0) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;
-      }
-      float4 o[8];
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        float x[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = __uint_as_float(v[j4 * 4 + u]);
-        if (p.epi == TC_EPI_BIAS_RELU) {
-          const float4 bv = *reinterpret_cast<const float4*>(&bias_s[c * 32 + j4 * 4]);
-          x[0] = fmaxf(x[0] + bv.x, 0.0f); x[1] = fmaxf(x[1] + bv.y, 0.0f); x[2] = fmaxf(x[2] + bv.z, 0.0f); x[3] = fmaxf(x[3] + bv.w, 0.0f);
-        } else if (mask) {
-          x[0] = hx[j4].x > 0.0f ? x[0] : 0.0f; x[1] = hx[j4].y > 0.0f ? x[1] : 0.0f;
-          x[2] = hx[j4].z > 0.0f ? x[2] : 0.0f; x[3] = hx[j4].w > 0.0f ? x[3] : 0.0f;
-        }
-        o[j4] = make_float4(x[0], x[1], x[2], x[3]);
-      }
-      if (p.tma_store) {
-        uint8_t* buf = stage + c * 4096;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)  // SWIZZLE_128B: 16-byte chunk j of row r sits at chunk j ^ (r & 7)
-          *reinterpret_cast<float4*>(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tmD, buf, nc, m0 + q * 32, split + bz);
-          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-        }
-      } else if (m < p.M) {
-        const bool vec = ((p.ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dp) & 15) == 0);
-        float* drow = Dp + (long long)m * p.ldd;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const int n = nc + j4 * 4;
-          if (vec && n + 3 < p.N) *reinterpret_cast<float4*>(drow + n) = o[j4];
-          else {
-            const float x[4] = {o[j4].x, o[j4].y, o[j4].z, o[j4].w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) if (n + u < p.N) drow[n + u] = x[u];
-          }
-        }
-      }
+      // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
     }
     if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");  // smem must outlive the reads
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
+#undef TILE_COORDS
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -355,7 +400,14 @@ int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb
     if (int s = set_smem_attr<A_MN, B_MN>()) return s;
     attr_set = true;
   }
-  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BLOCK_N - 1) / BLOCK_N, a.batch > 1 ? a.batch : a.splits);
+  const long long tiles = (long long)((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N) * (a.batch > 1 ? a.batch : a.splits);
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);  // persistent: one CTA per SM, tiles dealt round-robin
   tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, td, a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;

@@ -23,16 +23,18 @@ ap.add_argument("--mem", type=int, default=1 << 20)
 ap.add_argument("--eval-every", type=int, default=25)
 ap.add_argument("--seed", type=int, default=1231)
 ap.add_argument("--sigma", type=float, default=0.1)
+ap.add_argument("--tc", type=int, default=1, help="TF32 tensor cores for the 250x500 products")
+ap.add_argument("--noise", default="gn", choices=["gn", "ou"])
 args = ap.parse_args()
 
 train = sb.series.synth_charger98(4320, seed=98)
 evals = sb.series.synth_charger98(1440, seed=99)
 env = sb.Shems(72, train, n_envs=args.envs)
 ev = sb.Shems(72, evals, n_envs=1024)          # evaluation: 1024 random 72-step windows of the eval series, deterministic policy
-le = sb.Learner(params=sb.default_ddpg_params(batch=args.batch))   # γ=0.99, τ=1e-3, η=1e-4/1e-3, 250/500 (README.md:68-86)
+le = sb.Learner(params=sb.default_ddpg_params(batch=args.batch, use_tensor_cores=args.tc))   # γ=0.99, τ=1e-3, η=1e-4/1e-3, 250/500 (README.md:68-86)
 le.init(args.seed)
 drv = sb.Driver(env, ev, learner=le, mem_size=args.mem, ep_length=72, sigma=args.sigma, updates_per_step=args.updates_per_step,
-                rng_run=args.seed)
+                rng_run=args.seed, noise_type=args.noise)
 t0 = time.time()
 drv.populate_memory()
 drv.min_max_buffer()
