@@ -117,6 +117,11 @@ typedef struct ShemsEnv ShemsEnv; /* N instances of `Shems` (shems_LU1.jl:169-17
 SHEMS_API int32_t shems_create(const ShemsParams* params, const float* series_host,
                                int32_t nrows, int32_t maxsteps, int64_t n_envs,
                                int32_t device, ShemsEnv** out);
+/* The same for n_groups (<= 16) groups of instances: group g = group_sizes[g] consecutive instances with the constants params[g]
+ * (one charger each, shems_LU1.jl:45-59) and, when series_per_group != 0, its own series (series_host [G][8][nrows], else
+ * [8][nrows] shared).  The reference needs one Julia process per charger (JOB_ID digits, shems_LU1.jl:17,45). */
+SHEMS_API int32_t shems_create_groups(const ShemsParams* params, int32_t n_groups, const int64_t* group_sizes, const float* series_host,
+                                      int32_t series_per_group, int32_t nrows, int32_t maxsteps, int32_t device, ShemsEnv** out);
 SHEMS_API int32_t shems_destroy(ShemsEnv* env);
 /* use an existing CUDA stream (cudaStream_t) for all launches of this handle */
 SHEMS_API int32_t shems_set_stream(ShemsEnv* env, void* cuda_stream);
@@ -197,6 +202,11 @@ SHEMS_API int64_t replay_capacity(const ShemsReplay* rp);
 SHEMS_API int32_t replay_push(ShemsReplay* rp, const float* s_dev /*[9][n]*/, const float* a_dev /*[2][n]*/,
                               const float* r_dev /*[n]*/, const float* s2_dev /*[9][n]*/,
                               const float* done_dev /*[n] or NULL*/, int64_t n);
+/* remember() for a population of learners in one launch: the arrays are structure-of-arrays over all N = n_groups*n_per instances
+ * ([9][N], [2][N], [N]; what an environment handle with N instances produces); learner l = instances l*n_per .. l*n_per+n_per-1
+ * pushes its n_per transitions into rps[l].  All memories must live on one device; rps[0]'s stream is used. */
+SHEMS_API int32_t replay_push_groups(ShemsReplay* const* rps, int32_t n_groups, const float* s_dev, const float* a_dev, const float* r_dev,
+                                     const float* s2_dev, const float* done_dev, int64_t n_per);
 /* getData(batch) (memory_plotting_saving.jl:31-42): i.i.d. WITH replacement.
  * idx_host != NULL: the caller's 0-based logical indices (0 = oldest), else Philox(seed).
  * Outputs are device arrays [9][B], [2][B], [B], [9][B], [B]. */
@@ -256,6 +266,11 @@ SHEMS_API int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* s
  *   when sigma > 0 (GNoise, DDPG.jl:57-61), no noise when sigma == 0 (train == false). */
 SHEMS_API int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step,
                            int64_t env_id_base, const float* noise_dev, float* a_dev, float* scaled_dev);
+/* ddpg_act with every array laid out as ONE structure-of-arrays over all N = P*n instances of a population (learner l owns
+ * instances l*n .. l*n+n-1): obs_dev [9][N] is the state array of an environment handle (shems_state_ptr), scaled_dev [2][N] the
+ * action array shems_step takes, noise_dev / a_dev [2][N].  For P == 1 it equals ddpg_act. */
+SHEMS_API int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                               const float* noise_dev, float* a_dev, float* scaled_dev);
 /* act() with Ornstein-Uhlenbeck exploration noise (noise_type == "ou": sample_noise(ou::OUNoise) DDPG.jl:49-55, :157-158;
  * OUNoise(μ, σ, θ, dt, X) input.jl:190-234).  ou_x_dev [2][n] is OUNoise.X of every instance, read and advanced in place
  * (the reference never resets it, not even between episodes); z_dev [2][n]: the standard normal draws randn(2) (Float64)

@@ -14,7 +14,7 @@ def __getattr__(name):  # torch-dependent parts are imported lazily (the ABI/sym
     if name in ("Shems", "ShemsAction", "reset_", "step_", "action", "finished", "state", "actions"):
         from . import env
         return getattr(env, name)
-    if name in ("Replay", "Learner", "Driver"):
+    if name in ("Replay", "Learner", "Driver", "PopulationDriver"):
         from . import ddpg
         return getattr(ddpg, name)
     raise AttributeError(name)

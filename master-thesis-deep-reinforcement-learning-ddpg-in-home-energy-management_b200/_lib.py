@@ -66,6 +66,7 @@ SIGNATURES = {
     "shems_device_count": (I32, []),
     "shems_params_for_charger": (I32, [I32, C.POINTER(ShemsParams)]),
     "shems_create": (I32, [C.POINTER(ShemsParams), PF, I32, I32, I64, I32, C.POINTER(VP)]),
+    "shems_create_groups": (I32, [C.POINTER(ShemsParams), I32, C.POINTER(I64), PF, I32, I32, I32, I32, C.POINTER(VP)]),
     "shems_destroy": (I32, [VP]),
     "shems_set_stream": (I32, [VP, VP]),
     "shems_sync": (I32, [VP]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "replay_length": (I64, [VP]),
     "replay_capacity": (I64, [VP]),
     "replay_push": (I32, [VP, VP, VP, VP, VP, VP, I64]),
+    "replay_push_groups": (I32, [C.POINTER(VP), I32, VP, VP, VP, VP, VP, I64]),
     "replay_sample": (I32, [VP, I32, PI, U64, VP, VP, VP, VP, VP]),
     "replay_minmax": (I32, [VP, I64, PI, U64, PF, PF]),
     "replay_get": (I32, [VP, PF, PF, PF, PF, PF]),
@@ -102,6 +104,7 @@ SIGNATURES = {
     "ddpg_num_params": (I64, [VP, I32]),
     "ddpg_set_norm": (I32, [VP, PF, PF]),
     "ddpg_act": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
+    "ddpg_act_soa": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
     "ddpg_act_ou": (I32, [VP, VP, I64, F32, F32, F32, F32, VP, U64, I64, I64, VP, VP, VP]),
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),

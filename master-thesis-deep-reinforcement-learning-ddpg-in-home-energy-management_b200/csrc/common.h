@@ -74,6 +74,8 @@ struct DevParams {
 __host__ __device__ __forceinline__ size_t ring_base(long long slot) { return ((size_t)(slot >> 5) * RING_FIELDS) * 32 + (size_t)(slot & 31); }
 __host__ __device__ __forceinline__ size_t ring_off(long long slot, int k) { return ring_base(slot) + (size_t)k * 32; }
 
+#define SHEMS_MAX_GROUPS 16
+
 struct ShemsReplay {
   int device;
   cudaStream_t stream;
@@ -82,6 +84,7 @@ struct ShemsReplay {
   int32_t* idx_scratch;  // device scratch for sampled indices
   int64_t idx_scratch_n;
   float* minmax_scratch; // [18]
+  void* group_refs; int group_refs_n;  // device scratch of replay_push_groups (ring / capacity / head of every learner's memory)
 };
 
 struct ShemsEnv {
@@ -100,6 +103,11 @@ struct ShemsEnv {
   bool was_reset;
   bool consistent;    // state fields 2..8 equal series row idx (false after shems_set_state)
   int32_t* scratch_i; float* scratch_f; // staging for reset host draws
+  // groups of instances with their own constants (several chargers in one handle): group g = instances gstart[g] .. gstart[g+1]-1
+  int n_groups;
+  DevParams gdp[SHEMS_MAX_GROUPS];
+  float4* gseries[SHEMS_MAX_GROUPS];
+  long long gstart[SHEMS_MAX_GROUPS + 1];
 };
 
 int replay_after_rollout(ShemsReplay* rp, int64_t n_written);

@@ -1472,31 +1472,34 @@ extern "C" int32_t ddpg_get_losses(Ddpg* h, float* loss_crit, float* loss_act) {
 // normalize (memory_plotting_saving.jl:55-57) of SoA obs [9][n] -> x [n][9]
 __global__ void __launch_bounds__(256)
 ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* __restrict__ norm, float* __restrict__ x, long long pop_stride,
-                      long long act_stride) {
+                      long long act_stride, long long osl, long long osk) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  obs += (long long)blockIdx.y * 9 * n; norm += (long long)blockIdx.y * pop_stride; x += (long long)blockIdx.y * act_stride;  // learner
+  // learner l = blockIdx.y; state field k of its instance j sits at obs[l*osl + k*osk + j]
+  // (packed [P][9][n]: osl = 9n, osk = n; one SoA over all N = P*n instances, as an env handle stores it: osl = n, osk = N)
+  obs += (long long)blockIdx.y * osl; norm += (long long)blockIdx.y * pop_stride; x += (long long)blockIdx.y * act_stride;
 #pragma unroll
   for (int k = 0; k < 9; ++k) {
     const float den = __fadd_rn(__fsub_rn(norm[9 + k], norm[k]), 1e-8f);
-    x[j * 9 + k] = __fdiv_rn(__fsub_rn(obs[k * n + j], norm[k]), den);
+    x[j * 9 + k] = __fdiv_rn(__fsub_rn(obs[k * osk + j], norm[k]), den);
   }
 }
 // clamp(actor + noise, -1, 1) and scale_action (DDPG.jl:172-184); noise: given, or σ·N(0,1) by Box-Muller on Philox
 __global__ void __launch_bounds__(256)
 ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float sigma, unsigned long long seed, long long step,
                          long long env_id_base, const float* __restrict__ noise, float lo0, float lo1, float hi0, float hi1,
-                         float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride) {
+                         float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride, long long asl, long long ask) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  {  // blockIdx.y = learner of a population: arrays carry a leading [pop] dimension, noise streams are keyed by the global env id
+  {  // blockIdx.y = learner l of a population: component k of its instance j sits at [l*asl + k*ask + j] in noise / a / scaled
+     // (packed [P][2][n]: asl = 2n, ask = n; SoA over all instances: asl = n, ask = N); noise streams are keyed by the global env id
     const long long l = blockIdx.y;
-    y += l * act_stride; a_out += l * 2 * n; env_id_base += l * n;
-    if (noise) noise += l * 2 * n;
-    if (scaled_out) scaled_out += l * 2 * n;
+    y += l * act_stride; a_out += l * asl; env_id_base += l * n;
+    if (noise) noise += l * asl;
+    if (scaled_out) scaled_out += l * asl;
   }
   float nz0 = 0.0f, nz1 = 0.0f;
-  if (noise) { nz0 = noise[j]; nz1 = noise[n + j]; }
+  if (noise) { nz0 = noise[j]; nz1 = noise[ask + j]; }
   else if (sigma > 0.0f) {
     uint32_t w[4];
     philox4x32_10(seed, (uint64_t)(env_id_base + j), (uint32_t)step, STREAM_NOISE, w);
@@ -1510,11 +1513,11 @@ ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, fl
   float a0 = __fadd_rn(y[j * 2 + 0], nz0), a1 = __fadd_rn(y[j * 2 + 1], nz1);
   a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
   a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
-  a_out[j] = a0; a_out[n + j] = a1;
+  a_out[j] = a0; a_out[ask + j] = a1;
   if (scaled_out) {  // Float32.(LO .+ (a .+ 1.0) .* 0.5 .* (HI .- LO)) in Float64
     const double sp0 = (double)__fsub_rn(hi0, lo0), sp1 = (double)__fsub_rn(hi1, lo1);
     scaled_out[j] = (float)__dadd_rn((double)lo0, __dmul_rn(__dmul_rn(__dadd_rn((double)a0, 1.0), 0.5), sp0));
-    scaled_out[n + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
+    scaled_out[ask + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
   }
 }
 
@@ -1568,7 +1571,7 @@ ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n,
 }
 
 // actor(normalize(s)) for n states per learner -> h->act_y [n][2] (pre-noise); shared by the noise variants of act()
-static int act_forward(Ddpg* h, const float* obs_dev, int64_t n) {
+static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, long long osk) {
   const int l1 = h->ld1, l2 = h->ld2, pop = h->pop;
   if (h->act_cap < n) {  // scratch: per learner [x n*9 | h1 n*ld1 | h2 n*ld2 | y n*2], each part at a 256-byte boundary
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1581,7 +1584,7 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n) {
     h->act_cap = n;
   }
   const dim3 gn((unsigned)((n + 255) / 256), pop);
-  ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x, h->pop_stride, h->act_stride);
+  ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x, h->pop_stride, h->act_stride, osl, osk);
   CUDA_TRY(cudaGetLastError());
   const NetDims& da = h->dims[0];
   const float* actor = h->net[DDPG_NET_ACTOR];
@@ -1603,17 +1606,29 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n) {
   return SHEMS_OK;
 }
 
-extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
-                            const float* noise_dev, float* a_dev, float* scaled_dev) {
+static int act_gauss(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                     const float* noise_dev, float* a_dev, float* scaled_dev, bool soa) {
   REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
   GUARD(h->device);
-  TRY(act_forward(h, obs_dev, n));
+  const long long N = (long long)n * h->pop;
+  TRY(act_forward(h, obs_dev, n, soa ? n : 9 * n, soa ? N : n));
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
-                                                      h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev, h->act_stride);
+                                                      h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev, h->act_stride, soa ? n : 2 * n,
+                                                      soa ? N : n);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
+}
+extern "C" int32_t ddpg_act(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                            const float* noise_dev, float* a_dev, float* scaled_dev) {
+  return act_gauss(h, obs_dev, n, sigma, seed, step, env_id_base, noise_dev, a_dev, scaled_dev, false);
+}
+// the same with every array laid out as ONE structure-of-arrays over all N = P*n instances of the population (learner l owns
+// instances l*n .. l*n+n-1): obs [9][N] is exactly the state array of an environment handle, scaled_dev [2][N] its action input
+extern "C" int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
+                                const float* noise_dev, float* a_dev, float* scaled_dev) {
+  return act_gauss(h, obs_dev, n, sigma, seed, step, env_id_base, noise_dev, a_dev, scaled_dev, true);
 }
 
 extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
@@ -1622,7 +1637,7 @@ extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float t
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act_ou: n=%lld", (long long)n);
   REQUIRE(dt >= 0.0f, SHEMS_ERR_INVALID, "ddpg_act_ou: dt=%g (sqrt(dt) raises DomainError in the reference)", (double)dt);
   GUARD(h->device);
-  TRY(act_forward(h, obs_dev, n));
+  TRY(act_forward(h, obs_dev, n, 9 * n, n));
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_ou_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, theta, mu, sigma, dt, ou_x_dev, seed, step, env_id_base, z_dev,
                                                          h->p.act_lo[0], h->p.act_lo[1], h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev,

@@ -122,10 +122,11 @@ __device__ __forceinline__ Row8 load_row(const float4* __restrict__ series, int 
 __global__ void __launch_bounds__(256)
 shems_reset_kernel(DevParams P, const float4* __restrict__ series, int nrows, int maxsteps, long long N, int mode,
                    const int32_t* __restrict__ idx0_in, const float* __restrict__ socb0_in, unsigned long long seed,
-                   long long env_id_base, float* __restrict__ obs, int32_t* __restrict__ idx_out, int32_t* __restrict__ maxidx) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                   long long env_id_base, float* __restrict__ obs, int32_t* __restrict__ idx_out, int32_t* __restrict__ maxidx,
+                   long long n0, long long n1) {
+  const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // this launch covers one group: instances n0 .. n1-1
   int idx = 1;
-  if (n < N) {
+  if (n < n1) {
     const int hi = nrows - maxsteps;
     float Soc_b;
     if (mode == SHEMS_RESET_DETERMINISTIC) {  // rng == -1, :220-222
@@ -187,9 +188,9 @@ template <bool FROM_SERIES, bool WANT_TRACE>
 __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                   int32_t* __restrict__ idx_arr, const float* __restrict__ act, int track_neg,
-                  float* __restrict__ reward_out, float* __restrict__ obs_out, double* __restrict__ trace) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+                  float* __restrict__ reward_out, float* __restrict__ obs_out, double* __restrict__ trace, long long n0, long long n1) {
+  const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n1) return;
   const int idx = idx_arr[n];
   const float a0 = act[n], a1 = act[N + n];
   StepIn s;
@@ -248,9 +249,10 @@ shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, f
 // action(env, track) / action(env, a) for all instances
 template <bool RULE>
 __global__ void __launch_bounds__(256)
-shems_action_kernel(DevParams P, long long N, const float* __restrict__ obs, const float* __restrict__ target, float* __restrict__ bev) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+shems_action_kernel(DevParams P, long long N, const float* __restrict__ obs, const float* __restrict__ target, float* __restrict__ bev,
+                    long long n0, long long n1) {
+  const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n1) return;
   float B, EV;
   if (RULE) shems_action_rule(P, obs[0 * N + n], obs[1 * N + n], obs[3 * N + n], obs[4 * N + n], B, EV);
   else shems_action_drl(P, obs[0 * N + n], obs[1 * N + n], obs[2 * N + n], obs[3 * N + n], obs[4 * N + n], target[n], target[N + n], B, EV);
@@ -283,9 +285,9 @@ template <int POLICY, bool WANT_TRACE>
 __global__ void __launch_bounds__(ROLLOUT_THREADS, ROLLOUT_MIN_BLOCKS)
 shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                      int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
-                     const float* __restrict__ tape, RolloutSinks S) {
-  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+                     const float* __restrict__ tape, RolloutSinks S, long long n0, long long n1) {
+  const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n1) return;
   int idx = idx_arr[n];
   float st[9];
 #pragma unroll
@@ -372,11 +374,18 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
 // ----------------------------------------------------------------------------- C ABI
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 
-extern "C" int32_t shems_create(const ShemsParams* params, const float* series_host, int32_t nrows, int32_t maxsteps,
-                                int64_t n_envs, int32_t device, ShemsEnv** out) {
-  REQUIRE(params && series_host && out, SHEMS_ERR_INVALID, "shems_create: NULL argument");
-  REQUIRE(nrows >= 2 && maxsteps >= 1 && n_envs >= 1, SHEMS_ERR_INVALID, "shems_create: nrows=%d maxsteps=%d n_envs=%lld", nrows,
-          maxsteps, (long long)n_envs);
+// Shems(maxsteps, path) for G groups of instances (group g: group_sizes[g] consecutive instances with params[g] and, when
+// series_per_group, its own series): several chargers in one handle.  Every kernel is launched once per group on its slice.
+extern "C" int32_t shems_create_groups(const ShemsParams* params, int32_t n_groups, const int64_t* group_sizes, const float* series_host,
+                                       int32_t series_per_group, int32_t nrows, int32_t maxsteps, int32_t device, ShemsEnv** out) {
+  REQUIRE(params && series_host && out && group_sizes, SHEMS_ERR_INVALID, "shems_create: NULL argument");
+  REQUIRE(n_groups >= 1 && n_groups <= SHEMS_MAX_GROUPS, SHEMS_ERR_INVALID, "shems_create: n_groups=%d (1..%d)", n_groups, SHEMS_MAX_GROUPS);
+  int64_t n_envs = 0;
+  for (int g = 0; g < n_groups; ++g) {
+    REQUIRE(group_sizes[g] >= 1, SHEMS_ERR_INVALID, "shems_create: group_sizes[%d]=%lld", g, (long long)group_sizes[g]);
+    n_envs += group_sizes[g];
+  }
+  REQUIRE(nrows >= 2 && maxsteps >= 1, SHEMS_ERR_INVALID, "shems_create: nrows=%d maxsteps=%d", nrows, maxsteps);
   REQUIRE(nrows - maxsteps >= 1, SHEMS_ERR_INVALID,
           "shems_create: nrows - maxsteps = %d < 1: rand(1:(nrow-maxsteps)) would be empty (shems_LU1.jl:225)", nrows - maxsteps);
   REQUIRE(shems_device_count() > 0, SHEMS_ERR_CUDA, "shems_create: no CUDA device (this library has no CPU fallback)");
@@ -384,14 +393,17 @@ extern "C" int32_t shems_create(const ShemsParams* params, const float* series_h
   ShemsEnv* e = new (std::nothrow) ShemsEnv();
   REQUIRE(e, SHEMS_ERR_INVALID, "shems_create: out of host memory");
   memset(e, 0, sizeof(*e));
-  e->device = device; e->stream = 0; e->params = *params; e->dp = make_dev_params(*params);
+  e->device = device; e->stream = 0; e->params = params[0]; e->dp = make_dev_params(params[0]);
   e->nrows = nrows; e->maxsteps = maxsteps; e->n = n_envs; e->max_idx = 1; e->consistent = true;
+  e->n_groups = n_groups;
+  const int n_series = series_per_group ? n_groups : 1;
   // interleave the 8 columns into 32-byte rows
-  std::vector<float> rows((size_t)nrows * 8);
-  for (int r = 0; r < nrows; ++r)
-    for (int c = 0; c < 8; ++c) rows[(size_t)r * 8 + c] = series_host[(size_t)c * nrows + r];
+  std::vector<float> rows((size_t)n_series * nrows * 8);
+  for (int g = 0; g < n_series; ++g)
+    for (int r = 0; r < nrows; ++r)
+      for (int c = 0; c < 8; ++c) rows[((size_t)g * nrows + r) * 8 + c] = series_host[((size_t)g * 8 + c) * nrows + r];
   cudaError_t st = cudaSuccess;
-  if ((st = cudaMalloc(&e->series, sizeof(float) * 8 * (size_t)nrows)) != cudaSuccess ||
+  if ((st = cudaMalloc(&e->series, sizeof(float) * rows.size())) != cudaSuccess ||
       (st = cudaMalloc(&e->obs, sizeof(float) * 9 * (size_t)n_envs)) != cudaSuccess ||
       (st = cudaMalloc(&e->idx, sizeof(int32_t) * (size_t)n_envs)) != cudaSuccess ||
       (st = cudaMalloc(&e->d_maxidx, sizeof(int32_t))) != cudaSuccess ||
@@ -402,8 +414,19 @@ extern "C" int32_t shems_create(const ShemsParams* params, const float* series_h
     shems_destroy(e);
     return SHEMS_ERR_CUDA;
   }
+  for (int g = 0; g < n_groups; ++g) {
+    e->gdp[g] = make_dev_params(params[g]);
+    e->gseries[g] = e->series + (series_per_group ? (size_t)g * nrows * 2 : 0);
+    e->gstart[g + 1] = e->gstart[g] + group_sizes[g];
+  }
   *out = e;
   return SHEMS_OK;
+}
+
+extern "C" int32_t shems_create(const ShemsParams* params, const float* series_host, int32_t nrows, int32_t maxsteps,
+                                int64_t n_envs, int32_t device, ShemsEnv** out) {
+  REQUIRE(n_envs >= 1, SHEMS_ERR_INVALID, "shems_create: n_envs=%lld", (long long)n_envs);
+  return shems_create_groups(params, 1, &n_envs, series_host, 0, nrows, maxsteps, device, out);
 }
 
 extern "C" int32_t shems_destroy(ShemsEnv* e) {
@@ -457,8 +480,11 @@ extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_ho
     CUDA_TRY(cudaMemcpyAsync(e->scratch_f, socb0_host, sizeof(float) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
   }
   CUDA_TRY(cudaMemsetAsync(e->d_maxidx, 0, sizeof(int32_t), e->stream));
-  shems_reset_kernel<<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->series, e->nrows, e->maxsteps, e->n, mode, e->scratch_i,
-                                                                e->scratch_f, seed, env_id_base, e->obs, e->idx, e->d_maxidx);
+  for (int g = 0; g < e->n_groups; ++g) {
+    const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
+    shems_reset_kernel<<<grid_for(n1 - n0, 256), 256, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->nrows, e->maxsteps, e->n, mode, e->scratch_i,
+                                                                     e->scratch_f, seed, env_id_base, e->obs, e->idx, e->d_maxidx, n0, n1);
+  }
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(&e->max_idx, e->d_maxidx, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -476,12 +502,15 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
     return SHEMS_ERR_BOUNDS;
   }
   GUARD(e->device);
-  const unsigned g = grid_for(e->n, STEP_THREADS);
   const int tn = track < 0 ? 1 : 0;
-#define LAUNCH_STEP(FS, TR) \
-  shems_step_kernel<FS, TR><<<g, STEP_THREADS, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, act_dev, tn, reward_dev, obs_dev, trace_dev)
-  if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
-  else { if (trace_dev) LAUNCH_STEP(false, true); else LAUNCH_STEP(false, false); }
+#define LAUNCH_STEP(FS, TR)                                                                                                             \
+  shems_step_kernel<FS, TR><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, \
+                                                                                            act_dev, tn, reward_dev, obs_dev, trace_dev, n0, n1)
+  for (int g = 0; g < e->n_groups; ++g) {
+    const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
+    if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
+    else { if (trace_dev) LAUNCH_STEP(false, true); else LAUNCH_STEP(false, false); }
+  }
 #undef LAUNCH_STEP
   CUDA_TRY(cudaGetLastError());
   e->max_idx += 1;
@@ -493,14 +522,18 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
 extern "C" int32_t shems_action_rule(ShemsEnv* e, float* bev_dev) {
   REQUIRE(e && bev_dev, SHEMS_ERR_INVALID, "shems_action_rule: NULL argument");
   GUARD(e->device);
-  shems_action_kernel<true><<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->n, e->obs, nullptr, bev_dev);
+  for (int g = 0; g < e->n_groups; ++g)
+    shems_action_kernel<true><<<grid_for(e->gstart[g + 1] - e->gstart[g], 256), 256, 0, e->stream>>>(e->gdp[g], e->n, e->obs, nullptr, bev_dev,
+                                                                                                    e->gstart[g], e->gstart[g + 1]);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 extern "C" int32_t shems_action_drl(ShemsEnv* e, const float* target_dev, float* bev_dev) {
   REQUIRE(e && target_dev && bev_dev, SHEMS_ERR_INVALID, "shems_action_drl: NULL argument");
   GUARD(e->device);
-  shems_action_kernel<false><<<grid_for(e->n, 256), 256, 0, e->stream>>>(e->dp, e->n, e->obs, target_dev, bev_dev);
+  for (int g = 0; g < e->n_groups; ++g)
+    shems_action_kernel<false><<<grid_for(e->gstart[g + 1] - e->gstart[g], 256), 256, 0, e->stream>>>(e->gdp[g], e->n, e->obs, target_dev, bev_dev,
+                                                                                                     e->gstart[g], e->gstart[g + 1]);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -565,15 +598,17 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
     REQUIRE(e->n <= rp->capacity, SHEMS_ERR_INVALID, "shems_rollout: replay capacity %lld < n_envs %lld", (long long)rp->capacity, (long long)e->n);
     S.ring = rp->ring; S.cap = rp->capacity; S.head = rp->head;
   }
-  const unsigned gro = grid_for(e->n, ROLLOUT_THREADS);
 #define LAUNCH_RO(POL, TR)                                                                                                          \
-  shems_rollout_kernel<POL, TR><<<gro, ROLLOUT_THREADS, 0, e->stream>>>(e->dp, e->series, e->n, e->obs, e->idx, a->n_steps, e->step, a->seed,     \
-                                                          a->env_id_base, a->tape_dev, S)
+  shems_rollout_kernel<POL, TR><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                                  \
+      e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, a->n_steps, e->step, a->seed, a->env_id_base, a->tape_dev, S, n0, n1)
   const bool tr = a->trace_dev != nullptr;
-  switch (a->policy) {
-    case SHEMS_POLICY_RULE: if (tr) LAUNCH_RO(SHEMS_POLICY_RULE, true); else LAUNCH_RO(SHEMS_POLICY_RULE, false); break;
-    case SHEMS_POLICY_RANDOM: if (tr) LAUNCH_RO(SHEMS_POLICY_RANDOM, true); else LAUNCH_RO(SHEMS_POLICY_RANDOM, false); break;
-    default: if (tr) LAUNCH_RO(SHEMS_POLICY_TAPE, true); else LAUNCH_RO(SHEMS_POLICY_TAPE, false); break;
+  for (int g = 0; g < e->n_groups; ++g) {
+    const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
+    switch (a->policy) {
+      case SHEMS_POLICY_RULE: if (tr) LAUNCH_RO(SHEMS_POLICY_RULE, true); else LAUNCH_RO(SHEMS_POLICY_RULE, false); break;
+      case SHEMS_POLICY_RANDOM: if (tr) LAUNCH_RO(SHEMS_POLICY_RANDOM, true); else LAUNCH_RO(SHEMS_POLICY_RANDOM, false); break;
+      default: if (tr) LAUNCH_RO(SHEMS_POLICY_TAPE, true); else LAUNCH_RO(SHEMS_POLICY_TAPE, false); break;
+    }
   }
 #undef LAUNCH_RO
   CUDA_TRY(cudaGetLastError());

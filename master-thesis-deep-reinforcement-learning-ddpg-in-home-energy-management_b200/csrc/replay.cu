@@ -34,7 +34,7 @@ extern "C" int32_t replay_create(int64_t capacity, int32_t device, ShemsReplay**
 extern "C" int32_t replay_destroy(ShemsReplay* rp) {
   if (!rp) return SHEMS_OK;
   GUARD(rp->device);
-  cudaFree(rp->ring); cudaFree(rp->idx_scratch); cudaFree(rp->minmax_scratch);
+  cudaFree(rp->ring); cudaFree(rp->idx_scratch); cudaFree(rp->minmax_scratch); cudaFree(rp->group_refs);
   delete rp;
   return SHEMS_OK;
 }
@@ -84,6 +84,59 @@ extern "C" int32_t replay_push(ShemsReplay* rp, const float* s_dev, const float*
                                                                            done_dev, n, first);
   CUDA_TRY(cudaGetLastError());
   return replay_after_rollout(rp, n);
+}
+
+// remember() for a population: arrays are SoA over all N = P*n_per instances, learner l = instances l*n_per .. l*n_per+n_per-1
+// pushes its slice into its own ring (blockIdx.y = learner)
+struct RingRef { float* ring; long long cap, head; };
+__global__ void __launch_bounds__(256)
+replay_push_groups_kernel(const RingRef* __restrict__ refs, const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ r,
+                          const float* __restrict__ s2, const float* __restrict__ done, long long n_per, long long N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_per) return;
+  const RingRef ref = refs[blockIdx.y];
+  const long long g = (long long)blockIdx.y * n_per + i;  // global instance
+  long long slot = ref.head + i;
+  slot -= (slot / ref.cap) * ref.cap;
+  float* q = ref.ring + ring_base(slot);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) q[(RING_S + k) * 32] = s[k * N + g];
+  q[(RING_A + 0) * 32] = a[g];
+  q[(RING_A + 1) * 32] = a[N + g];
+  q[RING_R * 32] = r[g];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) q[(RING_S2 + k) * 32] = s2[k * N + g];
+  q[RING_DONE * 32] = done ? done[g] : 0.0f;
+}
+
+extern "C" int32_t replay_push_groups(ShemsReplay* const* rps, int32_t n_groups, const float* s_dev, const float* a_dev, const float* r_dev,
+                                      const float* s2_dev, const float* done_dev, int64_t n_per) {
+  REQUIRE(rps && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "replay_push_groups: NULL argument");
+  REQUIRE(n_groups >= 1 && n_per >= 1, SHEMS_ERR_INVALID, "replay_push_groups: n_groups=%d n_per=%lld", n_groups, (long long)n_per);
+  ShemsReplay* r0 = rps[0];
+  REQUIRE(r0, SHEMS_ERR_INVALID, "replay_push_groups: rps[0] is NULL");
+  GUARD(r0->device);
+  std::vector<RingRef> refs((size_t)n_groups);
+  for (int g = 0; g < n_groups; ++g) {
+    ShemsReplay* rp = rps[g];
+    REQUIRE(rp && rp->device == r0->device, SHEMS_ERR_INVALID, "replay_push_groups: rps[%d] missing or on another device", g);
+    REQUIRE(n_per <= rp->capacity, SHEMS_ERR_INVALID, "replay_push_groups: n_per=%lld exceeds the capacity %lld of rps[%d]", (long long)n_per,
+            (long long)rp->capacity, g);
+    refs[g].ring = rp->ring; refs[g].cap = rp->capacity; refs[g].head = rp->head;
+  }
+  if (r0->group_refs_n < n_groups) {
+    CUDA_TRY(cudaStreamSynchronize(r0->stream));
+    cudaFree(r0->group_refs); r0->group_refs = nullptr; r0->group_refs_n = 0;
+    CUDA_TRY(cudaMalloc(&r0->group_refs, sizeof(RingRef) * (size_t)n_groups));
+    r0->group_refs_n = n_groups;
+  }
+  CUDA_TRY(cudaMemcpyAsync(r0->group_refs, refs.data(), sizeof(RingRef) * (size_t)n_groups, cudaMemcpyHostToDevice, r0->stream));
+  replay_push_groups_kernel<<<dim3((unsigned)((n_per + 255) / 256), n_groups), 256, 0, r0->stream>>>((const RingRef*)r0->group_refs, s_dev, a_dev,
+                                                                                                r_dev, s2_dev, done_dev, n_per,
+                                                                                                n_per * n_groups);
+  CUDA_TRY(cudaGetLastError());
+  for (int g = 0; g < n_groups; ++g) replay_after_rollout(rps[g], n_per);
+  return SHEMS_OK;
 }
 
 // getData(): gather B sampled transitions into SoA minibatch arrays [k][B].

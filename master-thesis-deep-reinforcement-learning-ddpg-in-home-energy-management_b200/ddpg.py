@@ -172,15 +172,24 @@ class Learner:
         mn, mx = np.ascontiguousarray(s_min, np.float32), np.ascontiguousarray(s_max, np.float32)
         L.check(self.lib.ddpg_set_norm(self._h, mn.ctypes.data_as(L.PF), mx.ctypes.data_as(L.PF)))
 
-    def act(self, obs, train=True, sigma=0.1, rng_act=0, step=0, env_id_base=0, noise=None):
-        """act(normalize(s); train) + scale_action for obs [9][n] -> (a [2][n] in [-1,1], scaled [2][n])."""
-        n = obs.shape[-1]
-        shape = (2, n) if self.population == 1 else (self.population, 2, n)   # population: obs [P][9][n] -> [P][2][n]
-        assert obs.numel() == 9 * n * self.population
+    def act(self, obs, train=True, sigma=0.1, rng_act=0, step=0, env_id_base=0, noise=None, soa=False):
+        """act(normalize(s); train) + scale_action for obs [9][n] -> (a [2][n] in [-1,1], scaled [2][n]).
+        Population handles: obs [P][9][n] -> [P][2][n]; with soa=True every array is one SoA over all N = P*n instances
+        (obs [9][N] = the state tensor of an environment handle, outputs [2][N] = what its step() takes)."""
+        if soa:
+            N = obs.shape[-1]
+            n = N // self.population
+            assert obs.numel() == 9 * N and n * self.population == N
+            shape = (2, N)
+        else:
+            n = obs.shape[-1]
+            shape = (2, n) if self.population == 1 else (self.population, 2, n)
+            assert obs.numel() == 9 * n * self.population
         a = torch.empty(shape, dtype=torch.float32, device=self._dev)
         sc = torch.empty(shape, dtype=torch.float32, device=self._dev)
         sg = float(sigma) if (train and noise is None) else 0.0
-        L.check(self.lib.ddpg_act(self._h, _ptr(obs), n, sg, int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(noise), _ptr(a), _ptr(sc)))
+        fn = self.lib.ddpg_act_soa if soa else self.lib.ddpg_act
+        L.check(fn(self._h, _ptr(obs), n, sg, int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(noise), _ptr(a), _ptr(sc)))
         return a, sc
 
     def act_ou(self, obs, ou_x, theta=0.15, mu=0.0, sigma=0.1, dt=1e-2, rng_act=0, step=0, env_id_base=0, z=None):
@@ -381,3 +390,85 @@ class Driver:
             out = env.rollout(L.POLICY_RULE, num_steps, want_trace=True)
             return out["ep_return"], out["trace"]
         return self.episode(env, num_steps=num_steps, train=False, track=track, rng_ep=-1)
+
+
+def push_groups(mems, s, a, r, s2, done=None):
+    """remember() for a population in one launch: SoA arrays over all N = P*n_per instances, learner l's slice -> mems[l]."""
+    P = len(mems)
+    n_per = r.numel() // P
+    hs = (C.c_void_p * P)(*[m._h for m in mems])
+    L.check(mems[0].lib.replay_push_groups(hs, P, _ptr(s), _ptr(a), _ptr(r), _ptr(s2), _ptr(done), n_per))
+
+
+class PopulationDriver:
+    """BASELINE configs[4]: P independent DDPG runs (the reference launches one Julia process per seed / JOB_ID,
+    RL-SHEMS_bs_scheduler_*.sh:73-81) advanced together.  Learner l owns n_envs environment instances (its charger's capacities,
+    its own seed), a replay memory and normalisation constants.  All instances live in ONE environment handle (one group per
+    run of equal chargers), so a vector step is: act (population) -> step (one launch per charger) -> remember (one launch)
+    -> replay() (population).
+
+    chargers[l] is learner l's charger id (shems_LU1.jl:47-59), equal ids must be adjacent; seeds[l] its rng_run (input.jl:136)."""
+
+    def __init__(self, series, chargers, seeds, n_envs=64, mem_size=24_000, ep_length=72, sigma=0.1, device=0, use_tensor_cores=1, **ddpg_kw):
+        from .env import Shems
+        assert len(chargers) == len(seeds)
+        self.P, self.n_envs, self.ep_length, self.sigma, self.mem_size = len(chargers), int(n_envs), int(ep_length), float(sigma), int(mem_size)
+        self.seeds = [int(x) for x in seeds]
+        self.chargers = [int(c) for c in chargers]
+        groups = []                                      # runs of equal chargers -> instance groups
+        for c in self.chargers:
+            if groups and groups[-1][0] == c:
+                groups[-1][1] += self.n_envs
+            else:
+                groups.append([c, self.n_envs])
+        assert len({c for c, _ in groups}) == len(groups), "learners of the same charger must be adjacent"
+        self.env = Shems(ep_length, series, device=device, env_id_base=self.seeds[0] * self.n_envs, groups=groups)
+        self.N = self.env.n_envs
+        self.mems = [Replay(mem_size, device=device) for _ in range(self.P)]
+        self.learner = Learner(params=L.default_ddpg_params(population=self.P, use_tensor_cores=use_tensor_cores, **ddpg_kw), device=device)
+        self.learner.init(self.seeds[0])            # learner l: Philox(seeds[0] + l)
+        self._dev = torch.device("cuda", int(device))
+        self._s_prev = torch.empty((9, self.N), dtype=torch.float32, device=self._dev)
+        self.n_env_steps = 0
+
+    def populate_memory(self):                       # memory_plotting_saving.jl:9-29 for every learner: a = 2U-1 per step, rng += 1 per episode
+        rng = self.seeds[0]
+        g = torch.Generator(device=self._dev).manual_seed(rng)
+        while len(self.mems[-1]) < self.mem_size:
+            self.env.reset(rng=rng)
+            for step in range(self.ep_length):
+                a = torch.rand((2, self.N), device=self._dev, generator=g) * 2.0 - 1.0
+                self._s_prev.copy_(self.env.state_tensor())
+                r, s2 = self.env.step((a + 1.0) * 0.5)
+                push_groups(self.mems, self._s_prev, a, r, s2)
+            rng += 1
+
+    def min_max_buffer(self):                        # driver :30, per learner
+        for l, mem in enumerate(self.mems):
+            mn, mx = mem.min_max_buffer(self.mem_size, rng_mm=self.seeds[l])
+            self.learner.select(l).set_norm(mn, mx)
+
+    def episode(self, train=True, rng_ep=0, updates_per_step=1):
+        """episode!(env; train) for every learner in lock step -> mean return per learner [P] (Float64)."""
+        env = self.env
+        env.reset(rng=rng_ep * 1009 + self.seeds[0])
+        ret = torch.zeros(self.N, dtype=torch.float64, device=self._dev)
+        for step in range(1, self.ep_length + 1):
+            rng_step = (rng_ep * 1000003 + step) & (2**63 - 1)
+            obs = env.state_tensor()
+            a, scaled = self.learner.act(obs, train=train, sigma=self.sigma, rng_act=rng_step, step=step, env_id_base=env.env_id_base, soa=True)
+            if train:
+                self._s_prev.copy_(obs)
+            r, s2 = env.step(scaled)
+            ret += r.double()
+            if train:
+                push_groups(self.mems, self._s_prev, a, r, s2)      # remember(s, a, r, s′, done) — the unscaled action (DDPG.jl:229)
+                self.learner.replay(self.mems, rng_rpl=rng_step, n_updates=updates_per_step)
+                self.n_env_steps += self.N
+        return ret.view(self.P, self.n_envs).mean(dim=1)
+
+    def evaluate_rule_based(self, rng=4242):
+        """the rule-based controller (`track = -0.5`) on the same kind of windows, mean return per learner [P]"""
+        self.env.reset(rng=rng)
+        ret = self.env.rollout(L.POLICY_RULE, self.ep_length)["ep_return"]
+        return ret.view(self.P, self.n_envs).mean(dim=1).cpu().numpy()

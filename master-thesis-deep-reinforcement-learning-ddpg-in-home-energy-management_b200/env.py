@@ -51,24 +51,40 @@ class ShemsAction:
 
 
 class Shems:
-    def __init__(self, maxsteps, path, n_envs=1, charger_id=98, device=0, params=None, env_id_base=0):
+    def __init__(self, maxsteps, path, n_envs=1, charger_id=98, device=0, params=None, env_id_base=0, groups=None):
+        """groups=[(charger_id, n_instances), ...] puts several chargers into one handle (shems_create_groups): group g owns
+        n_instances consecutive instances with charger g's capacities (the reference needs one process per charger); `path` may
+        then also be a [G][8][nrows] array with one series per group.  n_envs / charger_id / params are ignored in that case."""
         self.lib = L.lib()
         self.maxsteps = int(maxsteps)
         self.path = path if isinstance(path, str) else "<array>"
         ser = _series.load_csv(path) if isinstance(path, str) else np.ascontiguousarray(path, dtype=np.float32)
-        if ser.ndim != 2 or ser.shape[0] != 8:
-            raise ValueError("series must be float32 [8][nrows]")
+        per_group = groups is not None and ser.ndim == 3
+        if not ((ser.ndim == 2 and ser.shape[0] == 8) or (per_group and ser.shape[0] == len(groups) and ser.shape[1] == 8)):
+            raise ValueError("series must be float32 [8][nrows] (or [G][8][nrows] with groups)")
         self.series = ser
-        self.nrows = ser.shape[1]
-        self.n_envs = int(n_envs)
+        self.nrows = ser.shape[-1]
         self.device = int(device)
         self.env_id_base = int(env_id_base)
-        self.params = params if params is not None else L.params_for_charger(charger_id)
         self.a = ShemsAction()
         self.reward = None
         h = C.c_void_p()
-        L.check(self.lib.shems_create(C.byref(self.params), ser.ctypes.data_as(L.PF), self.nrows, self.maxsteps, self.n_envs,
-                                      self.device, C.byref(h)))
+        if groups is None:
+            self.n_envs = int(n_envs)
+            self.params = params if params is not None else L.params_for_charger(charger_id)
+            self.groups = None
+            L.check(self.lib.shems_create(C.byref(self.params), ser.ctypes.data_as(L.PF), self.nrows, self.maxsteps, self.n_envs,
+                                          self.device, C.byref(h)))
+        else:
+            self.groups = [(int(c), int(k)) for c, k in groups]
+            G = len(self.groups)
+            self.group_params = [L.params_for_charger(c) for c, _ in self.groups]
+            self.params = self.group_params[0]
+            self.n_envs = sum(k for _, k in self.groups)
+            pa = (L.ShemsParams * G)(*self.group_params)
+            sz = (C.c_int64 * G)(*[k for _, k in self.groups])
+            L.check(self.lib.shems_create_groups(pa, G, sz, ser.ctypes.data_as(L.PF), 1 if per_group else 0, self.nrows, self.maxsteps,
+                                                 self.device, C.byref(h)))
         self._h = h
         self._torch_dev = torch.device("cuda", self.device)
         obs_p, idx_p = C.c_void_p(), C.c_void_p()

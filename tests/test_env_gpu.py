@@ -242,3 +242,47 @@ def test_tracker_csv_and_checkpoint_roundtrip(sb, charger98_test_series, cuda_ok
     for net in range(4):
         for k in range(3):
             np.testing.assert_array_equal(le.get_layer(net, k)[0], le2.get_layer(net, k)[0])
+
+
+def test_instance_groups_equal_separate_handles(sb, O, train_series):
+    """shems_create_groups: three chargers in one handle (instance groups with their own constants, two of them with their own
+    series) must produce bit-identical states and rewards to three single-charger handles — reset, step API, fused rollout."""
+    import torch
+    ser2 = sb.series.synth_charger98(4320, seed=7)
+    sers = np.stack([train_series, ser2, train_series])
+    groups = [(98, 40), (4, 24), (6, 32)]
+    multi = sb.Shems(72, sers, groups=groups)
+    singles, base = [], 0
+    for g, (cid, k) in enumerate(groups):
+        singles.append(sb.Shems(72, sers[g], n_envs=k, charger_id=cid, env_id_base=base))
+        base += k
+    multi.reset(rng=5)
+    for e in singles:
+        e.reset(rng=5)
+    cat = lambda xs: torch.cat(xs, dim=-1)
+    assert torch.equal(multi.state_tensor(), cat([e.state_tensor() for e in singles]))
+    rng = np.random.default_rng(0)
+    for step in range(20):
+        a = torch.as_tensor(rng.uniform(0, 1, (2, multi.n_envs)).astype(np.float32), device="cuda")
+        r, s2 = multi.step(a)
+        rs, ss, off = [], [], 0
+        for e in singles:
+            ri, si = e.step(a[:, off:off + e.n_envs].contiguous())
+            rs.append(ri.clone()); ss.append(si.clone()); off += e.n_envs
+        assert torch.equal(r, cat(rs)) and torch.equal(s2, cat(ss))
+    multi.reset(rng=9)
+    out = multi.rollout(sb.POLICY_RANDOM, 40, seed=3, want_obs=True, want_reward=True)
+    off = 0
+    for e in singles:
+        e.reset(rng=9)
+        o = e.rollout(sb.POLICY_RANDOM, 40, seed=3, want_obs=True, want_reward=True)
+        sl = slice(off, off + e.n_envs)
+        assert torch.equal(out["obs"][:, :, sl], o["obs"]) and torch.equal(out["reward"][:, sl], o["reward"])
+        assert torch.equal(out["ep_return"][sl], o["ep_return"])
+        off += e.n_envs
+    # rule-based controller sees each group's battery size
+    b = multi.action(-0.5)
+    off = 0
+    for e in singles:
+        assert torch.equal(b[:, off:off + e.n_envs], e.action(-0.5))
+        off += e.n_envs

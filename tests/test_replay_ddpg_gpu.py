@@ -507,3 +507,24 @@ def test_fused_peer_allreduce_two_processes():
            "--master-port", str(port), os.path.join(root, "tests", "dp_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0 and "DP_OK world=2" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
+
+
+def test_population_driver_trains_end_to_end(sb, train_series):
+    """configs[4] in miniature: 4 learners (two chargers x two seeds) act, step their own environments, remember and replay()
+    together; returns and losses stay finite and every learner's critic actually moves."""
+    drv = sb.PopulationDriver(train_series, chargers=[98, 98, 4, 4], seeds=[11, 12, 13, 14], n_envs=32, mem_size=32 * 72, batch=64, l1=48, l2=64,
+                              use_tensor_cores=1)
+    drv.populate_memory()
+    drv.min_max_buffer()
+    w0 = [drv.learner.select(l).get_layer(1, 1)[0].copy() for l in range(4)]
+    r1 = drv.episode(train=True, rng_ep=1)
+    r2 = drv.episode(train=False, rng_ep=2)
+    assert r1.shape == (4,) and torch.isfinite(r1).all() and torch.isfinite(r2).all()
+    for l in range(4):
+        lc, la = drv.learner.select(l).losses()
+        assert np.isfinite(lc) and np.isfinite(la)
+        assert np.abs(drv.learner.get_layer(1, 1)[0] - w0[l]).max() > 1e-4
+    # different chargers see different physics: learner 0 (Charger98, 6.75 kWh battery) vs learner 2 (charger 4, 9.9 kWh)
+    assert drv.env.group_params[0].b_soc_max != drv.env.group_params[1].b_soc_max and drv.env.n_envs == 4 * 32
+    rb = drv.evaluate_rule_based()
+    assert rb.shape == (4,) and np.isfinite(rb).all()
