@@ -197,44 +197,47 @@ def ddpg_large_batch(sb, torch, ser_train, batch=8192, n_updates=100):
 POP_CHARGERS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)  # capacities of shems_LU1.jl:47-59; 10 chargers x 64 seeds = 640 learners on 8 GPUs
 
 
-def ddpg_population(sb, torch, dist, rank, world, ser_train, per_gpu=80, n_updates=40, tc=1):
+def ddpg_population(sb, torch, dist, rank, world, ser_train, per_gpu=80, n_updates=40, tc=1, n_envs=64, episodes=3):
     """BASELINE configs[4]: independent-seed learners (the reference's one-process-per-seed parallelism), per_gpu of them per
     rank advanced by the same launches; learner g = rank*per_gpu + l trains charger POP_CHARGERS[(g // 64) % 10] with seed g.
+    Two numbers: replay() alone (learner_updates_per_s) and the whole training loop act -> step! -> remember -> replay()
+    (train_learner_updates_per_s; every learner steps n_envs instances of its own charger, all in one environment handle).
     No collective during training; rank 0 gathers the rates."""
     dev = torch.cuda.current_device()
-    mems = []
-    for l in range(per_gpu):
-        g = rank * per_gpu + l
-        env = sb.Shems(72, ser_train, n_envs=500, charger_id=POP_CHARGERS[(g // 64) % len(POP_CHARGERS)], device=dev, env_id_base=500 * g)
-        mem = sb.Replay(24_000, device=dev)
-        env.reset(rng=1 + g)
-        env.rollout(sb.POLICY_RANDOM, 48, seed=1 + g, replay=mem, want_return=False)
-        mems.append(mem)
-        env.close()
-    le = sb.Learner(params=sb.default_ddpg_params(population=per_gpu, use_tensor_cores=tc), device=dev)
-    le.init(1 + rank * per_gpu)
-    for l in range(per_gpu):
-        mn, mx = mems[l].min_max_buffer(24_000, rng_mm=l)
-        le.select(l).set_norm(mn, mx)
+    gids = [rank * per_gpu + l for l in range(per_gpu)]
+    drv = sb.PopulationDriver(ser_train, chargers=[POP_CHARGERS[(g // 64) % len(POP_CHARGERS)] for g in gids], seeds=[1 + g for g in gids],
+                              n_envs=n_envs, device=dev, use_tensor_cores=tc)
+    drv.populate_memory()
+    drv.min_max_buffer()
+    le, mems = drv.learner, drv.mems
     le.replay(mems, rng_rpl=7, n_updates=5)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    le.replay(mems, rng_rpl=11, n_updates=n_updates)
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+
+    def timed(fn):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms = timed(lambda: le.replay(mems, rng_rpl=11, n_updates=n_updates))
+    drv.episode(train=True, rng_ep=1)
+    ms_train = timed(lambda: [drv.episode(train=True, rng_ep=2 + e) for e in range(episodes)])
     lc, la = le.select(0).losses()
+    steps = episodes * drv.ep_length
     return dict(learners=per_gpu * world, learners_per_gpu=per_gpu, chargers=sorted({POP_CHARGERS[(g // 64) % 10] for g in range(per_gpu * world)}),
                 batch=120, l1=250, l2=500, precision="tf32 products, fp32 accumulate" if tc else "fp32",
                 learner_updates_per_s=per_gpu * world * n_updates / (ms * 1e-3), us_per_population_update=1e3 * ms / n_updates,
-                tflops=10 * 256_500 * 120 * per_gpu * world * n_updates / (ms * 1e-3) / 1e12, collective="none (independent seeds)",
-                loss_crit_learner0=lc, loss_act_learner0=la)
+                tflops=10 * 256_500 * 120 * per_gpu * world * n_updates / (ms * 1e-3) / 1e12,
+                train_learner_updates_per_s=per_gpu * world * steps / (ms_train * 1e-3), train_us_per_vector_step=1e3 * ms_train / steps,
+                train_env_steps_per_s=per_gpu * world * n_envs * steps / (ms_train * 1e-3), envs_per_learner=n_envs,
+                collective="none (independent seeds)", loss_crit_learner0=lc, loss_act_learner0=la)
 
 
 def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
