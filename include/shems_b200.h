@@ -109,6 +109,12 @@ typedef struct ShemsParams {
  * SHEMS_ERR_KEY (the reference raises KeyError at module load). */
 SHEMS_API int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* out);
 
+/* CSV.read(env.path, DataFrame) (shems_LU1.jl:217, :265) done ONCE: parses `data/ChargerXX_all_{train,eval,test}_fix.csv` by column
+ * name (21-column schema of Data_preparation_v2.ipynb cell 35) into the [8][nrows] float32 layout shems_create takes.
+ * series_out == NULL: only *nrows_out is set (call again with a [8][capacity] buffer, capacity >= that row count; column k
+ * then starts at series_out + k*capacity).  A missing column -> SHEMS_ERR_KEY; unreadable file / field -> SHEMS_ERR_INVALID. */
+SHEMS_API int32_t shems_series_from_csv(const char* path, float* series_out, int32_t capacity, int32_t* nrows_out);
+
 typedef struct ShemsEnv ShemsEnv; /* N instances of `Shems` (shems_LU1.jl:169-177) */
 
 /* Shems(maxsteps, path) for n_envs instances (shems_LU1.jl:203) — the series

@@ -8,6 +8,7 @@ from ._lib import (POLICY_RANDOM, POLICY_RULE, POLICY_TAPE, RESET_DETERMINISTIC,
                    ShemsBoundsError, ShemsError, ShemsKeyError, default_ddpg_params, params_for_charger)
 from . import series  # noqa: F401
 from . import tracker  # noqa: F401
+from . import dataprep  # noqa: F401
 
 
 def __getattr__(name):  # torch-dependent parts are imported lazily (the ABI/symbol tests run without CUDA)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "shems_version": (I32, []),
     "shems_device_count": (I32, []),
     "shems_params_for_charger": (I32, [I32, C.POINTER(ShemsParams)]),
+    "shems_series_from_csv": (I32, [C.c_char_p, PF, I32, PI]),
     "shems_create": (I32, [C.POINTER(ShemsParams), PF, I32, I32, I64, I32, C.POINTER(VP)]),
     "shems_create_groups": (I32, [C.POINTER(ShemsParams), I32, C.POINTER(I64), PF, I32, I32, I32, I32, C.POINTER(VP)]),
     "shems_destroy": (I32, [VP]),

@@ -89,6 +89,18 @@ def synth_charger98(nrows=4320, seed=98, interpolate_soc=True):
 
 
 def load_csv(path):
+    """Parse a `ChargerXX_all_*_fix.csv` (21-column schema, by header name) once, with the library's native parser
+    (shems_series_from_csv; csrc/series.cu).  `load_csv_python` is the independent pure-Python restatement used to test it."""
+    import ctypes as C
+    from . import _lib as L
+    n = C.c_int32()
+    L.check(L.lib().shems_series_from_csv(str(path).encode(), None, 0, C.byref(n)))
+    out = np.empty((8, n.value), np.float32)
+    L.check(L.lib().shems_series_from_csv(str(path).encode(), out.ctypes.data_as(L.PF), n.value, C.byref(n)))
+    return out
+
+
+def load_csv_python(path):
     """Parse a `ChargerXX_all_*_fix.csv` (21-column schema, by header name) once.
 
     Values are converted Float64 -> Float32 exactly as `env.state.x = df[idx, :col]` does
