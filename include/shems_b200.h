@@ -103,11 +103,25 @@ typedef struct ShemsParams {
   double sell_discount;        /* Float64(0.2f0)                  :99, :86 */
   double discomfort_weight_ev; /* Float64(0.01f0)                 :40, :87 */
   double disc_pot;             /* Float64(2f0)                    :41, :88 */
+  /* sibling environments, all zero for shems_LU1: */
+  double penalty_weight_f64;   /* `penalty_weight = 0.1` is a Float64 in shems_LU7.jl:35 and shems_LU1_input0607.jl:52, so
+                                * `(1 - EV_target) * penalty_weight` is a Float64 product there (used when penalty_in_f64 != 0) */
+  int32_t penalty_in_f64;
+  int32_t reward_form;         /* 0: profit - w*discomfort^pot - penalty (shems_LU1.jl:467-470; shems_LU7.jl:465-468 with pot = 1)
+                                * 1: profit - (discomfort*w)^pot - penalty (shems_LU1_input0607.jl:481-484) */
 } ShemsParams;
 
 /* capacities[charger_id] lookup (shems_LU1.jl:45-59, 92-99).  Unknown id ->
  * SHEMS_ERR_KEY (the reference raises KeyError at module load). */
 SHEMS_API int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* out);
+/* the same for the sibling environment files of RL_environments/envs/ (module-level constants of each file):
+ *   SHEMS_ENV_LU1            shems_LU1.jl (== shems_params_for_charger)
+ *   SHEMS_ENV_LU7            shems_LU7.jl: battery 10 kWh / Float64(4.6f0) kW for every charger (:91), sell_discount 0.3f0, discomfort
+ *                            weight 1 with a linear term (:94, :465-468), penalty_weight 0.1::Float64 (:35), EV capacities :42-55
+ *   SHEMS_ENV_LU1_INPUT0607  shems_LU1_input0607.jl: (discomfort*w)^pot with pot = 1f0 (:49, :481-484), w = 0.1f0 (JOB digit 0; set
+ *                            discomfort_weight_ev for the other grid-search alternatives :38-47), penalty_weight 0.1::Float64 (:52) */
+enum { SHEMS_ENV_LU1 = 0, SHEMS_ENV_LU7 = 1, SHEMS_ENV_LU1_INPUT0607 = 2 };
+SHEMS_API int32_t shems_params_for_env(int32_t env_variant, int32_t charger_id, ShemsParams* out);
 
 /* CSV.read(env.path, DataFrame) (shems_LU1.jl:217, :265) done ONCE: parses `data/ChargerXX_all_{train,eval,test}_fix.csv` by column
  * name (21-column schema of Data_preparation_v2.ipynb cell 35) into the [8][nrows] float32 layout shems_create takes.

@@ -5,7 +5,8 @@ directory — whose name is not a valid Python identifier — under that name).
 """
 from . import _lib
 from ._lib import (POLICY_RANDOM, POLICY_RULE, POLICY_TAPE, RESET_DETERMINISTIC, RESET_DEVICE_PHILOX, RESET_HOST_DRAWS,  # noqa: F401
-                   ShemsBoundsError, ShemsError, ShemsKeyError, default_ddpg_params, params_for_charger)
+                   ShemsBoundsError, ShemsError, ShemsKeyError, default_ddpg_params, params_for_charger, params_for_env, ENV_LU1, ENV_LU7,
+                   ENV_LU1_INPUT0607)
 from . import series  # noqa: F401
 from . import tracker  # noqa: F401
 from . import dataprep  # noqa: F401

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("SHEMS_B200_LIB", os.path.join(HERE, "libshems_b200.so
 OK, ERR_INVALID, ERR_CUDA, ERR_BOUNDS, ERR_KEY, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
 RESET_DETERMINISTIC, RESET_HOST_DRAWS, RESET_DEVICE_PHILOX = 0, 1, 2
 POLICY_RULE, POLICY_RANDOM, POLICY_TAPE = 0, 1, 2
+ENV_LU1, ENV_LU7, ENV_LU1_INPUT0607 = 0, 1, 2
 NET_ACTOR, NET_CRITIC, NET_ACTOR_TARGET, NET_CRITIC_TARGET = 0, 1, 2, 3
 DP_HANDLE_BYTES = 192
 
@@ -22,6 +23,7 @@ class ShemsParams(C.Structure):
         ("b_rate_max", C.c_double), ("b_loss", C.c_float), ("ev_soc_min", C.c_float), ("ev_soc_max", C.c_float),
         ("ev_rate_max", C.c_float), ("penalty_weight", C.c_float), ("sell_discount", C.c_double),
         ("discomfort_weight_ev", C.c_double), ("disc_pot", C.c_double),
+        ("penalty_weight_f64", C.c_double), ("penalty_in_f64", C.c_int32), ("reward_form", C.c_int32),
     ]
 
 
@@ -65,6 +67,7 @@ SIGNATURES = {
     "shems_version": (I32, []),
     "shems_device_count": (I32, []),
     "shems_params_for_charger": (I32, [I32, C.POINTER(ShemsParams)]),
+    "shems_params_for_env": (I32, [I32, I32, C.POINTER(ShemsParams)]),
     "shems_series_from_csv": (I32, [C.c_char_p, PF, I32, PI]),
     "shems_create": (I32, [C.POINTER(ShemsParams), PF, I32, I32, I64, I32, C.POINTER(VP)]),
     "shems_create_groups": (I32, [C.POINTER(ShemsParams), I32, C.POINTER(I64), PF, I32, I32, I32, I32, C.POINTER(VP)]),
@@ -156,6 +159,13 @@ def check(status):
 def params_for_charger(charger_id):
     p = ShemsParams()
     check(lib().shems_params_for_charger(int(charger_id), C.byref(p)))
+    return p
+
+
+def params_for_env(variant, charger_id):
+    """module-level constants of shems_LU1.jl (0), shems_LU7.jl (1) or shems_LU1_input0607.jl (2) for a charger"""
+    p = ShemsParams()
+    check(lib().shems_params_for_env(int(variant), int(charger_id), C.byref(p)))
     return p
 
 

@@ -53,6 +53,9 @@ struct DevParams {
   float span;        // b.soc_max - b.soc_min
   float R_f;         // Float32(b.rate_max) (only where the Float64 min is provably equivalent)
   double R, sell, dw, pot;
+  double pw_d;               // Float64 penalty weight of the sibling envs (pen_f64 != 0)
+  int pen_f64, reward_form;
+  int reward_mode;           // 0: w*discomfort^2 in form 0 (shems_LU1, the fast path); 1: anything else (shems_discomfort_term)
   double eta_d, one_m_l_d, C_d, smax95;
   // division by the constants eta / span / C as multiply + 2 FMA (see fdiv_const / ddiv_const in shems_device.cuh)
   float r_eta_f, r_span_f;   // Float32(1/eta), Float32(1/span)

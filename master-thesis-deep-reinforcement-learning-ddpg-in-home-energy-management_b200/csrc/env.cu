@@ -56,9 +56,46 @@ extern "C" int32_t shems_params_for_charger(int32_t charger_id, ShemsParams* p) 
     p->sell_discount = (double)0.2f;
     p->discomfort_weight_ev = (double)0.01f;
     p->disc_pot = 2.0;
+    p->penalty_weight_f64 = 0.0; p->penalty_in_f64 = 0; p->reward_form = 0;
     return SHEMS_OK;
   }
   shems_set_error("KeyError: key %d not found in capacities (shems_LU1.jl:47-59)", charger_id);
+  return SHEMS_ERR_KEY;
+}
+
+// module-level constants of the sibling environment files
+extern "C" int32_t shems_params_for_env(int32_t env_variant, int32_t charger_id, ShemsParams* p) {
+  REQUIRE(p != nullptr, SHEMS_ERR_INVALID, "shems_params_for_env: out is NULL");
+  REQUIRE(env_variant >= SHEMS_ENV_LU1 && env_variant <= SHEMS_ENV_LU1_INPUT0607, SHEMS_ERR_INVALID, "shems_params_for_env: unknown variant %d", env_variant);
+  if (env_variant == SHEMS_ENV_LU1) return shems_params_for_charger(charger_id, p);
+  if (env_variant == SHEMS_ENV_LU1_INPUT0607) {
+    // capacities as shems_LU1.jl without charger 97 (shems_LU1_input0607.jl:57-68)
+    REQUIRE(charger_id != 97, SHEMS_ERR_KEY, "KeyError: key 97 not found in capacities (shems_LU1_input0607.jl:57-68)");
+    const int32_t st = shems_params_for_charger(charger_id, p);
+    if (st) return st;
+    p->discomfort_weight_ev = (double)0.1f;  // fourth ternary digit 0 (:38-47)
+    p->disc_pot = (double)1.0f;              // DISC_POT = 1f0 (:49)
+    p->penalty_weight_f64 = 0.1; p->penalty_in_f64 = 1;  // penalty_weight = 0.1 (:52)
+    p->reward_form = 1;                      // (discomfort * w)^pot (:481-484)
+    return SHEMS_OK;
+  }
+  // shems_LU7.jl: ev_capacities :42-55 (ids 1-9, 98, 99), Battery(0.95f0, 0f0, 10f0, 4.6f0, 0.00003f0) :91, Market(0.3f0, 1) :94
+  struct Row { int id; float ev_cap; };
+  static const Row rows[] = {{1, 48.250f}, {2, 36.271f}, {3, 45.508f}, {4, 78.993f}, {5, 37.207f}, {6, 35.816f}, {7, 36.521f}, {8, 45.728f},
+                             {9, 21.935f}, {99, 35.816f}, {98, 35.816f}};
+  for (const Row& r : rows) {
+    if (r.id != charger_id) continue;
+    p->pv_eta = 1.0f; p->b_eta = 0.95f; p->b_soc_min = 0.0f; p->b_soc_max = 10.0f;
+    p->b_rate_max = (double)4.6f;            // rate_max::Float64 <- 4.6f0
+    p->b_loss = 0.00003f; p->ev_soc_min = 0.0f; p->ev_soc_max = r.ev_cap; p->ev_rate_max = 11.0f;
+    p->penalty_weight = 0.1f;                // unused: the Float64 weight below is the one LU7 defines
+    p->sell_discount = (double)0.3f;
+    p->discomfort_weight_ev = 1.0;           // DISCOMFORT_WEIGHT_EV = 1 (Int -> Float64 field)
+    p->disc_pot = 1.0;                       // linear term: discomfort * w == w * discomfort^1.0 exactly
+    p->penalty_weight_f64 = 0.1; p->penalty_in_f64 = 1; p->reward_form = 0;
+    return SHEMS_OK;
+  }
+  shems_set_error("KeyError: key %d not found in ev_capacities (shems_LU7.jl:42-55)", charger_id);
   return SHEMS_ERR_KEY;
 }
 
@@ -96,6 +133,8 @@ static DevParams make_dev_params(const ShemsParams& p) {
   d.one_m_l = oml; d.one_m_l_e = omle; d.C = C; d.span = span;
   d.R_f = (float)p.b_rate_max;
   d.R = p.b_rate_max; d.sell = p.sell_discount; d.dw = p.discomfort_weight_ev; d.pot = p.disc_pot;
+  d.pw_d = p.penalty_weight_f64; d.pen_f64 = p.penalty_in_f64 != 0; d.reward_form = p.reward_form != 0;
+  d.reward_mode = (d.reward_form == 0 && p.disc_pot == 2.0) ? 0 : 1;
   d.eta_d = (double)p.b_eta; d.one_m_l_d = (double)d.one_m_l; d.C_d = (double)d.C;
   d.smax95 = 0.95 * (double)p.b_soc_max;
   { volatile float r1 = 1.0f / p.b_eta, r2 = 1.0f / d.span; d.r_eta_f = r1; d.r_span_f = r2; }

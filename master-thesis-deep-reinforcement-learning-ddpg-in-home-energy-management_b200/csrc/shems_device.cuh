@@ -76,6 +76,13 @@ __device__ __forceinline__ void shems_action_rule(const DevParams& P, float Soc_
 
 // step! :343-485 given the feasible (B, EV) and the recorded EV target.  track_neg <=> track < 0
 // (no penalty in the reward, :466-471).
+// w * discomfort^pot (shems_LU1 / shems_LU7) or (discomfort * w)^pot (shems_LU1_input0607) for the exponents other than LU1's 2
+__device__ __noinline__ double shems_discomfort_term(int reward_form, double dw, double pot, double dd) {
+  if (!reward_form) return dw * ((pot == 2.0) ? dd * dd : (pot == 1.0) ? dd : pow(dd, pot));
+  const double dwd = dd * dw;
+  return (pot == 1.0) ? dwd : (pot == 2.0) ? dwd * dwd : pow(dwd, pot);
+}
+
 template <bool WANT_TRACE>
 __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn& s, float B, float EV, float EVt,
                                                bool track_neg, StepTrace* tr) {
@@ -134,26 +141,32 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   float Soc_ev_new = s.Soc_ev;
   if (T != 0.0) Soc_ev_new = (float)((double)s.Soc_ev + ddiv_const(T, P.C_d, P.r_C_d, P.fast_d));
   // :438-449
-  float disc = 0.0f, pen = 0.0f, EX_EV = 0.0f;
+  float disc = 0.0f, EX_EV = 0.0f;
+  double pen = 0.0;
   if (s.c_ev == 0.0f && Soc_ev_new < 1.0f) {
     const float short_ = 1.0f - Soc_ev_new;
     disc = short_ * 100.0f;
     EX_EV = short_ * P.C;
     Soc_ev_new = 1.0f;
   } else if (s.c_ev < 0.0f && EVt < 0.99f) {  // F32 < 0.99 (Float64) <=> F32 < 0.99f0
-    pen = (1.0f - EVt) * P.pw;
+    // shems_LU1: Float32 product with penalty_weight::Float32; LU7 / input0607: penalty_weight is a Float64 -> Float64 product
+    const float om = 1.0f - EVt;
+    pen = (double)(om * P.pw);
+    if (P.pen_f64) pen = (double)om * P.pw_d;
   }
   o.Soc_ev = Soc_ev_new;
   // :464  profit = (sell * p_buy * (PV_GR + B_GR)) - (p_buy * (GR_DE + GR_B + GR_EV + EX_EV))   [Float64]
   const double pb = (double)s.p_buy;
   const double profit = ((P.sell * pb) * pv_d) - (pb * ((GR_DE + GR_EV) + (double)EX_EV));
   const double dd = (double)disc;
-  const double dpow = (P.pot == 2.0) ? dd * dd : pow(dd, P.pot);  // Float32^Float64 promotes; x*x is exact for F32 x
-  const double base = profit - P.dw * dpow;
-  if (track_neg) pen = 0.0f;  // :466-468
-  o.reward = track_neg ? base : (base - (double)pen);
+  // Float32^Float64 promotes; x*x is exact for F32 x, x^1.0 is x
+  double dterm = P.dw * (dd * dd);                                   // reward_mode 0: shems_LU1's w * discomfort^2
+  if (P.reward_mode != 0) dterm = shems_discomfort_term(P.reward_form, P.dw, P.pot, dd);      // every other combination (uniform branch, off the hot path)
+  const double base = profit - dterm;
+  if (track_neg) pen = 0.0;  // :466-468
+  o.reward = track_neg ? base : (base - pen);
   if (WANT_TRACE) {
-    tr->EV = (double)EV; tr->profit = profit; tr->discomfort = dd; tr->penalty = (double)pen;
+    tr->EV = (double)EV; tr->profit = profit; tr->discomfort = dd; tr->penalty = pen;
     tr->PV_DE = (double)PV_DE; tr->B_DE = B_DE; tr->GR_DE = GR_DE; tr->PV_B = PV_B; tr->PV_GR = pv_d;
     tr->PV_EV = (double)PV_EV; tr->B_EV = B_EV; tr->GR_EV = GR_EV; tr->EX_EV = (double)EX_EV; tr->B = (double)B;
   }

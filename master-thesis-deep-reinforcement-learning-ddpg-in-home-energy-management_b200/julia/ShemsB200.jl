@@ -27,6 +27,7 @@ struct ShemsParams
     b_rate_max::Cdouble; b_loss::Cfloat; ev_soc_min::Cfloat; ev_soc_max::Cfloat
     ev_rate_max::Cfloat; penalty_weight::Cfloat; sell_discount::Cdouble
     discomfort_weight_ev::Cdouble; disc_pot::Cdouble
+    penalty_weight_f64::Cdouble; penalty_in_f64::Cint; reward_form::Cint   # sibling envs (shems_LU7 / shems_LU1_input0607), zero for LU1
 end
 
 last_error() = unsafe_string(ccall((:shems_last_error, LIB), Cstring, ()))

@@ -8,6 +8,7 @@ extern "C" {
 #endif
 int oracle_set_threads(int n);
 int oracle_params_for_charger(int charger_id, ShemsParams* p);
+int oracle_params_for_env(int variant, int charger_id, ShemsParams* p);
 void oracle_action_drl(const ShemsParams* P, const float* s, float B_target, float EV_target, float* out);
 void oracle_action_rule(const ShemsParams* P, const float* s, float* out);
 int oracle_step(const ShemsParams* P, const float* series, int nrows, float* state, int* idx_io,

@@ -19,6 +19,7 @@ class ShemsParams(C.Structure):
         ("b_rate_max", C.c_double), ("b_loss", C.c_float), ("ev_soc_min", C.c_float), ("ev_soc_max", C.c_float),
         ("ev_rate_max", C.c_float), ("penalty_weight", C.c_float), ("sell_discount", C.c_double),
         ("discomfort_weight_ev", C.c_double), ("disc_pot", C.c_double),
+        ("penalty_weight_f64", C.c_double), ("penalty_in_f64", C.c_int32), ("reward_form", C.c_int32),
     ]
 
 
@@ -74,6 +75,8 @@ def lib():
         PP = C.POINTER(ShemsParams)
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_params_for_charger.argtypes = [C.c_int, PP]
+        L.oracle_params_for_env.argtypes = [C.c_int, C.c_int, PP]
+        L.oracle_params_for_env.restype = C.c_int
         L.oracle_action_drl.argtypes = [PP, PF, C.c_float, C.c_float, PF]
         L.oracle_action_drl.restype = None
         L.oracle_action_rule.argtypes = [PP, PF, PF]
@@ -128,6 +131,15 @@ def set_threads(n):
 def params_for_charger(cid=98):
     p = ShemsParams()
     st = lib().oracle_params_for_charger(cid, C.byref(p))
+    if st != 0:
+        raise KeyError(cid)
+    return p
+
+
+def params_for_env(variant, cid=98):
+    """module constants of a sibling env file: 0 shems_LU1, 1 shems_LU7, 2 shems_LU1_input0607"""
+    p = ShemsParams()
+    st = lib().oracle_params_for_env(int(variant), int(cid), C.byref(p))
     if st != 0:
         raise KeyError(cid)
     return p

@@ -129,6 +129,39 @@ int oracle_params_for_charger(int charger_id, ShemsParams* p) {
   p->sell_discount = (double)0.2f;        /* Market(0.2f0, …) with Float64 fields :85-89, :99 */
   p->discomfort_weight_ev = (double)0.01f; /* :40 */
   p->disc_pot = (double)2.0f;             /* :41 */
+  p->penalty_weight_f64 = 0.0; p->penalty_in_f64 = 0; p->reward_form = 0;
+  return 0;
+}
+
+/* module-level constants of the sibling environment files:
+ *   shems_LU7.jl: ev_capacities :42-55; b = Battery(0.95f0, 0f0, 10f0, 4.6f0, 0.00003f0) :91 (rate_max::Float64);
+ *                 m = Market(0.3f0, DISCOMFORT_WEIGHT_EV = 1) :94, :25; penalty_weight = 0.1 (Float64) :35; linear discomfort :465-468
+ *   shems_LU1_input0607.jl: capacities :57-68 (no 97); DISC_POT = 1f0 :49; DISCOMFORT_WEIGHT_EV by JOB digit :38-47 (0.1f0 here);
+ *                 penalty_weight = 0.1 (Float64) :52; (discomfort * w)^pot :481-484 */
+int oracle_params_for_env(int variant, int charger_id, ShemsParams* p) {
+  if (variant == SHEMS_ENV_LU1) return oracle_params_for_charger(charger_id, p);
+  if (variant == SHEMS_ENV_LU1_INPUT0607) {
+    if (charger_id == 97) return SHEMS_ERR_KEY;
+    int st = oracle_params_for_charger(charger_id, p);
+    if (st) return st;
+    p->discomfort_weight_ev = (double)0.1f; p->disc_pot = (double)1.0f;
+    p->penalty_weight_f64 = 0.1; p->penalty_in_f64 = 1; p->reward_form = 1;
+    return 0;
+  }
+  if (variant != SHEMS_ENV_LU7) return SHEMS_ERR_INVALID;
+  float ev_cap;
+  switch (charger_id) {
+    case 1: ev_cap = 48.250f; break; case 2: ev_cap = 36.271f; break; case 3: ev_cap = 45.508f; break; case 4: ev_cap = 78.993f; break;
+    case 5: ev_cap = 37.207f; break; case 6: ev_cap = 35.816f; break; case 7: ev_cap = 36.521f; break; case 8: ev_cap = 45.728f; break;
+    case 9: ev_cap = 21.935f; break; case 99: ev_cap = 35.816f; break; case 98: ev_cap = 35.816f; break;
+    default: return SHEMS_ERR_KEY;
+  }
+  p->pv_eta = 1.0f;
+  p->b_eta = 0.95f; p->b_soc_min = 0.f; p->b_soc_max = 10.f; p->b_rate_max = (double)4.6f; p->b_loss = 0.00003f;
+  p->ev_soc_min = 0.f; p->ev_soc_max = ev_cap; p->ev_rate_max = 11.f;
+  p->penalty_weight = 0.1f;
+  p->sell_discount = (double)0.3f; p->discomfort_weight_ev = 1.0; p->disc_pot = 1.0;
+  p->penalty_weight_f64 = 0.1; p->penalty_in_f64 = 1; p->reward_form = 0;
   return 0;
 }
 
@@ -282,7 +315,8 @@ int oracle_step(const ShemsParams* P, const float* series, int nrows, float* sta
     EX_EV = jmul(jsub(J_I(1), J_F(Soc_ev_new)), jsub(ev_soc_max, ev_soc_min));        /* :445 */
     Soc_ev_new = 1.0f;                                                                /* :446 */
   } else if (jlt(c_ev, J_I(0)) && jlt(EV_target, J_D(0.99))) {                        /* :447 */
-    penalty = jmul(jsub(J_I(1), EV_target), J_F(P->penalty_weight));                  /* :448 */
+    /* :448; penalty_weight is a Float32 in shems_LU1.jl:43 and a Float64 in shems_LU7.jl:35 / shems_LU1_input0607.jl:52 */
+    penalty = jmul(jsub(J_I(1), EV_target), P->penalty_in_f64 ? J_D(P->penalty_weight_f64) : J_F(P->penalty_weight));
   }
 
   /* next_state!(env) :264-281 with idx = env.idx + 1 */
@@ -309,11 +343,14 @@ int oracle_step(const ShemsParams* P, const float* series, int nrows, float* sta
   profit = jsub(jmul(jmul(sell, p_buy), jadd(PV_GR, B_GR)),
                 jmul(p_buy, jadd(jadd(jadd(GR_DE, GR_B), GR_EV), EX_EV)));
   jl reward;
+  /* shems_LU1.jl:467-470 m.discomfort_weight_ev * (discomfort ^ m.disc_pot); shems_LU7.jl:465-468 discomfort * m.discomfort_weight_ev
+   * (pot = 1: identical value); shems_LU1_input0607.jl:481-484 (discomfort * m.discomfort_weight_ev) ^ (m.disc_pot) */
+  jl dterm = P->reward_form ? jpow(jmul(discomfort, dw), pot) : jmul(dw, jpow(discomfort, pot));
   if (track < 0) { /* :466-468 */
-    reward = jsub(profit, jmul(dw, jpow(discomfort, pot)));
+    reward = jsub(profit, dterm);
     penalty = J_I(0);
   } else {         /* :470 */
-    reward = jsub(jsub(profit, jmul(dw, jpow(discomfort, pot))), penalty);
+    reward = jsub(jsub(profit, dterm), penalty);
   }
   *reward_out = to_f64(reward); /* env.reward::Float64 */
 

@@ -286,3 +286,53 @@ def test_instance_groups_equal_separate_handles(sb, O, train_series):
     for e in singles:
         assert torch.equal(b[:, off:off + e.n_envs], e.action(-0.5))
         off += e.n_envs
+
+
+@pytest.mark.parametrize("variant,cid,dw,pot", [(1, 98, None, None), (1, 4, None, None), (2, 98, None, None), (2, 6, 0.04, 2.0), (0, 98, 0.01, 1.5)])
+def test_sibling_env_variants_parity(sb, O, train_series, cuda_ok, variant, cid, dw, pot):
+    """f4: shems_LU7.jl (fixed 10 kWh / 4.6f0 kW battery, sell_discount 0.3f0, linear discomfort with weight 1, Float64
+    penalty_weight) and shems_LU1_input0607.jl ((discomfort*w)^pot, Float64 penalty_weight) are shems_LU1 with other module
+    constants and two type differences; CUDA vs oracle on random states + a 72-step closed rollout, states bit-exact."""
+    Pg = sb.params_for_env(variant, cid)
+    Po = O.params_for_env(variant, cid)
+    for f, _ in Pg._fields_:
+        assert getattr(Pg, f) == getattr(Po, f), f                      # library and oracle agree on the module constants
+    if dw is not None:
+        Pg.discomfort_weight_ev = Po.discomfort_weight_ev = float(np.float32(dw))
+        Pg.disc_pot = Po.disc_pot = pot
+    n = 50_000
+    rng = np.random.default_rng(7 + variant)
+    obs, idx = random_states(rng, n, train_series, Po)
+    obs[1, : n // 4] = np.where(obs[2, : n // 4] >= 0, rng.uniform(0, 0.9, n // 4), 1.0)   # many unfinished sessions
+    obs[2, : n // 8] = 0.0                                                                   # ... departing now: discomfort term
+    ref = O.OracleEnv(Po, train_series, 72, n)
+    ref.obs[:] = obs
+    ref.idx[:] = idx
+    env = sb.Shems(72, train_series, n_envs=n, params=Pg)
+    env.set_state(obs, idx)
+    act = rng.uniform(0, 1, (2, n)).astype(np.float32)
+    r_ref, s_ref, tr_ref = ref.step(act, track=1, want_trace=True)
+    r, s2, tr = env.step(dev(act), track=1)
+    np.testing.assert_array_equal(s2.cpu().numpy(), s_ref)
+    np.testing.assert_allclose(tr.cpu().numpy(), tr_ref, rtol=1e-12, atol=0)
+    assert (tr_ref[7] > 0).sum() > 100 and (tr_ref[8] > 0).sum() > 100     # both the discomfort and the penalty term were exercised
+    if variant != 0:  # Float64 penalty weight: (1 - EV_target)::Float32 * 0.1::Float64, not the Float32 product of shems_LU1
+        k = np.flatnonzero(tr_ref[8] > 0)[:1000]
+        np.testing.assert_array_equal(tr_ref[8][k], (np.float32(1) - act[1, k]).astype(np.float64) * 0.1)
+    env.reset(rng=3)
+    ref.reset(mode=2, seed=3)
+    out = env.rollout(sb.POLICY_RANDOM, 72, seed=3, want_obs=True, want_reward=True)
+    want = ref.rollout(1, 72, seed=3, want_transitions=True)
+    np.testing.assert_array_equal(out["obs"].cpu().numpy(), want["s2"])
+    np.testing.assert_array_equal(out["reward"].cpu().numpy(), want["r"])
+    np.testing.assert_allclose(out["ep_return"].cpu().numpy(), want["ep_return"], rtol=1e-12, atol=0)
+
+
+def test_sibling_env_unknown_keys(sb):
+    with pytest.raises(sb.ShemsKeyError):
+        sb.params_for_env(sb.ENV_LU7, 97)           # shems_LU7.jl's ev_capacities has no charger 97
+    with pytest.raises(sb.ShemsKeyError):
+        sb.params_for_env(sb.ENV_LU1_INPUT0607, 97)
+    assert sb.params_for_env(sb.ENV_LU7, 99).ev_soc_max == np.float32(35.816)
+    with pytest.raises(sb.ShemsError):
+        sb.params_for_env(7, 98)

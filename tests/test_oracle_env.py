@@ -210,3 +210,42 @@ def test_rollout_equals_step_loop(O, P98, train_series):
         np.testing.assert_array_equal(out["s2"][t], s2)
         np.testing.assert_array_equal(out["r"][t], r.astype(np.float32))
     np.testing.assert_array_equal(out["ep_return"], ret)
+
+
+def test_sibling_env_constants_and_reward_terms(O, train_series):
+    """f4: module constants of shems_LU7.jl / shems_LU1_input0607.jl and their two type-level differences to shems_LU1
+    (hand-checked against the source: shems_LU7.jl:25, :35, :91, :94, :465-468; shems_LU1_input0607.jl:38-52, :481-484)."""
+    lu7 = O.params_for_env(1, 98)
+    assert lu7.b_soc_max == 10.0 and lu7.b_rate_max == float(np.float32(4.6)) and lu7.sell_discount == float(np.float32(0.3))
+    assert lu7.discomfort_weight_ev == 1.0 and lu7.disc_pot == 1.0 and lu7.penalty_in_f64 == 1 and lu7.penalty_weight_f64 == 0.1
+    i67 = O.params_for_env(2, 98)
+    assert i67.b_soc_max == np.float32(7.5) * np.float32(0.9) and i67.reward_form == 1 and i67.disc_pot == 1.0
+    assert i67.discomfort_weight_ev == float(np.float32(0.1)) and i67.penalty_weight_f64 == 0.1
+    lu1 = O.params_for_env(0, 98)
+    assert lu1.penalty_in_f64 == 0 and lu1.reward_form == 0 and lu1.disc_pot == 2.0
+    with pytest.raises(KeyError):
+        O.params_for_env(1, 97)
+    # one absent-EV step with EV_target = 0.5: penalty = (1 - 0.5f0) * w.  LU1: Float32 product 0.05f0; siblings: Float64 0.5 * 0.1
+    ser = train_series
+    row = int(np.flatnonzero(ser[1] < 0)[5]) + 1
+    st = np.concatenate([[2.0], ser[:, row - 1]]).astype(np.float32)
+    a = np.array([0.3, 0.5], np.float32)
+    tr1 = O.step_single(lu1, ser, st, row, a, track=1)[3]
+    tr7 = O.step_single(lu7, ser, st, row, a, track=1)[3]
+    assert tr1[8] == float(np.float32(0.5) * np.float32(0.1)) and tr7[8] == 0.5 * 0.1
+    # departure with an unfinished charge: discomfort d = (1 - Soc_ev') * 100; LU1 subtracts w*d^2, LU7 d*1, input0607 (d*w)^pot
+    row0 = int(np.flatnonzero(ser[1] == 0)[0]) + 1
+    st0 = np.concatenate([[0.0], ser[:, row0 - 1]]).astype(np.float32)
+    st0[1] = 0.5
+    a0 = np.array([0.0, 0.0], np.float32)
+    out = {}
+    for name, Pv in (("lu1", lu1), ("lu7", lu7), ("i67", i67)):
+        tr = O.step_single(Pv, ser, st0, row0, a0, track=1)[3]
+        out[name] = tr
+        assert tr[7] == 50.0                                     # (1 - 0.5f0) * 100
+    assert out["lu1"][5] == out["lu1"][6] - float(np.float32(0.01)) * 50.0 ** 2
+    assert out["lu7"][5] == out["lu7"][6] - 50.0 * 1.0
+    assert out["i67"][5] == out["i67"][6] - 50.0 * float(np.float32(0.1))
+    i67.disc_pot = 2.0
+    tr = O.step_single(i67, ser, st0, row0, a0, track=1)[3]
+    assert tr[5] == tr[6] - (50.0 * float(np.float32(0.1))) ** 2.0
