@@ -194,6 +194,26 @@ def ddpg_large_batch(sb, torch, ser_train, batch=8192, n_updates=100):
     return out
 
 
+def rule_based_config2(sb, torch, ser_train, n_envs=4096, T=72, reps=50):
+    """BASELINE configs[1]: the rule-based controller (`track = -0.5`) on 4096 instances x 72 steps, one fused launch per episode:
+    0.26 MB per step — latency-bound by construction, reported as a time."""
+    env = sb.Shems(T, ser_train, n_envs=n_envs)
+    for _ in range(3):
+        env.reset(rng=-1)
+        env.rollout(sb.POLICY_RULE, T)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        env.reset(rng=-1)
+        out = env.rollout(sb.POLICY_RULE, T)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return dict(envs=n_envs, steps=T, us_per_episode_batch=1e3 * ms, env_steps_per_s=n_envs * T / (ms * 1e-3),
+                mean_return=float(out["ep_return"].mean()), note="reset!(rng=-1) + one fused 72-step launch; launch/latency bound")
+
+
 POP_CHARGERS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)  # capacities of shems_LU1.jl:47-59; 10 chargers x 64 seeds = 640 learners on 8 GPUs
 
 
@@ -204,9 +224,15 @@ def ddpg_population(sb, torch, dist, rank, world, ser_train, per_gpu=80, n_updat
     (train_learner_updates_per_s; every learner steps n_envs instances of its own charger, all in one environment handle).
     No collective during training; rank 0 gathers the rates."""
     dev = torch.cuda.current_device()
-    gids = [rank * per_gpu + l for l in range(per_gpu)]
-    drv = sb.PopulationDriver(ser_train, chargers=[POP_CHARGERS[(g // 64) % len(POP_CHARGERS)] for g in gids], seeds=[1 + g for g in gids],
-                              n_envs=n_envs, device=dev, use_tensor_cores=tc)
+    from shems_b200 import sharding
+    if per_gpu * world == 640:          # the full configs[4] population: 10 chargers x 64 seeds
+        gids, chargers, seeds = sharding.population_shard(rank, world)
+    else:                               # fewer GPUs: the first per_gpu*world learners of it
+        gids = [rank * per_gpu + l for l in range(per_gpu)]
+        chargers = [POP_CHARGERS[(g // 64) % len(POP_CHARGERS)] for g in gids]
+        seeds = [int("123%d" % (g % 64 + 1)) for g in gids]
+    drv = sb.PopulationDriver(ser_train, chargers=chargers, seeds=[1000 * g + s for g, s in zip(gids, seeds)], n_envs=n_envs, device=dev,
+                              use_tensor_cores=tc)
     drv.populate_memory()
     drv.min_max_buffer()
     le, mems = drv.learner, drv.mems
@@ -440,6 +466,10 @@ def main():
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:  # never lose the env number to the secondary metric
             line["ddpg"] = dict(error=str(e))
+        try:
+            line["rule_based_4096x72"] = rule_based_config2(sb, torch, sb.series.synth_charger98(4320, seed=98))
+        except Exception as e:
+            line["rule_based_4096x72"] = dict(error=str(e))
         try:
             line["ddpg_large_batch"] = ddpg_large_batch(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:

@@ -34,3 +34,20 @@ def gather_concat(x, dist=None):
     out = [torch.empty_like(x) for _ in range(dist.get_world_size())]
     dist.all_gather(out, x)
     return torch.cat(out)
+
+
+POPULATION_CHARGERS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)   # capacities of shems_LU1.jl:47-59 without the spare id 97
+
+
+def population_shard(rank, world, chargers=POPULATION_CHARGERS, seeds_per_charger=64):
+    """BASELINE configs[4] — `len(chargers)` chargers x `seeds_per_charger` seeds = one independent learner each (the reference
+    starts one Julia process per (JOB_ID, seed), RL-SHEMS_bs_scheduler_*.sh:73-81) — split over `world` ranks in contiguous,
+    balanced blocks of global learner ids g = charger_index * seeds_per_charger + seed_index.  Returns the rank's
+    (global_ids, charger_ids, seeds): learners of one charger stay adjacent, which is what PopulationDriver's instance groups
+    need; seeds follow input.jl:136 (`rng_run = parse(Int, "123" * "$seed")`)."""
+    total = len(chargers) * int(seeds_per_charger)
+    base, count = shard_range(total, rank, world)
+    gids = list(range(base, base + count))
+    cids = [int(chargers[g // seeds_per_charger]) for g in gids]
+    seeds = [int("123" + str(g % seeds_per_charger + 1)) for g in gids]
+    return gids, cids, seeds

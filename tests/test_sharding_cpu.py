@@ -58,3 +58,23 @@ def test_two_rank_sharded_rollout_equals_single(O, sb):
     want = env.rollout(1, T, seed=21)["ep_return"]
     np.testing.assert_array_equal(got, want)   # results do not depend on the number of ranks
     assert tmax == 11.0                        # device time = max over ranks
+
+
+def test_population_shard_covers_every_learner_once():
+    """configs[4]: 10 chargers x 64 seeds over 1/2/4/8 ranks — disjoint, complete, balanced; a rank's learners of one charger are
+    adjacent (instance groups) and the seeds follow input.jl:136."""
+    from shems_b200 import sharding
+    for world in (1, 2, 4, 8, 3):
+        seen = []
+        for rank in range(world):
+            gids, cids, seeds = sharding.population_shard(rank, world)
+            assert len(gids) == len(cids) == len(seeds) and abs(len(gids) - 640 / world) < 1
+            assert gids == list(range(gids[0], gids[0] + len(gids)))
+            runs = [c for i, c in enumerate(cids) if i == 0 or cids[i - 1] != c]
+            assert len(runs) == len(set(runs))                     # equal chargers adjacent
+            for g, c, s in zip(gids, cids, seeds):
+                assert c == sharding.POPULATION_CHARGERS[g // 64] and s == int("123%d" % (g % 64 + 1))
+            seen += gids
+        assert sorted(seen) == list(range(640))
+    gids, cids, seeds = sharding.population_shard(0, 8)
+    assert len(gids) == 80 and cids[:64] == [1] * 64 and cids[64:] == [2] * 16 and seeds[0] == 1231 and seeds[63] == 12364 and seeds[64] == 1231
