@@ -166,6 +166,47 @@ def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
                 kernels_per_update=21, flops_per_update=3.078e8)
 
 
+def ddpg_cpu_baseline(torch, batch=120, l1=250, l2=500, n_updates=200, gamma=0.99, tau=1e-3):
+    """replay() (DDPG.jl:121-145) restated with torch on the host cores — what the reference's Flux/Zygote update costs on a CPU
+    (Julia is not installed; a baseline, not the target).  Same nets, losses, ADAM(1e-4 / 1e-3), Polyak."""
+    import torch.nn as nn
+    cores = cpu_cores()
+    torch.set_num_threads(cores)
+
+    def mlp(i, o, last):
+        return nn.Sequential(nn.Linear(i, l1), nn.ReLU(), nn.Linear(l1, l2), nn.ReLU(), nn.Linear(l2, o), last)
+
+    actor, critic = mlp(9, 2, nn.Tanh()), mlp(11, 1, nn.Identity())
+    actor_t, critic_t = mlp(9, 2, nn.Tanh()), mlp(11, 1, nn.Identity())
+    actor_t.load_state_dict(actor.state_dict()); critic_t.load_state_dict(critic.state_dict())
+    oa, oc = torch.optim.Adam(actor.parameters(), lr=1e-4, eps=1e-8), torch.optim.Adam(critic.parameters(), lr=1e-3, eps=1e-8)
+    g = torch.Generator().manual_seed(0)
+    mem = [torch.rand((24_000, k), generator=g) for k in (9, 2, 1, 9)]
+
+    def update():
+        idx = torch.randint(0, 24_000, (batch,), generator=g)
+        s, a, r, s2 = (m[idx] for m in mem)
+        with torch.no_grad():
+            y = r + gamma * critic_t(torch.cat([s2, actor_t(s2)], 1))
+        lc = ((critic(torch.cat([s, a], 1)) - y) ** 2).mean()
+        oc.zero_grad(); lc.backward(); oc.step()
+        la = -critic(torch.cat([s, actor(s)], 1)).mean()
+        oa.zero_grad(); la.backward(); oa.step()
+        with torch.no_grad():
+            for t, m in ((actor_t, actor), (critic_t, critic)):
+                for pt, pm in zip(t.parameters(), m.parameters()):
+                    pt.mul_(1 - tau).add_(pm, alpha=tau)
+
+    for _ in range(20):
+        update()
+    t0 = time.perf_counter()
+    for _ in range(n_updates):
+        update()
+    dt = time.perf_counter() - t0
+    return dict(updates_per_s=n_updates / dt, us_per_update=1e6 * dt / n_updates, threads=cores, kind="port",
+                what="torch-CPU restatement of replay() at B=%d, %d/%d" % (batch, l1, l2))
+
+
 def ddpg_large_batch(sb, torch, ser_train, batch=8192, n_updates=100):
     """DDPG updates/s where batch x width is a dense contraction (BASELINE configs[3], 8192 parallel instances): the 250x500
     products run on the TF32 tcgen05 kernel; tensor-pipe evidence in profiles/."""
@@ -481,6 +522,11 @@ def main():
     if not args.skip_cpu_baseline:
         cb, _ = cpu_baseline(ser, T, args.cpu_sample_envs)
         line["cpu_baseline"] = cb
+        if not args.skip_ddpg and isinstance(line.get("ddpg"), dict):
+            try:
+                line["ddpg"]["cpu_baseline"] = ddpg_cpu_baseline(torch)
+            except Exception as e:
+                line["ddpg"]["cpu_baseline"] = dict(error=str(e))
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
