@@ -528,3 +528,42 @@ def test_population_driver_trains_end_to_end(sb, train_series):
     assert drv.env.group_params[0].b_soc_max != drv.env.group_params[1].b_soc_max and drv.env.n_envs == 4 * 32
     rb = drv.evaluate_rule_based()
     assert rb.shape == (4,) and np.isfinite(rb).all()
+
+
+def test_act_soa_and_push_groups_equal_packed_layout(sb, train_series):
+    """ddpg_act_soa / replay_push_groups work on ONE structure-of-arrays over all P*n instances (what an environment handle with
+    instance groups holds); they must equal the packed [P][k][n] calls bit for bit."""
+    from shems_b200.ddpg import push_groups
+    P, n = 3, 50
+    N = P * n
+    rng = np.random.default_rng(4)
+    pop = sb.Learner(params=sb.default_ddpg_params(population=P, batch=32, l1=48, l2=64))
+    pop.init(8)
+    for l in range(P):
+        pop.select(l).set_norm(np.zeros(9, np.float32), rng.uniform(1, 4, 9).astype(np.float32))
+    obs_soa = torch.as_tensor(rng.uniform(0, 3, (9, N)).astype(np.float32), device="cuda")
+    noise_soa = torch.as_tensor(rng.normal(0, 0.1, (2, N)).astype(np.float32), device="cuda")
+    packed = lambda x, k: x.view(k, P, n).permute(1, 0, 2).contiguous()          # [k][N] -> [P][k][n]
+    a1, s1 = pop.act(obs_soa, noise=noise_soa, soa=True)
+    a2, s2 = pop.act(packed(obs_soa, 9), noise=packed(noise_soa, 2))
+    assert a1.shape == (2, N) and torch.equal(packed(a1, 2), a2) and torch.equal(packed(s1, 2), s2)
+    a3, _ = pop.act(obs_soa, train=True, sigma=0.1, rng_act=5, step=2, env_id_base=100, soa=True)   # Philox noise keyed by the global env id
+    a4, _ = pop.act(packed(obs_soa, 9), train=True, sigma=0.1, rng_act=5, step=2, env_id_base=100)
+    assert torch.equal(packed(a3, 2), a4) and not torch.equal(a3, a1)
+    # remember(): one launch for all learners vs one push per learner
+    mems_a = [sb.Replay(120) for _ in range(P)]
+    mems_b = [sb.Replay(120) for _ in range(P)]
+    for rep in range(3):                                                          # 3 x 50 transitions into 120 slots: the rings wrap
+        r = torch.as_tensor(rng.uniform(-3, 1, N).astype(np.float32), device="cuda")
+        s_next = torch.as_tensor(rng.uniform(0, 3, (9, N)).astype(np.float32), device="cuda")
+        push_groups(mems_a, obs_soa, a1, r, s_next)
+        for l in range(P):
+            sl = slice(l * n, (l + 1) * n)
+            mems_b[l].push(obs_soa[:, sl].contiguous(), a1[:, sl].contiguous(), r[sl].contiguous(), s_next[:, sl].contiguous())
+        obs_soa = s_next
+    for l in range(P):
+        assert len(mems_a[l]) == len(mems_b[l]) == 120
+        for x, y in zip(mems_a[l].get(), mems_b[l].get()):
+            np.testing.assert_array_equal(x, y)
+    with pytest.raises(sb.ShemsError):                                           # more transitions per learner than a ring holds
+        push_groups([sb.Replay(10) for _ in range(P)], obs_soa, a1, r, s_next)
