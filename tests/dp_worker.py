@@ -20,7 +20,8 @@ def main():
     device = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
     torch.cuda.set_device(device)
     dist.init_process_group("gloo")
-    n, T, B, K = 64, 72, 32, 3
+    n, T, K = 64, 72, 3
+    B, tc = int(os.environ.get("DP_BATCH", "32")), int(os.environ.get("DP_TC", "0"))   # per-rank minibatch; TF32 tensor cores
     ser = sb.series.synth_charger98(4320, seed=98)
     env = sb.Shems(T, ser, n_envs=n, device=device)
     mem = sb.Replay(n * T, device=device)
@@ -28,7 +29,7 @@ def main():
     env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)       # identical transitions on every rank
     mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
     idx = np.random.default_rng(0).integers(0, len(mem), (K, world * B)).astype(np.int32)
-    le = sb.Learner(params=sb.default_ddpg_params(batch=B), device=device)
+    le = sb.Learner(params=sb.default_ddpg_params(batch=B, use_tensor_cores=tc), device=device)
     le.init(3)
     le.set_norm(mn, mx)
     le.dp_connect_dist(dist)
@@ -40,7 +41,7 @@ def main():
     dist.gather_object((status, mine), everyone, dst=0)
     if rank == 0:
         assert all(st == 0 for st, _ in everyone), [st for st, _ in everyone]
-        full = sb.Learner(params=sb.default_ddpg_params(batch=world * B), device=device)
+        full = sb.Learner(params=sb.default_ddpg_params(batch=world * B, use_tensor_cores=tc), device=device)
         full.init(3)
         full.set_norm(mn, mx)
         full.replay(mem, n_updates=K, idx=idx)
@@ -52,9 +53,13 @@ def main():
                 w, b = everyone[r][1][j]
                 np.testing.assert_array_equal(w, everyone[0][1][j][0])           # bit-identical replicas
                 np.testing.assert_array_equal(b, everyone[0][1][j][1])
-                np.testing.assert_allclose(w, wf, rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
-                np.testing.assert_allclose(b, bf, rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
-        print("DP_OK world=%d devices=%d" % (world, torch.cuda.device_count()), flush=True)
+                if not tc:
+                    np.testing.assert_allclose(w, wf, rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
+                    np.testing.assert_allclose(b, bf, rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
+                else:  # TF32 products on both sides, different tiling of the batch: ADAM sign noise on near-zero gradients
+                    d = np.abs(w - wf)
+                    assert d.max() <= 2.0 * lrs[net] * K + 1e-6 and np.quantile(d, 0.99) <= 0.1 * lrs[net] * K + 1e-7, (net, k, d.max())
+        print("DP_OK world=%d devices=%d batch=%d tc=%d" % (world, torch.cuda.device_count(), B, tc), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

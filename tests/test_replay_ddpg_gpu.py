@@ -494,8 +494,9 @@ def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series):
                 np.testing.assert_array_equal(x, y)
 
 
-def test_fused_peer_allreduce_two_processes():
-    """Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
+@pytest.mark.parametrize("batch,tc", [(32, 0), (512, 1)])
+def test_fused_peer_allreduce_two_processes(batch, tc):
+    """(512, 1): the large-batch tensor-core path under the fused exchange.  Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
     bit-identical and equal to one learner on the full minibatch — checked inside tests/dp_worker.py.  On a one-GPU box both
     ranks share the device (time-sliced contexts): the same IPC code path, just slower."""
     import os
@@ -505,8 +506,9 @@ def test_fused_peer_allreduce_two_processes():
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(root, "tests", "dp_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
-    assert out.returncode == 0 and "DP_OK world=2" in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
+    env = dict(os.environ, DP_BATCH=str(batch), DP_TC=str(tc))
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0 and "DP_OK world=2" in out.stdout and ("batch=%d tc=%d" % (batch, tc)) in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
 
 
 def test_population_driver_trains_end_to_end(sb, train_series):
