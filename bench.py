@@ -232,6 +232,13 @@ def ddpg_large_batch(sb, torch, ser_train, batch=8192, n_updates=100):
                          tflops=10 * 256_500 * batch * n_updates / (ms * 1e-3) / 1e12)
         le.close()
     out.update(batch=batch, l1=250, l2=500, flops_per_update=10 * 256_500 * batch)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = float(json.load(open(peaks_path))["bf16_tflops"]) if os.path.exists(peaks_path) else 1665.0
+    # TF32 dense tensor rate = half the bf16 rate; the update's algorithmic FLOPs over its whole duration, thin
+    # streaming kernels and ADAM included — see DESIGN §4.4(ii) for why K = 250 products sit far below the tensor peak
+    out["roofline"] = dict(bound="tensor", achieved=out["tf32_tcgen05"]["tflops"], peak=bf16 / 2, unit="TFLOP/s",
+                           frac=out["tf32_tcgen05"]["tflops"] / (bf16 / 2), peak_source="MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense)",
+                           note="whole replay() incl. streaming kernels and ADAM; the 250x500 products alone: profiles/r1_tc_gemm.md")
     return out
 
 
