@@ -197,8 +197,11 @@ def ddpg_cpu_baseline(torch, batch=120, l1=250, l2=500, n_updates=200, gamma=0.9
                 for pt, pm in zip(t.parameters(), m.parameters()):
                     pt.mul_(1 - tau).add_(pm, alpha=tau)
 
-    for _ in range(20):
+    t0 = time.perf_counter()
+    for _ in range(5):
         update()
+    per = (time.perf_counter() - t0) / 5
+    n_updates = int(max(5, min(n_updates, 4.0 / max(per, 1e-6))))     # bounded: about 4 s of CPU work
     t0 = time.perf_counter()
     for _ in range(n_updates):
         update()
@@ -526,7 +529,7 @@ def main():
         line["ddpg_data_parallel"] = ddpg_dp
     if ddpg_pop is not None:
         line["ddpg_population"] = ddpg_pop
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:   # the CPU baselines are timed on rank 0 at N = 1 only
         cb, _ = cpu_baseline(ser, T, args.cpu_sample_envs)
         line["cpu_baseline"] = cb
         if not args.skip_ddpg and isinstance(line.get("ddpg"), dict):
