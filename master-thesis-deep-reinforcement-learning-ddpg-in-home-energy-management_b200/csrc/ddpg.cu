@@ -228,20 +228,37 @@ __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const GemmBatch gb) {
   GemmProblem p = gb.p[blockIdx.y];
   if (blockIdx.z) gemm_shift(p, blockIdx.z * gb.ls_w, blockIdx.z * gb.ls_x);
+  // the one or two weight columns are shared by the block's 8 rows: staged once in shared memory (K <= SKINNY_MAX_K)
+  constexpr int SKINNY_MAX_K = 1024;
+  __shared__ float bsm[2][SKINNY_MAX_K];
+  const bool two = p.N > 1, staged = p.K <= SKINNY_MAX_K;
+  if (staged) {
+    for (int k = threadIdx.x; k < p.K; k += 256) {
+      bsm[0][k] = __ldg(p.B + (long long)k * p.sBk);
+      bsm[1][k] = two ? __ldg(p.B + (long long)k * p.sBk + p.sBn) : 0.0f;
+    }
+    __syncthreads();
+  }
   const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (m >= p.M) return;
   float a0 = 0.0f, a1 = 0.0f;
   const float* arow = p.A + (long long)m * p.sAm;
-  const bool two = p.N > 1;
-  for (int kb = 0; kb < p.K; kb += 512) {  // 16 k-values per lane and pass: all 48 loads are issued before the first FMA
+  for (int kb = 0; kb < p.K; kb += 512) {  // 16 k-values per lane and pass: all loads of the row are issued before the first FMA
     float av[16], b0[16], b1[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int k = kb + i * 32 + lane;
+      av[i] = (k < p.K) ? __ldg(arow + k) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = kb + i * 32 + lane;
       const bool ok = k < p.K;
-      av[i] = ok ? __ldg(arow + k) : 0.0f;
-      b0[i] = ok ? __ldg(p.B + (long long)k * p.sBk) : 0.0f;
-      b1[i] = (ok && two) ? __ldg(p.B + (long long)k * p.sBk + p.sBn) : 0.0f;
+      if (staged) { b0[i] = ok ? bsm[0][k] : 0.0f; b1[i] = ok ? bsm[1][k] : 0.0f; }
+      else {
+        b0[i] = ok ? __ldg(p.B + (long long)k * p.sBk) : 0.0f;
+        b1[i] = (ok && two) ? __ldg(p.B + (long long)k * p.sBk + p.sBn) : 0.0f;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a0 = fmaf(av[i], b0[i], a0); a1 = fmaf(av[i], b1[i], a1); }
@@ -273,25 +290,37 @@ splitk_reduce_kernel(const float* __restrict__ ws, long long stride, int splits,
 template <int J>
 __global__ void __launch_bounds__(256)
 wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, const float* __restrict__ w, int rows_per, long long stride,
-                       float* __restrict__ ws, long long pop_stride) {
+                       float* __restrict__ ws, long long pop_stride, float* __restrict__ out_final, unsigned* __restrict__ counters) {
   constexpr int JJ = J > 0 ? J : 1;
+  constexpr int CHUNK = 256;  // rows whose weights are staged in shared memory at a time
   Z += (long long)blockIdx.z * pop_stride; ws += (long long)blockIdx.z * pop_stride;  // learner of a population (one slab: writes the gradient itself)
   if (J > 0) w += (long long)blockIdx.z * pop_stride;
   __shared__ float red[8][32][JJ];
+  __shared__ float wsm[CHUNK * JJ];
+  __shared__ int is_last;
   const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + c;
   const int r0 = blockIdx.y * rows_per, r1 = min(B, r0 + rows_per);
-  float acc[JJ];
+  float acc[JJ], bsum = 0.0f;
 #pragma unroll
   for (int j = 0; j < JJ; ++j) acc[j] = 0.0f;
-  if (n < N) {
-#pragma unroll 4
-    for (int r = r0 + rl; r < r1; r += 8) {
-      const float z = Z[(long long)r * ld + n];
-      if (J == 0) acc[0] += z;
-      else {
+  for (int cb = r0; cb < r1; cb += CHUNK) {
+    const int ce = min(r1, cb + CHUNK);
+    if (J > 0) {
+      __syncthreads();
+      for (int e = threadIdx.x; e < (ce - cb) * J; e += 256) wsm[e] = w[(long long)cb * J + e];
+      __syncthreads();
+      if (blockIdx.x == 0 && c < J) for (int r = cb + rl; r < ce; r += 8) bsum += wsm[(r - cb) * J + c];  // bias gradient: sum_b w[b][j]
+    }
+    if (n < N) {
+#pragma unroll 8
+      for (int r = cb + rl; r < ce; r += 8) {
+        const float z = Z[(long long)r * ld + n];
+        if (J == 0) acc[0] += z;
+        else {
 #pragma unroll
-        for (int j = 0; j < JJ; ++j) acc[j] = fmaf(z, w[(long long)r * J + j], acc[j]);
+          for (int j = 0; j < JJ; ++j) acc[j] = fmaf(z, wsm[(r - cb) * J + j], acc[j]);
+        }
       }
     }
   }
@@ -308,11 +337,9 @@ wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, 
       out[(long long)n * JJ + j] = t;
     }
   }
-  if (J > 0 && blockIdx.x == 0) {  // bias gradient of the output layer: sum_b w[b][j]
+  if (J > 0 && blockIdx.x == 0) {
     __syncthreads();
-    float t = 0.0f;
-    if (c < J) for (int r = r0 + rl; r < r1; r += 8) t += w[(long long)r * J + c];
-    red[rl][c][0] = t;
+    red[rl][c][0] = bsum;
     __syncthreads();
     if (rl == 0 && c < J) {
       float u = red[0][c][0];
@@ -321,10 +348,34 @@ wcolsum_partial_kernel(const float* __restrict__ Z, long long ld, int B, int N, 
       out[(long long)N * J + c] = u;
     }
   }
+  if (gridDim.y == 1) return;  // a single slab wrote the result itself
+  // several slabs: the last block of this column group to finish adds the slabs' partial sums in slab order (deterministic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (old == gridDim.y - 1);
+    if (is_last) counters[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int e = threadIdx.x; e < 32 * JJ; e += 256) {
+    const int cc = e / JJ, j = e - cc * JJ, nn = blockIdx.x * 32 + cc;
+    if (nn >= N) continue;
+    float t = 0.0f;
+    for (unsigned sl = 0; sl < gridDim.y; ++sl) t += __ldcg(ws + (long long)sl * stride + (long long)nn * JJ + j);
+    out_final[(long long)nn * JJ + j] = t;
+  }
+  if (J > 0 && blockIdx.x == 0 && threadIdx.x < J) {
+    float t = 0.0f;
+    for (unsigned sl = 0; sl < gridDim.y; ++sl) t += __ldcg(ws + (long long)sl * stride + (long long)N * J + threadIdx.x);
+    out_final[(long long)N * J + threadIdx.x] = t;
+  }
 }
 
 // First layer for many rows (K = 9 or 11 inputs): Y[m][n] = relu(b[n] + sum_k X[m][k] W[k][n]), up to 3 problems per launch.
-// A thread keeps its 4 weight columns in registers and walks 16 rows; stores are 16-byte, coalesced along n.
+// A thread keeps its 4 weight columns in registers and walks 8 rows; stores are 16-byte, coalesced along n.
 struct L1Batch { const float* X[3]; const float* W[3]; const float* bias[3]; float* Y[3]; int K[3]; int M, N, ldx, ldy, count; long long ls_w, ls_x; };
 __global__ void __launch_bounds__(256)
 l1_fwd_kernel(const L1Batch a) {
@@ -332,9 +383,9 @@ l1_fwd_kernel(const L1Batch a) {
   const float* __restrict__ X = a.X[z] + learner * a.ls_x; const float* __restrict__ W = a.W[z] + learner * a.ls_w;
   const float* __restrict__ bias = a.bias[z] + learner * a.ls_w;
   float* __restrict__ Y = a.Y[z] + learner * a.ls_x;
-  __shared__ float xs[64][12];
-  const int m0 = blockIdx.x * 64;
-  for (int e = threadIdx.x; e < 64 * 12; e += 256) {
+  __shared__ float xs[32][12];
+  const int m0 = blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * 12; e += 256) {
     const int r = e / 12, k = e - r * 12;
     xs[r][k] = (m0 + r < a.M && k < K) ? X[(long long)(m0 + r) * a.ldx + k] : 0.0f;
   }
@@ -349,8 +400,8 @@ l1_fwd_kernel(const L1Batch a) {
   __syncthreads();
   if (n >= a.N) return;
 #pragma unroll 4
-  for (int i = 0; i < 16; ++i) {
-    const int r = rg * 16 + i, m = m0 + r;
+  for (int i = 0; i < 8; ++i) {
+    const int r = rg * 8 + i, m = m0 + r;
     if (m >= a.M) break;
     float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -394,13 +445,22 @@ outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, con
 #pragma unroll
     for (int u = 0; u < 4; ++u) hv[u] = (n + u < N) ? hrow[u] : 0.0f;
   }
+  float wv[4 * J];  // W[n..n+3][0..J-1] is contiguous: J 16-byte loads when aligned
+  if (n + 3 < N && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < J; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(W + (long long)n * J + q * 4);
+      wv[q * 4 + 0] = t.x; wv[q * 4 + 1] = t.y; wv[q * 4 + 2] = t.z; wv[q * 4 + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4 * J; ++e) wv[e] = (n + e / J < N) ? W[(long long)n * J + e] : 0.0f;
+  }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     float v = 0.0f;
-    if (n + u < N) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) v = fmaf(dz[j], W[(long long)(n + u) * J + j], v);
-    }
+    for (int j = 0; j < J; ++j) v = fmaf(dz[j], wv[u * J + j], v);
     o[u] = hv[u] > 0.0f ? v : 0.0f;
   }
   float* x = dX + (long long)b * ld + n;
@@ -460,6 +520,7 @@ struct Ddpg {
   bool ctrl_init;
   int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 32 floats = 128 bytes)
   bool tc;         // layer-2 contractions on TF32 tensor cores (use_tensor_cores, batch >= 256, operands 16-byte aligned)
+  unsigned* counters;  // [WS_COUNTERS] arrival counters of the fused slab reductions (zero between kernels)
   float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
   long long ws_floats;
   // population: `pop` independent learners in one handle.  Every float buffer above lives in one slab per learner
@@ -483,6 +544,7 @@ static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows
 #endif
 #define SPLITK_MIN_BATCH 1024
 #define SPLITK_MAX 32
+#define WS_COUNTERS 1024
 
 static void make_dims(NetDims& d, int in, int l1, int l2, int out) {
   const int ins[3] = {in, l1, l2}, outs[3] = {l1, l2, out};
@@ -537,6 +599,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   h->tc = p->use_tensor_cores && (p->l2 % 4 == 0) && (h->dims[0].l[1].w_off % 4 == 0) && (h->dims[1].l[1].w_off % 4 == 0);
   h->ws_floats = (long long)SPLITK_MAX * ((long long)p->l1 * p->l2 + p->l2 + (long long)C * p->l1 + p->l1 + (long long)p->l2 * A + A);
   DMALLOC(h->ws, h->ws_floats);
+  DMALLOC(h->counters, WS_COUNTERS);
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
@@ -591,7 +654,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph_dp_exec) cudaGraphExecDestroy(h->graph_dp_exec);
   if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
   for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
-  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_flags);
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_flags); cudaFree(h->counters);
   delete h;
   return SHEMS_OK;
 }
@@ -999,13 +1062,14 @@ static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float*
   TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? h->ws : nullptr, bt));
   const int slabs = h->pop > 1 ? 1 : max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
   if (slabs == 1) {  // small batch: the column sums are the bias gradient (every learner of a population in one launch)
-    wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, 1, h->pop), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, grad + L.b_off, h->pop_stride);
+    wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, 1, h->pop), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, grad + L.b_off, h->pop_stride,
+                                                                                 nullptr, nullptr);
     CUDA_TRY(cudaGetLastError());
     return SHEMS_OK;
   }
-  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws, 0);
-  CUDA_TRY(cudaGetLastError());
-  splitk_reduce_kernel<<<(L.out + 255) / 256, 256, 0, st>>>(h->ws, L.out, slabs, grad + L.b_off, L.out);
+  REQUIRE((L.out + 31) / 32 <= WS_COUNTERS, SHEMS_ERR_INVALID, "tc_dw: layer too wide for the reduction counters");
+  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws, 0, grad + L.b_off,
+                                                                            h->counters);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1019,7 +1083,7 @@ static int big_l1(cudaStream_t st, int count, const float* const* X, int ldx, in
     REQUIRE(L[i]->in <= 12 && L[i]->out == L[0]->out, SHEMS_ERR_INVALID, "big_l1: unsupported first-layer shape");
   }
   a.M = M; a.N = L[0]->out; a.ldx = ldx; a.ldy = ldy;
-  l1_fwd_kernel<<<dim3((M + 63) / 64, (a.N + 255) / 256, count * pop), 256, 0, st>>>(a);
+  l1_fwd_kernel<<<dim3((M + 31) / 32, (a.N + 255) / 256, count * pop), 256, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1039,13 +1103,10 @@ static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const 
   const long long stride = (long long)N * J + J;
   const dim3 grid((N + 31) / 32, slabs, h->pop);
   float* out = slabs == 1 ? grad + L.w_off : h->ws;  // a single slab is the gradient block [W3 | b3] itself
-  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride);
-  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride);
+  REQUIRE((N + 31) / 32 <= WS_COUNTERS, SHEMS_ERR_INVALID, "big_out_bwd: layer too wide for the reduction counters");
+  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, h->counters);
+  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, h->counters);
   CUDA_TRY(cudaGetLastError());
-  if (slabs > 1) {
-    splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, slabs, grad + L.w_off, stride);
-    CUDA_TRY(cudaGetLastError());
-  }
   return launch_outer_mask(h, st, dZ, J, net + L.w_off, H, ldh, B, N, dX);
 }
 static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows * h->pop >= TC_MIN_ROWS; }
