@@ -297,6 +297,14 @@ SHEMS_API int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float s
  * or NULL -> Philox(seed, global env id, step) + Box-Muller.  Population handles: arrays gain a leading [P] dimension. */
 SHEMS_API int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
                               uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev);
+/* episode!(env; NUM_STEPS, train, track = 0, rng_ep) (DDPG.jl:186-242) for every instance of `env`, enqueued by ONE call with no host
+ * round trip per step: act(normalize(s)) (+ GNoise when train) -> scale_action -> step! -> remember -> replay() x updates_per_step.
+ * reset! (:189) stays with the caller.  env holds N = P*n instances: learner l owns instances l*n .. l*n+n-1 and the memory rps[l]
+ * (P = 1: the reference's loop).  Seeds: rng_step = (seed*1000003 + step) mod 2^63 keys the noise (with the global env id) and, as
+ * rng_step + l, learner l's minibatch draws.  ep_return_dev [N] (Float64, or NULL) receives reward_eps (:223).  The three handles
+ * must share one CUDA stream; the call returns as soon as the work is enqueued. */
+SHEMS_API int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps, int32_t n_steps, int32_t train, float sigma, uint64_t seed,
+                               int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev);
 /* replay() (DDPG.jl:121-145) n_updates times: sample -> TD target -> critic step -> actor step
  * -> Polyak.  idx_host ([n_updates][batch], 0-based logical indices) or NULL -> Philox(seed, update counter). */
 SHEMS_API int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed);

@@ -537,6 +537,8 @@ struct Ddpg {
   unsigned* dp_flags;      // [DP_MAX_WORLD] exchange numbers published by the ranks (written by the peers)
   void* dp_opened[2 * DP_MAX_WORLD]; int dp_n_opened;
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
+  // ddpg_episode scratch: a, scaled [2][N], s_prev [9][N], r [N]
+  float *ep_a, *ep_scaled, *ep_sprev, *ep_r; long long ep_cap;
 };
 static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows start on 128-byte lines: one L2 request per TMA box row
 #ifndef TC_MIN_ROWS
@@ -651,6 +653,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph) cudaGraphDestroy(h->graph);
   cudaFree(h->slab);
   cudaFree(h->act_x);  // act() scratch: one allocation (x | h1 | h2 | y per learner)
+  cudaFree(h->ep_a);   // episode scratch: one allocation
   if (h->graph_dp_exec) cudaGraphExecDestroy(h->graph_dp_exec);
   if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
   for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
@@ -1704,6 +1707,66 @@ extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float t
                                                          h->p.act_lo[0], h->p.act_lo[1], h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev,
                                                          h->act_stride);
   CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+// ----------------------------------------------------------------------------- episode!
+// reward_eps += r (DDPG.jl:223; Float64 accumulation of the Float32 step rewards as the vectorised loop sees them)
+__global__ void __launch_bounds__(256)
+ddpg_accum_return_kernel(const float* __restrict__ r, double* __restrict__ ret, long long n, int first) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ret[i] = (first ? 0.0 : ret[i]) + (double)r[i];
+}
+
+// episode!(env; NUM_STEPS, train, track = 0, rng_ep) (DDPG.jl:186-242) for all instances of `env`, enqueued in one call with no host
+// round trip per step: act(normalize(s)) [+ gn noise when train] -> scale_action -> step! -> remember -> replay() x updates_per_step.
+// The environment must have been reset by the caller (reset! is :189).  env holds N = P*n instances, learner l owns instances
+// l*n .. l*n+n-1 and the replay memory rps[l].  Per-step seeds: rng_step = (seed*1000003 + step) mod 2^63 feeds the noise stream
+// (keyed by the global env id) and, as rng_step + l, learner l's minibatch stream — the same rule the Python Driver uses.
+// All three handles must be bound to the same CUDA stream.  ep_return_dev [N] (Float64) receives the summed rewards, or NULL.
+extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps, int32_t n_steps, int32_t train, float sigma, uint64_t seed,
+                                int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev) {
+  REQUIRE(h && env, SHEMS_ERR_INVALID, "ddpg_episode: NULL argument");
+  REQUIRE(n_steps >= 1 && updates_per_step >= 0, SHEMS_ERR_INVALID, "ddpg_episode: n_steps=%d updates_per_step=%d", n_steps, updates_per_step);
+  REQUIRE(!train || rps, SHEMS_ERR_INVALID, "ddpg_episode: training needs the replay memories");
+  REQUIRE(env->device == h->device, SHEMS_ERR_INVALID, "ddpg_episode: env on device %d, learner on %d", env->device, h->device);
+  REQUIRE(env->n % h->pop == 0, SHEMS_ERR_INVALID, "ddpg_episode: %lld instances do not split over %d learners", (long long)env->n, h->pop);
+  REQUIRE(env->stream == h->stream && (!train || rps[0]->stream == h->stream), SHEMS_ERR_STATE,
+          "ddpg_episode: bind the environment, the learner and the replay memories to one CUDA stream");
+  REQUIRE(env->was_reset, SHEMS_ERR_STATE, "ddpg_episode: reset! must come first");
+  if ((int64_t)env->max_idx + n_steps > env->nrows) {  // nothing is enqueued for an episode that would leave the series
+    shems_set_error("BoundsError: episode of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", n_steps, env->max_idx,
+                    env->nrows);
+    return SHEMS_ERR_BOUNDS;
+  }
+  GUARD(h->device);
+  const long long N = env->n, n = N / h->pop;
+  if (h->ep_cap < N) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->ep_a); h->ep_a = nullptr; h->ep_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->ep_a, sizeof(float) * 14 * (size_t)N));
+    h->ep_scaled = h->ep_a + 2 * N; h->ep_sprev = h->ep_a + 4 * N; h->ep_r = h->ep_a + 13 * N;
+    h->ep_cap = N;
+  }
+  std::vector<uint64_t> seeds((size_t)h->pop);
+  for (int step = 1; step <= n_steps; ++step) {
+    const uint64_t rng_step = (seed * 1000003ull + (uint64_t)step) & 0x7fffffffffffffffull;
+    TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
+    if (train) CUDA_TRY(cudaMemcpyAsync(h->ep_sprev, env->obs, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, nullptr, nullptr));
+    if (ep_return_dev) {
+      ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r, ep_return_dev, N, step == 1);
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (train) {
+      TRY(replay_push_groups(rps, h->pop, h->ep_sprev, h->ep_a, h->ep_r, env->obs, nullptr, n));   // the unscaled action is stored (:229)
+      if (updates_per_step > 0) {
+        for (int l = 0; l < h->pop; ++l) seeds[l] = rng_step + (uint64_t)l;
+        TRY(ddpg_update_population(h, rps, updates_per_step, nullptr, seeds.data()));                  // replay(rng_rpl = rng_step) (:231)
+      }
+    }
+  }
   return SHEMS_OK;
 }
 

@@ -203,6 +203,19 @@ class Learner:
                                      int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(z), _ptr(a), _ptr(sc)))
         return a, sc
 
+    def episode(self, env, memories, n_steps, train=True, sigma=0.1, rng_ep=0, updates_per_step=1):
+        """ddpg_episode: episode!(env; train, track = 0) for all instances of `env`, enqueued by one call (no host round trip per
+        step).  memories: the learners' Replay objects (one for a single learner) or None when train is False.  Returns reward_eps [N] float64."""
+        ret = torch.empty(env.n_envs, dtype=torch.float64, device=self._dev)
+        hs = None
+        if memories is not None:
+            mems = list(memories) if isinstance(memories, (list, tuple)) else [memories]
+            assert len(mems) == self.population
+            hs = (C.c_void_p * self.population)(*[m._h for m in mems])
+        L.check(self.lib.ddpg_episode(self._h, env._h, hs, int(n_steps), 1 if train else 0, float(sigma), int(rng_ep) & (2**64 - 1),
+                                      int(updates_per_step), int(env.env_id_base), _ptr(ret)))
+        return ret
+
     def replay(self, memory, rng_rpl=0, n_updates=1, idx=None):
         """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back.  Population handles: `memory` is the list of the
         learners' Replay objects, rng_rpl an int (learner l uses rng_rpl + l) or one seed per learner, idx [P][n_updates][batch]."""
@@ -297,13 +310,14 @@ class Driver:
     (Julia's string-concatenated MersenneTwister seeds cannot be reproduced)."""
 
     def __init__(self, env_train, env_eval=None, learner=None, mem_size=24_000, ep_length=72, sigma=0.1, updates_per_step=1,
-                 rng_run=1231, noise_type="gn", theta=0.15, ou_dt=1e-2):
+                 rng_run=1231, noise_type="gn", theta=0.15, ou_dt=1e-2, native=True):
         self.env_train, self.env_eval = env_train, env_eval
         self.learner = learner if learner is not None else Learner(device=env_train.device)
         self.memory = Replay(mem_size, device=env_train.device)
         self.mem_size, self.ep_length, self.sigma = int(mem_size), int(ep_length), float(sigma)
         self.updates_per_step = int(updates_per_step)
         self.rng_run = int(rng_run)
+        self.native = bool(native)      # False: run episode! step by step from Python (reference-shaped loop; used to test the native one)
         self.s_min = self.s_max = None
         self.n_env_steps = 0
         assert noise_type in ("gn", "ou"), "parameter noise (pn) and epsilon noise (en) are out of scope (SURVEY §2)"
@@ -332,6 +346,13 @@ class Driver:
         T = self.ep_length if num_steps is None else num_steps
         env.reset(rng=rng_ep)
         n = env.n_envs
+        if track == 0 and self.native and (self.noise_type == "gn" or not train):
+            # the whole loop below as one native call (ddpg_episode): same seeds, same kernels, no host round trip per step
+            r = self.learner.episode(env, self.memory if train else None, T, train=train, sigma=self.sigma, rng_ep=rng_ep,
+                                     updates_per_step=self.updates_per_step)
+            if train:
+                self.n_env_steps += n * T
+            return r, T, 0.0
         reward_eps = torch.zeros(n, dtype=torch.float64, device=env._torch_dev)
         noise_eps = 0.0
         traces = []
@@ -409,9 +430,11 @@ class PopulationDriver:
 
     chargers[l] is learner l's charger id (shems_LU1.jl:47-59), equal ids must be adjacent; seeds[l] its rng_run (input.jl:136)."""
 
-    def __init__(self, series, chargers, seeds, n_envs=64, mem_size=24_000, ep_length=72, sigma=0.1, device=0, use_tensor_cores=1, **ddpg_kw):
+    def __init__(self, series, chargers, seeds, n_envs=64, mem_size=24_000, ep_length=72, sigma=0.1, device=0, use_tensor_cores=1, native=True,
+                 **ddpg_kw):
         from .env import Shems
         assert len(chargers) == len(seeds)
+        self.native = bool(native)
         self.P, self.n_envs, self.ep_length, self.sigma, self.mem_size = len(chargers), int(n_envs), int(ep_length), float(sigma), int(mem_size)
         self.seeds = [int(x) for x in seeds]
         self.chargers = [int(c) for c in chargers]
@@ -452,6 +475,12 @@ class PopulationDriver:
         """episode!(env; train) for every learner in lock step -> mean return per learner [P] (Float64)."""
         env = self.env
         env.reset(rng=rng_ep * 1009 + self.seeds[0])
+        if self.native:
+            ret = self.learner.episode(env, self.mems if train else None, self.ep_length, train=train, sigma=self.sigma, rng_ep=rng_ep,
+                                       updates_per_step=updates_per_step)
+            if train:
+                self.n_env_steps += self.N * self.ep_length
+            return ret.view(self.P, self.n_envs).mean(dim=1)
         ret = torch.zeros(self.N, dtype=torch.float64, device=self._dev)
         for step in range(1, self.ep_length + 1):
             rng_step = (rng_ep * 1000003 + step) & (2**63 - 1)

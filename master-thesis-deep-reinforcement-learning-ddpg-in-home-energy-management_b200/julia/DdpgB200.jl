@@ -9,7 +9,7 @@
 #     act(s; train, rng_act)               DDPG.jl:148-176 — takes the RAW state: normalize() is fused into the kernel
 #     scale_action(a)                      :178-184
 #     replay(; rng_rpl)                    :121-145
-#     episode!(env; NUM_STEPS, train, render, track, rng_ep)   :186-242
+#     episode!(env; NUM_STEPS, train, render, track, rng_ep)   :186-242 (track == 0: one native ddpg_episode call)
 #     pull_actor!(actor)                   copies the learner's actor into a Flux Chain so saveBSON (:263-270) is unchanged
 # Globals read from input.jl exactly like the reference: BATCH_SIZE, MEM_SIZE, L1, L2, γ, τ, η_act, η_crit, EP_LENGTH, noise_type,
 # gn / ou, ACTION_BOUND_LO / HI, rng_run.
@@ -106,6 +106,15 @@ end
 # ------------------------------------------------------------------ episode!  (DDPG.jl:186-242)
 function episode!(env::Shems; NUM_STEPS=EP_LENGTH["train"], train=true, render=false, track=0, rng_ep=0)
     reset!(env; rng=rng_ep)
+    if track == 0 && noise_type == "gn"
+        # the whole loop below as ONE native call (ddpg_episode): no host round trip per step, same per-step seeds
+        ret = CUDA.zeros(Float64, env.n_envs)
+        mems = Ptr{Cvoid}[_memory]
+        check(ccall((:ddpg_episode, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cfloat, UInt64, Cint, Int64, CUDA.CuPtr{Cdouble}),
+                    _learner, env.handle, train ? mems : C_NULL, NUM_STEPS, train ? 1 : 0, gn.σ_act, UInt64(abs(rng_ep)), 1, 0, ret))
+        return Array(ret)[1], NUM_STEPS, 0f0
+    end
     reward_eps, noise_eps, last_step = 0.0, 0f0, 1
     results = Matrix{Float64}(undef, 0, 23)
     for step = 1:NUM_STEPS

@@ -569,3 +569,39 @@ def test_act_soa_and_push_groups_equal_packed_layout(sb, train_series):
             np.testing.assert_array_equal(x, y)
     with pytest.raises(sb.ShemsError):                                           # more transitions per learner than a ring holds
         push_groups([sb.Replay(10) for _ in range(P)], obs_soa, a1, r, s_next)
+
+
+@pytest.mark.parametrize("population", [1, 3])
+def test_native_episode_equals_python_loop(sb, train_series, population):
+    """ddpg_episode (episode! enqueued by one native call) must do exactly what the step-by-step Python loop does — same seeds,
+    same kernels: returns and every weight bit-identical, for one learner and for a population."""
+    kw = dict(batch=32, l1=48, l2=64)
+    outs = []
+    for native in (False, True):
+        if population == 1:
+            env = sb.Shems(72, train_series, n_envs=16)
+            drv = sb.Driver(env, None, learner=sb.Learner(params=sb.default_ddpg_params(**kw)), mem_size=16 * 72, ep_length=72, sigma=0.1,
+                            rng_run=77, native=native)
+            drv.learner.init(5)
+            drv.populate_memory()
+            drv.min_max_buffer()
+            rets = [drv.episode(env, train=True, rng_ep=3)[0], drv.episode(env, train=False, rng_ep=4)[0]]
+            le, P = drv.learner, 1
+        else:
+            drv = sb.PopulationDriver(train_series, chargers=[98, 98, 4], seeds=[11, 12, 13], n_envs=16, mem_size=16 * 72, use_tensor_cores=0,
+                                      native=native, **kw)
+            drv.populate_memory()
+            drv.min_max_buffer()
+            rets = [drv.episode(train=True, rng_ep=3), drv.episode(train=False, rng_ep=4)]
+            le, P = drv.learner, 3
+        ws = []
+        for l in range(P):
+            le.select(l)
+            ws += [le.get_layer(net, k) for net in range(4) for k in range(3)]
+        outs.append((rets, ws))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert torch.equal(a, b)
+    for (w0, b0), (w1, b1) in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(w0, w1)
+        np.testing.assert_array_equal(b0, b1)
+    assert float(outs[0][0][0].abs().sum()) > 0
