@@ -20,7 +20,7 @@
 # minibatch indices, warm-up actions and exploration noise come from the library's Philox streams keyed by the same integer seeds.
 
 import CUDA
-using .ShemsB200: Shems, LIB, check
+using .ShemsB200: ShemsB200, Shems, LIB, check
 
 struct DdpgParams                        # must match include/shems_b200.h
     state_size::Cint; action_size::Cint; l1::Cint; l2::Cint; batch::Cint
@@ -113,6 +113,7 @@ function episode!(env::Shems; NUM_STEPS=EP_LENGTH["train"], train=true, render=f
         check(ccall((:ddpg_episode, LIB), Cint,
                     (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Cint, Cint, Cfloat, UInt64, Cint, Int64, CUDA.CuPtr{Cdouble}),
                     _learner, env.handle, train ? mems : C_NULL, NUM_STEPS, train ? 1 : 0, gn.σ_act, UInt64(abs(rng_ep)), 1, 0, ret))
+        ShemsB200.pull!(env)                          # refresh env.state / env.idx / env.step mirrors from the device
         return Array(ret)[1], NUM_STEPS, 0f0
     end
     reward_eps, noise_eps, last_step = 0.0, 0f0, 1
