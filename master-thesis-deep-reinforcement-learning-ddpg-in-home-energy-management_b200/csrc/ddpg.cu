@@ -431,10 +431,10 @@ outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, con
     const long long lo = (long long)blockIdx.y * pop_stride;
     dZ += lo; W += lo; H += lo; dX += lo;
   }
-  const int n4 = (N + 3) / 4;
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)B * n4) return;
-  const int b = (int)(e / n4), n = (int)(e - (long long)b * n4) * 4;
+  const unsigned n4 = (unsigned)(N + 3) / 4u;
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;   // B * n4 < 2^31 (checked by the launcher): 32-bit division
+  if (e >= (unsigned)B * n4) return;
+  const int b = (int)(e / n4), n = (int)(e - (unsigned)b * n4) * 4;
   float dz[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) dz[j] = dZ[(long long)b * J + j];
@@ -1093,6 +1093,7 @@ static int big_l1(cudaStream_t st, int count, const float* const* X, int ldx, in
 // output layer backward: dW3 (+db3) by weighted column sums, dX by the masked outer product (large batches and populations)
 static int launch_outer_mask(Ddpg* h, cudaStream_t st, const float* dZ, int J, const float* W, const float* H, int ld, int B, int N, float* dX) {
   const long long ne = (long long)B * ((N + 3) / 4);
+  REQUIRE(ne < (1ll << 31), SHEMS_ERR_INVALID, "launch_outer_mask: batch x width too large");
   const dim3 grid((unsigned)((ne + 255) / 256), h->pop);
   if (J == 1) outer_mask_kernel<1><<<grid, 256, 0, st>>>(dZ, W, H, ld, B, N, dX, h->pop_stride);
   else outer_mask_kernel<2><<<grid, 256, 0, st>>>(dZ, W, H, ld, B, N, dX, h->pop_stride);
