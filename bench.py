@@ -265,6 +265,27 @@ def rule_based_config2(sb, torch, ser_train, n_envs=4096, T=72, reps=50):
                 mean_return=float(out["ep_return"].mean()), note="reset!(rng=-1) + one fused 72-step launch; launch/latency bound")
 
 
+def rollout_returns_only(sb, torch, ser, n_envs=1 << 20, T=2000, reps=3):
+    """The same random-action rollout with the episode returns as its only output (8 B per instance per launch): no HBM roofline
+    applies — this is the arithmetic ceiling of the Julia-exact step, reported as env-steps/s."""
+    env = sb.Shems(T, ser, n_envs=n_envs)
+    env.reset(rng=1)
+    env.rollout(sb.POLICY_RANDOM, T, seed=1)
+    torch.cuda.synchronize()
+    ms = []
+    for rep in range(reps):
+        env.reset(rng=2 + rep)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        env.rollout(sb.POLICY_RANDOM, T, seed=2 + rep)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = sorted(ms)[len(ms) // 2]
+    return dict(envs=n_envs, steps=T, env_steps_per_s=n_envs * T / (t * 1e-3), ms_per_launch=t,
+                note="no per-step sink: bound by instruction issue, not by bytes")
+
+
 POP_CHARGERS = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)  # capacities of shems_LU1.jl:47-59; 10 chargers x 64 seeds = 640 learners on 8 GPUs
 
 
@@ -517,6 +538,10 @@ def main():
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:  # never lose the env number to the secondary metric
             line["ddpg"] = dict(error=str(e))
+        try:
+            line["rollout_returns_only"] = rollout_returns_only(sb, torch, ser)
+        except Exception as e:
+            line["rollout_returns_only"] = dict(error=str(e))
         try:
             line["rule_based_4096x72"] = rule_based_config2(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:
