@@ -605,3 +605,57 @@ def test_native_episode_equals_python_loop(sb, train_series, population):
         np.testing.assert_array_equal(w0, w1)
         np.testing.assert_array_equal(b0, b1)
     assert float(outs[0][0][0].abs().sum()) > 0
+
+
+def test_full_size_properties_ddpg(sb, train_series):
+    """BASELINE configs[3] shape (B = 8192, 250/500, TF32 tensor cores) and configs[4] shape (80 learners, B = 120) through
+    size-independent properties: zero learning rates leave the models untouched and tau = 1 makes the targets equal to them;
+    the update is deterministic (two identical learners stay bit-identical); losses are finite."""
+    env = sb.Shems(72, train_series, n_envs=8192)
+    mem = sb.Replay(8192 * 8)
+    env.reset(rng=1)
+    env.rollout(sb.POLICY_RANDOM, 8, seed=1, replay=mem, want_return=False)
+    mn, mx = mem.min_max_buffer(20_000, rng_mm=1)
+
+    def make(**kw):
+        le = sb.Learner(params=sb.default_ddpg_params(batch=8192, use_tensor_cores=1, **kw))
+        le.init(3)
+        le.set_norm(mn, mx)
+        return le
+
+    frozen = make(lr_actor=0.0, lr_critic=0.0, tau=1.0)
+    before = [frozen.get_layer(net, k) for net in (0, 1) for k in range(3)]
+    for net in (2, 3):   # make the targets differ from the models first
+        for k in range(3):
+            w, b = frozen.get_layer(net, k)
+            frozen.set_layer(net, k, w * np.float32(0.5), b + np.float32(0.25))
+    frozen.replay(mem, rng_rpl=4, n_updates=2)
+    after = [frozen.get_layer(net, k) for net in (0, 1) for k in range(3)]
+    targets = [frozen.get_layer(net, k) for net in (2, 3) for k in range(3)]
+    for (w0, b0), (w1, b1), (wt, bt) in zip(before, after, targets):
+        np.testing.assert_array_equal(w0, w1); np.testing.assert_array_equal(b0, b1)      # eta = 0: x - 0
+        np.testing.assert_array_equal(w1, wt); np.testing.assert_array_equal(b1, bt)      # tau = 1: 0*p_t + 1*p_m
+    lc, la = frozen.losses()
+    assert np.isfinite(lc) and np.isfinite(la)
+    g = [frozen.get_grad(net, k)[0] for net in (0, 1) for k in range(3)]
+    assert all(np.isfinite(x).all() and np.abs(x).max() > 0 for x in g)
+    a, b = make(), make()
+    a.replay(mem, rng_rpl=9, n_updates=3)
+    b.replay(mem, rng_rpl=9, n_updates=3)
+    for net in range(4):
+        for k in range(3):
+            np.testing.assert_array_equal(a.get_layer(net, k)[0], b.get_layer(net, k)[0])
+    # 80 learners: deterministic as well, and learners with different seeds end up different
+    mems = [mem] * 80
+    pops = []
+    for _ in range(2):
+        pop = sb.Learner(params=sb.default_ddpg_params(population=80, use_tensor_cores=1))
+        pop.init(5)
+        for l in (0, 41, 79):
+            pop.select(l).set_norm(mn, mx)
+        pop.replay(mems, rng_rpl=2, n_updates=2)
+        pops.append(pop)
+    for l in (0, 41, 79):
+        x, y = pops[0].select(l).get_layer(1, 1)[0], pops[1].select(l).get_layer(1, 1)[0]
+        np.testing.assert_array_equal(x, y)
+    assert not np.array_equal(pops[0].select(0).get_layer(1, 1)[0], pops[0].select(79).get_layer(1, 1)[0])
