@@ -162,3 +162,18 @@ def test_oracle_ou_noise_matches_numpy_typed_restatement(O):
         np.testing.assert_array_equal(x, xn)
         np.testing.assert_array_equal(out, xn)
     assert np.abs(x).max() < 1.0 and x.std() > 0.01
+
+
+def test_oracle_matches_committed_ddpg_fixture(O):
+    """tests/golden/oracle_ddpg_small.npz (oracle outputs, committed with its generator): the oracle reproduces it bit for bit."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_ddpg_fixture", os.path.join(here, "make_ddpg_fixture.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = np.load(os.path.join(here, "oracle_ddpg_small.npz"))
+    got = mod.run(O)
+    assert sorted(want.files) == sorted(got.keys())
+    for k in want.files:
+        np.testing.assert_array_equal(want[k], got[k], err_msg=k)

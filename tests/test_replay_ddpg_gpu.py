@@ -659,3 +659,28 @@ def test_full_size_properties_ddpg(sb, train_series):
         x, y = pops[0].select(l).get_layer(1, 1)[0], pops[1].select(l).get_layer(1, 1)[0]
         np.testing.assert_array_equal(x, y)
     assert not np.array_equal(pops[0].select(0).get_layer(1, 1)[0], pops[0].select(79).get_layer(1, 1)[0])
+
+
+def test_cuda_matches_committed_ddpg_fixture(sb):
+    """CUDA replay()/act() against the committed oracle vectors of tests/golden/oracle_ddpg_small.npz (same Philox init, same
+    minibatches): losses 1e-4, weights within 2 % of lr*K, actions 2e-4."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_ddpg_small.npz"))
+    B, l1, l2, K, seed = 24, 20, 28, 4, 2024
+    le = sb.Learner(params=sb.default_ddpg_params(batch=B, l1=l1, l2=l2))
+    le.init(seed)
+    le.set_norm(z["s_min"], z["s_max"])
+    for u in range(K):
+        le.update_batch(dev(z[f"s{u}"]), dev(z[f"a{u}"]), dev(z[f"r{u}"]), dev(z[f"s2_{u}"]))
+        lc, la = le.losses()
+        assert lc == pytest.approx(float(z[f"loss{u}"][0]), rel=1e-4) and la == pytest.approx(float(z[f"loss{u}"][1]), rel=1e-4, abs=1e-6)
+    p = le.p
+    lrs = [p.lr_actor, p.lr_critic, p.lr_actor * p.tau, p.lr_critic * p.tau]
+    for net in range(4):
+        for k in range(3):
+            w, b = le.get_layer(net, k)
+            np.testing.assert_allclose(w, z[f"w{net}{k}"], rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
+            np.testing.assert_allclose(b, z[f"b{net}{k}"], rtol=1e-5, atol=0.02 * lrs[net] * K + 1e-7)
+    a, sc = le.act(dev(z["obs"]), noise=dev(z["noise"]))
+    np.testing.assert_allclose(a.cpu().numpy(), z["act"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(sc.cpu().numpy(), z["scaled"], rtol=2e-4, atol=2e-5)
