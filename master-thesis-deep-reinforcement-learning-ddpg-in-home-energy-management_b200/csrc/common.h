@@ -101,7 +101,9 @@ struct ShemsEnv {
   float* obs;       // [9][n]  == env.state of every instance
   int32_t* idx;     // [n] 1-based row (env.idx)
   int32_t* d_maxidx;  // device scalar: max idx after reset
-  int32_t max_idx;    // host mirror (advances by 1 per step)
+  int32_t max_idx;    // host mirror: the largest row any instance is on, or (while max_pending) an upper bound of it; +1 per step
+  int32_t* h_maxidx;  // pinned host word the reset kernel's maximum is copied to (asynchronously)
+  cudaEvent_t ev_maxidx; bool max_pending;  // the exact value is fetched only when the upper bound does not settle a bounds check
   int32_t step;       // env.step (instances run in lockstep)
   bool was_reset;
   bool consistent;    // state fields 2..8 equal series row idx (false after shems_set_state)
@@ -114,3 +116,5 @@ struct ShemsEnv {
 };
 
 int replay_after_rollout(ShemsReplay* rp, int64_t n_written);
+// may every instance advance `need` more rows (next_state! reads row idx+1)?  0 = yes, else the furthest instance's row (env.cu)
+int32_t ensure_rows(ShemsEnv* e, int64_t need);

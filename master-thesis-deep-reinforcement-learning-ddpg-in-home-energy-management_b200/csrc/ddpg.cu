@@ -1736,7 +1736,7 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
   REQUIRE(env->stream == h->stream && (!train || rps[0]->stream == h->stream), SHEMS_ERR_STATE,
           "ddpg_episode: bind the environment, the learner and the replay memories to one CUDA stream");
   REQUIRE(env->was_reset, SHEMS_ERR_STATE, "ddpg_episode: reset! must come first");
-  if ((int64_t)env->max_idx + n_steps > env->nrows) {  // nothing is enqueued for an episode that would leave the series
+  if (ensure_rows(env, n_steps)) {  // nothing is enqueued for an episode that would leave the series
     shems_set_error("BoundsError: episode of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", n_steps, env->max_idx,
                     env->nrows);
     return SHEMS_ERR_BOUNDS;

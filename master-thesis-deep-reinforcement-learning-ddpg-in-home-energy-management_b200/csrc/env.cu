@@ -453,6 +453,12 @@ extern "C" int32_t shems_create_groups(const ShemsParams* params, int32_t n_grou
     shems_destroy(e);
     return SHEMS_ERR_CUDA;
   }
+  if ((st = cudaMallocHost((void**)&e->h_maxidx, sizeof(int32_t))) != cudaSuccess ||
+      (st = cudaEventCreateWithFlags(&e->ev_maxidx, cudaEventDisableTiming)) != cudaSuccess) {
+    shems_set_error("shems_create: %s", cudaGetErrorString(st));
+    shems_destroy(e);
+    return SHEMS_ERR_CUDA;
+  }
   for (int g = 0; g < n_groups; ++g) {
     e->gdp[g] = make_dev_params(params[g]);
     e->gseries[g] = e->series + (series_per_group ? (size_t)g * nrows * 2 : 0);
@@ -472,6 +478,8 @@ extern "C" int32_t shems_destroy(ShemsEnv* e) {
   if (!e) return SHEMS_OK;
   GUARD(e->device);
   cudaFree(e->series); cudaFree(e->obs); cudaFree(e->idx); cudaFree(e->d_maxidx); cudaFree(e->scratch_i); cudaFree(e->scratch_f);
+  if (e->h_maxidx) cudaFreeHost(e->h_maxidx);
+  if (e->ev_maxidx) cudaEventDestroy(e->ev_maxidx);
   delete e;
   return SHEMS_OK;
 }
@@ -500,6 +508,18 @@ extern "C" int32_t shems_finished(const ShemsEnv* e, int32_t* out) {
   return SHEMS_OK;
 }
 
+// may the instances advance `need` more rows?  0 = yes; otherwise the row the furthest instance would read (for the message)
+int32_t ensure_rows(ShemsEnv* e, int64_t need) {
+  if ((int64_t)e->max_idx + need <= e->nrows) return 0;
+  if (e->max_pending) {  // the upper bound does not settle it: wait for the exact maximum of the last reset
+    cudaEventSynchronize(e->ev_maxidx);
+    e->max_idx = *e->h_maxidx + e->step;
+    e->max_pending = false;
+    if ((int64_t)e->max_idx + need <= e->nrows) return 0;
+  }
+  return e->max_idx;
+}
+
 extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_host, const float* socb0_host, uint64_t seed,
                                int64_t env_id_base) {
   REQUIRE(e, SHEMS_ERR_INVALID, "shems_reset: NULL handle");
@@ -525,8 +545,15 @@ extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_ho
                                                                      e->scratch_f, seed, env_id_base, e->obs, e->idx, e->d_maxidx, n0, n1);
   }
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(&e->max_idx, e->d_maxidx, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(cudaStreamSynchronize(e->stream));
+  // Bounds pre-check of the following steps (Julia's BoundsError at :266-268) without stalling the host: every start row is
+  // <= nrows - maxsteps, which settles every episode of <= maxsteps steps; the exact maximum travels to a pinned word
+  // asynchronously and is only waited for when that bound is not enough (ensure_rows).
+  if (mode == SHEMS_RESET_DETERMINISTIC) { e->max_idx = 1; e->max_pending = false; }
+  else {
+    CUDA_TRY(cudaMemcpyAsync(e->h_maxidx, e->d_maxidx, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaEventRecord(e->ev_maxidx, e->stream));
+    e->max_idx = hi; e->max_pending = true;
+  }
   e->step = 0;          // :210
   e->was_reset = true;
   e->consistent = true;
@@ -536,7 +563,7 @@ extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_ho
 extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, float* reward_dev, float* obs_dev, double* trace_dev) {
   REQUIRE(e && act_dev, SHEMS_ERR_INVALID, "shems_step: NULL argument");
   REQUIRE(e->was_reset, SHEMS_ERR_STATE, "shems_step: reset! (or shems_set_state) must come first");
-  if (e->max_idx + 1 > e->nrows) {
+  if (ensure_rows(e, 1)) {
     shems_set_error("BoundsError: attempt to access %d-row series at row %d (next_state!, shems_LU1.jl:266-268)", e->nrows, e->max_idx + 1);
     return SHEMS_ERR_BOUNDS;
   }
@@ -603,7 +630,7 @@ extern "C" int32_t shems_set_state(ShemsEnv* e, const float* obs_host, const int
   CUDA_TRY(cudaMemcpyAsync(e->obs, obs_host, sizeof(float) * 9 * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaMemcpyAsync(e->idx, idx_host, sizeof(int32_t) * (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(cudaStreamSynchronize(e->stream));
-  e->max_idx = mx;
+  e->max_idx = mx; e->max_pending = false;
   e->was_reset = true;
   e->consistent = false;
   return SHEMS_OK;
@@ -615,7 +642,7 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
   REQUIRE(a->n_steps >= 1, SHEMS_ERR_INVALID, "shems_rollout: n_steps=%d", a->n_steps);
   REQUIRE(a->policy >= 0 && a->policy <= 2, SHEMS_ERR_INVALID, "shems_rollout: unknown policy %d", a->policy);
   REQUIRE(a->policy != SHEMS_POLICY_TAPE || a->tape_dev, SHEMS_ERR_INVALID, "shems_rollout: POLICY_TAPE needs tape_dev");
-  if ((int64_t)e->max_idx + a->n_steps > e->nrows) {
+  if (ensure_rows(e, a->n_steps)) {
     shems_set_error("BoundsError: rollout of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", a->n_steps,
                     e->max_idx, e->nrows);
     return SHEMS_ERR_BOUNDS;
