@@ -297,6 +297,9 @@ SHEMS_API int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float s
  * or NULL -> Philox(seed, global env id, step) + Box-Muller.  Population handles: arrays gain a leading [P] dimension. */
 SHEMS_API int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
                               uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev);
+/* noise_type for ddpg_episode (input.jl:111): kind 0 = "gn" (default; sigma is passed per episode), 1 = "ou" with OUNoise(mu, sigma,
+ * theta, dt, X) (input.jl:190-234); X is kept in the handle per instance and, like the reference's global `ou`, never reset. */
+SHEMS_API int32_t ddpg_set_noise(Ddpg* h, int32_t kind, float theta, float mu, float dt);
 /* episode!(env; NUM_STEPS, train, track = 0, rng_ep) (DDPG.jl:186-242) for every instance of `env`, enqueued by ONE call with no host
  * round trip per step: act(normalize(s)) (+ GNoise when train) -> scale_action -> step! -> remember -> replay() x updates_per_step.
  * reset! (:189) stays with the caller.  env holds N = P*n instances: learner l owns instances l*n .. l*n+n-1 and the memory rps[l]

@@ -110,6 +110,7 @@ SIGNATURES = {
     "ddpg_act": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
     "ddpg_act_soa": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
     "ddpg_act_ou": (I32, [VP, VP, I64, F32, F32, F32, F32, VP, U64, I64, I64, VP, VP, VP]),
+    "ddpg_set_noise": (I32, [VP, I32, F32, F32, F32]),
     "ddpg_episode": (I32, [VP, VP, C.POINTER(VP), I32, I32, F32, U64, I32, I64, VP]),
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),

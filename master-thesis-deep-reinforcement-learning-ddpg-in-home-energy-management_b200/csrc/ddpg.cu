@@ -539,6 +539,8 @@ struct Ddpg {
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
   // ddpg_episode scratch: a, scaled [2][N], s_prev [9][N], r [N]
   float *ep_a, *ep_scaled, *ep_sprev, *ep_r; long long ep_cap;
+  int noise_kind; float ou_theta, ou_mu, ou_dt;   // ddpg_set_noise
+  float* ou_x; long long ou_cap;                   // OUNoise.X of every instance of ddpg_episode's environment ([2][N])
 };
 static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows start on 128-byte lines: one L2 request per TMA box row
 #ifndef TC_MIN_ROWS
@@ -654,6 +656,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   cudaFree(h->slab);
   cudaFree(h->act_x);  // act() scratch: one allocation (x | h1 | h2 | y per learner)
   cudaFree(h->ep_a);   // episode scratch: one allocation
+  cudaFree(h->ou_x);
   if (h->graph_dp_exec) cudaGraphExecDestroy(h->graph_dp_exec);
   if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
   for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
@@ -1594,17 +1597,18 @@ ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, fl
 __global__ void __launch_bounds__(256)
 ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float theta, float mu, float sigma, float dt, float* __restrict__ ou_x,
                             unsigned long long seed, long long step, long long env_id_base, const double* __restrict__ z, float lo0, float lo1,
-                            float hi0, float hi1, float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride) {
+                            float hi0, float hi1, float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride,
+                            long long asl, long long ask) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  {
+  {  // learner l = blockIdx.y; component k of its instance j at [l*asl + k*ask + j] (packed: asl = 2n, ask = n; SoA: asl = n, ask = N)
     const long long l = blockIdx.y;
-    y += l * act_stride; a_out += l * 2 * n; ou_x += l * 2 * n; env_id_base += l * n;
-    if (z) z += l * 2 * n;
-    if (scaled_out) scaled_out += l * 2 * n;
+    y += l * act_stride; a_out += l * asl; ou_x += l * asl; env_id_base += l * n;
+    if (z) z += l * asl;
+    if (scaled_out) scaled_out += l * asl;
   }
   double z0, z1;
-  if (z) { z0 = z[j]; z1 = z[n + j]; }
+  if (z) { z0 = z[j]; z1 = z[ask + j]; }
   else {
     uint32_t w[4];
     philox4x32_10(seed, (uint64_t)(env_id_base + j), (uint32_t)step, STREAM_NOISE, w);
@@ -1618,20 +1622,20 @@ ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n,
   float nz[2];
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    const float x = ou_x[k * n + j];
+    const float x = ou_x[k * ask + j];
     float dx = __fmul_rn(__fmul_rn(theta, __fsub_rn(mu, x)), dt);
     dx = (float)__dadd_rn((double)dx, __dmul_rn((double)ssd, k == 0 ? z0 : z1));
     nz[k] = __fadd_rn(x, dx);
-    ou_x[k * n + j] = nz[k];
+    ou_x[k * ask + j] = nz[k];
   }
   float a0 = __fadd_rn(y[j * 2 + 0], nz[0]), a1 = __fadd_rn(y[j * 2 + 1], nz[1]);
   a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
   a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
-  a_out[j] = a0; a_out[n + j] = a1;
+  a_out[j] = a0; a_out[ask + j] = a1;
   if (scaled_out) {
     const double sp0 = (double)__fsub_rn(hi0, lo0), sp1 = (double)__fsub_rn(hi1, lo1);
     scaled_out[j] = (float)__dadd_rn((double)lo0, __dmul_rn(__dmul_rn(__dadd_rn((double)a0, 1.0), 0.5), sp0));
-    scaled_out[n + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
+    scaled_out[ask + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
   }
 }
 
@@ -1696,18 +1700,31 @@ extern "C" int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float 
   return act_gauss(h, obs_dev, n, sigma, seed, step, env_id_base, noise_dev, a_dev, scaled_dev, true);
 }
 
-extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
-                               uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev) {
+static int act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev, uint64_t seed,
+                  int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev, bool soa) {
   REQUIRE(h && obs_dev && a_dev && ou_x_dev, SHEMS_ERR_INVALID, "ddpg_act_ou: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act_ou: n=%lld", (long long)n);
   REQUIRE(dt >= 0.0f, SHEMS_ERR_INVALID, "ddpg_act_ou: dt=%g (sqrt(dt) raises DomainError in the reference)", (double)dt);
   GUARD(h->device);
-  TRY(act_forward(h, obs_dev, n, 9 * n, n));
+  const long long N = (long long)n * h->pop;
+  TRY(act_forward(h, obs_dev, n, soa ? n : 9 * n, soa ? N : n));
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_ou_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, theta, mu, sigma, dt, ou_x_dev, seed, step, env_id_base, z_dev,
                                                          h->p.act_lo[0], h->p.act_lo[1], h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev,
-                                                         h->act_stride);
+                                                         h->act_stride, soa ? n : 2 * n, soa ? N : n);
   CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev,
+                               uint64_t seed, int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev) {
+  return act_ou(h, obs_dev, n, theta, mu, sigma, dt, ou_x_dev, seed, step, env_id_base, z_dev, a_dev, scaled_dev, false);
+}
+// noise_type of ddpg_episode (input.jl:111): 0 = "gn" (GNoise, the default), 1 = "ou" (OUNoise(mu, sigma, theta, dt, X), input.jl:190-234;
+// X lives in the handle, one pair per instance, and — like the reference's global `ou` — is never reset)
+extern "C" int32_t ddpg_set_noise(Ddpg* h, int32_t kind, float theta, float mu, float dt) {
+  REQUIRE(h && (kind == 0 || kind == 1), SHEMS_ERR_INVALID, "ddpg_set_noise: kind=%d (0 gn, 1 ou)", kind);
+  REQUIRE(dt >= 0.0f, SHEMS_ERR_INVALID, "ddpg_set_noise: dt=%g", (double)dt);
+  h->noise_kind = kind; h->ou_theta = theta; h->ou_mu = mu; h->ou_dt = dt;
   return SHEMS_OK;
 }
 
@@ -1750,10 +1767,20 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
     h->ep_scaled = h->ep_a + 2 * N; h->ep_sprev = h->ep_a + 4 * N; h->ep_r = h->ep_a + 13 * N;
     h->ep_cap = N;
   }
+  if (train && h->noise_kind == 1 && h->ou_cap != N) {  // first use (or another environment size): X = zeros (input.jl:234)
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->ou_x); h->ou_x = nullptr; h->ou_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->ou_x, sizeof(float) * 2 * (size_t)N));
+    CUDA_TRY(cudaMemsetAsync(h->ou_x, 0, sizeof(float) * 2 * (size_t)N, h->stream));
+    h->ou_cap = N;
+  }
   std::vector<uint64_t> seeds((size_t)h->pop);
   for (int step = 1; step <= n_steps; ++step) {
     const uint64_t rng_step = (seed * 1000003ull + (uint64_t)step) & 0x7fffffffffffffffull;
-    TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
+    if (train && h->noise_kind == 1)
+      TRY(act_ou(h, env->obs, n, h->ou_theta, h->ou_mu, sigma, h->ou_dt, h->ou_x, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
+    else
+      TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
     if (train) CUDA_TRY(cudaMemcpyAsync(h->ep_sprev, env->obs, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
     TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, nullptr, nullptr));
     if (ep_return_dev) {

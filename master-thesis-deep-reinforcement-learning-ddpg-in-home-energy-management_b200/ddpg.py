@@ -203,6 +203,10 @@ class Learner:
                                      int(rng_act) & (2**64 - 1), int(step), int(env_id_base), _ptr(z), _ptr(a), _ptr(sc)))
         return a, sc
 
+    def set_noise(self, kind="gn", theta=0.15, mu=0.0, dt=1e-2):
+        """noise_type of the native episode loop: "gn" or "ou" (OUNoise state is kept per instance inside the handle)."""
+        L.check(self.lib.ddpg_set_noise(self._h, {"gn": 0, "ou": 1}[kind], float(theta), float(mu), float(dt)))
+
     def episode(self, env, memories, n_steps, train=True, sigma=0.1, rng_ep=0, updates_per_step=1):
         """ddpg_episode: episode!(env; train, track = 0) for all instances of `env`, enqueued by one call (no host round trip per
         step).  memories: the learners' Replay objects (one for a single learner) or None when train is False.  Returns reward_eps [N] float64."""
@@ -323,6 +327,7 @@ class Driver:
         assert noise_type in ("gn", "ou"), "parameter noise (pn) and epsilon noise (en) are out of scope (SURVEY §2)"
         self.noise_type, self.theta, self.ou_dt = noise_type, float(theta), float(ou_dt)
         self._ou_x = None  # OUNoise.X per training instance; like the reference's global `ou` it is never reset (input.jl:234)
+        self.learner.set_noise(noise_type, theta=self.theta, mu=0.0, dt=self.ou_dt)
 
     # populate_memory(env; rng) — memory_plotting_saving.jl:9-29 (fused random-policy rollouts)
     def populate_memory(self, rng=None):
@@ -346,7 +351,7 @@ class Driver:
         T = self.ep_length if num_steps is None else num_steps
         env.reset(rng=rng_ep)
         n = env.n_envs
-        if track == 0 and self.native and (self.noise_type == "gn" or not train):
+        if track == 0 and self.native:
             # the whole loop below as one native call (ddpg_episode): same seeds, same kernels, no host round trip per step
             r = self.learner.episode(env, self.memory if train else None, T, train=train, sigma=self.sigma, rng_ep=rng_ep,
                                      updates_per_step=self.updates_per_step)

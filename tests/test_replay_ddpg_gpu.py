@@ -571,8 +571,8 @@ def test_act_soa_and_push_groups_equal_packed_layout(sb, train_series):
         push_groups([sb.Replay(10) for _ in range(P)], obs_soa, a1, r, s_next)
 
 
-@pytest.mark.parametrize("population", [1, 3])
-def test_native_episode_equals_python_loop(sb, train_series, population):
+@pytest.mark.parametrize("population,noise", [(1, "gn"), (3, "gn"), (1, "ou")])
+def test_native_episode_equals_python_loop(sb, train_series, population, noise):
     """ddpg_episode (episode! enqueued by one native call) must do exactly what the step-by-step Python loop does — same seeds,
     same kernels: returns and every weight bit-identical, for one learner and for a population."""
     kw = dict(batch=32, l1=48, l2=64)
@@ -581,7 +581,7 @@ def test_native_episode_equals_python_loop(sb, train_series, population):
         if population == 1:
             env = sb.Shems(72, train_series, n_envs=16)
             drv = sb.Driver(env, None, learner=sb.Learner(params=sb.default_ddpg_params(**kw)), mem_size=16 * 72, ep_length=72, sigma=0.1,
-                            rng_run=77, native=native)
+                            rng_run=77, native=native, noise_type=noise)
             drv.learner.init(5)
             drv.populate_memory()
             drv.min_max_buffer()
