@@ -1144,10 +1144,13 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     g[2] = gp_fwd(h->xs, 11, B, actor, da.l[0], h->a_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 3, h->pop, h->pop_stride, h->pop_stride));
   }
-  if (tc) {
-    TRY(tc_fwd(h, st, h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, h->pop_stride));
-    TRY(tc_fwd(h, st, h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, h->pop_stride));
-    TRY(tc_fwd(h, st, h->a_h1, l1, B, actor, da.l[1], h->a_h2, l2, h->pop_stride));
+  if (tc) {  // the three layer-2 forward products have one shape: a single persistent launch deals their tiles over the SMs
+    const TcOperand As[3] = {{h->t_h1, l1, false}, {h->c_h1, l1, false}, {h->a_h1, l1, false}};
+    const TcOperand Bs[3] = {{actor_t + da.l[1].w_off, da.l[1].out, true}, {critic + dc.l[1].w_off, dc.l[1].out, true}, {actor + da.l[1].w_off, da.l[1].out, true}};
+    float* Ds[3] = {h->t_h2, h->c_h2, h->a_h2};
+    const float* bs[3] = {actor_t + da.l[1].b_off, critic + dc.l[1].b_off, actor + da.l[1].b_off};
+    TcBatch bt; bt.count = h->pop; bt.sA = bt.sB = bt.sD = bt.sBias = h->pop_stride;
+    TRY(tc_gemm_multi(st, 3, As, Bs, Ds, l2, B, da.l[1].out, da.l[1].in, TC_EPI_BIAS_RELU, bs, nullptr, 0, 1, nullptr, bt));
   } else {
     g[0] = gp_fwd(h->t_h1, l1, B, actor_t, da.l[1], h->t_h2, l2, EPI_BIAS_RELU);
     g[1] = gp_fwd(h->c_h1, l1, B, critic, dc.l[1], h->c_h2, l2, EPI_BIAS_RELU);

@@ -22,6 +22,8 @@
 
 namespace {
 
+struct TcMaps { CUtensorMap a[TC_MAX_PROBLEMS], b[TC_MAX_PROBLEMS], d[TC_MAX_PROBLEMS]; };
+
 constexpr int BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32, UMMA_K = 8;
 constexpr int STAGES = 5;                                    // 5 x 32 KB operand ring: one persistent CTA per SM keeps it full across tiles
 constexpr int TILE_BYTES = BLOCK_M * BLOCK_K * 4;            // 16 KB per operand and stage
@@ -125,8 +127,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 //   warps 2-5: epilogue              tcgen05.ld -> fused epilogue -> swizzled smem chunk (double-buffered) -> bulk tensor store
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
-               const TcGemmArgs p) {
+tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SW128 needs 1024 B
   uint8_t* staging = smem + STAGES * 2 * TILE_BYTES;
@@ -136,7 +137,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BLOCK_M - 1) / BLOCK_M, nt = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int nz = p.batch > 1 ? p.batch : p.splits;
-  const int total_tiles = mt * nt * nz;
+  const int total_tiles = mt * nt * nz * p.nprob;  // several same-shape problems (own tensor maps / pointers) share one launch
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
 
@@ -144,9 +145,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&acc_full_bar[a], 1); mbar_init(&acc_empty_bar[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
-    if (p.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmD) : "memory");
+    for (int q = 0; q < p.nprob; ++q) {
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[q]) : "memory");
+      asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b[q]) : "memory");
+      if (p.tma_store) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.d[q]) : "memory");
+    }
   }
   if (warp == 1) {  // TMEM allocation: 2 x 128 fp32 accumulator columns × 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
@@ -159,7 +162,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // tile -> (m0, n0, split, bz, first k-block, number of k-blocks); m-tiles vary fastest so that concurrently running CTAs share B tiles in L2
 #define TILE_COORDS(tile)                                                               \
-  const int z_ = (tile) / (mt * nt), r_ = (tile) - z_ * (mt * nt);                      \
+  const int prob = (tile) / (mt * nt * nz), t_ = (tile) - prob * (mt * nt * nz);        \
+  const int z_ = t_ / (mt * nt), r_ = t_ - z_ * (mt * nt);                              \
   const int m0 = (r_ % mt) * BLOCK_M, n0 = (r_ / mt) * BLOCK_N;                         \
   const int split = p.batch > 1 ? 0 : z_, bz = p.batch > 1 ? z_ : 0;                    \
   const int kb_begin = split * kb_per;                                                  \
@@ -180,15 +184,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int k0 = (kb_begin + i) * BLOCK_K;
           if (A_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &tmA, &full_bar[s], m0 + j * 32, k0, bz);  // box {32 rows(MN), 32 k}
+            for (int j = 0; j < 4; ++j) tma_load_3d(sa + j * 4096, &maps.a[prob], &full_bar[s], m0 + j * 32, k0, bz);  // box {32 rows(MN), 32 k}
           } else {
-            tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, bz);                                               // box {32 k, 128 rows}
+            tma_load_3d(sa, &maps.a[prob], &full_bar[s], k0, m0, bz);                                               // box {32 k, 128 rows}
           }
           if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 4096, &tmB, &full_bar[s], n0 + j * 32, k0, bz);
+            for (int j = 0; j < 4; ++j) tma_load_3d(sb + j * 4096, &maps.b[prob], &full_bar[s], n0 + j * 32, k0, bz);
           } else {
-            tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, bz);
+            tma_load_3d(sb, &maps.b[prob], &full_bar[s], k0, n0, bz);
           }
         }
       }
@@ -202,7 +206,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int g = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         TILE_COORDS(tile)
-        (void)m0; (void)n0; (void)bz;
+        (void)m0; (void)n0; (void)bz; (void)prob;
         const int acc = it & 1, use = it >> 1;
         mbar_wait(&acc_empty_bar[acc], (use & 1) ^ 1);  // the epilogue has drained this accumulator (passes at once on first use)
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -233,7 +237,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // store: full 128-byte lines, clipped at M / N by the tensor map.  Otherwise every thread stores its row segment directly.
     const int q = warp & 3;
     const bool mask = (p.epi == TC_EPI_RELU_MASK);
-    const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((p.bs_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    const bool aux_vec = mask && ((p.auxld & 3) == 0) && ((p.bs_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux[0]) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.aux[1]) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.aux[2]) & 15) == 0);
     uint8_t* stage = staging + q * (2 * 4096);  // this warp's two 32x32 fp32 chunk buffers (4 KB each, 1024-byte aligned)
     int it = 0, chunk_no = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -241,14 +246,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int acc = it & 1, use = it >> 1;
       const int m = m0 + q * 32 + lane;
       // this tile's bias slice (double-buffered: the named barrier of tile it+1 proves everyone is done with tile it-1's slice)
-      bias_s[it & 1][threadIdx.x - 64] = (p.epi == TC_EPI_BIAS_RELU && n0 + (int)threadIdx.x - 64 < p.N) ? p.bias[(long long)bz * p.bs_bias + n0 + threadIdx.x - 64] : 0.0f;
+      bias_s[it & 1][threadIdx.x - 64] = (p.epi == TC_EPI_BIAS_RELU && n0 + (int)threadIdx.x - 64 < p.N) ? p.bias[prob][(long long)bz * p.bs_bias + n0 + threadIdx.x - 64] : 0.0f;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      const float* auxrow = mask ? p.aux + (long long)bz * p.bs_aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
+      const float* auxrow = mask ? p.aux[prob] + (long long)bz * p.bs_aux + (long long)min(m, p.M - 1) * p.auxld : nullptr;
       if (num_kb > 0) {
         mbar_wait(&acc_full_bar[acc], use & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       }
-      float* Dp = p.D + (long long)(split + bz) * p.split_stride;  // split_stride doubles as the batch stride of D
+      float* Dp = p.D[prob] + (long long)(split + bz) * p.split_stride;  // split_stride doubles as the batch stride of D
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int nc = n0 + c * 32;
@@ -296,7 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmD, buf, nc, m0 + q * 32, split + bz);
+            tma_store_3d(&maps.d[prob], buf, nc, m0 + q * 32, split + bz);
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
           }
           ++chunk_no;
@@ -394,13 +399,13 @@ int make_tmap_out(CUtensorMap* tm, float* ptr, long long N, long long M, long lo
 }
 
 template <bool A_MN, bool B_MN>
-int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const TcGemmArgs& a) {
+int launch_variant(cudaStream_t st, const TcMaps& maps, const TcGemmArgs& a) {
   static bool attr_set = false;
   if (!attr_set) {
     if (int s = set_smem_attr<A_MN, B_MN>()) return s;
     attr_set = true;
   }
-  const long long tiles = (long long)((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N) * (a.batch > 1 ? a.batch : a.splits);
+  const long long tiles = (long long)((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N) * (a.batch > 1 ? a.batch : a.splits) * a.nprob;
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -408,7 +413,7 @@ int launch_variant(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb
     CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);  // persistent: one CTA per SM, tiles dealt round-robin
-  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(ta, tb, td, a);
+  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(maps, a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -426,42 +431,61 @@ int tc_gemm_prepare() {
   return SHEMS_OK;
 }
 
-// D = epi(A·B): see tc_gemm.h.  With splits > 1, `workspace` must hold splits*M*N floats; the partial tiles are summed in a
-// fixed order by a second kernel (deterministic, unlike atomics).  bt.count > 1: that many independent products of the
-// same shape in one launch (grid.z), operand i found bt.s* floats behind operand i-1 (no split-K then).
-int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
-            const float* bias, const float* aux, long long auxld, int splits, float* workspace, const TcBatch& bt) {
+// D_q = epi(A_q·B_q) for q < nprob same-shape products in ONE launch (own operands, outputs, bias / mask pointers; shared M, N, K,
+// leading dimensions, major-ness, epilogue and batch strides).  With splits > 1 (single problem only) `workspace` must hold
+// splits*M*N floats; the partial tiles are summed in a fixed order by a second kernel (deterministic, unlike atomics).
+// bt.count > 1: that many independent products per problem (grid.z), entry i bt.s* floats behind entry i-1 (no split-K then).
+int tc_gemm_multi(cudaStream_t st, int nprob, const TcOperand* A, const TcOperand* B, float* const* D, long long ldd, int M, int N, int K, int epi,
+                  const float* const* bias, const float* const* aux, long long auxld, int splits, float* workspace, const TcBatch& bt) {
+  REQUIRE(nprob >= 1 && nprob <= TC_MAX_PROBLEMS, SHEMS_ERR_INVALID, "tc_gemm: nprob=%d", nprob);
   REQUIRE(M >= 1 && N >= 1 && K >= 1 && splits >= 1 && bt.count >= 1, SHEMS_ERR_INVALID, "tc_gemm: M=%d N=%d K=%d splits=%d batch=%d", M, N, K, splits, bt.count);
-  REQUIRE(splits == 1 || (workspace && epi == TC_EPI_NONE && ldd == N && bt.count == 1), SHEMS_ERR_INVALID,
+  REQUIRE(splits == 1 || (workspace && epi == TC_EPI_NONE && ldd == N && bt.count == 1 && nprob == 1), SHEMS_ERR_INVALID,
           "tc_gemm: split-K needs a workspace, no epilogue, ldd == N and a single product");
-  CUtensorMap ta, tb;
-  int s;
-  // K-major: dim0 = K, dim1 = rows, box {32 k, 128 rows}; MN-major: dim0 = rows, dim1 = K, box {32 rows, 32 k}
-  if ((s = A.mn_major ? make_tmap(&ta, A.ptr, M, K, A.ld, 32, BLOCK_K, true, bt.count, bt.sA) : make_tmap(&ta, A.ptr, K, M, A.ld, BLOCK_K, BLOCK_M, false, bt.count, bt.sA))) return s;
-  if ((s = B.mn_major ? make_tmap(&tb, B.ptr, N, K, B.ld, 32, BLOCK_K, true, bt.count, bt.sB) : make_tmap(&tb, B.ptr, K, N, B.ld, BLOCK_K, BLOCK_N, false, bt.count, bt.sB))) return s;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
   TcGemmArgs a;
   memset(&a, 0, sizeof(a));
-  a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.bias = bias; a.aux = aux; a.auxld = auxld;
+  a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.auxld = auxld; a.nprob = nprob;
   a.batch = bt.count; a.bs_bias = bt.sBias; a.bs_aux = bt.sAux;
-  if (splits == 1) { a.D = D; a.ldd = ldd; a.split_stride = bt.count > 1 ? bt.sD : 0; }
-  else { a.D = workspace; a.ldd = N; a.split_stride = (long long)M * N; }
-  // TMA store of the output tile when D's rows are 16-byte aligned (activations with padded ld, gradients, the split-K workspace)
-  CUtensorMap td;
-  memset(&td, 0, sizeof(td));
-  a.tma_store = (((uintptr_t)a.D & 15) == 0 && (a.ldd % 4) == 0 && (a.split_stride % 4) == 0) ? 1 : 0;
+  if (splits == 1) { a.ldd = ldd; a.split_stride = bt.count > 1 ? bt.sD : 0; }
+  else { a.ldd = N; a.split_stride = (long long)M * N; }
   const int nz = bt.count > 1 ? bt.count : splits;
-  if (a.tma_store && (s = make_tmap_out(&td, a.D, N, M, nz, a.ldd, a.split_stride))) return s;
-  if (A.mn_major && B.mn_major) s = launch_variant<true, true>(st, ta, tb, td, a);
-  else if (A.mn_major) s = launch_variant<true, false>(st, ta, tb, td, a);
-  else if (B.mn_major) s = launch_variant<false, true>(st, ta, tb, td, a);
-  else s = launch_variant<false, false>(st, ta, tb, td, a);
+  a.tma_store = ((a.ldd % 4) == 0 && (a.split_stride % 4) == 0) ? 1 : 0;
+  for (int q = 0; q < nprob; ++q) {
+    REQUIRE(A[q].mn_major == A[0].mn_major && B[q].mn_major == B[0].mn_major && A[q].ld == A[0].ld && B[q].ld == B[0].ld, SHEMS_ERR_INVALID,
+            "tc_gemm: the problems of one launch must share layout and leading dimensions");
+    a.D[q] = splits == 1 ? D[q] : workspace;
+    a.bias[q] = bias ? bias[q] : nullptr; a.aux[q] = aux ? aux[q] : nullptr;
+    if (((uintptr_t)a.D[q] & 15) != 0) a.tma_store = 0;
+  }
+  for (int q = nprob; q < TC_MAX_PROBLEMS; ++q) { a.D[q] = a.D[0]; a.bias[q] = a.bias[0]; a.aux[q] = a.aux[0]; }
+  int s;
+  for (int q = 0; q < nprob; ++q) {
+    // K-major: dim0 = K, dim1 = rows, box {32 k, 128 rows}; MN-major: dim0 = rows, dim1 = K, box {32 rows, 32 k}
+    if ((s = A[q].mn_major ? make_tmap(&maps.a[q], A[q].ptr, M, K, A[q].ld, 32, BLOCK_K, true, bt.count, bt.sA)
+                           : make_tmap(&maps.a[q], A[q].ptr, K, M, A[q].ld, BLOCK_K, BLOCK_M, false, bt.count, bt.sA))) return s;
+    if ((s = B[q].mn_major ? make_tmap(&maps.b[q], B[q].ptr, N, K, B[q].ld, 32, BLOCK_K, true, bt.count, bt.sB)
+                           : make_tmap(&maps.b[q], B[q].ptr, K, N, B[q].ld, BLOCK_K, BLOCK_N, false, bt.count, bt.sB))) return s;
+    // TMA store of the output tile when D's rows are 16-byte aligned (activations with padded ld, gradients, the split-K workspace)
+    if (a.tma_store && (s = make_tmap_out(&maps.d[q], a.D[q], N, M, nz, a.ldd, a.split_stride))) return s;
+  }
+  if (A[0].mn_major && B[0].mn_major) s = launch_variant<true, true>(st, maps, a);
+  else if (A[0].mn_major) s = launch_variant<true, false>(st, maps, a);
+  else if (B[0].mn_major) s = launch_variant<false, true>(st, maps, a);
+  else s = launch_variant<false, false>(st, maps, a);
   if (s) return s;
   if (splits > 1) {
     const long long ne = (long long)M * N;
-    tc_splitk_reduce_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(workspace, a.split_stride, splits, D, ne);
+    tc_splitk_reduce_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(workspace, a.split_stride, splits, D[0], ne);
     CUDA_TRY(cudaGetLastError());
   }
   return SHEMS_OK;
+}
+
+int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
+            const float* bias, const float* aux, long long auxld, int splits, float* workspace, const TcBatch& bt) {
+  float* Ds[1] = {D}; const float* bs[1] = {bias}; const float* as[1] = {aux};
+  return tc_gemm_multi(st, 1, &A, &B, Ds, ldd, M, N, K, epi, bs, as, auxld, splits, workspace, bt);
 }
 
 // test / benchmark entry point (device pointers): D[M×N] = A·B with the stated major-ness
