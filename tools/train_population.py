@@ -16,6 +16,7 @@ ap.add_argument("--learners", type=int, default=80)
 ap.add_argument("--envs", type=int, default=64)
 ap.add_argument("--episodes", type=int, default=20)
 ap.add_argument("--tc", type=int, default=1)
+ap.add_argument("--eval-every", type=int, default=0)
 args = ap.parse_args()
 CH = (1, 2, 3, 4, 5, 6, 7, 8, 9, 98)
 P = args.learners
@@ -30,10 +31,19 @@ t_pop = time.time() - t0
 rule = drv.evaluate_rule_based()
 first = drv.episode(train=False, rng_ep=999).cpu().numpy()
 t1 = time.time()
+t_eval = 0.0
 for ep in range(1, args.episodes + 1):
     r = drv.episode(train=True, rng_ep=ep)
+    if args.eval_every and ep % args.eval_every == 0:
+        torch.cuda.synchronize()
+        te = time.time()
+        ev = drv.episode(train=False, rng_ep=999).cpu().numpy()
+        t_eval += time.time() - te
+        lc = [drv.learner.select(l).losses()[0] for l in (0, P - 1)]
+        print(json.dumps(dict(episode=ep, train_return=float(r.mean()), eval_return_mean=float(ev.mean()), eval_return_best=float(ev.max()),
+                              eval_return_worst=float(ev.min()), beats_rule_based=int((ev > rule).sum()), loss_crit_first_last=lc)), flush=True)
 torch.cuda.synchronize()
-dt = time.time() - t1
+dt = time.time() - t1 - t_eval
 last = drv.episode(train=False, rng_ep=999).cpu().numpy()
 print(json.dumps(dict(learners=P, envs_per_learner=args.envs, episodes=args.episodes, populate_seconds=t_pop, train_seconds=dt,
                       vector_steps_per_s=args.episodes * 72 / dt, learner_updates_per_s=P * args.episodes * 72 / dt,
