@@ -25,6 +25,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "shems_LU1 env-steps/s (batched)"
 UNIT = "env-steps/s"
+DTYPE = "f32/f64 mixed (Julia promotion rules)"
+WORKLOAD = "BASELINE configs[2]: shems_LU1 random-action rollout writing replay transitions"
 ALG_BYTES_PER_ENV_STEP = 88  # s 36 + a 8 + r 4 + s' 36 + done 4 (rollout writing replay transitions)
 
 
@@ -98,10 +100,12 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = args.steps * n * args.horizon / dt
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32/f64 mixed",
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE,
                 data="synthetic", impl="reference",
-                config=dict(workload="shems_LU1 random-action rollout, bounded sample on host cores", envs=n, horizon=args.horizon,
-                            series_rows=args.horizon + 1, policy="random (populate_memory)", charger=98),
+                # the b200 arm's workload; the CPU arm runs a bounded sample of its instances per step (cpu_baseline.sample)
+                config=dict(workload=WORKLOAD, envs_per_gpu=args.envs_per_gpu, envs_total=args.envs_per_gpu * world, horizon=args.horizon,
+                            series_rows=args.horizon + 1, charger=98, sample_envs_per_step=n,
+                            note="the same rollout (same series, same Philox action streams) on the host cores, a bounded sample of the instances per step"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{n} instances x {args.horizon} steps per step, OpenMP over instances"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -523,8 +527,8 @@ def main():
                     kernel="shems_rollout_kernel<POLICY_RANDOM>", kernel_ms=kern_ms,
                     algorithmic_bytes_per_launch=ALG_BYTES_PER_ENV_STEP * n * T, peak_source=peak_src)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32/f64 mixed (Julia promotion rules)", data="synthetic",
-                config=dict(workload="BASELINE configs[2]: shems_LU1 random-action rollout writing replay transitions",
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE, data="synthetic",
+                config=dict(workload=WORKLOAD,
                             envs_per_gpu=n, envs_total=n * world, horizon=T, series_rows=T + 1, charger=98,
                             replay_ring_transitions=n * args.ring_slots, bytes_per_env_step=ALG_BYTES_PER_ENV_STEP,
                             l2_policy=f"working set per launch {ALG_BYTES_PER_ENV_STEP * n * args.ring_slots / 1e6:.0f} MB of ring >> 126 MB L2 (no flush needed)",
