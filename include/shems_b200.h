@@ -270,6 +270,13 @@ SHEMS_API int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out);
 SHEMS_API int32_t ddpg_destroy(Ddpg* h);
 SHEMS_API int32_t ddpg_set_stream(Ddpg* h, void* cuda_stream);
 SHEMS_API int32_t ddpg_sync(Ddpg* h);
+/* One learner at a small batch (batch % 8 == 0, batch <= 256, l1 <= 256, l2 <= 512, no tensor-core mode — the reference's B = 120,
+ * 250/500 of README.md:68-86) runs replay() (DDPG.jl:121-145) as two thread-block-cluster kernels that keep every minibatch row's
+ * forward/backward chain in shared memory (csrc/ddpg_fused.cu) instead of one launch per matrix product.  On by default where the
+ * shape allows (environment variable SHEMS_DDPG_FUSED=0 opts out at ddpg_create); on = 0 selects the tiled-GEMM sequence (the
+ * path populations, large batches and the data-parallel learner use).  Both are fp32 and deterministic; they differ by summation
+ * order.  Returns the resulting state (1 fused, 0 not) or a negative status. */
+SHEMS_API int32_t ddpg_set_fused(Ddpg* h, int32_t on);
 /* glorot_uniform hidden layers, U(-3e-3,3e-3) last layers, zero biases, targets = copies
  * (DDPG.jl:21-22, 30-46) from Philox(seed) (Julia's MersenneTwister stream is not reproduced). */
 SHEMS_API int32_t ddpg_init(Ddpg* h, uint64_t seed);

@@ -101,6 +101,7 @@ SIGNATURES = {
     "ddpg_destroy": (I32, [VP]),
     "ddpg_set_stream": (I32, [VP, VP]),
     "ddpg_sync": (I32, [VP]),
+    "ddpg_set_fused": (I32, [VP, I32]),
     "ddpg_init": (I32, [VP, U64]),
     "ddpg_set_layer": (I32, [VP, I32, I32, PF, PF]),
     "ddpg_get_layer": (I32, [VP, I32, I32, PF, PF]),

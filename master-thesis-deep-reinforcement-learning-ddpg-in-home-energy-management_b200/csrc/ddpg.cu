@@ -19,6 +19,7 @@
 #include <new>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #include <stddef.h>
 #include <math.h>
 #include <unistd.h>
@@ -26,6 +27,7 @@
 #include "common.h"
 #include "philox.cuh"
 #include "tc_gemm.h"
+#include "ddpg_fused.h"
 
 // ----------------------------------------------------------------------------- GEMM
 enum { EPI_NONE = 0, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_ID, EPI_RELU_MASK, EPI_TD_TARGET, EPI_TANH_GRAD, EPI_SCALE_MASK };
@@ -539,6 +541,8 @@ struct Ddpg {
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
   // ddpg_episode scratch: a, scaled [2][N], s_prev [9][N], r [N]
   float *ep_a, *ep_scaled, *ep_sprev, *ep_r; long long ep_cap;
+  // cluster-fused small-batch update (csrc/ddpg_fused.cu): per-cluster partial gradients [batch/8][n_params] of actor / critic
+  bool fused; float* parts[2];
   int noise_kind; float ou_theta, ou_mu, ou_dt;   // ddpg_set_noise
   float* ou_x; long long ou_cap;                   // OUNoise.X of every instance of ddpg_episode's environment ([2][N])
 };
@@ -624,6 +628,15 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   off = 0;
   for (const Carve& c : plan) { *c.ptr = h->slab + off; off += (c.count + 63) & ~63ll; }
   h->grad[1] = h->gradbuf; h->grad[0] = h->gradbuf + ((nc + 63) & ~63ll);  // the actor part starts on a 256-byte boundary (TMA stores of dW)
+  // one learner at a small batch (the reference's B = 120): the update runs as two cluster kernels (SHEMS_DDPG_FUSED=0 opts out)
+  if (pop == 1 && !h->tc && ddpg_fused_shape_ok(B, p->l1, p->l2)) {
+    const char* ev = getenv("SHEMS_DDPG_FUSED");
+    int s_ = ddpg_fused_prepare();
+    if (s_) { ddpg_destroy(h); return s_; }
+    DMALLOC(h->parts[0], (long long)(B / FUSED_ROWS) * na);
+    DMALLOC(h->parts[1], (long long)(B / FUSED_ROWS) * nc);
+    h->fused = !(ev && ev[0] == '0');
+  }
   DMALLOC(h->ctrl, pop);
   DMALLOC(h->rings_dev, pop);
   DMALLOC(h->dp_flags, DP_MAX_WORLD);
@@ -654,6 +667,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->graph) cudaGraphDestroy(h->graph);
   cudaFree(h->slab);
+  cudaFree(h->parts[0]); cudaFree(h->parts[1]);
   cudaFree(h->act_x);  // act() scratch: one allocation (x | h1 | h2 | y per learner)
   cudaFree(h->ep_a);   // episode scratch: one allocation
   cudaFree(h->ou_x);
@@ -685,6 +699,18 @@ extern "C" int32_t ddpg_sync(Ddpg* h) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return SHEMS_OK;
 }
+extern "C" int32_t ddpg_set_fused(Ddpg* h, int32_t on) {
+  REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_set_fused: NULL handle");
+  GUARD(h->device);
+  const bool want = on != 0 && h->parts[0] && h->parts[1];   // shapes outside the fused plan keep the tiled-GEMM path
+  if (want != h->fused) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // re-captured by the next ddpg_update
+    h->fused = want;
+  }
+  return h->fused ? 1 : 0;
+}
+
 extern "C" int64_t ddpg_num_params(const Ddpg* h, int32_t net) { return (h && net >= 0 && net < 4) ? dims_of(h, net).n_params : 0; }
 
 extern "C" int32_t ddpg_set_layer(Ddpg* h, int32_t net, int32_t layer, const float* w_host, const float* b_host) {
@@ -900,6 +926,33 @@ adam_polyak_kernel(float* __restrict__ x, const float* __restrict__ g, float* __
   }
   // second Polyak pair: the critic target moves together with the actor step (DDPG.jl:142-143)
   for (long long j = k0 + tid; j < n2; j += stride)
+    target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
+  if (advance) adam_advance(ctrl, b1, b2);
+}
+
+// Cluster-fused small-batch path: the gradient of element j is the sum of `nparts` per-cluster partial copies, added here in a
+// fixed order (deterministic) — the reduction over the minibatch that ends the fused backward pass — then ADAM (+ Polyak) as
+// above.  The summed gradient is also stored to g_out (ddpg_get_grad).
+__global__ void __launch_bounds__(256)
+adam_polyak_parts_kernel(float* __restrict__ x, const float* __restrict__ parts, int nparts, long long part_stride, float* __restrict__ g_out,
+                         float* __restrict__ m, float* __restrict__ v, long long n, double b1, double b2, double eps, float eta,
+                         DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau, float* __restrict__ target2,
+                         const float* __restrict__ model2, long long n2, int advance) {
+  const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
+  const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
+  const float omt = __fsub_rn(1.0f, tau);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long j = tid; j < n; j += stride) {
+    float gj = parts[j];
+#pragma unroll 4
+    for (int c = 1; c < nparts; ++c) gj = __fadd_rn(gj, parts[(long long)c * part_stride + j]);
+    g_out[j] = gj;
+    const float xn = adam_element<false>(x[j], gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+    x[j] = xn;
+    if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
+  }
+  for (long long j = tid; j < n2; j += stride)
     target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
   if (advance) adam_advance(ctrl, b1, b2);
 }
@@ -1288,7 +1341,38 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   return SHEMS_OK;
 }
 
+// One learner at a small batch: critic pass -> ADAM(critic) -> actor pass -> ADAM(actor) + soft_update!, the two passes as
+// thread-block-cluster kernels that keep a row's whole forward/backward chain on chip (csrc/ddpg_fused.cu)
+static inline bool use_fused(const Ddpg* h) { return h->fused && h->parts[0] && h->parts[1]; }
+static int enqueue_update_fused(Ddpg* h, cudaStream_t st) {
+  const DdpgParams& p = h->p;
+  const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
+  float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
+  FusedArgs a; memset(&a, 0, sizeof(a));
+  a.actor = actor; a.critic = critic; a.actor_t = actor_t; a.critic_t = critic_t;
+  a.ao = FusedNetOff{(int)da.l[0].w_off, (int)da.l[0].b_off, (int)da.l[1].w_off, (int)da.l[1].b_off, (int)da.l[2].w_off, (int)da.l[2].b_off};
+  a.co = FusedNetOff{(int)dc.l[0].w_off, (int)dc.l[0].b_off, (int)dc.l[1].w_off, (int)dc.l[1].b_off, (int)dc.l[2].w_off, (int)dc.l[2].b_off};
+  a.l1 = p.l1; a.l2 = p.l2; a.B = p.batch;
+  a.xs = h->xs; a.xs2 = h->xs2; a.xspi = h->xspi; a.r = h->r; a.done = h->done; a.q = h->q; a.y = h->y; a.qpi = h->qpi;
+  a.gamma = p.gamma; a.inv_batch = 1.0f / (float)p.batch;
+  const int nparts = p.batch / FUSED_ROWS;
+  const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
+  a.part = h->parts[1]; a.part_stride = dc.n_params;
+  TRY(ddpg_fused_critic(st, a));
+  adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
+                                                         p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  CUDA_TRY(cudaGetLastError());
+  a.part = h->parts[0]; a.part_stride = da.n_params;
+  TRY(ddpg_fused_actor(st, a));
+  adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
+                                                         p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic,
+                                                         dc.n_params, 1);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
 static int enqueue_update_body(Ddpg* h, cudaStream_t st, bool dp = false) {
+  if (!dp && use_fused(h)) return enqueue_update_fused(h, st);
   int s0 = enqueue_phase0(h, st);
   if (!s0) s0 = enqueue_phase1(h, st, 1.0f, dp);
   if (!s0) s0 = enqueue_phase2(h, st, 1.0f, dp);

@@ -1,0 +1,439 @@
+// ddpg_fused.cu — the small-batch DDPG update (RL-SHEMS/algorithms/DDPG.jl replay :121-145, loss_crit :114, loss_act :116-119)
+// as TWO thread-block-cluster kernels.
+//
+// Why: at the reference's B = 120 one replay() is 3.1e8 FLOP (4 µs of fp32 peak) behind 19 DEPENDENT matrix products; launched one
+// by one, every product pays a launch, a trip of its operands through L2 and a grid drain (≈ 5 µs each).  The chain
+// is only sequential per SAMPLE: rows of the minibatch never meet before the weight gradients are summed.  So a cluster of 8 CTAs
+// takes 8 rows through the whole forward and backward chain:
+//   * layer widths are split over the cluster's CTAs (CTA c owns 1/8 of the 500 layer-2 units and 1/8 of the 250 layer-1 units);
+//   * layer 1 (K = 9 / 11) is recomputed by every CTA — cheaper than exchanging it;
+//   * the CTA's 250 x 63 slice of each W2 is staged in shared memory once (cp.async, overlapped with layer 1) and serves the forward
+//     product and the back-propagation through that layer;
+//   * what the CTAs owe each other — output-layer partial dot products (8 x 2 numbers) and the partial dX of layer 2 — moves through
+//     DISTRIBUTED SHARED MEMORY (st to the peer's smem + barrier.cluster), never through L2;
+//   * every cluster writes its 8-row partial of the weight gradients to its own copy in a workspace; the optimiser kernel adds the
+//     B/8 copies in a fixed order (deterministic, like everything else here) — the only grid-wide dependency left.
+// One update = gather, critic pass, ADAM(critic), actor pass, ADAM(actor)+Polyak: 5 launches instead of 21.
+// All sums are fp32 in a fixed order; they differ from the tiled-GEMM path only by summation order.
+#include <cooperative_groups.h>
+
+#include "common.h"
+#include "ddpg_fused.h"
+
+namespace cg = cooperative_groups;
+
+#define FT 256   // threads per CTA: 8 warps
+#define WP 65    // pitch (floats) of a staged W2 slice: column reads (one k per warp) and row reads (one k per lane) are conflict-free
+
+struct FusedSmem {
+  float W[2][FUSED_MAX_L1 * WP];   // two staged W2 slices [k][col]
+  float h1T[2][FUSED_MAX_L1 * 8];  // layer-1 activations of the cluster's 8 rows, unit-major [k][row] (one 32-byte broadcast per k)
+  float red[8 * 8 * 64];           // [warp][row][col] partial sums of the layer-2 product
+  float h2s[2][8 * 64];            // this CTA's slice of the layer-2 activations [row][col]
+  float dzT[64 * 8];               // gradient at this CTA's layer-2 slice, unit-major [col][row]
+  float x[2][8 * 12];              // network inputs [row][11] (pitch 12)
+  float xch[3][8 * 8 * 2];         // all-gather buffers [source CTA][row][j], filled by the peers
+  float rs[8 * 8 * 32];            // reduce-scatter buffer [source CTA][row][unit of my layer-1 slice], filled by the peers
+  float dz1s[8 * 32];              // gradient at this CTA's layer-1 slice [row][unit]
+  float dout[8 * 2];               // gradient at the net's output [row][j]
+  float qv[8], rr[8], dd[8];
+};
+
+__device__ __forceinline__ void cp_async4z(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;  // src-size 0: zero fill
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// stage W2[0..l1)[n0 .. n0+64) of a net into Ws[k][col] (columns >= nv are zero)
+__device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, int tid) {
+  for (int e = tid; e < l1 * 64; e += FT) {
+    const int k = e >> 6, col = e & 63;
+    const bool ok = col < nv;
+    cp_async4z(Ws + k * WP + col, ok ? W2 + (long long)k * l2 + n0 + col : W2, ok);
+  }
+  cp_commit();
+}
+
+// layer 1, all l1 units, the cluster's 8 rows: h1T[k][r] = relu(b1[k] + sum_i W1[i][k] x[r][i])      (Dense(in, L1, relu))
+__device__ __forceinline__ void f1(const float* __restrict__ W1, const float* __restrict__ b1, int K, int l1, const float* x, float* h1T, int tid) {
+  if (tid < l1) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
+    float w[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) w[i] = (i < K) ? __ldg(W1 + i * l1 + tid) : 0.0f;
+    const float b = __ldg(b1 + tid);
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+      if (i < K) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(x[r * 12 + i], w[i], acc[r]);
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { const float v = acc[r] + b; o[r] = v > 0.0f ? v : 0.0f; }
+    *reinterpret_cast<float4*>(h1T + tid * 8) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(h1T + tid * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// layer 2, this CTA's slice: h2s[r][col] = relu(b2[col] + sum_k h1[r][k] Ws[k][col]).  Warp w takes k = w, w+8, ...; lane the columns
+// lane and lane+32; the 8 warps' partial sums meet in shared memory in warp order.  Ends with a barrier (h2s visible, Ws/red free).
+__device__ __forceinline__ void f2(const float* Ws, const float* __restrict__ b2s, int l1, int nv, const float* h1T, float* red, float* h2s, int tid) {
+  const int w = tid >> 5, lane = tid & 31;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { a0[r] = 0.0f; a1[r] = 0.0f; }
+#pragma unroll 4
+  for (int k = w; k < l1; k += 8) {
+    const float w0 = Ws[k * WP + lane], w1 = Ws[k * WP + lane + 32];
+    const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
+    a0[0] = fmaf(ha.x, w0, a0[0]); a1[0] = fmaf(ha.x, w1, a1[0]);
+    a0[1] = fmaf(ha.y, w0, a0[1]); a1[1] = fmaf(ha.y, w1, a1[1]);
+    a0[2] = fmaf(ha.z, w0, a0[2]); a1[2] = fmaf(ha.z, w1, a1[2]);
+    a0[3] = fmaf(ha.w, w0, a0[3]); a1[3] = fmaf(ha.w, w1, a1[3]);
+    a0[4] = fmaf(hb.x, w0, a0[4]); a1[4] = fmaf(hb.x, w1, a1[4]);
+    a0[5] = fmaf(hb.y, w0, a0[5]); a1[5] = fmaf(hb.y, w1, a1[5]);
+    a0[6] = fmaf(hb.z, w0, a0[6]); a1[6] = fmaf(hb.z, w1, a1[6]);
+    a0[7] = fmaf(hb.w, w0, a0[7]); a1[7] = fmaf(hb.w, w1, a1[7]);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) { red[(w * 8 + r) * 64 + lane] = a0[r]; red[(w * 8 + r) * 64 + lane + 32] = a1[r]; }
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // output (row w, column c)
+    const int c = lane + 32 * h;
+    float v = red[w * 64 + c];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) v += red[(g * 8 + w) * 64 + c];
+    float o = 0.0f;
+    if (c < nv) { v += __ldg(b2s + c); o = v > 0.0f ? v : 0.0f; }
+    h2s[w * 64 + c] = o;
+  }
+  __syncthreads();
+}
+
+// output layer (J = 1 or 2 units): this CTA's share of the dot product over its layer-2 slice, row = warp, handed to every CTA of
+// the cluster (slot [my rank][row][j] of their all-gather buffer `buf`)
+__device__ __forceinline__ void f3_partial(const float* __restrict__ W3s, int J, int nv, const float* h2s, FusedSmem* S, int buf,
+                                           cg::cluster_group& cluster, int rank, int tid) {
+  const int w = tid >> 5, lane = tid & 31;
+  float p0 = 0.0f, p1 = 0.0f;
+  for (int c = lane; c < nv; c += 32) {
+    const float h = h2s[w * 64 + c];
+    p0 = fmaf(h, __ldg(W3s + c * J), p0);
+    if (J == 2) p1 = fmaf(h, __ldg(W3s + c * J + 1), p1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+  if (lane < FUSED_CLUSTER) {
+    FusedSmem* peer = cluster.map_shared_rank(S, lane);
+    peer->xch[buf][(rank * 8 + w) * 2 + 0] = p0;
+    peer->xch[buf][(rank * 8 + w) * 2 + 1] = p1;
+  }
+}
+__device__ __forceinline__ float xch_sum(const FusedSmem* S, int buf, int r, int j) {  // the 8 CTAs' shares in rank order
+  float v = S->xch[buf][r * 2 + j];
+#pragma unroll
+  for (int s = 1; s < FUSED_CLUSTER; ++s) v += S->xch[buf][(s * 8 + r) * 2 + j];
+  return v;
+}
+
+// back through the output layer: dW3 (and db3 on rank 0) of these 8 rows into the cluster's partial-gradient copy, and the gradient
+// at this CTA's layer-2 slice dzT[col][r] = (sum_j W3[col][j] dout[r][j]) * [h2 > 0]
+template <bool WRITE>
+__device__ __forceinline__ void b3(const float* __restrict__ W3s, int J, int nv, const float* h2s, const float* dout, float* dzT, float* part_w3s,
+                                   float* part_b3, int tid) {
+  if (WRITE) {
+    if (tid < nv * J) {
+      const int col = tid / J, j = tid - col * J;
+      float v = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v = fmaf(h2s[r * 64 + col], dout[r * 2 + j], v);
+      part_w3s[col * J + j] = v;
+    }
+    if (part_b3 && tid >= 128 && tid < 128 + J) {
+      const int j = tid - 128;
+      float v = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += dout[r * 2 + j];
+      part_b3[j] = v;
+    }
+  }
+  const int col = tid & 63, r0 = (tid >> 6) * 2;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int r = r0 + q;
+    float v = 0.0f;
+    if (col < nv) {
+      v = __ldg(W3s + col * J) * dout[r * 2];
+      if (J == 2) v = fmaf(__ldg(W3s + col * J + 1), dout[r * 2 + 1], v);
+      v = (h2s[r * 64 + col] > 0.0f) ? v : 0.0f;
+    }
+    dzT[col * 8 + r] = v;
+  }
+}
+
+// dW2 of these 8 rows, this CTA's columns: part[k][col] = sum_r h1[r][k] dz[r][col]; db2[col] = sum_r dz[r][col]
+__device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, int l2, int nv, float* part_w2s, float* part_b2s, int tid) {
+  const int w = tid >> 5, lane = tid & 31;
+  const float4 d0a = *reinterpret_cast<const float4*>(dzT + lane * 8), d0b = *reinterpret_cast<const float4*>(dzT + lane * 8 + 4);
+  const float4 d1a = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8), d1b = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8 + 4);
+  const bool ok0 = lane < nv, ok1 = lane + 32 < nv;
+#pragma unroll 4
+  for (int k = w; k < l1; k += 8) {
+    const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
+    float o0 = ha.x * d0a.x, o1 = ha.x * d1a.x;
+    o0 = fmaf(ha.y, d0a.y, o0); o1 = fmaf(ha.y, d1a.y, o1);
+    o0 = fmaf(ha.z, d0a.z, o0); o1 = fmaf(ha.z, d1a.z, o1);
+    o0 = fmaf(ha.w, d0a.w, o0); o1 = fmaf(ha.w, d1a.w, o1);
+    o0 = fmaf(hb.x, d0b.x, o0); o1 = fmaf(hb.x, d1b.x, o1);
+    o0 = fmaf(hb.y, d0b.y, o0); o1 = fmaf(hb.y, d1b.y, o1);
+    o0 = fmaf(hb.z, d0b.z, o0); o1 = fmaf(hb.z, d1b.z, o1);
+    o0 = fmaf(hb.w, d0b.w, o0); o1 = fmaf(hb.w, d1b.w, o1);
+    float* row = part_w2s + (long long)k * l2;
+    if (ok0) row[lane] = o0;
+    if (ok1) row[lane + 32] = o1;
+  }
+  if (tid < nv) {
+    float v = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += dzT[tid * 8 + r];
+    part_b2s[tid] = v;
+  }
+}
+
+// back through layer 2: this CTA's share (its columns) of dX[r][k] = sum_col W2[k][col] dz[r][col], thread = k, scattered to the CTA
+// that owns layer-1 unit k (slot [my rank][row][k - its first unit] of its reduce-scatter buffer)
+__device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, int nv, int n1s, FusedSmem* S, cg::cluster_group& cluster, int rank, int tid) {
+  if (tid < l1) {
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
+    const float* wr = Ws + tid * WP;
+#pragma unroll 4
+    for (int c = 0; c < nv; ++c) {
+      const float wv = wr[c];
+      const float4 da = *reinterpret_cast<const float4*>(dzT + c * 8), db = *reinterpret_cast<const float4*>(dzT + c * 8 + 4);
+      acc[0] = fmaf(wv, da.x, acc[0]); acc[1] = fmaf(wv, da.y, acc[1]); acc[2] = fmaf(wv, da.z, acc[2]); acc[3] = fmaf(wv, da.w, acc[3]);
+      acc[4] = fmaf(wv, db.x, acc[4]); acc[5] = fmaf(wv, db.y, acc[5]); acc[6] = fmaf(wv, db.z, acc[6]); acc[7] = fmaf(wv, db.w, acc[7]);
+    }
+    const int owner = tid / n1s, kk = tid - owner * n1s;
+    FusedSmem* peer = cluster.map_shared_rank(S, owner);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) peer->rs[(rank * 8 + r) * 32 + kk] = acc[r];
+  }
+}
+// after the cluster barrier: add the 8 shares in rank order and apply layer 1's ReLU mask -> dz1s[r][kk] (this CTA's layer-1 units)
+__device__ __forceinline__ void rs_finish(FusedSmem* S, const float* h1T, int k0, int n1v, int tid) {
+  const int r = tid >> 5, kk = tid & 31;
+  float v = 0.0f;
+  if (kk < n1v) {
+    v = S->rs[r * 32 + kk];
+#pragma unroll
+    for (int s = 1; s < FUSED_CLUSTER; ++s) v += S->rs[(s * 8 + r) * 32 + kk];
+    v = (h1T[(k0 + kk) * 8 + r] > 0.0f) ? v : 0.0f;
+  }
+  S->dz1s[r * 32 + kk] = v;
+}
+
+// dW1 / db1 of these 8 rows for this CTA's layer-1 units: part[i][k] = sum_r x[r][i] dz1[r][k]
+__device__ __forceinline__ void bw1(const float* x, int K1, const float* dz1s, int l1, int n1v, float* part_w1s, float* part_b1s, int tid) {
+  for (int e = tid; e < K1 * 32; e += FT) {
+    const int i = e >> 5, kk = e & 31;
+    if (kk < n1v) {
+      float v = 0.0f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v = fmaf(x[r * 12 + i], dz1s[r * 32 + kk], v);
+      part_w1s[i * l1 + kk] = v;
+    }
+  }
+  if (tid < n1v) {
+    float v = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += dz1s[r * 32 + tid];
+    part_b1s[tid] = v;
+  }
+}
+
+struct Geo { int rank, row0, n0, nv, k0, n1v, n1s; };
+__device__ __forceinline__ Geo make_geo(const FusedArgs& a, cg::cluster_group& cluster) {
+  Geo g;
+  g.rank = (int)cluster.block_rank();
+  g.row0 = (int)(blockIdx.x / FUSED_CLUSTER) * FUSED_ROWS;
+  const int n2s = (a.l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  g.n1s = (a.l1 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  g.n0 = min(g.rank * n2s, a.l2); g.nv = min(n2s, a.l2 - g.n0);
+  g.k0 = min(g.rank * g.n1s, a.l1); g.n1v = min(g.n1s, a.l1 - g.k0);
+  return g;
+}
+
+// ---- critic pass: y = r + γ(1-done) critic_t(s', actor_t(s'));  loss_crit = mse(critic(s,a), y);  partial ∇critic      (DDPG.jl:131-137)
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FT, 1)
+ddpg_fused_critic_kernel(const FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const Geo g = make_geo(a, cluster);
+  const int l1 = a.l1, l2 = a.l2;
+  float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
+  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, tid);   // group: actor_target W2
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, tid);    // group: critic W2
+  if (tid < 88) {
+    const int r = tid / 11, i = tid - r * 11;
+    S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
+    if (i < 9) S->x[0][r * 12 + i] = a.xs2[(long long)(g.row0 + r) * 11 + i];      // s'_n
+  } else if (tid >= 96 && tid < 104) {
+    S->rr[tid - 96] = a.r[g.row0 + tid - 96]; S->dd[tid - 96] = a.done[g.row0 + tid - 96];
+  }
+  cluster.sync();  // every CTA of the cluster runs (its shared memory may be written from now on); also a CTA barrier for x
+  // actor_target(s'_n)
+  f1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<1>();
+  __syncthreads();
+  f2(S->W[0], a.actor_t + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, tid);  // group: critic_target W2 (slot 0 is free again)
+  f3_partial(a.actor_t + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
+  // critic(s_n, a)
+  f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[1], S->h1T[1], tid);
+  cp_wait<1>();
+  __syncthreads();
+  f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
+  f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);
+  cluster.sync();
+  if (tid < 16) {
+    const int r = tid >> 1, j = tid & 1;
+    S->x[0][r * 12 + 9 + j] = tanhf(xch_sum(S, 0, r, j) + __ldg(a.actor_t + a.ao.b3 + j));   // a' -> vcat(s'_n, a')
+  } else if (tid >= 32 && tid < 40) {
+    const int r = tid - 32;
+    S->qv[r] = xch_sum(S, 1, r, 0) + __ldg(a.critic + a.co.b3);
+  }
+  __syncthreads();
+  // critic_target(s'_n, a')
+  f1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<0>();
+  __syncthreads();
+  f2(S->W[0], a.critic_t + a.co.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  f3_partial(a.critic_t + a.co.w3 + g.n0, 1, g.nv, S->h2s[0], S, 2, cluster, g.rank, tid);
+  cluster.sync();
+  if (tid < 8) {  // y = r + γ(1-done) q'  (:133);  d mse / d q = 2 (q - y) / B
+    const int r = tid;
+    const float q2 = xch_sum(S, 2, r, 0) + __ldg(a.critic_t + a.co.b3);
+    const float y = S->rr[r] + (a.gamma * (1.0f - S->dd[r])) * q2;
+    S->dout[r * 2] = 2.0f * (S->qv[r] - y) * a.inv_batch;
+    S->dout[r * 2 + 1] = 0.0f;
+    if (g.rank == 0) { a.q[g.row0 + r] = S->qv[r]; a.y[g.row0 + r] = y; }
+  }
+  __syncthreads();
+  // critic backward
+  b3<true>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, part + a.co.w3 + g.n0, g.rank == 0 ? part + a.co.b3 : nullptr, tid);
+  __syncthreads();
+  bw2(S->h1T[1], S->dzT, l1, l2, g.nv, part + a.co.w2 + g.n0, part + a.co.b2 + g.n0, tid);
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  cluster.sync();
+  rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
+  __syncthreads();
+  bw1(S->x[1], 11, S->dz1s, l1, g.n1v, part + a.co.w1 + g.k0, part + a.co.b1 + g.k0, tid);
+}
+
+// ---- actor pass: loss_act = -mean critic(s, actor(s)) with the UPDATED critic; partial ∇actor                          (DDPG.jl:116-119, :140)
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FT, 1)
+ddpg_fused_actor_kernel(const FusedArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const Geo g = make_geo(a, cluster);
+  const int l1 = a.l1, l2 = a.l2;
+  float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, tid);
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, tid);
+  if (tid < 72) {
+    const int r = tid / 9, i = tid - r * 9;
+    S->x[0][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];   // s_n
+  }
+  cluster.sync();
+  // actor(s_n)
+  f1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<1>();
+  __syncthreads();
+  f2(S->W[0], a.actor + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  f3_partial(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
+  cluster.sync();
+  if (tid < 16) {
+    const int r = tid >> 1, j = tid & 1;
+    const float pi = tanhf(xch_sum(S, 0, r, j) + __ldg(a.actor + a.ao.b3 + j));
+    S->x[0][r * 12 + 9 + j] = pi;                                   // vcat(s_n, actions)
+    if (g.rank == 0) a.xspi[(long long)(g.row0 + r) * 11 + 9 + j] = pi;
+  }
+  __syncthreads();
+  // critic(s_n, actor(s_n)), d(-mean q)/dq = -1/B
+  f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[0], S->h1T[1], tid);
+  if (tid < 16) S->dout[tid] = (tid & 1) ? 0.0f : -a.inv_batch;
+  cp_wait<0>();
+  __syncthreads();
+  f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
+  f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);   // q(s, actor(s)): reporting only
+  b3<false>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, nullptr, nullptr, tid);
+  __syncthreads();
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  cluster.sync();
+  if (g.rank == 0 && tid >= 64 && tid < 72) a.qpi[g.row0 + tid - 64] = xch_sum(S, 1, tid - 64, 0) + __ldg(a.critic + a.co.b3);
+  rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
+  __syncthreads();
+  {  // back through critic layer 1 to the two action inputs: this CTA's layer-1 units' share, row = warp
+    const int w = tid >> 5, lane = tid & 31;
+    float p0 = 0.0f, p1 = 0.0f;
+    if (lane < g.n1v) {
+      const float d = S->dz1s[w * 32 + lane];
+      p0 = __ldg(a.critic + a.co.w1 + 9 * l1 + g.k0 + lane) * d;
+      p1 = __ldg(a.critic + a.co.w1 + 10 * l1 + g.k0 + lane) * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+    if (lane < FUSED_CLUSTER) {
+      FusedSmem* peer = cluster.map_shared_rank(S, lane);
+      peer->xch[2][(g.rank * 8 + w) * 2 + 0] = p0;
+      peer->xch[2][(g.rank * 8 + w) * 2 + 1] = p1;
+    }
+  }
+  cluster.sync();
+  if (tid < 16) {  // times tanh'
+    const int r = tid >> 1, j = tid & 1;
+    const float pi = S->x[0][r * 12 + 9 + j];
+    S->dout[r * 2 + j] = xch_sum(S, 2, r, j) * (1.0f - pi * pi);
+  }
+  __syncthreads();
+  // actor backward
+  b3<true>(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S->dout, S->dzT, part + a.ao.w3 + g.n0 * 2, g.rank == 0 ? part + a.ao.b3 : nullptr, tid);
+  __syncthreads();
+  bw2(S->h1T[0], S->dzT, l1, l2, g.nv, part + a.ao.w2 + g.n0, part + a.ao.b2 + g.n0, tid);
+  bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  cluster.sync();
+  rs_finish(S, S->h1T[0], g.k0, g.n1v, tid);
+  __syncthreads();
+  bw1(S->x[0], 9, S->dz1s, l1, g.n1v, part + a.ao.w1 + g.k0, part + a.ao.b1 + g.k0, tid);
+}
+
+int ddpg_fused_prepare() {
+  CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+  return SHEMS_OK;
+}
+int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) {
+  ddpg_fused_critic_kernel<<<(a.B / FUSED_ROWS) * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a) {
+  ddpg_fused_actor_kernel<<<(a.B / FUSED_ROWS) * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}

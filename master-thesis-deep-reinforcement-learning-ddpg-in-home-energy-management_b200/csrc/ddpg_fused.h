@@ -1,0 +1,32 @@
+// ddpg_fused.h — cluster-fused small-batch DDPG update (csrc/ddpg_fused.cu): the reference's own configuration
+// (B = 120, 250/500; RL-SHEMS/algorithms/DDPG.jl:121-145) as two thread-block-cluster kernels instead of 19 dependent GEMM launches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FUSED_CLUSTER 8        // CTAs per cluster (the portable maximum); a cluster owns FUSED_ROWS minibatch rows
+#define FUSED_ROWS 8
+#define FUSED_MAX_L1 256       // layer widths the kernels' shared-memory plan covers
+#define FUSED_MAX_L2 512
+#define FUSED_MAX_BATCH 256    // partial-gradient workspace = batch/8 copies of a net
+
+struct FusedNetOff { int w1, b1, w2, b2, w3, b3; };  // float offsets of a net's layers inside its flat buffer [W1|b1|W2|b2|W3|b3]
+struct FusedArgs {
+  const float *actor, *critic, *actor_t, *critic_t;  // flat parameter buffers (Flux layout Wt[in][out] per layer)
+  FusedNetOff ao, co;
+  int l1, l2, B;
+  const float *xs, *xs2;     // [B][11] normalised (s | a) and (s' | .) rows of the gathered minibatch
+  float* xspi;               // [B][11] (s | actor(s)): columns 9, 10 are written by the actor pass
+  const float *r, *done;     // [B]
+  float *q, *y, *qpi;        // [B] critic(s,a), TD target, critic(s, actor(s))  (loss reporting)
+  float* part;               // partial gradients of the net this pass differentiates: [B/8][n_params], one copy per cluster
+  long long part_stride;     // = n_params of that net
+  float gamma, inv_batch;
+};
+// may this shape run fused?  (widths within the shared-memory plan, whole clusters of 8 rows)
+static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
+  return B >= FUSED_ROWS && B % FUSED_ROWS == 0 && B <= FUSED_MAX_BATCH && l1 >= 1 && l1 <= FUSED_MAX_L1 && l2 >= 1 && l2 <= FUSED_MAX_L2;
+}
+int ddpg_fused_prepare();                                    // shared-memory attribute of both kernels on the current device
+int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a);  // targets, TD target, critic forward/backward -> part (critic)
+int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a);   // actor-loss forward/backward through the critic -> part (actor)

@@ -135,6 +135,14 @@ class Learner:
     def sync(self):
         L.check(self.lib.ddpg_sync(self._h))
 
+    def set_fused(self, on=True):
+        """ddpg_set_fused: cluster-fused small-batch replay() (True where the shape allows it) or the tiled-GEMM sequence.
+        Returns the resulting state."""
+        r = int(self.lib.ddpg_set_fused(self._h, int(bool(on))))
+        if r < 0:
+            L.check(r)
+        return bool(r)
+
     def select(self, learner):
         """ddpg_select_learner: the learner of a population that set/get_layer, get_grad, set_norm and losses address."""
         L.check(self.lib.ddpg_select_learner(self._h, int(learner)))

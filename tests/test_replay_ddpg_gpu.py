@@ -478,6 +478,7 @@ def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series):
     env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
     mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
     plain, fused = (sb.Learner(params=sb.default_ddpg_params(batch=B)) for _ in range(2))
+    plain.set_fused(False)   # the data-parallel learner runs the tiled-GEMM sequence: bit-identity holds against that path
     for le in (plain, fused):
         le.init(3)
         le.set_norm(mn, mx)
@@ -684,3 +685,64 @@ def test_cuda_matches_committed_ddpg_fixture(sb):
     a, sc = le.act(dev(z["obs"]), noise=dev(z["noise"]))
     np.testing.assert_allclose(a.cpu().numpy(), z["act"], rtol=2e-4, atol=2e-5)
     np.testing.assert_allclose(sc.cpu().numpy(), z["scaled"], rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,l1,l2", [(120, 250, 500), (256, 256, 512), (64, 250, 500), (32, 48, 64), (8, 16, 24), (16, 3, 5), (40, 255, 497)])
+def test_cluster_fused_update_equals_tiled_gemm_path(sb, O, B, l1, l2):
+    """ddpg_set_fused: the two cluster kernels (csrc/ddpg_fused.cu) against the one-launch-per-product sequence on identical
+    weights and minibatches.  Both are fp32; they differ by summation order only: gradients within 2e-5 of the layer's largest
+    entry, losses within 1e-5 relative, and after K updates every weight within 2 % of what ADAM can move it (as in the
+    oracle tests).  Shapes: the reference's, the largest the fused plan covers, ragged slices (255/497), widths below the
+    cluster size (3/5: CTAs with empty slices)."""
+    rng = np.random.default_rng(B + l1)
+    kw = dict(batch=B, l1=l1, l2=l2)
+    fused, tiled = sb.Learner(params=sb.default_ddpg_params(**kw)), sb.Learner(params=sb.default_ddpg_params(**kw))
+    assert fused.set_fused(True) is True and tiled.set_fused(False) is False
+    orc = O.OracleDdpg(O.default_ddpg_params(**kw))
+    orc.init(11)
+    for net in (0, 1):
+        for k in range(3):
+            w, b = orc.get_layer(net, k)
+            b = rng.normal(0, 0.05, b.shape).astype(np.float32)
+            orc.set_layer(net, k, w, b)
+            orc.set_layer(net + 2, k, w * np.float32(0.9), b * np.float32(1.1))
+    _sync_nets(fused, orc)
+    _sync_nets(tiled, orc)
+    s_min = rng.uniform(-1, 0, 9).astype(np.float32)
+    s_max = (s_min + rng.uniform(0.5, 3, 9)).astype(np.float32)
+    for le in (fused, tiled):
+        le.set_norm(s_min, s_max)
+    K = 4
+    for step in range(K):
+        s = rng.uniform(-1, 3, (9, B)).astype(np.float32)
+        a = rng.uniform(-1, 1, (2, B)).astype(np.float32)
+        r = rng.uniform(-5, 1, B).astype(np.float32)
+        s2 = rng.uniform(-1, 3, (9, B)).astype(np.float32)
+        d = (rng.uniform(0, 1, B) < 0.1).astype(np.float32)
+        for le in (fused, tiled):
+            le.update_batch(dev(s), dev(a), dev(r), dev(s2), dev(d))
+        if step == 0:
+            for net in (0, 1):
+                for k in range(3):
+                    for gf, gt in zip(fused.get_grad(net, k), tiled.get_grad(net, k)):
+                        sc = max(np.abs(gt).max(), 1e-12)
+                        assert np.abs(gf - gt).max() <= 2e-5 * sc, (net, k, np.abs(gf - gt).max() / sc)
+        (lcf, laf), (lct, lat) = fused.losses(), tiled.losses()
+        assert lcf == pytest.approx(lct, rel=1e-5) and laf == pytest.approx(lat, rel=1e-5, abs=1e-7)
+    p = fused.p
+    travel = {0: p.lr_actor * K, 1: p.lr_critic * K, 2: p.lr_actor * K * p.tau, 3: p.lr_critic * K * p.tau}
+    for net in range(4):
+        for k in range(3):
+            for x, y in zip(fused.get_layer(net, k), tiled.get_layer(net, k)):
+                assert np.abs(x - y).max() <= 0.02 * travel[net] + (1e-7 if net >= 2 else 0.0), (net, k, np.abs(x - y).max())
+    # the fused path is deterministic: another learner fed the last minibatch twice from the same state ends bit-identical
+    twins = [sb.Learner(params=sb.default_ddpg_params(**kw)) for _ in range(2)]
+    for le in twins:
+        _sync_nets(le, orc)
+        le.set_norm(s_min, s_max)
+        for _ in range(2):
+            le.update_batch(dev(s), dev(a), dev(r), dev(s2), dev(d))
+    for net in range(4):
+        for k in range(3):
+            for x, y in zip(twins[0].get_layer(net, k), twins[1].get_layer(net, k)):
+                np.testing.assert_array_equal(x, y)
