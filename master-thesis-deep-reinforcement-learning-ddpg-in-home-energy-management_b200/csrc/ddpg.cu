@@ -1355,6 +1355,8 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st) {
   a.l1 = p.l1; a.l2 = p.l2; a.B = p.batch;
   a.xs = h->xs; a.xs2 = h->xs2; a.xspi = h->xspi; a.r = h->r; a.done = h->done; a.q = h->q; a.y = h->y; a.qpi = h->qpi;
   a.gamma = p.gamma; a.inv_batch = 1.0f / (float)p.batch;
+  // every slab buffer starts on a 256-byte boundary: W2 rows are 16-byte aligned iff l2 and both W2 offsets are multiples of 4 floats
+  a.bulk = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
   const int nparts = p.batch / FUSED_ROWS;
   const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
   a.part = h->parts[1]; a.part_stride = dc.n_params;

@@ -7,8 +7,8 @@
 // takes 8 rows through the whole forward and backward chain:
 //   * layer widths are split over the cluster's CTAs (CTA c owns 1/8 of the 500 layer-2 units and 1/8 of the 250 layer-1 units);
 //   * layer 1 (K = 9 / 11) is recomputed by every CTA — cheaper than exchanging it;
-//   * the CTA's 250 x 63 slice of each W2 is staged in shared memory once (cp.async, overlapped with layer 1) and serves the forward
-//     product and the back-propagation through that layer;
+//   * the CTA's 250 x 64 slice of each W2 is staged in shared memory once (one bulk async copy per row completing on an mbarrier,
+//     overlapped with layer 1) and serves the forward product and the back-propagation through that layer;
 //   * what the CTAs owe each other — output-layer partial dot products (8 x 2 numbers) and the partial dX of layer 2 — moves through
 //     DISTRIBUTED SHARED MEMORY (st to the peer's smem + barrier.cluster), never through L2;
 //   * every cluster writes its 8-row partial of the weight gradients to its own copy in a workspace; the optimiser kernel adds the
@@ -23,7 +23,8 @@
 namespace cg = cooperative_groups;
 
 #define FT 256   // threads per CTA: 8 warps
-#define WP 65    // pitch (floats) of a staged W2 slice: column reads (one k per warp) and row reads (one k per lane) are conflict-free
+#define WP 68    // pitch (floats) of a staged W2 slice: rows start on 16-byte boundaries (bulk copies); a warp reading one row, or 32
+                 // rows as float4 (quarter-warp phases of 8 rows x 16 bytes, 272 bytes apart), is free of bank conflicts
 
 struct FusedSmem {
   float W[2][FUSED_MAX_L1 * WP];   // two staged W2 slices [k][col]
@@ -37,6 +38,7 @@ struct FusedSmem {
   float dz1s[8 * 32];              // gradient at this CTA's layer-1 slice [row][unit]
   float dout[8 * 2];               // gradient at the net's output [row][j]
   float qv[8], rr[8], dd[8];
+  unsigned long long bar[2];       // mbarriers of the two W2 slots (bulk-copy staging)
 };
 
 __device__ __forceinline__ void cp_async4z(float* smem_dst, const float* gsrc, bool valid) {
@@ -48,14 +50,65 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// stage W2[0..l1)[n0 .. n0+64) of a net into Ws[k][col] (columns >= nv are zero)
-__device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, int tid) {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FWAIT_DONE;\n"
+      "bra FWAIT_LOOP;\n"
+      "FWAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one row of a W2 slice: global -> shared bulk async copy (TMA 1-D; 16-byte aligned on both sides, bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// stage W2[0..l1)[n0 .. n0+nv) of a net into Ws[k][col].  bulk: one bulk async copy per row, issued by thread k, which also arms
+// the slot's mbarrier with the row's bytes (the barrier expects l1 arrivals per use).  Otherwise (rows not 16-byte aligned):
+// 4-byte cp.async, columns >= nv zero-filled, one commit group per slice.
+__device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, bool bulk, unsigned long long* bar,
+                                         int tid) {
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic-proxy reads of this slot precede the async-proxy writes
+    if (tid < l1) {
+      if (nv > 0) {
+        mbar_expect_tx(bar, (unsigned)nv * 4u);
+        bulk_g2s(Ws + tid * WP, W2 + (long long)tid * l2 + n0, (unsigned)nv * 4u, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+    return;
+  }
   for (int e = tid; e < l1 * 64; e += FT) {
     const int k = e >> 6, col = e & 63;
     const bool ok = col < nv;
     cp_async4z(Ws + k * WP + col, ok ? W2 + (long long)k * l2 + n0 + col : W2, ok);
   }
   cp_commit();
+}
+// the slice staged into a slot has landed (this thread's view; follow with __syncthreads for the 4-byte path)
+template <int PENDING>
+__device__ __forceinline__ void stage_wait(bool bulk, unsigned long long* bar, unsigned parity) {
+  if (bulk) mbar_wait(bar, parity);
+  else cp_wait<PENDING>();
 }
 
 // layer 1, all l1 units, the cluster's 8 rows: h1T[k][r] = relu(b1[k] + sum_i W1[i][k] x[r][i])      (Dense(in, L1, relu))
@@ -211,14 +264,27 @@ __device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, 
 
 // back through layer 2: this CTA's share (its columns) of dX[r][k] = sum_col W2[k][col] dz[r][col], thread = k, scattered to the CTA
 // that owns layer-1 unit k (slot [my rank][row][k - its first unit] of its reduce-scatter buffer)
-__device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, int nv, int n1s, FusedSmem* S, cg::cluster_group& cluster, int rank, int tid) {
+__device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, int nv, int n1s, bool vec, FusedSmem* S, cg::cluster_group& cluster,
+                                    int rank, int tid) {
   if (tid < l1) {
     float acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
     const float* wr = Ws + tid * WP;
-#pragma unroll 4
-    for (int c = 0; c < nv; ++c) {
+    int c = 0;
+    if (vec) {  // nv % 4 == 0: four columns per shared-memory read of the row
+      for (; c + 4 <= nv; c += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + c);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 da = *reinterpret_cast<const float4*>(dzT + (c + u) * 8), db = *reinterpret_cast<const float4*>(dzT + (c + u) * 8 + 4);
+          acc[0] = fmaf(wv[u], da.x, acc[0]); acc[1] = fmaf(wv[u], da.y, acc[1]); acc[2] = fmaf(wv[u], da.z, acc[2]); acc[3] = fmaf(wv[u], da.w, acc[3]);
+          acc[4] = fmaf(wv[u], db.x, acc[4]); acc[5] = fmaf(wv[u], db.y, acc[5]); acc[6] = fmaf(wv[u], db.z, acc[6]); acc[7] = fmaf(wv[u], db.w, acc[7]);
+        }
+      }
+    }
+    for (; c < nv; ++c) {
       const float wv = wr[c];
       const float4 da = *reinterpret_cast<const float4*>(dzT + c * 8), db = *reinterpret_cast<const float4*>(dzT + c * 8 + 4);
       acc[0] = fmaf(wv, da.x, acc[0]); acc[1] = fmaf(wv, da.y, acc[1]); acc[2] = fmaf(wv, da.z, acc[2]); acc[3] = fmaf(wv, da.w, acc[3]);
@@ -267,7 +333,8 @@ __device__ __forceinline__ Geo make_geo(const FusedArgs& a, cg::cluster_group& c
   Geo g;
   g.rank = (int)cluster.block_rank();
   g.row0 = (int)(blockIdx.x / FUSED_CLUSTER) * FUSED_ROWS;
-  const int n2s = (a.l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  int n2s = (a.l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  if (a.bulk) n2s = (n2s + 3) & ~3;   // slices start on 16-byte boundaries of the W2 rows
   g.n1s = (a.l1 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
   g.n0 = min(g.rank * n2s, a.l2); g.nv = min(n2s, a.l2 - g.n0);
   g.k0 = min(g.rank * g.n1s, a.l1); g.n1v = min(g.n1s, a.l1 - g.k0);
@@ -284,8 +351,13 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   const Geo g = make_geo(a, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, tid);   // group: actor_target W2
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, tid);    // group: critic W2
+  const bool bulk = a.bulk != 0;
+  if (bulk) {
+    if (tid == 0) { mbar_init(&S->bar[0], (unsigned)l1); mbar_init(&S->bar[1], (unsigned)l1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    __syncthreads();
+  }
+  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);   // slot 0: actor_target W2
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[1], tid);    // slot 1: critic W2
   if (tid < 88) {
     const int r = tid / 11, i = tid - r * 11;
     S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
@@ -296,14 +368,14 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   cluster.sync();  // every CTA of the cluster runs (its shared memory may be written from now on); also a CTA barrier for x
   // actor_target(s'_n)
   f1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
-  cp_wait<1>();
+  stage_wait<1>(bulk, &S->bar[0], 0);
   __syncthreads();
   f2(S->W[0], a.actor_t + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
-  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, tid);  // group: critic_target W2 (slot 0 is free again)
+  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);  // slot 0 is free again: critic_target W2
   f3_partial(a.actor_t + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
   // critic(s_n, a)
   f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[1], S->h1T[1], tid);
-  cp_wait<1>();
+  stage_wait<1>(bulk, &S->bar[1], 0);
   __syncthreads();
   f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
   f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);
@@ -318,7 +390,7 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   __syncthreads();
   // critic_target(s'_n, a')
   f1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, S->x[0], S->h1T[0], tid);
-  cp_wait<0>();
+  stage_wait<0>(bulk, &S->bar[0], 1);   // second use of slot 0
   __syncthreads();
   f2(S->W[0], a.critic_t + a.co.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
   f3_partial(a.critic_t + a.co.w3 + g.n0, 1, g.nv, S->h2s[0], S, 2, cluster, g.rank, tid);
@@ -336,7 +408,7 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   b3<true>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, part + a.co.w3 + g.n0, g.rank == 0 ? part + a.co.b3 : nullptr, tid);
   __syncthreads();
   bw2(S->h1T[1], S->dzT, l1, l2, g.nv, part + a.co.w2 + g.n0, part + a.co.b2 + g.n0, tid);
-  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
   cluster.sync();
   rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
   __syncthreads();
@@ -353,8 +425,13 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   const Geo g = make_geo(a, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, tid);
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, tid);
+  const bool bulk = a.bulk != 0;
+  if (bulk) {
+    if (tid == 0) { mbar_init(&S->bar[0], (unsigned)l1); mbar_init(&S->bar[1], (unsigned)l1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+    __syncthreads();
+  }
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[1], tid);
   if (tid < 72) {
     const int r = tid / 9, i = tid - r * 9;
     S->x[0][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];   // s_n
@@ -362,7 +439,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   cluster.sync();
   // actor(s_n)
   f1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
-  cp_wait<1>();
+  stage_wait<1>(bulk, &S->bar[0], 0);
   __syncthreads();
   f2(S->W[0], a.actor + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
   f3_partial(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
@@ -377,13 +454,13 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   // critic(s_n, actor(s_n)), d(-mean q)/dq = -1/B
   f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[0], S->h1T[1], tid);
   if (tid < 16) S->dout[tid] = (tid & 1) ? 0.0f : -a.inv_batch;
-  cp_wait<0>();
+  stage_wait<0>(bulk, &S->bar[1], 0);
   __syncthreads();
   f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
   f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);   // q(s, actor(s)): reporting only
   b3<false>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, nullptr, nullptr, tid);
   __syncthreads();
-  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
   cluster.sync();
   if (g.rank == 0 && tid >= 64 && tid < 72) a.qpi[g.row0 + tid - 64] = xch_sum(S, 1, tid - 64, 0) + __ldg(a.critic + a.co.b3);
   rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
@@ -415,7 +492,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   b3<true>(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S->dout, S->dzT, part + a.ao.w3 + g.n0 * 2, g.rank == 0 ? part + a.ao.b3 : nullptr, tid);
   __syncthreads();
   bw2(S->h1T[0], S->dzT, l1, l2, g.nv, part + a.ao.w2 + g.n0, part + a.ao.b2 + g.n0, tid);
-  bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, S, cluster, g.rank, tid);
+  bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
   cluster.sync();
   rs_finish(S, S->h1T[0], g.k0, g.n1v, tid);
   __syncthreads();

@@ -22,6 +22,7 @@ struct FusedArgs {
   float* part;               // partial gradients of the net this pass differentiates: [B/8][n_params], one copy per cluster
   long long part_stride;     // = n_params of that net
   float gamma, inv_batch;
+  int bulk;                  // W2 rows are 16-byte aligned in both nets: slices are staged with bulk async copies (else 4-byte cp.async)
 };
 // may this shape run fused?  (widths within the shared-memory plan, whole clusters of 8 rows)
 static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
