@@ -7,8 +7,8 @@
 // takes 8 rows through the whole forward and backward chain:
 //   * layer widths are split over the cluster's CTAs (CTA c owns 1/8 of the 500 layer-2 units and 1/8 of the 250 layer-1 units);
 //   * layer 1 (K = 9 / 11) is recomputed by every CTA — cheaper than exchanging it;
-//   * the CTA's 250 x 64 slice of each W2 is staged in shared memory once (one bulk async copy per row completing on an mbarrier,
-//     overlapped with layer 1) and serves the forward product and the back-propagation through that layer;
+//   * the CTA's 250 x 64 slice of each W2 is staged in shared memory once (16-byte cp.async, overlapped with layer 1) and serves
+//     the forward product and the back-propagation through that layer;
 //   * what the CTAs owe each other — output-layer partial dot products (8 x 2 numbers) and the partial dX of layer 2 — moves through
 //     DISTRIBUTED SHARED MEMORY (st to the peer's smem + barrier.cluster), never through L2;
 //   * every cluster writes its 8-row partial of the weight gradients to its own copy in a workspace; the optimiser kernel adds the
@@ -34,11 +34,10 @@ struct FusedSmem {
   float dzT[64 * 8];               // gradient at this CTA's layer-2 slice, unit-major [col][row]
   float x[2][8 * 12];              // network inputs [row][11] (pitch 12)
   float xch[3][8 * 8 * 2];         // all-gather buffers [source CTA][row][j], filled by the peers
-  float rs[8 * 8 * 32];            // reduce-scatter buffer [source CTA][row][unit of my layer-1 slice], filled by the peers
+  float rs[8 * 32 * 8];            // reduce-scatter buffer [source CTA][unit of my layer-1 slice][row], filled by the peers
   float dz1s[8 * 32];              // gradient at this CTA's layer-1 slice [row][unit]
   float dout[8 * 2];               // gradient at the net's output [row][j]
   float qv[8], rr[8], dd[8];
-  unsigned long long bar[2];       // mbarriers of the two W2 slots (bulk-copy staging)
 };
 
 __device__ __forceinline__ void cp_async4z(float* smem_dst, const float* gsrc, bool valid) {
@@ -50,87 +49,75 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "FWAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra FWAIT_DONE;\n"
-      "bra FWAIT_LOOP;\n"
-      "FWAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// one row of a W2 slice: global -> shared bulk async copy (TMA 1-D; 16-byte aligned on both sides, bytes % 16 == 0)
-__device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
 }
 
-// stage W2[0..l1)[n0 .. n0+nv) of a net into Ws[k][col].  bulk: one bulk async copy per row, issued by thread k, which also arms
-// the slot's mbarrier with the row's bytes (the barrier expects l1 arrivals per use).  Otherwise (rows not 16-byte aligned):
-// 4-byte cp.async, columns >= nv zero-filled, one commit group per slice.
-__device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, bool bulk, unsigned long long* bar,
-                                         int tid) {
-  if (bulk) {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic-proxy reads of this slot precede the async-proxy writes
-    if (tid < l1) {
-      if (nv > 0) {
-        mbar_expect_tx(bar, (unsigned)nv * 4u);
-        bulk_g2s(Ws + tid * WP, W2 + (long long)tid * l2 + n0, (unsigned)nv * 4u, bar);
-      } else {
-        mbar_arrive(bar);
-      }
+// stage W2[0..l1)[n0 .. n0+nv) of a net into Ws[k][col], one commit group per slice.  vec: rows are 16-byte aligned on both sides and
+// nv % 4 == 0 -> 16-byte cp.async (16 per thread and slice at 250/500; columns >= nv are never read as weights).  Otherwise 4-byte
+// cp.async with columns >= nv zero-filled.
+// (One bulk async copy per row, completing on an mbarrier, was measured first: issuing the 250 small copies of a slice costs the CTA
+//  1.0 µs — the TMA unit takes one 256-byte copy every ~8 cycles — against ~0.1 µs for these.)
+__device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, bool vec, int tid) {
+  if (vec) {
+    const int chunks = nv >> 2;
+    for (int e = tid; e < l1 * 16; e += FT) {
+      const int k = e >> 4, ch = e & 15;
+      if (ch < chunks) cp_async16(Ws + k * WP + ch * 4, W2 + (long long)k * l2 + n0 + ch * 4);
     }
-    return;
-  }
-  for (int e = tid; e < l1 * 64; e += FT) {
-    const int k = e >> 6, col = e & 63;
-    const bool ok = col < nv;
-    cp_async4z(Ws + k * WP + col, ok ? W2 + (long long)k * l2 + n0 + col : W2, ok);
+  } else {
+    for (int e = tid; e < l1 * 64; e += FT) {
+      const int k = e >> 6, col = e & 63;
+      const bool ok = col < nv;
+      cp_async4z(Ws + k * WP + col, ok ? W2 + (long long)k * l2 + n0 + col : W2, ok);
+    }
   }
   cp_commit();
 }
-// the slice staged into a slot has landed (this thread's view; follow with __syncthreads for the 4-byte path)
-template <int PENDING>
-__device__ __forceinline__ void stage_wait(bool bulk, unsigned long long* bar, unsigned parity) {
-  if (bulk) mbar_wait(bar, parity);
-  else cp_wait<PENDING>();
+
+// Everything small a CTA reads from a net — its W1 column and b1 (thread = layer-1 unit), its slice of b2 and W3 (lane = columns
+// lane, lane+32) — is loaded into registers when the kernel starts: the global-memory latency is paid once, under the W2 staging,
+// instead of once per dependent step of the chain.
+struct L1Regs { float w[11]; float b; };
+__device__ __forceinline__ L1Regs load_l1(const float* __restrict__ W1, const float* __restrict__ b1, int K, int l1, int tid) {
+  L1Regs R;
+  const bool ok = tid < l1;
+#pragma unroll
+  for (int i = 0; i < 11; ++i) R.w[i] = (ok && i < K) ? __ldg(W1 + i * l1 + tid) : 0.0f;
+  R.b = ok ? __ldg(b1 + tid) : 0.0f;
+  return R;
+}
+struct TailRegs { float b2[2]; float w3[2][2]; };
+__device__ __forceinline__ TailRegs load_tail(const float* __restrict__ b2s, const float* __restrict__ W3s, int J, int nv, int lane) {
+  TailRegs T;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = lane + 32 * h;
+    const bool ok = c < nv;
+    T.b2[h] = ok ? __ldg(b2s + c) : 0.0f;
+    T.w3[h][0] = ok ? __ldg(W3s + c * J) : 0.0f;
+    T.w3[h][1] = (ok && J == 2) ? __ldg(W3s + c * J + 1) : 0.0f;
+  }
+  return T;
 }
 
 // layer 1, all l1 units, the cluster's 8 rows: h1T[k][r] = relu(b1[k] + sum_i W1[i][k] x[r][i])      (Dense(in, L1, relu))
-__device__ __forceinline__ void f1(const float* __restrict__ W1, const float* __restrict__ b1, int K, int l1, const float* x, float* h1T, int tid) {
+__device__ __forceinline__ void f1(const L1Regs& R, int K, int l1, const float* x, float* h1T, int tid) {
   if (tid < l1) {
     float acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
-    float w[11];
-#pragma unroll
-    for (int i = 0; i < 11; ++i) w[i] = (i < K) ? __ldg(W1 + i * l1 + tid) : 0.0f;
-    const float b = __ldg(b1 + tid);
 #pragma unroll
     for (int i = 0; i < 11; ++i) {
       if (i < K) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = fmaf(x[r * 12 + i], w[i], acc[r]);
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(x[r * 12 + i], R.w[i], acc[r]);
       }
     }
     float o[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { const float v = acc[r] + b; o[r] = v > 0.0f ? v : 0.0f; }
+    for (int r = 0; r < 8; ++r) { const float v = acc[r] + R.b; o[r] = v > 0.0f ? v : 0.0f; }
     *reinterpret_cast<float4*>(h1T + tid * 8) = make_float4(o[0], o[1], o[2], o[3]);
     *reinterpret_cast<float4*>(h1T + tid * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
   }
@@ -138,7 +125,7 @@ __device__ __forceinline__ void f1(const float* __restrict__ W1, const float* __
 
 // layer 2, this CTA's slice: h2s[r][col] = relu(b2[col] + sum_k h1[r][k] Ws[k][col]).  Warp w takes k = w, w+8, ...; lane the columns
 // lane and lane+32; the 8 warps' partial sums meet in shared memory in warp order.  Ends with a barrier (h2s visible, Ws/red free).
-__device__ __forceinline__ void f2(const float* Ws, const float* __restrict__ b2s, int l1, int nv, const float* h1T, float* red, float* h2s, int tid) {
+__device__ __forceinline__ void f2(const float* Ws, const TailRegs& T, int l1, int nv, const float* h1T, float* red, float* h2s, int tid) {
   const int w = tid >> 5, lane = tid & 31;
   float a0[8], a1[8];
 #pragma unroll
@@ -166,7 +153,7 @@ __device__ __forceinline__ void f2(const float* Ws, const float* __restrict__ b2
 #pragma unroll
     for (int g = 1; g < 8; ++g) v += red[(g * 8 + w) * 64 + c];
     float o = 0.0f;
-    if (c < nv) { v += __ldg(b2s + c); o = v > 0.0f ? v : 0.0f; }
+    if (c < nv) { v += T.b2[h]; o = v > 0.0f ? v : 0.0f; }
     h2s[w * 64 + c] = o;
   }
   __syncthreads();
@@ -174,15 +161,11 @@ __device__ __forceinline__ void f2(const float* Ws, const float* __restrict__ b2
 
 // output layer (J = 1 or 2 units): this CTA's share of the dot product over its layer-2 slice, row = warp, handed to every CTA of
 // the cluster (slot [my rank][row][j] of their all-gather buffer `buf`)
-__device__ __forceinline__ void f3_partial(const float* __restrict__ W3s, int J, int nv, const float* h2s, FusedSmem* S, int buf,
-                                           cg::cluster_group& cluster, int rank, int tid) {
+__device__ __forceinline__ void f3_partial(const TailRegs& T, const float* h2s, FusedSmem* S, int buf, cg::cluster_group& cluster, int rank, int tid) {
   const int w = tid >> 5, lane = tid & 31;
-  float p0 = 0.0f, p1 = 0.0f;
-  for (int c = lane; c < nv; c += 32) {
-    const float h = h2s[w * 64 + c];
-    p0 = fmaf(h, __ldg(W3s + c * J), p0);
-    if (J == 2) p1 = fmaf(h, __ldg(W3s + c * J + 1), p1);
-  }
+  const float h0 = h2s[w * 64 + lane], h1 = h2s[w * 64 + lane + 32];   // zero beyond the slice, like the weights
+  float p0 = fmaf(h1, T.w3[1][0], h0 * T.w3[0][0]);
+  float p1 = fmaf(h1, T.w3[1][1], h0 * T.w3[0][1]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
   if (lane < FUSED_CLUSTER) {
@@ -198,38 +181,37 @@ __device__ __forceinline__ float xch_sum(const FusedSmem* S, int buf, int r, int
   return v;
 }
 
-// back through the output layer: dW3 (and db3 on rank 0) of these 8 rows into the cluster's partial-gradient copy, and the gradient
-// at this CTA's layer-2 slice dzT[col][r] = (sum_j W3[col][j] dout[r][j]) * [h2 > 0]
-template <bool WRITE>
-__device__ __forceinline__ void b3(const float* __restrict__ W3s, int J, int nv, const float* h2s, const float* dout, float* dzT, float* part_w3s,
-                                   float* part_b3, int tid) {
-  if (WRITE) {
-    if (tid < nv * J) {
-      const int col = tid / J, j = tid - col * J;
-      float v = 0.0f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v = fmaf(h2s[r * 64 + col], dout[r * 2 + j], v);
-      part_w3s[col * J + j] = v;
-    }
-    if (part_b3 && tid >= 128 && tid < 128 + J) {
-      const int j = tid - 128;
-      float v = 0.0f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) v += dout[r * 2 + j];
-      part_b3[j] = v;
-    }
-  }
+// back through the output layer: the gradient at this CTA's layer-2 slice dzT[col][r] = (sum_j W3[col][j] dout[r][j]) * [h2 > 0];
+// w3c0/1 = W3[col = tid & 63][0/1] (preloaded)
+__device__ __forceinline__ void b3_dz(float w3c0, float w3c1, int J, int nv, const float* h2s, const float* dout, float* dzT, int tid) {
   const int col = tid & 63, r0 = (tid >> 6) * 2;
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const int r = r0 + q;
     float v = 0.0f;
     if (col < nv) {
-      v = __ldg(W3s + col * J) * dout[r * 2];
-      if (J == 2) v = fmaf(__ldg(W3s + col * J + 1), dout[r * 2 + 1], v);
+      v = w3c0 * dout[r * 2];
+      if (J == 2) v = fmaf(w3c1, dout[r * 2 + 1], v);
       v = (h2s[r * 64 + col] > 0.0f) ? v : 0.0f;
     }
     dzT[col * 8 + r] = v;
+  }
+}
+// dW3 (and db3 on rank 0) of these 8 rows into the cluster's partial-gradient copy
+__device__ __forceinline__ void b3_grads(int J, int nv, const float* h2s, const float* dout, float* part_w3s, float* part_b3, int tid) {
+  if (tid < nv * J) {
+    const int col = tid / J, j = tid - col * J;
+    float v = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v = fmaf(h2s[r * 64 + col], dout[r * 2 + j], v);
+    part_w3s[col * J + j] = v;
+  }
+  if (part_b3 && tid >= 128 && tid < 128 + J) {
+    const int j = tid - 128;
+    float v = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v += dout[r * 2 + j];
+    part_b3[j] = v;
   }
 }
 
@@ -263,7 +245,7 @@ __device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, 
 }
 
 // back through layer 2: this CTA's share (its columns) of dX[r][k] = sum_col W2[k][col] dz[r][col], thread = k, scattered to the CTA
-// that owns layer-1 unit k (slot [my rank][row][k - its first unit] of its reduce-scatter buffer)
+// that owns layer-1 unit k (slot [my rank][k - its first unit][row] of its reduce-scatter buffer)
 __device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, int nv, int n1s, bool vec, FusedSmem* S, cg::cluster_group& cluster,
                                     int rank, int tid) {
   if (tid < l1) {
@@ -292,8 +274,9 @@ __device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, i
     }
     const int owner = tid / n1s, kk = tid - owner * n1s;
     FusedSmem* peer = cluster.map_shared_rank(S, owner);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) peer->rs[(rank * 8 + r) * 32 + kk] = acc[r];
+    float4* dst = reinterpret_cast<float4*>(peer->rs + (rank * 32 + kk) * 8);   // two 16-byte stores into the owner's shared memory
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 // after the cluster barrier: add the 8 shares in rank order and apply layer 1's ReLU mask -> dz1s[r][kk] (this CTA's layer-1 units)
@@ -301,9 +284,9 @@ __device__ __forceinline__ void rs_finish(FusedSmem* S, const float* h1T, int k0
   const int r = tid >> 5, kk = tid & 31;
   float v = 0.0f;
   if (kk < n1v) {
-    v = S->rs[r * 32 + kk];
+    v = S->rs[kk * 8 + r];
 #pragma unroll
-    for (int s = 1; s < FUSED_CLUSTER; ++s) v += S->rs[(s * 8 + r) * 32 + kk];
+    for (int s = 1; s < FUSED_CLUSTER; ++s) v += S->rs[(s * 32 + kk) * 8 + r];
     v = (h1T[(k0 + kk) * 8 + r] > 0.0f) ? v : 0.0f;
   }
   S->dz1s[r * 32 + kk] = v;
@@ -328,6 +311,20 @@ __device__ __forceinline__ void bw1(const float* x, int K1, const float* dz1s, i
   }
 }
 
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+
+// -DFUSED_TRACE (tools/trace_fused.py builds that variant): thread 0 of CTA 0 stamps clock64() at the marked points
+#ifdef FUSED_TRACE
+__device__ long long fused_trace[2][32];
+#define STAMP(k, i) do { if (blockIdx.x == 0 && threadIdx.x == 0) fused_trace[k][i] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int ddpg_fused_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fused_trace, sizeof(fused_trace));
+}
+#else
+#define STAMP(k, i) do { } while (0)
+#endif
+
 struct Geo { int rank, row0, n0, nv, k0, n1v, n1s; };
 __device__ __forceinline__ Geo make_geo(const FusedArgs& a, cg::cluster_group& cluster) {
   Geo g;
@@ -347,17 +344,18 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const Geo g = make_geo(a, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  const bool bulk = a.bulk != 0;
-  if (bulk) {
-    if (tid == 0) { mbar_init(&S->bar[0], (unsigned)l1); mbar_init(&S->bar[1], (unsigned)l1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-    __syncthreads();
-  }
-  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);   // slot 0: actor_target W2
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[1], tid);    // slot 1: critic W2
+  const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
+STAMP(0, 0);
+    cluster_arrive();  // "this CTA runs": waited for before the first write into a peer's shared memory
+  STAMP(0, 16);
+  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);   // slot 0: actor_target W2
+  STAMP(0, 17);
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);    // slot 1: critic W2
+  STAMP(0, 18);
   if (tid < 88) {
     const int r = tid / 11, i = tid - r * 11;
     S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
@@ -365,54 +363,84 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   } else if (tid >= 96 && tid < 104) {
     S->rr[tid - 96] = a.r[g.row0 + tid - 96]; S->dd[tid - 96] = a.done[g.row0 + tid - 96];
   }
-  cluster.sync();  // every CTA of the cluster runs (its shared memory may be written from now on); also a CTA barrier for x
+  STAMP(0, 19);
+  // the small operands of all three nets, into registers (one exposed global-memory latency for the whole kernel)
+  const L1Regs Rat = load_l1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, tid);
+  const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
+  const L1Regs Rct = load_l1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, tid);
+  const TailRegs Tat = load_tail(a.actor_t + a.ao.b2 + g.n0, a.actor_t + a.ao.w3 + g.n0 * 2, 2, g.nv, lane);
+  const TailRegs Tc = load_tail(a.critic + a.co.b2 + g.n0, a.critic + a.co.w3 + g.n0, 1, g.nv, lane);
+  const TailRegs Tct = load_tail(a.critic_t + a.co.b2 + g.n0, a.critic_t + a.co.w3 + g.n0, 1, g.nv, lane);
+  const float w3c = ((tid & 63) < g.nv) ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;   // b3: column tid & 63
+  const float b3at = __ldg(a.actor_t + a.ao.b3 + (tid & 1)), b3c = __ldg(a.critic + a.co.b3), b3ct = __ldg(a.critic_t + a.co.b3);
+  STAMP(0, 20);
+  __syncthreads();   // x
+  STAMP(0, 1);
   // actor_target(s'_n)
-  f1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
-  stage_wait<1>(bulk, &S->bar[0], 0);
+  f1(Rat, 9, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<1>();
   __syncthreads();
-  f2(S->W[0], a.actor_t + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
-  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);  // slot 0 is free again: critic_target W2
-  f3_partial(a.actor_t + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
+  STAMP(0, 2);
+  f2(S->W[0], Tat, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  STAMP(0, 3);
+  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);  // slot 0 is free again: critic_target W2
+  cluster_wait();    // every CTA of the cluster runs: its shared memory may be written from now on
+  f3_partial(Tat, S->h2s[0], S, 0, cluster, g.rank, tid);
+  STAMP(0, 4);
   // critic(s_n, a)
-  f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[1], S->h1T[1], tid);
-  stage_wait<1>(bulk, &S->bar[1], 0);
+  f1(Rc, 11, l1, S->x[1], S->h1T[1], tid);
+  cp_wait<1>();
   __syncthreads();
-  f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
-  f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);
+  STAMP(0, 5);
+  f2(S->W[1], Tc, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
+  STAMP(0, 6);
+  f3_partial(Tc, S->h2s[1], S, 1, cluster, g.rank, tid);
   cluster.sync();
+  STAMP(0, 7);
   if (tid < 16) {
     const int r = tid >> 1, j = tid & 1;
-    S->x[0][r * 12 + 9 + j] = tanhf(xch_sum(S, 0, r, j) + __ldg(a.actor_t + a.ao.b3 + j));   // a' -> vcat(s'_n, a')
+    S->x[0][r * 12 + 9 + j] = tanhf(xch_sum(S, 0, r, j) + b3at);   // a' -> vcat(s'_n, a')
   } else if (tid >= 32 && tid < 40) {
     const int r = tid - 32;
-    S->qv[r] = xch_sum(S, 1, r, 0) + __ldg(a.critic + a.co.b3);
+    S->qv[r] = xch_sum(S, 1, r, 0) + b3c;
   }
   __syncthreads();
   // critic_target(s'_n, a')
-  f1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, S->x[0], S->h1T[0], tid);
-  stage_wait<0>(bulk, &S->bar[0], 1);   // second use of slot 0
+  f1(Rct, 11, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<0>();   // second use of slot 0
   __syncthreads();
-  f2(S->W[0], a.critic_t + a.co.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
-  f3_partial(a.critic_t + a.co.w3 + g.n0, 1, g.nv, S->h2s[0], S, 2, cluster, g.rank, tid);
+  STAMP(0, 8);
+  f2(S->W[0], Tct, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  STAMP(0, 9);
+  f3_partial(Tct, S->h2s[0], S, 2, cluster, g.rank, tid);
   cluster.sync();
+  STAMP(0, 10);
   if (tid < 8) {  // y = r + γ(1-done) q'  (:133);  d mse / d q = 2 (q - y) / B
     const int r = tid;
-    const float q2 = xch_sum(S, 2, r, 0) + __ldg(a.critic_t + a.co.b3);
+    const float q2 = xch_sum(S, 2, r, 0) + b3ct;
     const float y = S->rr[r] + (a.gamma * (1.0f - S->dd[r])) * q2;
     S->dout[r * 2] = 2.0f * (S->qv[r] - y) * a.inv_batch;
     S->dout[r * 2 + 1] = 0.0f;
-    if (g.rank == 0) { a.q[g.row0 + r] = S->qv[r]; a.y[g.row0 + r] = y; }
+    S->rr[r] = y;
   }
   __syncthreads();
-  // critic backward
-  b3<true>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, part + a.co.w3 + g.n0, g.rank == 0 ? part + a.co.b3 : nullptr, tid);
+  // critic backward.  Everything that goes to global memory waits until after the last cluster barrier: the barrier's release
+  // fence would otherwise sit on the outstanding stores.
+  b3_dz(w3c, 0.0f, 1, g.nv, S->h2s[1], S->dout, S->dzT, tid);
   __syncthreads();
-  bw2(S->h1T[1], S->dzT, l1, l2, g.nv, part + a.co.w2 + g.n0, part + a.co.b2 + g.n0, tid);
+  STAMP(0, 11);
   bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
+  STAMP(0, 12);
   cluster.sync();
+  STAMP(0, 13);
+  if (g.rank == 0 && tid < 8) { a.q[g.row0 + tid] = S->qv[tid]; a.y[g.row0 + tid] = S->rr[tid]; }
+  b3_grads(1, g.nv, S->h2s[1], S->dout, part + a.co.w3 + g.n0, g.rank == 0 ? part + a.co.b3 : nullptr, tid);
+  bw2(S->h1T[1], S->dzT, l1, l2, g.nv, part + a.co.w2 + g.n0, part + a.co.b2 + g.n0, tid);
+  STAMP(0, 14);
   rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
   __syncthreads();
   bw1(S->x[1], 11, S->dz1s, l1, g.n1v, part + a.co.w1 + g.k0, part + a.co.b1 + g.k0, tid);
+  STAMP(0, 15);
 }
 
 // ---- actor pass: loss_act = -mean critic(s, actor(s)) with the UPDATED critic; partial ∇actor                          (DDPG.jl:116-119, :140)
@@ -421,58 +449,62 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const Geo g = make_geo(a, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  const bool bulk = a.bulk != 0;
-  if (bulk) {
-    if (tid == 0) { mbar_init(&S->bar[0], (unsigned)l1); mbar_init(&S->bar[1], (unsigned)l1); asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-    __syncthreads();
-  }
-  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[0], tid);
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, &S->bar[1], tid);
+  const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
+  cluster_arrive();
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);
   if (tid < 72) {
     const int r = tid / 9, i = tid - r * 9;
     S->x[0][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];   // s_n
   }
-  cluster.sync();
+  const L1Regs Ra = load_l1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, tid);
+  const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
+  const TailRegs Ta = load_tail(a.actor + a.ao.b2 + g.n0, a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, lane);
+  const TailRegs Tc = load_tail(a.critic + a.co.b2 + g.n0, a.critic + a.co.w3 + g.n0, 1, g.nv, lane);
+  const bool colok = (tid & 63) < g.nv;
+  const float w3c = colok ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;             // b3 through the critic: column tid & 63
+  const float w3a0 = colok ? __ldg(a.actor + a.ao.w3 + (g.n0 + (tid & 63)) * 2) : 0.0f;       // b3 through the actor
+  const float w3a1 = colok ? __ldg(a.actor + a.ao.w3 + (g.n0 + (tid & 63)) * 2 + 1) : 0.0f;
+  const float w1a0 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 9 * l1 + g.k0 + lane) : 0.0f;   // critic W1 rows of the two action inputs,
+  const float w1a1 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 10 * l1 + g.k0 + lane) : 0.0f;  // this CTA's layer-1 units
+  const float b3a = __ldg(a.actor + a.ao.b3 + (tid & 1)), b3c = __ldg(a.critic + a.co.b3);
+  __syncthreads();   // x
   // actor(s_n)
-  f1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, S->x[0], S->h1T[0], tid);
-  stage_wait<1>(bulk, &S->bar[0], 0);
+  f1(Ra, 9, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<1>();
   __syncthreads();
-  f2(S->W[0], a.actor + a.ao.b2 + g.n0, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
-  f3_partial(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S, 0, cluster, g.rank, tid);
+  f2(S->W[0], Ta, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  cluster_wait();
+  f3_partial(Ta, S->h2s[0], S, 0, cluster, g.rank, tid);
   cluster.sync();
   if (tid < 16) {
     const int r = tid >> 1, j = tid & 1;
-    const float pi = tanhf(xch_sum(S, 0, r, j) + __ldg(a.actor + a.ao.b3 + j));
+    const float pi = tanhf(xch_sum(S, 0, r, j) + b3a);
     S->x[0][r * 12 + 9 + j] = pi;                                   // vcat(s_n, actions)
-    if (g.rank == 0) a.xspi[(long long)(g.row0 + r) * 11 + 9 + j] = pi;
   }
   __syncthreads();
   // critic(s_n, actor(s_n)), d(-mean q)/dq = -1/B
-  f1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, S->x[0], S->h1T[1], tid);
+  f1(Rc, 11, l1, S->x[0], S->h1T[1], tid);
   if (tid < 16) S->dout[tid] = (tid & 1) ? 0.0f : -a.inv_batch;
-  stage_wait<0>(bulk, &S->bar[1], 0);
+  cp_wait<0>();
   __syncthreads();
-  f2(S->W[1], a.critic + a.co.b2 + g.n0, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
-  f3_partial(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S, 1, cluster, g.rank, tid);   // q(s, actor(s)): reporting only
-  b3<false>(a.critic + a.co.w3 + g.n0, 1, g.nv, S->h2s[1], S->dout, S->dzT, nullptr, nullptr, tid);
+  f2(S->W[1], Tc, l1, g.nv, S->h1T[1], S->red, S->h2s[1], tid);
+  f3_partial(Tc, S->h2s[1], S, 1, cluster, g.rank, tid);   // q(s, actor(s)): reporting only
+  b3_dz(w3c, 0.0f, 1, g.nv, S->h2s[1], S->dout, S->dzT, tid);
   __syncthreads();
   bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
   cluster.sync();
-  if (g.rank == 0 && tid >= 64 && tid < 72) a.qpi[g.row0 + tid - 64] = xch_sum(S, 1, tid - 64, 0) + __ldg(a.critic + a.co.b3);
+  if (tid >= 64 && tid < 72) S->qv[tid - 64] = xch_sum(S, 1, tid - 64, 0) + b3c;
   rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
   __syncthreads();
   {  // back through critic layer 1 to the two action inputs: this CTA's layer-1 units' share, row = warp
-    const int w = tid >> 5, lane = tid & 31;
-    float p0 = 0.0f, p1 = 0.0f;
-    if (lane < g.n1v) {
-      const float d = S->dz1s[w * 32 + lane];
-      p0 = __ldg(a.critic + a.co.w1 + 9 * l1 + g.k0 + lane) * d;
-      p1 = __ldg(a.critic + a.co.w1 + 10 * l1 + g.k0 + lane) * d;
-    }
+    const int w = tid >> 5;
+    const float d = S->dz1s[w * 32 + lane];   // zero beyond the slice
+    float p0 = w1a0 * d, p1 = w1a1 * d;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
     if (lane < FUSED_CLUSTER) {
@@ -488,12 +520,17 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
     S->dout[r * 2 + j] = xch_sum(S, 2, r, j) * (1.0f - pi * pi);
   }
   __syncthreads();
-  // actor backward
-  b3<true>(a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, S->h2s[0], S->dout, S->dzT, part + a.ao.w3 + g.n0 * 2, g.rank == 0 ? part + a.ao.b3 : nullptr, tid);
+  // actor backward (global-memory writes after the last cluster barrier, as in the critic pass)
+  b3_dz(w3a0, w3a1, 2, g.nv, S->h2s[0], S->dout, S->dzT, tid);
   __syncthreads();
-  bw2(S->h1T[0], S->dzT, l1, l2, g.nv, part + a.ao.w2 + g.n0, part + a.ao.b2 + g.n0, tid);
   bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
   cluster.sync();
+  if (g.rank == 0) {
+    if (tid < 16) a.xspi[(long long)(g.row0 + (tid >> 1)) * 11 + 9 + (tid & 1)] = S->x[0][(tid >> 1) * 12 + 9 + (tid & 1)];
+    else if (tid >= 64 && tid < 72) a.qpi[g.row0 + tid - 64] = S->qv[tid - 64];
+  }
+  b3_grads(2, g.nv, S->h2s[0], S->dout, part + a.ao.w3 + g.n0 * 2, g.rank == 0 ? part + a.ao.b3 : nullptr, tid);
+  bw2(S->h1T[0], S->dzT, l1, l2, g.nv, part + a.ao.w2 + g.n0, part + a.ao.b2 + g.n0, tid);
   rs_finish(S, S->h1T[0], g.k0, g.n1v, tid);
   __syncthreads();
   bw1(S->x[0], 9, S->dz1s, l1, g.n1v, part + a.ao.w1 + g.k0, part + a.ao.b1 + g.k0, tid);
