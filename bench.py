@@ -154,20 +154,28 @@ def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
     for ep in range(1):
         env.reset(rng=ep + 1)
         env.rollout(sb.POLICY_RANDOM, 24, seed=ep + 1, replay=mem, want_return=False)
-    le = sb.Learner()
-    le.init(1)
     mn, mx = mem.min_max_buffer(24_000, rng_mm=1)
-    le.set_norm(mn, mx)
-    le.replay(mem, rng_rpl=1, n_updates=50)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    le.replay(mem, rng_rpl=2, n_updates=n_updates)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+
+    def timed(fused):
+        le = sb.Learner()
+        le.set_fused(fused)
+        le.init(1)
+        le.set_norm(mn, mx)
+        le.replay(mem, rng_rpl=1, n_updates=50)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        le.replay(mem, rng_rpl=2, n_updates=n_updates)
+        e1.record()
+        torch.cuda.synchronize()
+        le.close()
+        return e0.elapsed_time(e1)
+
+    ms = timed(True)          # the default: two thread-block-cluster kernels per update (csrc/ddpg_fused.cu)
+    ms_tiled = timed(False)   # one launch per matrix product (the path populations and large batches use)
     return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, batch=120, l1=250, l2=500, mem=24_000,
-                kernels_per_update=21, flops_per_update=3.078e8)
+                kernels_per_update=5, flops_per_update=3.078e8, path="cluster-fused (gather, critic pass, ADAM, actor pass, ADAM+Polyak)",
+                tiled_gemm_path=dict(updates_per_s=n_updates / (ms_tiled * 1e-3), us_per_update=1e3 * ms_tiled / n_updates, kernels_per_update=21))
 
 
 def ddpg_cpu_baseline(torch, batch=120, l1=250, l2=500, n_updates=200, gamma=0.99, tau=1e-3):

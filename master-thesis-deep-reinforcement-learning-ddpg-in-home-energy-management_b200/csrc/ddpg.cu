@@ -706,6 +706,7 @@ extern "C" int32_t ddpg_set_fused(Ddpg* h, int32_t on) {
   if (want != h->fused) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }   // re-captured by the next ddpg_update
+    if (h->graph_dp_exec) { cudaGraphExecDestroy(h->graph_dp_exec); h->graph_dp_exec = nullptr; }
     h->fused = want;
   }
   return h->fused ? 1 : 0;
@@ -791,6 +792,8 @@ ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restri
                    const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
                    const int32_t* __restrict__ idx, long long idx_stride, const float* __restrict__ norm, int B, float* __restrict__ xs,
                    float* __restrict__ xs2, float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done, long long pop_stride) {
+  // the fused critic pass (csrc/ddpg_fused.cu) is launched as a programmatic dependent: it may start its prologue now
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = g / 9, k = g - j * 9;
   if (j >= B) return;
@@ -938,23 +941,56 @@ adam_polyak_parts_kernel(float* __restrict__ x, const float* __restrict__ parts,
                          float* __restrict__ m, float* __restrict__ v, long long n, double b1, double b2, double eps, float eta,
                          DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau, float* __restrict__ target2,
                          const float* __restrict__ model2, long long n2, int advance) {
+  // the fused actor pass is a programmatic dependent of ADAM(critic): its actor forward pass may run beside this kernel
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
   const float omt = __fsub_rn(1.0f, tau);
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (long long j = tid; j < n; j += stride) {
-    float gj = parts[j];
-#pragma unroll 4
-    for (int c = 1; c < nparts; ++c) gj = __fadd_rn(gj, parts[(long long)c * part_stride + j]);
-    g_out[j] = gj;
-    const float xn = adam_element<false>(x[j], gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
-    x[j] = xn;
-    if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
+  // one element per thread at the reference's sizes: every load of the element (partials, parameter, moments, both Polyak
+  // pairs) is issued before the first use, the partials eight at a time
+  for (long long j = tid; j < n || j < n2; j += stride) {
+    const bool in1 = j < n, in2 = j < n2;
+    float t2 = 0.0f, w2 = 0.0f, xj = 0.0f, tj = 0.0f;
+    if (in2) { t2 = target2[j]; w2 = model2[j]; }
+    if (in1) { xj = x[j]; if (target) tj = target[j]; }
+    if (in1) {
+      float gj = 0.0f;
+      for (int c0 = 0; c0 < nparts; c0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
+      }
+      g_out[j] = gj;
+      const float xn = adam_element<false>(xj, gj, m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+      x[j] = xn;
+      if (target) target[j] = __fadd_rn(__fmul_rn(omt, tj), __fmul_rn(tau, xn));
+    }
+    if (in2) target2[j] = __fadd_rn(__fmul_rn(omt, t2), __fmul_rn(tau, w2));
   }
-  for (long long j = tid; j < n2; j += stride)
-    target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
   if (advance) adam_advance(ctrl, b1, b2);
+}
+
+// data-parallel learner on the cluster-fused path: this rank's gradient = the fixed-order sum of its per-cluster partial copies,
+// written to the flat gradient buffer the peers read
+__global__ void __launch_bounds__(256)
+parts_reduce_kernel(const float* __restrict__ parts, int nparts, long long part_stride, float* __restrict__ g_out, long long n) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float gj = 0.0f;
+  for (int c0 = 0; c0 < nparts; c0 += 8) {
+    float t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
+  }
+  g_out[j] = gj;
 }
 
 // Data-parallel learner: gradient all-reduce FUSED into the optimiser step, over NVLink peer memory (no NCCL call, no
@@ -1344,7 +1380,7 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
 // One learner at a small batch: critic pass -> ADAM(critic) -> actor pass -> ADAM(actor) + soft_update!, the two passes as
 // thread-block-cluster kernels that keep a row's whole forward/backward chain on chip (csrc/ddpg_fused.cu)
 static inline bool use_fused(const Ddpg* h) { return h->fused && h->parts[0] && h->parts[1]; }
-static int enqueue_update_fused(Ddpg* h, cudaStream_t st) {
+static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp) {
   const DdpgParams& p = h->p;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
@@ -1361,20 +1397,32 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st) {
   const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
   a.part = h->parts[1]; a.part_stride = dc.n_params;
   TRY(ddpg_fused_critic(st, a));
-  adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
-                                                         p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  if (dp) {  // gradient exchange over NVLink fused into the optimiser step, as on the tiled path (enqueue_phase1)
+    parts_reduce_kernel<<<adam_blocks, 256, 0, st>>>(h->parts[1], nparts, dc.n_params, h->grad[1], dc.n_params);
+    adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
+                                                      p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  } else {
+    adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
+                                                           p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  }
   CUDA_TRY(cudaGetLastError());
   a.part = h->parts[0]; a.part_stride = da.n_params;
   TRY(ddpg_fused_actor(st, a));
-  adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
-                                                         p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic,
-                                                         dc.n_params, 1);
+  if (dp) {
+    parts_reduce_kernel<<<adam_blocks, 256, 0, st>>>(h->parts[0], nparts, da.n_params, h->grad[0], da.n_params);
+    adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, h->grad[0] - h->gradbuf, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
+                                                      p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
+  } else {
+    adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
+                                                           p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic,
+                                                           dc.n_params, 1);
+  }
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 
 static int enqueue_update_body(Ddpg* h, cudaStream_t st, bool dp = false) {
-  if (!dp && use_fused(h)) return enqueue_update_fused(h, st);
+  if (use_fused(h)) return enqueue_update_fused(h, st, dp);
   int s0 = enqueue_phase0(h, st);
   if (!s0) s0 = enqueue_phase1(h, st, 1.0f, dp);
   if (!s0) s0 = enqueue_phase2(h, st, 1.0f, dp);

@@ -16,6 +16,7 @@
 // One update = gather, critic pass, ADAM(critic), actor pass, ADAM(actor)+Polyak: 5 launches instead of 21.
 // All sums are fp32 in a fixed order; they differ from the tiled-GEMM path only by summation order.
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "common.h"
 #include "ddpg_fused.h"
@@ -325,6 +326,10 @@ extern "C" __attribute__((visibility("default"))) int ddpg_fused_trace_read(long
 #define STAMP(k, i) do { } while (0)
 #endif
 
+// programmatic dependent launch: the kernel may start while its predecessor in the stream still runs; everything the predecessor
+// writes is read only after grid_dependency_wait()
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 struct Geo { int rank, row0, n0, nv, k0, n1v, n1s; };
 __device__ __forceinline__ Geo make_geo(const FusedArgs& a, cg::cluster_group& cluster) {
   Geo g;
@@ -352,19 +357,12 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
 STAMP(0, 0);
     cluster_arrive();  // "this CTA runs": waited for before the first write into a peer's shared memory
   STAMP(0, 16);
+  // Launched as a programmatic dependent of the gather kernel: staging the W2 slices and loading the small operands of all three
+  // nets into registers (none of which the gather writes) overlap it; one exposed global-memory latency for the whole kernel.
   stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);   // slot 0: actor_target W2
   STAMP(0, 17);
   stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);    // slot 1: critic W2
   STAMP(0, 18);
-  if (tid < 88) {
-    const int r = tid / 11, i = tid - r * 11;
-    S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
-    if (i < 9) S->x[0][r * 12 + i] = a.xs2[(long long)(g.row0 + r) * 11 + i];      // s'_n
-  } else if (tid >= 96 && tid < 104) {
-    S->rr[tid - 96] = a.r[g.row0 + tid - 96]; S->dd[tid - 96] = a.done[g.row0 + tid - 96];
-  }
-  STAMP(0, 19);
-  // the small operands of all three nets, into registers (one exposed global-memory latency for the whole kernel)
   const L1Regs Rat = load_l1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, tid);
   const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
   const L1Regs Rct = load_l1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, tid);
@@ -373,6 +371,15 @@ STAMP(0, 0);
   const TailRegs Tct = load_tail(a.critic_t + a.co.b2 + g.n0, a.critic_t + a.co.w3 + g.n0, 1, g.nv, lane);
   const float w3c = ((tid & 63) < g.nv) ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;   // b3: column tid & 63
   const float b3at = __ldg(a.actor_t + a.ao.b3 + (tid & 1)), b3c = __ldg(a.critic + a.co.b3), b3ct = __ldg(a.critic_t + a.co.b3);
+  STAMP(0, 19);
+  grid_dependency_wait();   // the minibatch is gathered
+  if (tid < 88) {
+    const int r = tid / 11, i = tid - r * 11;
+    S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
+    if (i < 9) S->x[0][r * 12 + i] = a.xs2[(long long)(g.row0 + r) * 11 + i];      // s'_n
+  } else if (tid >= 96 && tid < 104) {
+    S->rr[tid - 96] = a.r[g.row0 + tid - 96]; S->dd[tid - 96] = a.done[g.row0 + tid - 96];
+  }
   STAMP(0, 20);
   __syncthreads();   // x
   STAMP(0, 1);
@@ -455,31 +462,34 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
   const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
   cluster_arrive();
+  // Launched as a programmatic dependent of ADAM(critic): the actor's forward pass does not read the critic and overlaps it.
   stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);
   if (tid < 72) {
     const int r = tid / 9, i = tid - r * 9;
     S->x[0][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];   // s_n
   }
   const L1Regs Ra = load_l1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, tid);
-  const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
   const TailRegs Ta = load_tail(a.actor + a.ao.b2 + g.n0, a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, lane);
-  const TailRegs Tc = load_tail(a.critic + a.co.b2 + g.n0, a.critic + a.co.w3 + g.n0, 1, g.nv, lane);
   const bool colok = (tid & 63) < g.nv;
-  const float w3c = colok ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;             // b3 through the critic: column tid & 63
-  const float w3a0 = colok ? __ldg(a.actor + a.ao.w3 + (g.n0 + (tid & 63)) * 2) : 0.0f;       // b3 through the actor
+  const float w3a0 = colok ? __ldg(a.actor + a.ao.w3 + (g.n0 + (tid & 63)) * 2) : 0.0f;       // b3 through the actor: column tid & 63
   const float w3a1 = colok ? __ldg(a.actor + a.ao.w3 + (g.n0 + (tid & 63)) * 2 + 1) : 0.0f;
-  const float w1a0 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 9 * l1 + g.k0 + lane) : 0.0f;   // critic W1 rows of the two action inputs,
-  const float w1a1 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 10 * l1 + g.k0 + lane) : 0.0f;  // this CTA's layer-1 units
-  const float b3a = __ldg(a.actor + a.ao.b3 + (tid & 1)), b3c = __ldg(a.critic + a.co.b3);
+  const float b3a = __ldg(a.actor + a.ao.b3 + (tid & 1));
   __syncthreads();   // x
   // actor(s_n)
   f1(Ra, 9, l1, S->x[0], S->h1T[0], tid);
-  cp_wait<1>();
+  cp_wait<0>();
   __syncthreads();
   f2(S->W[0], Ta, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
   cluster_wait();
   f3_partial(Ta, S->h2s[0], S, 0, cluster, g.rank, tid);
+  grid_dependency_wait();   // the critic is updated
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);
+  const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
+  const TailRegs Tc = load_tail(a.critic + a.co.b2 + g.n0, a.critic + a.co.w3 + g.n0, 1, g.nv, lane);
+  const float w3c = colok ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;             // b3 through the critic
+  const float w1a0 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 9 * l1 + g.k0 + lane) : 0.0f;   // critic W1 rows of the two action inputs,
+  const float w1a1 = (lane < g.n1v) ? __ldg(a.critic + a.co.w1 + 10 * l1 + g.k0 + lane) : 0.0f;  // this CTA's layer-1 units
+  const float b3c = __ldg(a.critic + a.co.b3);
   cluster.sync();
   if (tid < 16) {
     const int r = tid >> 1, j = tid & 1;
@@ -541,13 +551,21 @@ int ddpg_fused_prepare() {
   CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
   return SHEMS_OK;
 }
-int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) {
-  ddpg_fused_critic_kernel<<<(a.B / FUSED_ROWS) * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
-  CUDA_TRY(cudaGetLastError());
+// both kernels are launched as programmatic dependents of their predecessor in the stream (captured as such in the update's graph)
+template <typename K>
+static int launch_pdl(K kernel, cudaStream_t st, const FusedArgs& a) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((a.B / FUSED_ROWS) * FUSED_CLUSTER));
+  cfg.blockDim = dim3(FT);
+  cfg.dynamicSmemBytes = sizeof(FusedSmem);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
   return SHEMS_OK;
 }
-int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a) {
-  ddpg_fused_actor_kernel<<<(a.B / FUSED_ROWS) * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  return SHEMS_OK;
-}
+int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) { return launch_pdl(ddpg_fused_critic_kernel, st, a); }
+int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a) { return launch_pdl(ddpg_fused_actor_kernel, st, a); }

@@ -468,9 +468,10 @@ def test_act_ou_noise_parity(sb, O):
     assert torch.equal(x2, x3)                                                # reproducible per (seed, step)
 
 
-def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series):
+@pytest.mark.parametrize("cluster_fused", [True, False])
+def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series, cluster_fused):
     """ddpg_update_dp with a world of one rank (flags, exchange numbers, captured graph, in-kernel gradient read through the peer
-    table) must be bit-identical to the plain update."""
+    table) must be bit-identical to the plain update — on the cluster-fused small-batch path and on the tiled-GEMM sequence."""
     n, T, B, K = 64, 72, 64, 4
     env = sb.Shems(T, train_series, n_envs=n)
     mem = sb.Replay(n * T)
@@ -478,8 +479,8 @@ def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series):
     env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
     mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
     plain, fused = (sb.Learner(params=sb.default_ddpg_params(batch=B)) for _ in range(2))
-    plain.set_fused(False)   # the data-parallel learner runs the tiled-GEMM sequence: bit-identity holds against that path
     for le in (plain, fused):
+        assert le.set_fused(cluster_fused) is cluster_fused
         le.init(3)
         le.set_norm(mn, mx)
     with pytest.raises(sb.ShemsError):
