@@ -174,7 +174,7 @@ def ddpg_updates_per_s(sb, torch, ser_train, n_updates=2000):
     ms = timed(True)          # the default: two thread-block-cluster kernels per update (csrc/ddpg_fused.cu)
     ms_tiled = timed(False)   # one launch per matrix product (the path populations and large batches use)
     return dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, batch=120, l1=250, l2=500, mem=24_000,
-                kernels_per_update=5, flops_per_update=3.078e8, path="cluster-fused (gather, critic pass, ADAM, actor pass, ADAM+Polyak)",
+                kernels_per_update=4, flops_per_update=3.078e8, path="cluster-fused (critic pass incl. minibatch gather, ADAM, actor pass, ADAM+Polyak)",
                 tiled_gemm_path=dict(updates_per_s=n_updates / (ms_tiled * 1e-3), us_per_update=1e3 * ms_tiled / n_updates, kernels_per_update=21))
 
 

@@ -477,19 +477,7 @@ outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, con
 struct LayerDims { int in, out; long long w_off, b_off; };
 struct NetDims { LayerDims l[3]; long long n_params; };
 
-struct DdpgCtrl {  // device-side control block read by the gather kernel (graph replays need no host patching)
-  unsigned long long seed;
-  unsigned update;      // counts updates; Philox counter for minibatch draws
-  int use_idx;          // 1: indices supplied in idx buffer (consumed batch by batch)
-  long long len, head, cap;
-  int idx_cursor;
-  unsigned blocks_done; // last-block-done counter of the final kernel of an update (advances the counters below)
-  double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
-  double rc[2][2];      // 1 / (1 - βp): correctly rounded reciprocals of the two bias-correction divisors
-  unsigned dp_epoch;    // data-parallel learner: number of gradient exchanges completed (two per update)
-  unsigned dp_blocks_done;
-  int dp_error;         // set when a peer's signal did not arrive within DP_TIMEOUT_NS
-};
+// struct DdpgCtrl: ddpg_fused.h (the fused critic pass samples the minibatch itself)
 #define DP_MAX_WORLD 16
 #define DP_TIMEOUT_NS 4000000000ull
 // peers of a data-parallel learner: rank r's flat gradient buffer and flag array, mapped into this process (CUDA IPC over NVLink)
@@ -1380,7 +1368,8 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
 // One learner at a small batch: critic pass -> ADAM(critic) -> actor pass -> ADAM(actor) + soft_update!, the two passes as
 // thread-block-cluster kernels that keep a row's whole forward/backward chain on chip (csrc/ddpg_fused.cu)
 static inline bool use_fused(const Ddpg* h) { return h->fused && h->parts[0] && h->parts[1]; }
-static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp) {
+struct GatherSrc { bool from_rings; const float *s, *a, *r, *s2, *done; long long ld; };
+static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherSrc& src) {
   const DdpgParams& p = h->p;
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
@@ -1391,6 +1380,9 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp) {
   a.l1 = p.l1; a.l2 = p.l2; a.B = p.batch;
   a.xs = h->xs; a.xs2 = h->xs2; a.xspi = h->xspi; a.r = h->r; a.done = h->done; a.q = h->q; a.y = h->y; a.qpi = h->qpi;
   a.gamma = p.gamma; a.inv_batch = 1.0f / (float)p.batch;
+  a.rings = src.from_rings ? h->rings_dev : nullptr;
+  a.src_s = src.s; a.src_a = src.a; a.src_r = src.r; a.src_s2 = src.s2; a.src_d = src.done; a.src_ld = src.ld;
+  a.ctrl = h->ctrl; a.idx = h->idx_dev; a.norm = h->norm; a.xs_w = h->xs;
   // every slab buffer starts on a 256-byte boundary: W2 rows are 16-byte aligned iff l2 and both W2 offsets are multiples of 4 floats
   a.bulk = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
   const int nparts = p.batch / FUSED_ROWS;
@@ -1422,7 +1414,6 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp) {
 }
 
 static int enqueue_update_body(Ddpg* h, cudaStream_t st, bool dp = false) {
-  if (use_fused(h)) return enqueue_update_fused(h, st, dp);
   int s0 = enqueue_phase0(h, st);
   if (!s0) s0 = enqueue_phase1(h, st, 1.0f, dp);
   if (!s0) s0 = enqueue_phase2(h, st, 1.0f, dp);
@@ -1440,6 +1431,14 @@ static int enqueue_gather(Ddpg* h, cudaStream_t st, bool from_rings, const float
   return SHEMS_OK;
 }
 
+// one whole replay(): sample + update.  Fused path: 4 launches (the critic pass gathers); tiled path: gather kernel + the GEMM sequence
+static int enqueue_update(Ddpg* h, cudaStream_t st, bool dp, bool from_rings, const float* s, const float* a, const float* r, const float* s2,
+                          const float* done, long long ld) {
+  if (use_fused(h)) return enqueue_update_fused(h, st, dp, GatherSrc{from_rings, s, a, r, s2, done, ld});
+  TRY(enqueue_gather(h, st, from_rings, s, a, r, s2, done, ld));
+  return enqueue_update_body(h, st, dp);
+}
+
 // capture gather(from the replay rings) + body once; replays read everything that changes from the device control blocks
 static int ensure_graph(Ddpg* h, bool dp = false) {
   cudaGraph_t& graph = dp ? h->graph_dp : h->graph;
@@ -1450,8 +1449,7 @@ static int ensure_graph(Ddpg* h, bool dp = false) {
   CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) { cudaStreamDestroy(cs); shems_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return SHEMS_ERR_CUDA; }
-  int st = enqueue_gather(h, cs, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
-  if (!st) st = enqueue_update_body(h, cs, dp);
+  int st = enqueue_update(h, cs, dp, true, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   e = cudaStreamEndCapture(cs, &graph);
   cudaStreamDestroy(cs);
   if (st) return st;
@@ -1648,8 +1646,7 @@ extern "C" int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a
   REQUIRE(h && s_dev && a_dev && r_dev && s2_dev, SHEMS_ERR_INVALID, "ddpg_update_batch: NULL argument");
   REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_update_batch: not available for a population handle");
   GUARD(h->device);
-  TRY(enqueue_gather(h, h->stream, false, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch));
-  TRY(enqueue_update_body(h, h->stream));
+  TRY(enqueue_update(h, h->stream, false, false, s_dev, a_dev, r_dev, s2_dev, done_dev, h->p.batch));
   h->n_updates += 1;
   return SHEMS_OK;
 }

@@ -13,13 +13,15 @@
 //     DISTRIBUTED SHARED MEMORY (st to the peer's smem + barrier.cluster), never through L2;
 //   * every cluster writes its 8-row partial of the weight gradients to its own copy in a workspace; the optimiser kernel adds the
 //     B/8 copies in a fixed order (deterministic, like everything else here) — the only grid-wide dependency left.
-// One update = gather, critic pass, ADAM(critic), actor pass, ADAM(actor)+Polyak: 5 launches instead of 21.
+// One update = critic pass (which also samples and normalises its rows of the minibatch), ADAM(critic), actor pass,
+// ADAM(actor)+Polyak: 4 launches instead of 21.
 // All sums are fp32 in a fixed order; they differ from the tiled-GEMM path only by summation order.
 #include <cooperative_groups.h>
 #include <string.h>
 
 #include "common.h"
 #include "ddpg_fused.h"
+#include "philox.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -39,6 +41,7 @@ struct FusedSmem {
   float dz1s[8 * 32];              // gradient at this CTA's layer-1 slice [row][unit]
   float dout[8 * 2];               // gradient at the net's output [row][j]
   float qv[8], rr[8], dd[8];
+  unsigned long long src_row[8];   // where the cluster's 8 sampled transitions live (ring offset or column of the caller's arrays)
 };
 
 __device__ __forceinline__ void cp_async4z(float* smem_dst, const float* gsrc, bool valid) {
@@ -62,10 +65,11 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 //  1.0 µs — the TMA unit takes one 256-byte copy every ~8 cycles — against ~0.1 µs for these.)
 __device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2, int l1, int l2, int n0, int nv, bool vec, int tid) {
   if (vec) {
-    const int chunks = nv >> 2;
-    for (int e = tid; e < l1 * 16; e += FT) {
-      const int k = e >> 4, ch = e & 15;
-      if (ch < chunks) cp_async16(Ws + k * WP + ch * 4, W2 + (long long)k * l2 + n0 + ch * 4);
+    const int ch = tid & 15;   // a thread keeps its 16-byte column chunk and walks the rows tid/16, tid/16 + 16, ...
+    if (ch * 4 < nv) {
+      float* dst = Ws + (tid >> 4) * WP + ch * 4;
+      const float* src = W2 + (long long)(tid >> 4) * l2 + n0 + ch * 4;
+      for (int k = tid >> 4; k < l1; k += FT / 16, dst += (FT / 16) * WP, src += (long long)(FT / 16) * l2) cp_async16(dst, src);
     }
   } else {
     for (int e = tid; e < l1 * 64; e += FT) {
@@ -131,7 +135,7 @@ __device__ __forceinline__ void f2(const float* Ws, const TailRegs& T, int l1, i
   float a0[8], a1[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) { a0[r] = 0.0f; a1[r] = 0.0f; }
-#pragma unroll 4
+#pragma unroll 8
   for (int k = w; k < l1; k += 8) {
     const float w0 = Ws[k * WP + lane], w1 = Ws[k * WP + lane + 32];
     const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
@@ -222,7 +226,7 @@ __device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, 
   const float4 d0a = *reinterpret_cast<const float4*>(dzT + lane * 8), d0b = *reinterpret_cast<const float4*>(dzT + lane * 8 + 4);
   const float4 d1a = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8), d1b = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8 + 4);
   const bool ok0 = lane < nv, ok1 = lane + 32 < nv;
-#pragma unroll 4
+#pragma unroll 8
   for (int k = w; k < l1; k += 8) {
     const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
     float o0 = ha.x * d0a.x, o1 = ha.x * d1a.x;
@@ -256,6 +260,7 @@ __device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, i
     const float* wr = Ws + tid * WP;
     int c = 0;
     if (vec) {  // nv % 4 == 0: four columns per shared-memory read of the row
+#pragma unroll 2
       for (; c + 4 <= nv; c += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(wr + c);
         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -357,12 +362,33 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
 STAMP(0, 0);
     cluster_arrive();  // "this CTA runs": waited for before the first write into a peer's shared memory
   STAMP(0, 16);
-  // Launched as a programmatic dependent of the gather kernel: staging the W2 slices and loading the small operands of all three
-  // nets into registers (none of which the gather writes) overlap it; one exposed global-memory latency for the whole kernel.
+  // the cluster's 8 transitions: Philox (or host-supplied) indices into the replay ring, as ddpg_gather_kernel draws them (replay.cu
+  // sample spec: counter = (row, update number), stream SAMPLE), or the rows of a caller-supplied minibatch
+  const float* ring = a.rings ? a.rings[0] : nullptr;
+  if (tid < 8) {
+    const int j = g.row0 + tid;
+    unsigned long long where = (unsigned long long)j;
+    if (ring) {
+      const long long len = a.ctrl->len, head = a.ctrl->head, cap = a.ctrl->cap;
+      long long li;
+      if (a.ctrl->use_idx) li = a.idx[(long long)a.ctrl->idx_cursor * a.B + j];
+      else {
+        uint32_t w[4];
+        philox4x32_10(a.ctrl->seed, (uint64_t)j, a.ctrl->update, STREAM_SAMPLE, w);
+        li = (long long)(u53(w[0], w[1]) * (double)len);
+        if (li >= len) li = len - 1;
+      }
+      long long slot = head - len + li;
+      if (slot < 0) slot += cap;
+      where = (unsigned long long)ring_base(slot);
+    }
+    S->src_row[tid] = where;
+  }
   stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);   // slot 0: actor_target W2
   STAMP(0, 17);
   stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);    // slot 1: critic W2
   STAMP(0, 18);
+  // the small operands of all three nets, into registers: one exposed global-memory latency for the whole kernel
   const L1Regs Rat = load_l1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, tid);
   const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
   const L1Regs Rct = load_l1(a.critic_t + a.co.w1, a.critic_t + a.co.b1, 11, l1, tid);
@@ -372,13 +398,27 @@ STAMP(0, 0);
   const float w3c = ((tid & 63) < g.nv) ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;   // b3: column tid & 63
   const float b3at = __ldg(a.actor_t + a.ao.b3 + (tid & 1)), b3c = __ldg(a.critic + a.co.b3), b3ct = __ldg(a.critic_t + a.co.b3);
   STAMP(0, 19);
-  grid_dependency_wait();   // the minibatch is gathered
-  if (tid < 88) {
-    const int r = tid / 11, i = tid - r * 11;
-    S->x[1][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];                  // (s_n, a)
-    if (i < 9) S->x[0][r * 12 + i] = a.xs2[(long long)(g.row0 + r) * 11 + i];      // s'_n
-  } else if (tid >= 96 && tid < 104) {
-    S->rr[tid - 96] = a.r[g.row0 + tid - 96]; S->dd[tid - 96] = a.done[g.row0 + tid - 96];
+  __syncthreads();   // src_row
+  if (tid < 8 * RING_FIELDS) {  // thread = (row, field): the ring's field order s[9] a[2] r s'[9] done
+    const int r = tid / RING_FIELDS, f = tid - r * RING_FIELDS;
+    const unsigned long long where = S->src_row[r];
+    float v;
+    if (ring) v = ring[where + (unsigned long long)f * 32];
+    else if (f < RING_A) v = a.src_s[(long long)f * a.src_ld + where];
+    else if (f < RING_R) v = a.src_a[(long long)(f - RING_A) * a.src_ld + where];
+    else if (f == RING_R) v = a.src_r[where];
+    else if (f < RING_DONE) v = a.src_s2[(long long)(f - RING_S2) * a.src_ld + where];
+    else v = a.src_d ? a.src_d[where] : 0.0f;
+    const bool is_s = f < RING_A, is_s2 = f >= RING_S2 && f < RING_DONE;
+    if (is_s || is_s2) {  // normalize(s) = (s - s_min) / (s_max - s_min + 1f-8)
+      const int k = is_s ? f : f - RING_S2;
+      const float lo = a.norm[k];
+      const float den = __fadd_rn(__fsub_rn(a.norm[9 + k], lo), 1e-8f);
+      v = __fdiv_rn(__fsub_rn(v, lo), den);
+      if (is_s) S->x[1][r * 12 + k] = v; else S->x[0][r * 12 + k] = v;       // (s_n | a) and s'_n
+    } else if (f < RING_R) S->x[1][r * 12 + f] = v;
+    else if (f == RING_R) S->rr[r] = v;
+    else S->dd[r] = v;
   }
   STAMP(0, 20);
   __syncthreads();   // x
@@ -440,7 +480,13 @@ STAMP(0, 0);
   STAMP(0, 12);
   cluster.sync();
   STAMP(0, 13);
-  if (g.rank == 0 && tid < 8) { a.q[g.row0 + tid] = S->qv[tid]; a.y[g.row0 + tid] = S->rr[tid]; }
+  if (g.rank == 0) {
+    if (tid < 8) { a.q[g.row0 + tid] = S->qv[tid]; a.y[g.row0 + tid] = S->rr[tid]; }
+    else if (tid >= 32 && tid < 32 + 88) {  // the gathered (s_n | a) rows, for the actor pass
+      const int e = tid - 32, r = e / 11, i = e - r * 11;
+      a.xs_w[(long long)(g.row0 + r) * 11 + i] = S->x[1][r * 12 + i];
+    }
+  }
   b3_grads(1, g.nv, S->h2s[1], S->dout, part + a.co.w3 + g.n0, g.rank == 0 ? part + a.co.b3 : nullptr, tid);
   bw2(S->h1T[1], S->dzT, l1, l2, g.nv, part + a.co.w2 + g.n0, part + a.co.b2 + g.n0, tid);
   STAMP(0, 14);
@@ -551,7 +597,7 @@ int ddpg_fused_prepare() {
   CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
   return SHEMS_OK;
 }
-// both kernels are launched as programmatic dependents of their predecessor in the stream (captured as such in the update's graph)
+// launch as a programmatic dependent of the predecessor in the stream (captured as such in the update's graph)
 template <typename K>
 static int launch_pdl(K kernel, cudaStream_t st, const FusedArgs& a) {
   cudaLaunchConfig_t cfg;
@@ -567,5 +613,11 @@ static int launch_pdl(K kernel, cudaStream_t st, const FusedArgs& a) {
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, a));
   return SHEMS_OK;
 }
-int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) { return launch_pdl(ddpg_fused_critic_kernel, st, a); }
+// the critic pass opens the update (it reads what the previous update's optimiser wrote: an ordinary dependency) ...
+int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) {
+  ddpg_fused_critic_kernel<<<(a.B / FUSED_ROWS) * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+// ... the actor pass is a programmatic dependent of ADAM(critic)
 int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a) { return launch_pdl(ddpg_fused_actor_kernel, st, a); }

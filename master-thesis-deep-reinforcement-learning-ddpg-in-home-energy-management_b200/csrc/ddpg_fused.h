@@ -10,6 +10,20 @@
 #define FUSED_MAX_L2 512
 #define FUSED_MAX_BATCH 256    // partial-gradient workspace = batch/8 copies of a net
 
+struct DdpgCtrl {  // device-side control block read by the gather kernel (graph replays need no host patching)
+  unsigned long long seed;
+  unsigned update;      // counts updates; Philox counter for minibatch draws
+  int use_idx;          // 1: indices supplied in idx buffer (consumed batch by batch)
+  long long len, head, cap;
+  int idx_cursor;
+  unsigned blocks_done; // last-block-done counter of the final kernel of an update (advances the counters below)
+  double bp[2][2];      // βp of Flux.ADAM per optimiser (0 critic, 1 actor): β^t, advanced after every update
+  double rc[2][2];      // 1 / (1 - βp): correctly rounded reciprocals of the two bias-correction divisors
+  unsigned dp_epoch;    // data-parallel learner: number of gradient exchanges completed (two per update)
+  unsigned dp_blocks_done;
+  int dp_error;         // set when a peer's signal did not arrive within DP_TIMEOUT_NS
+};
+
 struct FusedNetOff { int w1, b1, w2, b2, w3, b3; };  // float offsets of a net's layers inside its flat buffer [W1|b1|W2|b2|W3|b3]
 struct FusedArgs {
   const float *actor, *critic, *actor_t, *critic_t;  // flat parameter buffers (Flux layout Wt[in][out] per layer)
@@ -22,7 +36,13 @@ struct FusedArgs {
   float* part;               // partial gradients of the net this pass differentiates: [B/8][n_params], one copy per cluster
   long long part_stride;     // = n_params of that net
   float gamma, inv_batch;
-  int bulk;                  // W2 rows are 16-byte aligned in both nets: slices are staged with bulk async copies (else 4-byte cp.async)
+  int bulk;                  // W2 rows are 16-byte aligned in both nets: 16-byte staging copies and shared-memory reads (else 4-byte)
+  // The critic pass samples and normalises its cluster's 8 transitions itself (what ddpg_gather_kernel does for the tiled path,
+  // getData + normalize of src/memory_plotting_saving.jl:31-57) and leaves the (s_n | a) rows in xs for the actor pass.
+  const float* const* rings; // replay ring of the learner (device array of pointers, entry 0), or NULL: caller-supplied SoA arrays
+  const float *src_s, *src_a, *src_r, *src_s2, *src_d; long long src_ld;   // [9][ld], [2][ld], [ld], [9][ld], [ld] or NULL (done = 0)
+  DdpgCtrl* ctrl; const int32_t* idx; const float* norm;
+  float* xs_w;               // = xs, written by the critic pass
 };
 // may this shape run fused?  (widths within the shared-memory plan, whole clusters of 8 rows)
 static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
