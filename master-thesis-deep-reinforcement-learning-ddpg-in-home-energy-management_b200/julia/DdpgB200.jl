@@ -43,6 +43,9 @@ const _memory = let h = Ref{Ptr{Cvoid}}(C_NULL)                                 
     h[]
 end
 memory_length() = Int(ccall((:replay_length, LIB), Int64, (Ptr{Cvoid},), _memory))
+# BATCH_SIZE = 120, L1/L2 = 250/500 run replay() as two thread-block-cluster kernels by default; `fused_replay(false)` selects the
+# one-launch-per-product sequence (returns the resulting state)
+fused_replay(on::Bool=true) = ccall((:ddpg_set_fused, LIB), Cint, (Ptr{Cvoid}, Cint), _learner, on ? 1 : 0) == 1
 
 # ------------------------------------------------------------------ replay memory
 function remember(state, action, reward, next_state, done)                                   # memory_plotting_saving.jl:46-47
