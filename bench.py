@@ -30,6 +30,25 @@ WORKLOAD = "BASELINE configs[2]: shems_LU1 random-action rollout writing replay 
 ALG_BYTES_PER_ENV_STEP = 88  # s 36 + a 8 + r 4 + s' 36 + done 4 (rollout writing replay transitions)
 
 
+# stdout carries exactly ONE line, the JSON: everything libraries print there (NCCL's version banner under NCCL_DEBUG, ...) is sent
+# to stderr by pointing file descriptor 1 at stderr for the whole run; emit() writes the line to the real stdout
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -109,7 +128,7 @@ def run_reference(args, rank, world):
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{n} instances x {args.horizon} steps per step, OpenMP over instances"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -410,6 +429,7 @@ def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
 
 def main():
     args = parse()
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -574,7 +594,7 @@ def main():
                 line["ddpg"]["cpu_baseline"] = ddpg_cpu_baseline(torch)
             except Exception as e:
                 line["ddpg"]["cpu_baseline"] = dict(error=str(e))
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
