@@ -1786,6 +1786,16 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, 
     h->act_h1 = h->act_x + o1; h->act_h2 = h->act_x + o2; h->act_y = h->act_x + o3;
     h->act_cap = n;
   }
+  if (use_fused(h) && pop == 1 && n <= FUSED_ACT_MAX_ROWS) {  // a handful of states (the reference acts on one): one cluster kernel
+    const NetDims& dA = h->dims[0]; const NetDims& dC = h->dims[1];
+    FusedActArgs a; memset(&a, 0, sizeof(a));
+    a.actor = h->net[DDPG_NET_ACTOR];
+    a.ao = FusedNetOff{(int)dA.l[0].w_off, (int)dA.l[0].b_off, (int)dA.l[1].w_off, (int)dA.l[1].b_off, (int)dA.l[2].w_off, (int)dA.l[2].b_off};
+    a.l1 = h->p.l1; a.l2 = h->p.l2;
+    a.bulk = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
+    a.n = n; a.obs = obs_dev; a.osk = osk; a.norm = h->norm; a.y = h->act_y;
+    return ddpg_fused_act(h->stream, a);
+  }
   const dim3 gn((unsigned)((n + 255) / 256), pop);
   ddpg_normalize_kernel<<<gn, 256, 0, h->stream>>>(obs_dev, n, h->norm, h->act_x, h->pop_stride, h->act_stride, osl, osk);
   CUDA_TRY(cudaGetLastError());

@@ -336,15 +336,15 @@ extern "C" __attribute__((visibility("default"))) int ddpg_fused_trace_read(long
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 struct Geo { int rank, row0, n0, nv, k0, n1v, n1s; };
-__device__ __forceinline__ Geo make_geo(const FusedArgs& a, cg::cluster_group& cluster) {
+__device__ __forceinline__ Geo make_geo(int l1, int l2, int bulk, cg::cluster_group& cluster) {
   Geo g;
   g.rank = (int)cluster.block_rank();
   g.row0 = (int)(blockIdx.x / FUSED_CLUSTER) * FUSED_ROWS;
-  int n2s = (a.l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
-  if (a.bulk) n2s = (n2s + 3) & ~3;   // slices start on 16-byte boundaries of the W2 rows
-  g.n1s = (a.l1 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
-  g.n0 = min(g.rank * n2s, a.l2); g.nv = min(n2s, a.l2 - g.n0);
-  g.k0 = min(g.rank * g.n1s, a.l1); g.n1v = min(g.n1s, a.l1 - g.k0);
+  int n2s = (l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  if (bulk) n2s = (n2s + 3) & ~3;   // slices start on 16-byte boundaries of the W2 rows
+  g.n1s = (l1 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
+  g.n0 = min(g.rank * n2s, l2); g.nv = min(n2s, l2 - g.n0);
+  g.k0 = min(g.rank * g.n1s, l1); g.n1v = min(g.n1s, l1 - g.k0);
   return g;
 }
 
@@ -355,7 +355,7 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31;
-  const Geo g = make_geo(a, cluster);
+  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
   const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
@@ -503,7 +503,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31;
-  const Geo g = make_geo(a, cluster);
+  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
   const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
@@ -592,9 +592,49 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   bw1(S->x[0], 9, S->dz1s, l1, g.n1v, part + a.ao.w1 + g.k0, part + a.ao.b1 + g.k0, tid);
 }
 
+// ---- act: y = actor(normalize(s)) for up to 8 states per cluster                                                        (DDPG.jl:148-176)
+__global__ void __cluster_dims__(FUSED_CLUSTER, 1, 1) __launch_bounds__(FT, 1)
+ddpg_fused_act_kernel(const FusedActArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
+  const int l1 = a.l1, l2 = a.l2;
+  cluster_arrive();
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, a.bulk != 0, tid);
+  if (tid < 72) {  // normalize(s) = (s - s_min) / (s_max - s_min + 1f-8); rows beyond n are zero
+    const int r = tid / 9, k = tid - r * 9;
+    const long long j = g.row0 + r;
+    float v = 0.0f;
+    if (j < a.n) {
+      const float lo = a.norm[k];
+      const float den = __fadd_rn(__fsub_rn(a.norm[9 + k], lo), 1e-8f);
+      v = __fdiv_rn(__fsub_rn(a.obs[(long long)k * a.osk + j], lo), den);
+    }
+    S->x[0][r * 12 + k] = v;
+  }
+  const L1Regs Ra = load_l1(a.actor + a.ao.w1, a.actor + a.ao.b1, 9, l1, tid);
+  const TailRegs Ta = load_tail(a.actor + a.ao.b2 + g.n0, a.actor + a.ao.w3 + g.n0 * 2, 2, g.nv, lane);
+  const float b3a = __ldg(a.actor + a.ao.b3 + (tid & 1));
+  __syncthreads();   // x
+  f1(Ra, 9, l1, S->x[0], S->h1T[0], tid);
+  cp_wait<0>();
+  __syncthreads();
+  f2(S->W[0], Ta, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
+  cluster_wait();
+  f3_partial(Ta, S->h2s[0], S, 0, cluster, g.rank, tid);
+  cluster.sync();
+  if (g.rank == 0 && tid < 16) {
+    const int r = tid >> 1, j = tid & 1;
+    if (g.row0 + r < a.n) a.y[(long long)(g.row0 + r) * 2 + j] = tanhf(xch_sum(S, 0, r, j) + b3a);
+  }
+}
+
 int ddpg_fused_prepare() {
   CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
   CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(ddpg_fused_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
   return SHEMS_OK;
 }
 // launch as a programmatic dependent of the predecessor in the stream (captured as such in the update's graph)
@@ -621,3 +661,9 @@ int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a) {
 }
 // ... the actor pass is a programmatic dependent of ADAM(critic)
 int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a) { return launch_pdl(ddpg_fused_actor_kernel, st, a); }
+int ddpg_fused_act(cudaStream_t st, const FusedActArgs& a) {
+  const unsigned clusters = (unsigned)((a.n + FUSED_ROWS - 1) / FUSED_ROWS);
+  ddpg_fused_act_kernel<<<clusters * FUSED_CLUSTER, FT, sizeof(FusedSmem), st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}

@@ -48,6 +48,15 @@ struct FusedArgs {
 static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
   return B >= FUSED_ROWS && B % FUSED_ROWS == 0 && B <= FUSED_MAX_BATCH && l1 >= 1 && l1 <= FUSED_MAX_L1 && l2 >= 1 && l2 <= FUSED_MAX_L2;
 }
+// act() for a handful of states (the reference's episode loop acts on ONE state per step, DDPG.jl:148-176): normalize + the actor's
+// three layers in one cluster kernel, 8 states per cluster; y [n][2] = actor(normalize(s)) before noise
+#define FUSED_ACT_MAX_ROWS 64
+struct FusedActArgs {
+  const float* actor; FusedNetOff ao; int l1, l2, bulk;
+  long long n; const float* obs; long long osk;   // state field k of instance j at obs[k*osk + j]
+  const float* norm; float* y;
+};
+int ddpg_fused_act(cudaStream_t st, const FusedActArgs& a);
 int ddpg_fused_prepare();                                    // shared-memory attribute of both kernels on the current device
 int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a);  // targets, TD target, critic forward/backward -> part (critic)
 int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a);   // actor-loss forward/backward through the critic -> part (actor)

@@ -747,3 +747,35 @@ def test_cluster_fused_update_equals_tiled_gemm_path(sb, O, B, l1, l2):
         for k in range(3):
             for x, y in zip(twins[0].get_layer(net, k), twins[1].get_layer(net, k)):
                 np.testing.assert_array_equal(x, y)
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 37, 64])
+def test_cluster_fused_act_small_n(sb, O, n):
+    """act() on a handful of states (the reference's episode loop acts on one state per step, DDPG.jl:148-176) runs normalize + the
+    actor's three layers as one cluster kernel: equal to the oracle within the fp32 tolerance of the large-n test, to the tiled
+    path within 1e-6 absolute (tanh outputs; summation order only), the same noise stream on both paths."""
+    rng = np.random.default_rng(n)
+    fused, tiled = sb.Learner(), sb.Learner()
+    assert fused.set_fused(True) is True and tiled.set_fused(False) is False
+    orc = O.OracleDdpg(O.default_ddpg_params())
+    orc.init(4)
+    for net in (0,):
+        for k in range(3):
+            w, b = orc.get_layer(net, k)
+            orc.set_layer(net, k, w, rng.normal(0, 0.05, b.shape).astype(np.float32))
+    _sync_nets(fused, orc)
+    _sync_nets(tiled, orc)
+    mn, mx = rng.uniform(-1, 0, 9).astype(np.float32), rng.uniform(1, 5, 9).astype(np.float32)
+    for le in (fused, tiled, orc):
+        le.set_norm(mn, mx)
+    obs = (rng.uniform(0, 1, (9, n)) * mx[:, None]).astype(np.float32)
+    a, sc = fused.act(dev(obs), train=False)
+    at, sct = tiled.act(dev(obs), train=False)
+    oa, _ = orc.act(obs)
+    np.testing.assert_allclose(a.cpu().numpy(), oa, rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(a.cpu().numpy(), at.cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(sc.cpu().numpy(), ((a.cpu().numpy().astype(np.float64) + 1) * 0.5).astype(np.float32))
+    a3, _ = fused.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=1)
+    a4, _ = tiled.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=1)
+    np.testing.assert_allclose(a3.cpu().numpy(), a4.cpu().numpy(), rtol=0, atol=1e-6)
+    assert not torch.equal(a3, a)
