@@ -28,6 +28,7 @@
 #include "philox.cuh"
 #include "tc_gemm.h"
 #include "ddpg_fused.h"
+#include "act_epilogue.cuh"
 
 // ----------------------------------------------------------------------------- GEMM
 enum { EPI_NONE = 0, EPI_BIAS_RELU, EPI_BIAS_TANH, EPI_BIAS_ID, EPI_RELU_MASK, EPI_TD_TARGET, EPI_TANH_GRAD, EPI_SCALE_MASK };
@@ -1700,27 +1701,11 @@ ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, fl
     if (noise) noise += l * asl;
     if (scaled_out) scaled_out += l * asl;
   }
-  float nz0 = 0.0f, nz1 = 0.0f;
-  if (noise) { nz0 = noise[j]; nz1 = noise[ask + j]; }
-  else if (sigma > 0.0f) {
-    uint32_t w[4];
-    philox4x32_10(seed, (uint64_t)(env_id_base + j), (uint32_t)step, STREAM_NOISE, w);
-    const double u1 = 1.0 - u53(w[0], w[1]), u2 = u53(w[2], w[3]);  // u1 in (0,1]
-    const double rad = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    nz0 = (float)((double)sigma * (rad * cs));  // Float32.(rand(Normal(μ=0, σ), 2))  (DDPG.jl:57-61)
-    nz1 = (float)((double)sigma * (rad * sn));
-  }
-  float a0 = __fadd_rn(y[j * 2 + 0], nz0), a1 = __fadd_rn(y[j * 2 + 1], nz1);
-  a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
-  a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
-  a_out[j] = a0; a_out[ask + j] = a1;
-  if (scaled_out) {  // Float32.(LO .+ (a .+ 1.0) .* 0.5 .* (HI .- LO)) in Float64
-    const double sp0 = (double)__fsub_rn(hi0, lo0), sp1 = (double)__fsub_rn(hi1, lo1);
-    scaled_out[j] = (float)__dadd_rn((double)lo0, __dmul_rn(__dmul_rn(__dadd_rn((double)a0, 1.0), 0.5), sp0));
-    scaled_out[ask + j] = (float)__dadd_rn((double)lo1, __dmul_rn(__dmul_rn(__dadd_rn((double)a1, 1.0), 0.5), sp1));
-  }
+  const bool have = noise != nullptr;
+  const ActOut o = act_gauss_epilogue(y[j * 2 + 0], y[j * 2 + 1], have, have ? noise[j] : 0.0f, have ? noise[ask + j] : 0.0f, sigma, seed, step,
+                                      env_id_base + j, lo0, lo1, hi0, hi1);
+  a_out[j] = o.a0; a_out[ask + j] = o.a1;
+  if (scaled_out) { scaled_out[j] = o.s0; scaled_out[ask + j] = o.s1; }
 }
 
 // OUNoise (DDPG.jl:49-55, input.jl:190-234) with Julia's types: θ, μ, σ, dt and X are Float32, randn is Float64:
@@ -1774,6 +1759,18 @@ ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n,
 }
 
 // actor(normalize(s)) for n states per learner -> h->act_y [n][2] (pre-noise); shared by the noise variants of act()
+// act() on a handful of states of one learner runs as one cluster kernel (csrc/ddpg_fused.cu)
+static inline bool fused_act_ok(const Ddpg* h, int64_t n) { return use_fused(h) && h->pop == 1 && n <= FUSED_ACT_MAX_ROWS; }
+static FusedActArgs fused_act_args(const Ddpg* h, const float* obs_dev, int64_t n, long long osk) {
+  const NetDims& dA = h->dims[0]; const NetDims& dC = h->dims[1];
+  FusedActArgs a; memset(&a, 0, sizeof(a));
+  a.actor = h->net[DDPG_NET_ACTOR];
+  a.ao = FusedNetOff{(int)dA.l[0].w_off, (int)dA.l[0].b_off, (int)dA.l[1].w_off, (int)dA.l[1].b_off, (int)dA.l[2].w_off, (int)dA.l[2].b_off};
+  a.l1 = h->p.l1; a.l2 = h->p.l2;
+  a.bulk = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
+  a.n = n; a.obs = obs_dev; a.osk = osk; a.norm = h->norm; a.y = h->act_y;
+  return a;
+}
 static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, long long osk) {
   const int l1 = h->ld1, l2 = h->ld2, pop = h->pop;
   if (h->act_cap < n) {  // scratch: per learner [x n*9 | h1 n*ld1 | h2 n*ld2 | y n*2], each part at a 256-byte boundary
@@ -1786,14 +1783,8 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, 
     h->act_h1 = h->act_x + o1; h->act_h2 = h->act_x + o2; h->act_y = h->act_x + o3;
     h->act_cap = n;
   }
-  if (use_fused(h) && pop == 1 && n <= FUSED_ACT_MAX_ROWS) {  // a handful of states (the reference acts on one): one cluster kernel
-    const NetDims& dA = h->dims[0]; const NetDims& dC = h->dims[1];
-    FusedActArgs a; memset(&a, 0, sizeof(a));
-    a.actor = h->net[DDPG_NET_ACTOR];
-    a.ao = FusedNetOff{(int)dA.l[0].w_off, (int)dA.l[0].b_off, (int)dA.l[1].w_off, (int)dA.l[1].b_off, (int)dA.l[2].w_off, (int)dA.l[2].b_off};
-    a.l1 = h->p.l1; a.l2 = h->p.l2;
-    a.bulk = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
-    a.n = n; a.obs = obs_dev; a.osk = osk; a.norm = h->norm; a.y = h->act_y;
+  if (fused_act_ok(h, n)) {  // a handful of states (the reference acts on one): one cluster kernel
+    FusedActArgs a = fused_act_args(h, obs_dev, n, osk);
     return ddpg_fused_act(h->stream, a);
   }
   const dim3 gn((unsigned)((n + 255) / 256), pop);
@@ -1819,12 +1810,22 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, 
   return SHEMS_OK;
 }
 
+// sprev_dev (optional, [9][N]): receives a copy of the raw states — the episode loop's s for `remember`
 static int act_gauss(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
-                     const float* noise_dev, float* a_dev, float* scaled_dev, bool soa) {
+                     const float* noise_dev, float* a_dev, float* scaled_dev, bool soa, float* sprev_dev = nullptr) {
   REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
   GUARD(h->device);
   const long long N = (long long)n * h->pop;
+  if (fused_act_ok(h, n)) {  // normalize, the actor's three layers, noise, clamp, scale_action (and the copy of s) in ONE cluster kernel
+    FusedActArgs a = fused_act_args(h, obs_dev, n, n);   // one learner: packed [9][n] and SoA [9][N] coincide
+    a.a_out = a_dev; a.scaled_out = scaled_dev; a.noise = noise_dev; a.ask = n;
+    a.sigma = sigma; a.seed = seed; a.step = step; a.env_id_base = env_id_base;
+    a.lo0 = h->p.act_lo[0]; a.lo1 = h->p.act_lo[1]; a.hi0 = h->p.act_hi[0]; a.hi1 = h->p.act_hi[1];
+    a.sprev = sprev_dev;
+    return ddpg_fused_act(h->stream, a);
+  }
+  if (sprev_dev) CUDA_TRY(cudaMemcpyAsync(sprev_dev, obs_dev, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
   TRY(act_forward(h, obs_dev, n, soa ? n : 9 * n, soa ? N : n));
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
@@ -1921,11 +1922,13 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
   std::vector<uint64_t> seeds((size_t)h->pop);
   for (int step = 1; step <= n_steps; ++step) {
     const uint64_t rng_step = (seed * 1000003ull + (uint64_t)step) & 0x7fffffffffffffffull;
-    if (train && h->noise_kind == 1)
+    if (train && h->noise_kind == 1) {
       TRY(act_ou(h, env->obs, n, h->ou_theta, h->ou_mu, sigma, h->ou_dt, h->ou_x, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
-    else
-      TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
-    if (train) CUDA_TRY(cudaMemcpyAsync(h->ep_sprev, env->obs, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_TRY(cudaMemcpyAsync(h->ep_sprev, env->obs, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true,
+                    train ? h->ep_sprev : nullptr));
+    }
     TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, nullptr, nullptr));
     if (ep_return_dev) {
       ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r, ep_return_dev, N, step == 1);

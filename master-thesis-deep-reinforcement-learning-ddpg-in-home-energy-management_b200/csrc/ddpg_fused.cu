@@ -22,6 +22,7 @@
 #include "common.h"
 #include "ddpg_fused.h"
 #include "philox.cuh"
+#include "act_epilogue.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -610,7 +611,9 @@ ddpg_fused_act_kernel(const FusedActArgs a) {
     if (j < a.n) {
       const float lo = a.norm[k];
       const float den = __fadd_rn(__fsub_rn(a.norm[9 + k], lo), 1e-8f);
-      v = __fdiv_rn(__fsub_rn(a.obs[(long long)k * a.osk + j], lo), den);
+      const float raw = a.obs[(long long)k * a.osk + j];
+      v = __fdiv_rn(__fsub_rn(raw, lo), den);
+      if (a.sprev && g.rank == 0) a.sprev[(long long)k * a.osk + j] = raw;
     }
     S->x[0][r * 12 + k] = v;
   }
@@ -627,7 +630,19 @@ ddpg_fused_act_kernel(const FusedActArgs a) {
   cluster.sync();
   if (g.rank == 0 && tid < 16) {
     const int r = tid >> 1, j = tid & 1;
-    if (g.row0 + r < a.n) a.y[(long long)(g.row0 + r) * 2 + j] = tanhf(xch_sum(S, 0, r, j) + b3a);
+    const long long row = g.row0 + r;
+    const float y = tanhf(xch_sum(S, 0, r, j) + b3a);
+    const float y_other = __shfl_xor_sync(0x0000ffffu, y, 1);   // lanes 2r, 2r+1 hold the two action components of row r
+    if (row < a.n) {
+      if (!a.a_out) a.y[row * 2 + j] = y;
+      else if (j == 0) {
+        const bool have = a.noise != nullptr;
+        const ActOut o = act_gauss_epilogue(y, y_other, have, have ? a.noise[row] : 0.0f, have ? a.noise[a.ask + row] : 0.0f, a.sigma, a.seed,
+                                            a.step, a.env_id_base + row, a.lo0, a.lo1, a.hi0, a.hi1);
+        a.a_out[row] = o.a0; a.a_out[a.ask + row] = o.a1;
+        if (a.scaled_out) { a.scaled_out[row] = o.s0; a.scaled_out[a.ask + row] = o.s1; }
+      }
+    }
   }
 }
 

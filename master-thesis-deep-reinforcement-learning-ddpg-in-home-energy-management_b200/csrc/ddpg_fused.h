@@ -54,7 +54,12 @@ static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
 struct FusedActArgs {
   const float* actor; FusedNetOff ao; int l1, l2, bulk;
   long long n; const float* obs; long long osk;   // state field k of instance j at obs[k*osk + j]
-  const float* norm; float* y;
+  const float* norm; float* y;                    // y [n][2] (written when a_out is NULL)
+  // optional epilogue in the same kernel (act_epilogue.cuh): a = clamp(y + noise, -1, 1), scaled = scale_action(a); component k of
+  // instance j at [k*ask + j].  sprev: copy of the raw states [9][osk] for `remember` (the episode loop's s before step!)
+  float* a_out; float* scaled_out; const float* noise; long long ask;
+  float sigma; unsigned long long seed; long long step, env_id_base; float lo0, lo1, hi0, hi1;
+  float* sprev;
 };
 int ddpg_fused_act(cudaStream_t st, const FusedActArgs& a);
 int ddpg_fused_prepare();                                    // shared-memory attribute of both kernels on the current device

@@ -779,3 +779,8 @@ def test_cluster_fused_act_small_n(sb, O, n):
     a4, _ = tiled.act(dev(obs), train=True, sigma=0.1, rng_act=5, step=1)
     np.testing.assert_allclose(a3.cpu().numpy(), a4.cpu().numpy(), rtol=0, atol=1e-6)
     assert not torch.equal(a3, a)
+    noise = rng.normal(0, 0.1, (2, n)).astype(np.float32)          # caller-supplied noise
+    a5, sc5 = fused.act(dev(obs), noise=dev(noise))
+    oa5, _ = orc.act(obs, noise=noise)
+    np.testing.assert_allclose(a5.cpu().numpy(), oa5, rtol=2e-4, atol=2e-6)
+    np.testing.assert_array_equal(sc5.cpu().numpy(), ((a5.cpu().numpy().astype(np.float64) + 1) * 0.5).astype(np.float32))
