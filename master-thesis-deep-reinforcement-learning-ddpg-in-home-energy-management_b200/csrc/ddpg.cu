@@ -1882,6 +1882,31 @@ ddpg_accum_return_kernel(const float* __restrict__ r, double* __restrict__ ret, 
   ret[i] = (first ? 0.0 : ret[i]) + (double)r[i];
 }
 
+// One learner's episode loop, after step!: remember (DDPG.jl:229 — the n transitions go to ring slots head .. head+n-1), reward_eps += r
+// (:223) and the host-owned part of the control block of the replay() that follows (seed, update number, ring geometry), all
+// passed BY VALUE: one launch in place of two kernels and three small host-to-device copies per step.
+__global__ void __launch_bounds__(256)
+ddpg_episode_post_step_kernel(float* __restrict__ ring, long long cap, long long head, const float* __restrict__ s, const float* __restrict__ a,
+                              const float* __restrict__ r, const float* __restrict__ s2, long long n, double* __restrict__ ep_ret, int first,
+                              DdpgCtrl* __restrict__ ctrl, CtrlHostPart hp, const float** __restrict__ rings_dev) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && ctrl) { *reinterpret_cast<CtrlHostPart*>(ctrl) = hp; rings_dev[0] = ring; }
+  if (i >= n) return;
+  long long slot = head + i;
+  slot -= (slot / cap) * cap;
+  float* q = ring + ring_base(slot);
+#pragma unroll
+  for (int k = 0; k < 9; ++k) q[(RING_S + k) * 32] = s[k * n + i];
+  q[(RING_A + 0) * 32] = a[i];
+  q[(RING_A + 1) * 32] = a[n + i];
+  const float ri = r[i];
+  q[RING_R * 32] = ri;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) q[(RING_S2 + k) * 32] = s2[k * n + i];
+  q[RING_DONE * 32] = 0.0f;
+  if (ep_ret) ep_ret[i] = (first ? 0.0 : ep_ret[i]) + (double)ri;
+}
+
 // episode!(env; NUM_STEPS, train, track = 0, rng_ep) (DDPG.jl:186-242) for all instances of `env`, enqueued in one call with no host
 // round trip per step: act(normalize(s)) [+ gn noise when train] -> scale_action -> step! -> remember -> replay() x updates_per_step.
 // The environment must have been reset by the caller (reset! is :189).  env holds N = P*n instances, learner l owns instances
@@ -1930,6 +1955,26 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
                     train ? h->ep_sprev : nullptr));
     }
     TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, nullptr, nullptr));
+    if (train && h->pop == 1 && !h->dp_on) {  // one learner: remember + reward_eps + the next replay()'s control block in one launch
+      ShemsReplay* rp = rps[0];
+      REQUIRE(rp && rp->device == h->device, SHEMS_ERR_INVALID, "ddpg_episode: replay memory missing or on another device");
+      REQUIRE(N <= rp->capacity, SHEMS_ERR_INVALID, "ddpg_episode: %lld instances exceed the memory's capacity %lld", N, (long long)rp->capacity);
+      const long long head = rp->head;
+      replay_after_rollout(rp, N);
+      CtrlHostPart hp; memset(&hp, 0, sizeof(hp));
+      hp.seed = rng_step; hp.update = (unsigned)h->n_updates; hp.use_idx = 0;
+      hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
+      ddpg_episode_post_step_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(rp->ring, rp->capacity, head, h->ep_sprev, h->ep_a, h->ep_r,
+                                                                                       env->obs, N, ep_return_dev, step == 1,
+                                                                                       updates_per_step > 0 ? h->ctrl : nullptr, hp, h->rings_dev);
+      CUDA_TRY(cudaGetLastError());
+      if (updates_per_step > 0) {
+        TRY(ensure_graph(h));
+        for (int u = 0; u < updates_per_step; ++u) CUDA_TRY(cudaGraphLaunch(h->graph_exec, h->stream));
+        h->n_updates += updates_per_step;
+      }
+      continue;
+    }
     if (ep_return_dev) {
       ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r, ep_return_dev, N, step == 1);
       CUDA_TRY(cudaGetLastError());
