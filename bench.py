@@ -296,6 +296,31 @@ def rule_based_config2(sb, torch, ser_train, n_envs=4096, T=72, reps=50):
                 mean_return=float(out["ep_return"].mean()), note="reset!(rng=-1) + one fused 72-step launch; launch/latency bound")
 
 
+def reference_training_loop(sb, torch, ser_train, episodes=30):
+    """BASELINE configs[0], the reference's own training loop (DDPG_reinforce_charger_v1.jl: ONE instance, EP_LENGTH = 72, BATCH = 120,
+    MEM = 24,000, 250/500): episode! = act -> step! -> remember -> replay() per step, through the native `ddpg_episode` loop."""
+    env = sb.Shems(72, ser_train, n_envs=1)
+    le = sb.Learner()
+    le.init(1231)
+    drv = sb.Driver(env, None, learner=le, mem_size=24_000, ep_length=72, sigma=0.1, updates_per_step=1, rng_run=1231)
+    drv.populate_memory()
+    drv.min_max_buffer()
+    for ep in range(3):
+        drv.episode(env, train=True, rng_ep=ep + 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for ep in range(episodes):
+        drv.episode(env, train=True, rng_ep=100 + ep)
+    e1.record()
+    torch.cuda.synchronize()
+    steps = episodes * 72
+    ms = e0.elapsed_time(e1)
+    return dict(instances=1, batch=120, mem=24_000, episodes_timed=episodes, training_steps_per_s=steps / (ms * 1e-3), us_per_step=1e3 * ms / steps,
+                full_run_seconds=72_072 * ms / steps * 1e-3,
+                note="one step = cluster-fused act kernel, step!, remember/return kernel, 4-kernel replay(); full_run = 1001 episodes x 72 steps")
+
+
 def rollout_returns_only(sb, torch, ser, n_envs=1 << 20, T=2000, reps=3):
     """The same random-action rollout with the episode returns as its only output (8 B per instance per launch): no HBM roofline
     applies — this is the arithmetic ceiling of the Julia-exact step, reported as env-steps/s."""
@@ -570,6 +595,10 @@ def main():
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:  # never lose the env number to the secondary metric
             line["ddpg"] = dict(error=str(e))
+        try:
+            line["reference_training_loop"] = reference_training_loop(sb, torch, sb.series.synth_charger98(4320, seed=98))
+        except Exception as e:
+            line["reference_training_loop"] = dict(error=str(e))
         try:
             line["rollout_returns_only"] = rollout_returns_only(sb, torch, ser)
         except Exception as e:

@@ -27,7 +27,7 @@
 namespace cg = cooperative_groups;
 
 #define FT 256   // threads per CTA: 8 warps
-#define WP 68    // pitch (floats) of a staged W2 slice: rows start on 16-byte boundaries (bulk copies); a warp reading one row, or 32
+#define WP 68    // pitch (floats) of a staged W2 slice: rows start on 16-byte boundaries (16-byte copies); a warp reading one row, or 32
                  // rows as float4 (quarter-warp phases of 8 rows x 16 bytes, 272 bytes apart), is free of bank conflicts
 
 struct FusedSmem {
