@@ -26,19 +26,25 @@
 
 namespace cg = cooperative_groups;
 
-#define FT 256   // threads per CTA: 8 warps
+#ifndef FUSED_THREADS
+#define FUSED_THREADS 256
+#endif
+#define FT FUSED_THREADS          // threads per CTA: 256 (8 warps) or 512 (16 warps: two threads per layer-1 unit, 16 k-groups)
+static_assert(FT == 256 || FT == 512, "FUSED_THREADS must be 256 or 512");
+constexpr int NW = FT / 32;       // warps = k-groups of the layer-2 products
+constexpr int HALVES = FT / 256;  // threads per layer-1 unit
 #define WP 68    // pitch (floats) of a staged W2 slice: rows start on 16-byte boundaries (16-byte copies); a warp reading one row, or 32
                  // rows as float4 (quarter-warp phases of 8 rows x 16 bytes, 272 bytes apart), is free of bank conflicts
 
 struct FusedSmem {
   float W[2][FUSED_MAX_L1 * WP];   // two staged W2 slices [k][col]
   float h1T[2][FUSED_MAX_L1 * 8];  // layer-1 activations of the cluster's 8 rows, unit-major [k][row] (one 32-byte broadcast per k)
-  float red[8 * 8 * 64];           // [warp][row][col] partial sums of the layer-2 product
+  float red[NW * 8 * 64];          // [warp][row][col] partial sums of the layer-2 product
   float h2s[2][8 * 64];            // this CTA's slice of the layer-2 activations [row][col]
   float dzT[64 * 8];               // gradient at this CTA's layer-2 slice, unit-major [col][row]
   float x[2][8 * 12];              // network inputs [row][11] (pitch 12)
   float xch[3][8 * 8 * 2];         // all-gather buffers [source CTA][row][j], filled by the peers
-  float rs[8 * 32 * 8];            // reduce-scatter buffer [source CTA][unit of my layer-1 slice][row], filled by the peers
+  float rs[8 * HALVES * 32 * 8];   // reduce-scatter buffer [source CTA x column half][unit of my layer-1 slice][row], filled by the peers
   float dz1s[8 * 32];              // gradient at this CTA's layer-1 slice [row][unit]
   float dout[8 * 2];               // gradient at the net's output [row][j]
   float qv[8], rr[8], dd[8];
@@ -88,10 +94,11 @@ __device__ __forceinline__ void stage_w2(float* Ws, const float* __restrict__ W2
 struct L1Regs { float w[11]; float b; };
 __device__ __forceinline__ L1Regs load_l1(const float* __restrict__ W1, const float* __restrict__ b1, int K, int l1, int tid) {
   L1Regs R;
-  const bool ok = tid < l1;
+  const int k = tid & 255;   // FT = 512: threads k and k + 256 share unit k
+  const bool ok = k < l1;
 #pragma unroll
-  for (int i = 0; i < 11; ++i) R.w[i] = (ok && i < K) ? __ldg(W1 + i * l1 + tid) : 0.0f;
-  R.b = ok ? __ldg(b1 + tid) : 0.0f;
+  for (int i = 0; i < 11; ++i) R.w[i] = (ok && i < K) ? __ldg(W1 + i * l1 + k) : 0.0f;
+  R.b = ok ? __ldg(b1 + k) : 0.0f;
   return R;
 }
 struct TailRegs { float b2[2]; float w3[2][2]; };
@@ -110,34 +117,37 @@ __device__ __forceinline__ TailRegs load_tail(const float* __restrict__ b2s, con
 
 // layer 1, all l1 units, the cluster's 8 rows: h1T[k][r] = relu(b1[k] + sum_i W1[i][k] x[r][i])      (Dense(in, L1, relu))
 __device__ __forceinline__ void f1(const L1Regs& R, int K, int l1, const float* x, float* h1T, int tid) {
-  if (tid < l1) {
-    float acc[8];
+  constexpr int RPT = 8 / HALVES;              // rows per thread
+  const int k = tid & 255, r0 = (tid >> 8) * RPT;
+  if (k < l1) {
+    float acc[RPT];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < RPT; ++r) acc[r] = 0.0f;
 #pragma unroll
     for (int i = 0; i < 11; ++i) {
       if (i < K) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = fmaf(x[r * 12 + i], R.w[i], acc[r]);
+        for (int r = 0; r < RPT; ++r) acc[r] = fmaf(x[(r0 + r) * 12 + i], R.w[i], acc[r]);
       }
     }
-    float o[8];
+    float o[RPT];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { const float v = acc[r] + R.b; o[r] = v > 0.0f ? v : 0.0f; }
-    *reinterpret_cast<float4*>(h1T + tid * 8) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(h1T + tid * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    for (int r = 0; r < RPT; ++r) { const float v = acc[r] + R.b; o[r] = v > 0.0f ? v : 0.0f; }
+#pragma unroll
+    for (int q = 0; q < RPT / 4; ++q)
+      *reinterpret_cast<float4*>(h1T + k * 8 + r0 + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
   }
 }
 
-// layer 2, this CTA's slice: h2s[r][col] = relu(b2[col] + sum_k h1[r][k] Ws[k][col]).  Warp w takes k = w, w+8, ...; lane the columns
-// lane and lane+32; the 8 warps' partial sums meet in shared memory in warp order.  Ends with a barrier (h2s visible, Ws/red free).
+// layer 2, this CTA's slice: h2s[r][col] = relu(b2[col] + sum_k h1[r][k] Ws[k][col]).  Warp w takes k = w, w+NW, ...; lane the columns
+// lane and lane+32; the warps' partial sums meet in shared memory in warp order.  Ends with a barrier (h2s visible, Ws/red free).
 __device__ __forceinline__ void f2(const float* Ws, const TailRegs& T, int l1, int nv, const float* h1T, float* red, float* h2s, int tid) {
   const int w = tid >> 5, lane = tid & 31;
   float a0[8], a1[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) { a0[r] = 0.0f; a1[r] = 0.0f; }
 #pragma unroll 8
-  for (int k = w; k < l1; k += 8) {
+  for (int k = w; k < l1; k += NW) {
     const float w0 = Ws[k * WP + lane], w1 = Ws[k * WP + lane + 32];
     const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
     a0[0] = fmaf(ha.x, w0, a0[0]); a1[0] = fmaf(ha.x, w1, a1[0]);
@@ -152,15 +162,17 @@ __device__ __forceinline__ void f2(const float* Ws, const TailRegs& T, int l1, i
 #pragma unroll
   for (int r = 0; r < 8; ++r) { red[(w * 8 + r) * 64 + lane] = a0[r]; red[(w * 8 + r) * 64 + lane + 32] = a1[r]; }
   __syncthreads();
+  const int c = tid & 63;                       // (c & 31) == lane: T.b2[c >> 5] is this column's bias
+  const float bias = (tid & 32) ? T.b2[1] : T.b2[0];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {  // output (row w, column c)
-    const int c = lane + 32 * h;
-    float v = red[w * 64 + c];
+  for (int o = 0; o < 512 / FT; ++o) {          // output (row, column c)
+    const int row = (tid >> 6) + o * (FT / 64);
+    float v = red[row * 64 + c];
 #pragma unroll
-    for (int g = 1; g < 8; ++g) v += red[(g * 8 + w) * 64 + c];
-    float o = 0.0f;
-    if (c < nv) { v += T.b2[h]; o = v > 0.0f ? v : 0.0f; }
-    h2s[w * 64 + c] = o;
+    for (int g = 1; g < NW; ++g) v += red[(g * 8 + row) * 64 + c];
+    float out = 0.0f;
+    if (c < nv) { v += bias; out = v > 0.0f ? v : 0.0f; }
+    h2s[row * 64 + c] = out;
   }
   __syncthreads();
 }
@@ -169,6 +181,7 @@ __device__ __forceinline__ void f2(const float* Ws, const TailRegs& T, int l1, i
 // the cluster (slot [my rank][row][j] of their all-gather buffer `buf`)
 __device__ __forceinline__ void f3_partial(const TailRegs& T, const float* h2s, FusedSmem* S, int buf, cg::cluster_group& cluster, int rank, int tid) {
   const int w = tid >> 5, lane = tid & 31;
+  if (w >= 8) return;                                                   // row = warp: warps 8.. (FT = 512) have no row
   const float h0 = h2s[w * 64 + lane], h1 = h2s[w * 64 + lane + 32];   // zero beyond the slice, like the weights
   float p0 = fmaf(h1, T.w3[1][0], h0 * T.w3[0][0]);
   float p1 = fmaf(h1, T.w3[1][1], h0 * T.w3[0][1]);
@@ -190,10 +203,10 @@ __device__ __forceinline__ float xch_sum(const FusedSmem* S, int buf, int r, int
 // back through the output layer: the gradient at this CTA's layer-2 slice dzT[col][r] = (sum_j W3[col][j] dout[r][j]) * [h2 > 0];
 // w3c0/1 = W3[col = tid & 63][0/1] (preloaded)
 __device__ __forceinline__ void b3_dz(float w3c0, float w3c1, int J, int nv, const float* h2s, const float* dout, float* dzT, int tid) {
-  const int col = tid & 63, r0 = (tid >> 6) * 2;
+  const int col = tid & 63;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int r = r0 + q;
+  for (int q = 0; q < 512 / FT; ++q) {
+    const int r = (tid >> 6) + q * (FT / 64);
     float v = 0.0f;
     if (col < nv) {
       v = w3c0 * dout[r * 2];
@@ -228,7 +241,7 @@ __device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, 
   const float4 d1a = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8), d1b = *reinterpret_cast<const float4*>(dzT + (lane + 32) * 8 + 4);
   const bool ok0 = lane < nv, ok1 = lane + 32 < nv;
 #pragma unroll 8
-  for (int k = w; k < l1; k += 8) {
+  for (int k = w; k < l1; k += NW) {
     const float4 ha = *reinterpret_cast<const float4*>(h1T + k * 8), hb = *reinterpret_cast<const float4*>(h1T + k * 8 + 4);
     float o0 = ha.x * d0a.x, o1 = ha.x * d1a.x;
     o0 = fmaf(ha.y, d0a.y, o0); o1 = fmaf(ha.y, d1a.y, o1);
@@ -250,19 +263,22 @@ __device__ __forceinline__ void bw2(const float* h1T, const float* dzT, int l1, 
   }
 }
 
-// back through layer 2: this CTA's share (its columns) of dX[r][k] = sum_col W2[k][col] dz[r][col], thread = k, scattered to the CTA
-// that owns layer-1 unit k (slot [my rank][k - its first unit][row] of its reduce-scatter buffer)
+// back through layer 2: this CTA's share (its columns) of dX[r][k] = sum_col W2[k][col] dz[r][col], thread = k (FT = 512: two
+// threads per k, 32 columns each), scattered to the CTA that owns layer-1 unit k (slot [my rank x half][k - its first unit][row] of its
+// reduce-scatter buffer)
 __device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, int nv, int n1s, bool vec, FusedSmem* S, cg::cluster_group& cluster,
                                     int rank, int tid) {
-  if (tid < l1) {
+  const int k = tid & 255, half = tid >> 8;
+  if (k < l1) {
     float acc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) acc[r] = 0.0f;
-    const float* wr = Ws + tid * WP;
-    int c = 0;
+    const float* wr = Ws + k * WP;
+    int c = half * (64 / HALVES);
+    const int c_end = min(nv, c + 64 / HALVES);
     if (vec) {  // nv % 4 == 0: four columns per shared-memory read of the row
 #pragma unroll 2
-      for (; c + 4 <= nv; c += 4) {
+      for (; c + 4 <= c_end; c += 4) {
         const float4 w4 = *reinterpret_cast<const float4*>(wr + c);
         const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -273,27 +289,28 @@ __device__ __forceinline__ void bx2(const float* Ws, const float* dzT, int l1, i
         }
       }
     }
-    for (; c < nv; ++c) {
+    for (; c < c_end; ++c) {
       const float wv = wr[c];
       const float4 da = *reinterpret_cast<const float4*>(dzT + c * 8), db = *reinterpret_cast<const float4*>(dzT + c * 8 + 4);
       acc[0] = fmaf(wv, da.x, acc[0]); acc[1] = fmaf(wv, da.y, acc[1]); acc[2] = fmaf(wv, da.z, acc[2]); acc[3] = fmaf(wv, da.w, acc[3]);
       acc[4] = fmaf(wv, db.x, acc[4]); acc[5] = fmaf(wv, db.y, acc[5]); acc[6] = fmaf(wv, db.z, acc[6]); acc[7] = fmaf(wv, db.w, acc[7]);
     }
-    const int owner = tid / n1s, kk = tid - owner * n1s;
+    const int owner = k / n1s, kk = k - owner * n1s;
     FusedSmem* peer = cluster.map_shared_rank(S, owner);
-    float4* dst = reinterpret_cast<float4*>(peer->rs + (rank * 32 + kk) * 8);   // two 16-byte stores into the owner's shared memory
+    float4* dst = reinterpret_cast<float4*>(peer->rs + ((rank * HALVES + half) * 32 + kk) * 8);   // two 16-byte stores into the owner's shared memory
     dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
-// after the cluster barrier: add the 8 shares in rank order and apply layer 1's ReLU mask -> dz1s[r][kk] (this CTA's layer-1 units)
+// after the cluster barrier: add the shares in source order and apply layer 1's ReLU mask -> dz1s[r][kk] (this CTA's layer-1 units)
 __device__ __forceinline__ void rs_finish(FusedSmem* S, const float* h1T, int k0, int n1v, int tid) {
+  if (tid >= 256) return;
   const int r = tid >> 5, kk = tid & 31;
   float v = 0.0f;
   if (kk < n1v) {
     v = S->rs[kk * 8 + r];
 #pragma unroll
-    for (int s = 1; s < FUSED_CLUSTER; ++s) v += S->rs[(s * 32 + kk) * 8 + r];
+    for (int s = 1; s < FUSED_CLUSTER * HALVES; ++s) v += S->rs[(s * 32 + kk) * 8 + r];
     v = (h1T[(k0 + kk) * 8 + r] > 0.0f) ? v : 0.0f;
   }
   S->dz1s[r * 32 + kk] = v;
@@ -560,11 +577,11 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   __syncthreads();
   {  // back through critic layer 1 to the two action inputs: this CTA's layer-1 units' share, row = warp
     const int w = tid >> 5;
-    const float d = S->dz1s[w * 32 + lane];   // zero beyond the slice
+    const float d = (w < 8) ? S->dz1s[w * 32 + lane] : 0.0f;   // zero beyond the slice; warps 8.. (FT = 512) have no row
     float p0 = w1a0 * d, p1 = w1a1 * d;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
-    if (lane < FUSED_CLUSTER) {
+    if (w < 8 && lane < FUSED_CLUSTER) {
       FusedSmem* peer = cluster.map_shared_rank(S, lane);
       peer->xch[2][(g.rank * 8 + w) * 2 + 0] = p0;
       peer->xch[2][(g.rank * 8 + w) * 2 + 1] = p1;
