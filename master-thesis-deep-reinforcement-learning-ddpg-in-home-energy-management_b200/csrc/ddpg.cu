@@ -1388,6 +1388,10 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
   a.bulk = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
   const int nparts = p.batch / FUSED_ROWS;
   const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
+#ifndef ADAM_PARTS_THREADS
+#define ADAM_PARTS_THREADS 256
+#endif
+  const unsigned ap_blocks = (unsigned)((dc.n_params + ADAM_PARTS_THREADS - 1) / ADAM_PARTS_THREADS);   // one element per thread
   a.part = h->parts[1]; a.part_stride = dc.n_params;
   TRY(ddpg_fused_critic(st, a));
   if (dp) {  // gradient exchange over NVLink fused into the optimiser step, as on the tiled path (enqueue_phase1)
@@ -1395,7 +1399,7 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
     adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
                                                       p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
   } else {
-    adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
+    adam_polyak_parts_kernel<<<ap_blocks, ADAM_PARTS_THREADS, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
                                                            p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
   }
   CUDA_TRY(cudaGetLastError());
@@ -1406,7 +1410,7 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
     adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, h->grad[0] - h->gradbuf, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
                                                       p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
   } else {
-    adam_polyak_parts_kernel<<<adam_blocks, 256, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
+    adam_polyak_parts_kernel<<<ap_blocks, ADAM_PARTS_THREADS, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
                                                            p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic,
                                                            dc.n_params, 1);
   }
