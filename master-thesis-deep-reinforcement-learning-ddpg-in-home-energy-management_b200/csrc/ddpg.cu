@@ -514,6 +514,9 @@ struct Ddpg {
   unsigned* counters;  // [WS_COUNTERS] arrival counters of the fused slab reductions (zero between kernels)
   float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
   long long ws_floats;
+  // Large batches / populations: the weight-gradient products of a backward pass (dW3, dW2, their bias sums) are off the dX critical
+  // path; they run on a side stream (a parallel branch of the update's graph) with their own workspace and arrival counters.
+  cudaStream_t side; cudaEvent_t ev_fork, ev_mid, ev_join; float* ws_side; unsigned* counters_side;
   // population: `pop` independent learners in one handle.  Every float buffer above lives in one slab per learner
   // (learner l's copy is l*pop_stride floats behind learner 0's), so a launch covers all learners through blockIdx.
   int pop, sel;            // sel: the learner get/set/init/losses address (ddpg_select_learner)
@@ -597,6 +600,15 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   h->ws_floats = (long long)SPLITK_MAX * ((long long)p->l1 * p->l2 + p->l2 + (long long)C * p->l1 + p->l1 + (long long)p->l2 * A + A);
   DMALLOC(h->ws, h->ws_floats);
   DMALLOC(h->counters, WS_COUNTERS);
+  DMALLOC(h->ws_side, h->ws_floats);
+  DMALLOC(h->counters_side, WS_COUNTERS);
+  {
+    cudaError_t e_ = cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking);
+    if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&h->ev_mid, cudaEventDisableTiming);
+    if (e_ == cudaSuccess) e_ = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    if (e_ != cudaSuccess) { shems_set_error("ddpg_create: side stream/events -> %s", cudaGetErrorString(e_)); ddpg_destroy(h); return SHEMS_ERR_CUDA; }
+  }
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
@@ -664,6 +676,11 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
   for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
   cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_flags); cudaFree(h->counters);
+  cudaFree(h->ws_side); cudaFree(h->counters_side);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_mid) cudaEventDestroy(h->ev_mid);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
   return SHEMS_OK;
 }
@@ -1103,8 +1120,9 @@ static int launch_gemms(cudaStream_t st, const GemmProblem* ps, int count, int p
 
 // dW-type product (K = batch) with its bias gradient.  From SPLITK_MIN_BATCH rows on the batch dimension is split over
 // blockIdx.z: every split writes [tile sums | column sums] into the workspace, splitk_reduce_kernel adds them in order.
-static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g) {
+static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g, bool side = false) {
   const int B = g.K;
+  float* const ws = side ? h->ws_side : h->ws;
   if (B < SPLITK_MIN_BATCH) return launch_gemms(st, &g, 1, h->pop, h->pop_stride, h->pop_stride);
   const long long mn = (long long)g.M * g.N, stride = mn + g.N;
   REQUIRE(g.ldc == g.N && g.dbias == g.C + mn && g.epi == EPI_NONE, SHEMS_ERR_INVALID, "launch_dw: not a contiguous [W|b] gradient block");
@@ -1112,12 +1130,12 @@ static int launch_dw(Ddpg* h, cudaStream_t st, const GemmProblem& g) {
   REQUIRE(stride * ksplit <= h->ws_floats, SHEMS_ERR_INVALID, "launch_dw: workspace too small");
   GemmBatch gb; memset(&gb, 0, sizeof(gb));
   gb.count = 1; gb.ksplit = ksplit; gb.split_stride = stride;
-  gb.p[0] = g; gb.p[0].C = h->ws; gb.p[0].dbias = h->ws + mn;
+  gb.p[0] = g; gb.p[0].C = ws; gb.p[0].dbias = ws + mn;
   const long long ctas32 = (long long)((g.M + 31) / 32) * ((g.N + 31) / 32) * ksplit;
   if (ctas32 < 296) gemm_batch_kernel<16, 16><<<dim3((g.M + 15) / 16, (g.N + 15) / 16, ksplit), 128, 0, st>>>(gb);
   else gemm_batch_kernel<32, 32><<<dim3((g.M + 31) / 32, (g.N + 31) / 32, ksplit), 512, 0, st>>>(gb);
   CUDA_TRY(cudaGetLastError());
-  splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(h->ws, stride, ksplit, g.C, stride);
+  splitk_reduce_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, st>>>(ws, stride, ksplit, g.C, stride);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1138,12 +1156,14 @@ static int tc_dx(const Ddpg* h, cudaStream_t st, const float* dZ, int lddz, int 
   return tc_gemm(st, A, Bo, dX, lddx, M, L.in, L.out, TC_EPI_RELU_MASK, nullptr, H, ldh, 1, nullptr, bt);
 }
 // dW = X^T · dZ (both MN-major, K = batch, split-K for one large-batch learner), db = column sums of dZ
-static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float* dZ, int lddz, int B, const LayerDims& L, float* grad) {
+static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float* dZ, int lddz, int B, const LayerDims& L, float* grad, bool side = false) {
+  float* const ws = side ? h->ws_side : h->ws;
+  unsigned* const counters = side ? h->counters_side : h->counters;
   const int tiles = ((L.in + 127) / 128) * ((L.out + 127) / 128), kb = (B + 31) / 32;
   const int splits = h->pop > 1 ? 1 : max(1, min(min(kb / 4, (148 + tiles - 1) / tiles), SPLITK_MAX));
   TcOperand A{X, ldx, true}, Bo{dZ, lddz, true};
   TcBatch bt; bt.count = h->pop; bt.sA = bt.sB = bt.sD = h->pop_stride;
-  TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? h->ws : nullptr, bt));
+  TRY(tc_gemm(st, A, Bo, grad + L.w_off, L.out, L.in, L.out, B, TC_EPI_NONE, nullptr, nullptr, 0, splits, splits > 1 ? ws : nullptr, bt));
   const int slabs = h->pop > 1 ? 1 : max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
   if (slabs == 1) {  // small batch: the column sums are the bias gradient (every learner of a population in one launch)
     wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, 1, h->pop), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, grad + L.b_off, h->pop_stride,
@@ -1152,8 +1172,8 @@ static int tc_dw(Ddpg* h, cudaStream_t st, const float* X, int ldx, const float*
     return SHEMS_OK;
   }
   REQUIRE((L.out + 31) / 32 <= WS_COUNTERS, SHEMS_ERR_INVALID, "tc_dw: layer too wide for the reduction counters");
-  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, h->ws, 0, grad + L.b_off,
-                                                                            h->counters);
+  wcolsum_partial_kernel<0><<<dim3((L.out + 31) / 32, slabs), 256, 0, st>>>(dZ, lddz, B, L.out, nullptr, rows_per, L.out, ws, 0, grad + L.b_off,
+                                                                            counters);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1181,18 +1201,31 @@ static int launch_outer_mask(Ddpg* h, cudaStream_t st, const float* dZ, int J, c
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
-static int big_out_bwd(Ddpg* h, cudaStream_t st, const float* H, int ldh, const float* dZ, int J, int B, const float* net, const LayerDims& L,
-                       float* grad, float* dX) {
-  REQUIRE(J == L.out && (J == 1 || J == 2), SHEMS_ERR_INVALID, "big_out_bwd: output layer must have 1 or 2 units");
+// dW3 (+db3) of an output layer with J <= 2 units by weighted column sums over slabs of rows
+static int out_bwd_dw(Ddpg* h, cudaStream_t st, const float* H, int ldh, const float* dZ, int J, int B, const LayerDims& L, float* grad, bool side = false) {
+  REQUIRE(J == L.out && (J == 1 || J == 2), SHEMS_ERR_INVALID, "out_bwd_dw: output layer must have 1 or 2 units");
+  float* const ws = side ? h->ws_side : h->ws;
+  unsigned* const counters = side ? h->counters_side : h->counters;
   const int N = L.in, slabs = h->pop > 1 ? 1 : max(1, min(SPLITK_MAX, B / 128)), rows_per = (B + slabs - 1) / slabs;
   const long long stride = (long long)N * J + J;
   const dim3 grid((N + 31) / 32, slabs, h->pop);
-  float* out = slabs == 1 ? grad + L.w_off : h->ws;  // a single slab is the gradient block [W3 | b3] itself
-  REQUIRE((N + 31) / 32 <= WS_COUNTERS, SHEMS_ERR_INVALID, "big_out_bwd: layer too wide for the reduction counters");
-  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, h->counters);
-  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, h->counters);
+  float* out = slabs == 1 ? grad + L.w_off : ws;  // a single slab is the gradient block [W3 | b3] itself
+  REQUIRE((N + 31) / 32 <= WS_COUNTERS, SHEMS_ERR_INVALID, "out_bwd_dw: layer too wide for the reduction counters");
+  if (J == 1) wcolsum_partial_kernel<1><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, counters);
+  else wcolsum_partial_kernel<2><<<grid, 256, 0, st>>>(H, ldh, B, N, dZ, rows_per, stride, out, h->pop_stride, grad + L.w_off, counters);
   CUDA_TRY(cudaGetLastError());
-  return launch_outer_mask(h, st, dZ, J, net + L.w_off, H, ldh, B, N, dX);
+  return SHEMS_OK;
+}
+// fork / join of the side stream (inside a stream capture these become parallel branches of the graph)
+static int side_after(Ddpg* h, cudaStream_t st, cudaEvent_t ev) {   // the side stream continues after what `st` has enqueued so far
+  CUDA_TRY(cudaEventRecord(ev, st));
+  CUDA_TRY(cudaStreamWaitEvent(h->side, ev, 0));
+  return SHEMS_OK;
+}
+static int side_join(Ddpg* h, cudaStream_t st) {                     // `st` continues after everything enqueued on the side stream
+  CUDA_TRY(cudaEventRecord(h->ev_join, h->side));
+  CUDA_TRY(cudaStreamWaitEvent(st, h->ev_join, 0));
+  return SHEMS_OK;
 }
 static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows * h->pop >= TC_MIN_ROWS; }
 
@@ -1256,21 +1289,32 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   g[0].aux = h->r; g[0].aux2 = h->done; g[0].aux3 = h->q; g[0].out2 = h->dq; g[0].alpha = p.gamma; g[0].inv_batch = 1.0f / (float)B;
   TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   // P7-P9: critic backward (:137, :105-108)
-  if (big) TRY(big_out_bwd(h, st, h->c_h2, l2, h->dq, 1, B, critic, dc.l[2], h->grad[1], h->dz2));
-  else {
-    g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
-    g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, p.l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
-    TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
+  if (big) {
+    // the dX chain (dz2 -> dz1 -> dW1) is the critical path; dW3, dW2 and their bias sums run beside it on the side stream
+    TRY(side_after(h, st, h->ev_fork));                                                                       // dq, c_h2 are ready
+    TRY(out_bwd_dw(h, h->side, h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1], true));
+    TRY(launch_outer_mask(h, st, h->dq, 1, critic + dc.l[2].w_off, h->c_h2, l2, B, p.l2, h->dz2));
+    TRY(side_after(h, st, h->ev_mid));                                                                        // dz2 is ready
+    if (tc) {
+      TRY(tc_dw(h, h->side, h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1], true));
+      TRY(tc_dx(h, st, h->dz2, l2, B, critic, dc.l[1], h->dz1, l1, h->c_h1, l1));
+    } else {
+      g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
+      g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
+      TRY(launch_dw(h, h->side, g[0], true));
+      TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride));
+    }
+    g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
+    TRY(launch_dw(h, st, g[0]));
+    TRY(side_join(h, st));
+    return SHEMS_OK;
   }
-  if (tc) {
-    TRY(tc_dw(h, st, h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]));
-    TRY(tc_dx(h, st, h->dz2, l2, B, critic, dc.l[1], h->dz1, l1, h->c_h1, l1));
-  } else {
-    g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
-    g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
-    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride)); }
-    else TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
-  }
+  g[0] = gp_dw(h->c_h2, l2, h->dq, 1, B, dc.l[2], h->grad[1]);
+  g[1] = gp_dx(h->dq, 1, B, critic, dc.l[2], 0, p.l2, h->dz2, l2, EPI_RELU_MASK, h->c_h2, l2);
+  TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
+  g[0] = gp_dw(h->c_h1, l1, h->dz2, l2, B, dc.l[1], h->grad[1]);
+  g[1] = gp_dx(h->dz2, l2, B, critic, dc.l[1], 0, p.l1, h->dz1, l1, EPI_RELU_MASK, h->c_h1, l1);
+  TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   g[0] = gp_dw(h->xs, 11, h->dz1, l1, B, dc.l[0], h->grad[1]);
   TRY(launch_dw(h, st, g[0]));
   return SHEMS_OK;
@@ -1323,21 +1367,34 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
   TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   // P16-P18: actor backward
-  if (big) TRY(big_out_bwd(h, st, h->a_h2, l2, h->dza3, 2, B, actor, da.l[2], h->grad[0], h->dza2));
-  else {
-    g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
-    g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, p.l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
-    TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
+  if (big) {  // as in the critic's backward pass: dW3, dW2 (and the reporting-only q(s, actor(s))) beside the dX chain
+    TRY(side_after(h, st, h->ev_fork));                                                                       // dza3 is ready
+    TRY(out_bwd_dw(h, h->side, h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0], true));
+    g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
+    TRY(launch_gemms(h->side, g, 1, h->pop, h->pop_stride, h->pop_stride));
+    TRY(launch_outer_mask(h, st, h->dza3, 2, actor + da.l[2].w_off, h->a_h2, l2, B, p.l2, h->dza2));
+    TRY(side_after(h, st, h->ev_mid));                                                                        // dza2 is ready
+    if (tc) {
+      TRY(tc_dw(h, h->side, h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0], true));
+      TRY(tc_dx(h, st, h->dza2, l2, B, actor, da.l[1], h->dza1, l1, h->a_h1, l1));
+    } else {
+      g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
+      g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
+      TRY(launch_dw(h, h->side, g[0], true));
+      TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride));
+    }
+    g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
+    g[0].M = 9;  // only the 9 state columns of xs feed the actor
+    TRY(launch_dw(h, st, g[0]));
+    TRY(side_join(h, st));
+    return SHEMS_OK;
   }
-  if (tc) {
-    TRY(tc_dw(h, st, h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]));
-    TRY(tc_dx(h, st, h->dza2, l2, B, actor, da.l[1], h->dza1, l1, h->a_h1, l1));
-  } else {
-    g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
-    g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
-    if (big) { TRY(launch_dw(h, st, g[0])); TRY(launch_gemms(st, g + 1, 1, h->pop, h->pop_stride, h->pop_stride)); }
-    else TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
-  }
+  g[0] = gp_dw(h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0]);
+  g[1] = gp_dx(h->dza3, 2, B, actor, da.l[2], 0, p.l2, h->dza2, l2, EPI_RELU_MASK, h->a_h2, l2);
+  TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
+  g[0] = gp_dw(h->a_h1, l1, h->dza2, l2, B, da.l[1], h->grad[0]);
+  g[1] = gp_dx(h->dza2, l2, B, actor, da.l[1], 0, p.l1, h->dza1, l1, EPI_RELU_MASK, h->a_h1, l1);
+  TRY(launch_gemms(st, g, 2, h->pop, h->pop_stride, h->pop_stride));
   g[0] = gp_dw(h->xs, 11, h->dza1, l1, B, da.l[0], h->grad[0]);
   g[0].M = 9;  // only the 9 state columns of xs feed the actor
   TRY(launch_dw(h, st, g[0]));
