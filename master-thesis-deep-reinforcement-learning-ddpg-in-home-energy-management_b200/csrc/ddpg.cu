@@ -1442,7 +1442,7 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
   a.src_s = src.s; a.src_a = src.a; a.src_r = src.r; a.src_s2 = src.s2; a.src_d = src.done; a.src_ld = src.ld;
   a.ctrl = h->ctrl; a.idx = h->idx_dev; a.norm = h->norm; a.xs_w = h->xs;
   // every slab buffer starts on a 256-byte boundary: W2 rows are 16-byte aligned iff l2 and both W2 offsets are multiples of 4 floats
-  a.bulk = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
+  a.vec16 = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
   const int nparts = p.batch / FUSED_ROWS;
   const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
 #ifndef ADAM_PARTS_THREADS
@@ -1828,7 +1828,7 @@ static FusedActArgs fused_act_args(const Ddpg* h, const float* obs_dev, int64_t 
   a.actor = h->net[DDPG_NET_ACTOR];
   a.ao = FusedNetOff{(int)dA.l[0].w_off, (int)dA.l[0].b_off, (int)dA.l[1].w_off, (int)dA.l[1].b_off, (int)dA.l[2].w_off, (int)dA.l[2].b_off};
   a.l1 = h->p.l1; a.l2 = h->p.l2;
-  a.bulk = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
+  a.vec16 = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
   a.n = n; a.obs = obs_dev; a.osk = osk; a.norm = h->norm; a.y = h->act_y;
   return a;
 }

@@ -354,12 +354,12 @@ extern "C" __attribute__((visibility("default"))) int ddpg_fused_trace_read(long
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 
 struct Geo { int rank, row0, n0, nv, k0, n1v, n1s; };
-__device__ __forceinline__ Geo make_geo(int l1, int l2, int bulk, cg::cluster_group& cluster) {
+__device__ __forceinline__ Geo make_geo(int l1, int l2, int vec16, cg::cluster_group& cluster) {
   Geo g;
   g.rank = (int)cluster.block_rank();
   g.row0 = (int)(blockIdx.x / FUSED_CLUSTER) * FUSED_ROWS;
   int n2s = (l2 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
-  if (bulk) n2s = (n2s + 3) & ~3;   // slices start on 16-byte boundaries of the W2 rows
+  if (vec16) n2s = (n2s + 3) & ~3;   // slices start on 16-byte boundaries of the W2 rows
   g.n1s = (l1 + FUSED_CLUSTER - 1) / FUSED_CLUSTER;
   g.n0 = min(g.rank * n2s, l2); g.nv = min(n2s, l2 - g.n0);
   g.k0 = min(g.rank * g.n1s, l1); g.n1v = min(g.n1s, l1 - g.k0);
@@ -373,10 +373,10 @@ ddpg_fused_critic_kernel(const FusedArgs a) {
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31;
-  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
+  const Geo g = make_geo(a.l1, a.l2, a.vec16, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
+  const bool vec16 = a.vec16 != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
 STAMP(0, 0);
     cluster_arrive();  // "this CTA runs": waited for before the first write into a peer's shared memory
   STAMP(0, 16);
@@ -402,9 +402,9 @@ STAMP(0, 0);
     }
     S->src_row[tid] = where;
   }
-  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);   // slot 0: actor_target W2
+  stage_w2(S->W[0], a.actor_t + a.ao.w2, l1, l2, g.n0, g.nv, vec16, tid);   // slot 0: actor_target W2
   STAMP(0, 17);
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);    // slot 1: critic W2
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, vec16, tid);    // slot 1: critic W2
   STAMP(0, 18);
   // the small operands of all three nets, into registers: one exposed global-memory latency for the whole kernel
   const L1Regs Rat = load_l1(a.actor_t + a.ao.w1, a.actor_t + a.ao.b1, 9, l1, tid);
@@ -448,7 +448,7 @@ STAMP(0, 0);
   STAMP(0, 2);
   f2(S->W[0], Tat, l1, g.nv, S->h1T[0], S->red, S->h2s[0], tid);
   STAMP(0, 3);
-  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);  // slot 0 is free again: critic_target W2
+  stage_w2(S->W[0], a.critic_t + a.co.w2, l1, l2, g.n0, g.nv, vec16, tid);  // slot 0 is free again: critic_target W2
   cluster_wait();    // every CTA of the cluster runs: its shared memory may be written from now on
   f3_partial(Tat, S->h2s[0], S, 0, cluster, g.rank, tid);
   STAMP(0, 4);
@@ -494,7 +494,7 @@ STAMP(0, 0);
   b3_dz(w3c, 0.0f, 1, g.nv, S->h2s[1], S->dout, S->dzT, tid);
   __syncthreads();
   STAMP(0, 11);
-  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, vec16, S, cluster, g.rank, tid);
   STAMP(0, 12);
   cluster.sync();
   STAMP(0, 13);
@@ -521,13 +521,13 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31;
-  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
+  const Geo g = make_geo(a.l1, a.l2, a.vec16, cluster);
   const int l1 = a.l1, l2 = a.l2;
   float* part = a.part + (long long)(blockIdx.x / FUSED_CLUSTER) * a.part_stride;
-  const bool bulk = a.bulk != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
+  const bool vec16 = a.vec16 != 0;   // 16-byte aligned W2 rows: vector staging and vector shared-memory reads
   cluster_arrive();
   // Launched as a programmatic dependent of ADAM(critic): the actor's forward pass does not read the critic and overlaps it.
-  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, bulk, tid);
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, vec16, tid);
   if (tid < 72) {
     const int r = tid / 9, i = tid - r * 9;
     S->x[0][r * 12 + i] = a.xs[(long long)(g.row0 + r) * 11 + i];   // s_n
@@ -547,7 +547,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   cluster_wait();
   f3_partial(Ta, S->h2s[0], S, 0, cluster, g.rank, tid);
   grid_dependency_wait();   // the critic is updated
-  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, bulk, tid);
+  stage_w2(S->W[1], a.critic + a.co.w2, l1, l2, g.n0, g.nv, vec16, tid);
   const L1Regs Rc = load_l1(a.critic + a.co.w1, a.critic + a.co.b1, 11, l1, tid);
   const TailRegs Tc = load_tail(a.critic + a.co.b2 + g.n0, a.critic + a.co.w3 + g.n0, 1, g.nv, lane);
   const float w3c = colok ? __ldg(a.critic + a.co.w3 + g.n0 + (tid & 63)) : 0.0f;             // b3 through the critic
@@ -570,7 +570,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   f3_partial(Tc, S->h2s[1], S, 1, cluster, g.rank, tid);   // q(s, actor(s)): reporting only
   b3_dz(w3c, 0.0f, 1, g.nv, S->h2s[1], S->dout, S->dzT, tid);
   __syncthreads();
-  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
+  bx2(S->W[1], S->dzT, l1, g.nv, g.n1s, vec16, S, cluster, g.rank, tid);
   cluster.sync();
   if (tid >= 64 && tid < 72) S->qv[tid - 64] = xch_sum(S, 1, tid - 64, 0) + b3c;
   rs_finish(S, S->h1T[1], g.k0, g.n1v, tid);
@@ -597,7 +597,7 @@ ddpg_fused_actor_kernel(const FusedArgs a) {
   // actor backward (global-memory writes after the last cluster barrier, as in the critic pass)
   b3_dz(w3a0, w3a1, 2, g.nv, S->h2s[0], S->dout, S->dzT, tid);
   __syncthreads();
-  bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, bulk, S, cluster, g.rank, tid);
+  bx2(S->W[0], S->dzT, l1, g.nv, g.n1s, vec16, S, cluster, g.rank, tid);
   cluster.sync();
   if (g.rank == 0) {
     if (tid < 16) a.xspi[(long long)(g.row0 + (tid >> 1)) * 11 + 9 + (tid & 1)] = S->x[0][(tid >> 1) * 12 + 9 + (tid & 1)];
@@ -617,10 +617,10 @@ ddpg_fused_act_kernel(const FusedActArgs a) {
   FusedSmem* S = reinterpret_cast<FusedSmem*>(smem_raw);
   cg::cluster_group cluster = cg::this_cluster();
   const int tid = threadIdx.x, lane = tid & 31;
-  const Geo g = make_geo(a.l1, a.l2, a.bulk, cluster);
+  const Geo g = make_geo(a.l1, a.l2, a.vec16, cluster);
   const int l1 = a.l1, l2 = a.l2;
   cluster_arrive();
-  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, a.bulk != 0, tid);
+  stage_w2(S->W[0], a.actor + a.ao.w2, l1, l2, g.n0, g.nv, a.vec16 != 0, tid);
   if (tid < 72) {  // normalize(s) = (s - s_min) / (s_max - s_min + 1f-8); rows beyond n are zero
     const int r = tid / 9, k = tid - r * 9;
     const long long j = g.row0 + r;

@@ -36,7 +36,7 @@ struct FusedArgs {
   float* part;               // partial gradients of the net this pass differentiates: [B/8][n_params], one copy per cluster
   long long part_stride;     // = n_params of that net
   float gamma, inv_batch;
-  int bulk;                  // W2 rows are 16-byte aligned in both nets: 16-byte staging copies and shared-memory reads (else 4-byte)
+  int vec16;                  // W2 rows are 16-byte aligned in both nets: 16-byte staging copies and shared-memory reads (else 4-byte)
   // The critic pass samples and normalises its cluster's 8 transitions itself (what ddpg_gather_kernel does for the tiled path,
   // getData + normalize of src/memory_plotting_saving.jl:31-57) and leaves the (s_n | a) rows in xs for the actor pass.
   const float* const* rings; // replay ring of the learner (device array of pointers, entry 0), or NULL: caller-supplied SoA arrays
@@ -52,7 +52,7 @@ static inline bool ddpg_fused_shape_ok(int B, int l1, int l2) {
 // three layers in one cluster kernel, 8 states per cluster; y [n][2] = actor(normalize(s)) before noise
 #define FUSED_ACT_MAX_ROWS 64
 struct FusedActArgs {
-  const float* actor; FusedNetOff ao; int l1, l2, bulk;
+  const float* actor; FusedNetOff ao; int l1, l2, vec16;
   long long n; const float* obs; long long osk;   // state field k of instance j at obs[k*osk + j]
   const float* norm; float* y;                    // y [n][2] (written when a_out is NULL)
   // optional epilogue in the same kernel (act_epilogue.cuh): a = clamp(y + noise, -1, 1), scaled = scale_action(a); component k of
