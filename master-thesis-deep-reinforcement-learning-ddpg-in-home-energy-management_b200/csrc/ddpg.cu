@@ -798,8 +798,6 @@ ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restri
                    const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
                    const int32_t* __restrict__ idx, long long idx_stride, const float* __restrict__ norm, int B, float* __restrict__ xs,
                    float* __restrict__ xs2, float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done, long long pop_stride) {
-  // the fused critic pass (csrc/ddpg_fused.cu) is launched as a programmatic dependent: it may start its prologue now
-  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = g / 9, k = g - j * 9;
   if (j >= B) return;
