@@ -163,13 +163,14 @@ SHEMS_API int32_t shems_reset(ShemsEnv* env, int32_t mode, const int32_t* idx0_h
 /* step!(env, s, a; track) for all instances (shems_LU1.jl:343-485).
  *   act_dev   [2][N] float: track >= 0 -> (B_target, EV_target) in [0,1]; track < 0 -> (B, EV) kWh.
  *   track     0 learning, 1 DRL inference, <0 rule-based bookkeeping (only the sign is used, :346-354, :466-471).
- *   reward_dev[N] float or NULL: Float32(env.reward).
+ *   reward_dev[N] float or NULL: Float32(env.reward) (what `cu` makes of the memory's rewards, memory_plotting_saving.jl:37).
+ *   reward64_dev[N] double or NULL: env.reward::Float64 (:171, :467-470) — what episode! sums into reward_eps (DDPG.jl:223).
  *   obs_dev   [9][N] float or NULL: Vector{Float32}(env.state) after the step (NULL: read it
  *             later through shems_state_ptr — the handle's own state IS that array).
  *   trace_dev [23][N] double or NULL: the `results` row (:476-478).
  * Fails with SHEMS_ERR_BOUNDS (nothing launched) when any instance would read row idx+1 > nrows. */
 SHEMS_API int32_t shems_step(ShemsEnv* env, const float* act_dev, int32_t track,
-                             float* reward_dev, float* obs_dev, double* trace_dev);
+                             float* reward_dev, double* reward64_dev, float* obs_dev, double* trace_dev);
 
 /* action(env, track) — the rule-based controller (shems_LU1.jl:318-340) -> (B, EV) [2][N] */
 SHEMS_API int32_t shems_action_rule(ShemsEnv* env, float* bev_dev);
@@ -192,7 +193,9 @@ SHEMS_API int32_t shems_num_rows(const ShemsEnv* env); /* nrow(df) of the series
 enum {
   SHEMS_POLICY_RULE = 0,    /* a = action(env, track); step!(env, s, a, track=-0.5)  (DDPG.jl:209-212) */
   SHEMS_POLICY_RANDOM = 1,  /* a = 2U-1 (stored), scaled to [0,1]^2, track=0        (memory_plotting_saving.jl:14-21) */
-  SHEMS_POLICY_TAPE = 2     /* scaled targets read from tape_dev [T][2][N], track=0 */
+  SHEMS_POLICY_TAPE = 2     /* targets read from tape_dev [T][2][N], track=0: scaled to [0,1] (tape_unscaled = 0) or the unscaled
+                             * actions in [-1,1] that remember() stores, scale_action applied on the device (tape_unscaled = 1; the
+                             * only form allowed together with a replay sink) */
 };
 typedef struct ShemsReplay ShemsReplay;
 typedef struct ShemsRolloutArgs {
@@ -206,6 +209,7 @@ typedef struct ShemsRolloutArgs {
   double* trace_dev;          /* [T][23][N] or NULL */
   float* obs_traj_dev;        /* [T][9][N] post-step observations or NULL */
   float* reward_traj_dev;     /* [T][N] or NULL */
+  int32_t tape_unscaled;      /* SHEMS_POLICY_TAPE: 1 = the tape holds a in [-1,1] (DDPG.jl:229), scaled by scale_action (:178-184) */
 } ShemsRolloutArgs;
 SHEMS_API int32_t shems_rollout(ShemsEnv* env, const ShemsRolloutArgs* args);
 
@@ -278,7 +282,8 @@ SHEMS_API int32_t ddpg_sync(Ddpg* h);
  * order.  Returns the resulting state (1 fused, 0 not) or a negative status. */
 SHEMS_API int32_t ddpg_set_fused(Ddpg* h, int32_t on);
 /* glorot_uniform hidden layers, U(-3e-3,3e-3) last layers, zero biases, targets = copies
- * (DDPG.jl:21-22, 30-46) from Philox(seed) (Julia's MersenneTwister stream is not reproduced). */
+ * (DDPG.jl:21-22, 30-46) from Philox(seed) (Julia's MersenneTwister stream is not reproduced); fresh optimisers
+ * (ADAM moments zero, βp = β, update counter 0: input.jl:126-127). */
 SHEMS_API int32_t ddpg_init(Ddpg* h, uint64_t seed);
 /* Flux layout: layer weight is out×in column-major (element (o,i) at o + out*i), bias[out].
  * layer in 0..2.  Setting ACTOR/CRITIC does not touch the targets. */
@@ -311,12 +316,26 @@ SHEMS_API int32_t ddpg_set_noise(Ddpg* h, int32_t kind, float theta, float mu, f
  * round trip per step: act(normalize(s)) (+ GNoise when train) -> scale_action -> step! -> remember -> replay() x updates_per_step.
  * reset! (:189) stays with the caller.  env holds N = P*n instances: learner l owns instances l*n .. l*n+n-1 and the memory rps[l]
  * (P = 1: the reference's loop).  Seeds: rng_step = (seed*1000003 + step) mod 2^63 keys the noise (with the global env id) and, as
- * rng_step + l, learner l's minibatch draws.  ep_return_dev [N] (Float64, or NULL) receives reward_eps (:223).  The three handles
- * must share one CUDA stream; the call returns as soon as the work is enqueued. */
+ * rng_step + l, learner l's minibatch draws.  ep_return_dev [N] (Float64, or NULL) receives reward_eps (:223), noise_eps_dev [N]
+ * (Float32, or NULL) noise_eps = the sum over the steps of mean(noise) (:224; what run_episodes stores in noise_mean).  The three handles
+ * must share one CUDA stream; the call returns as soon as the work is enqueued.  On a handle connected with ddpg_dp_connect every
+ * replay() is the data-parallel one (ddpg_update_dp: all ranks must make the same calls), so the replicas stay identical. */
 SHEMS_API int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps, int32_t n_steps, int32_t train, float sigma, uint64_t seed,
-                               int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev);
+                               int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev, float* noise_eps_dev);
+/* episode!(env; NUM_STEPS, train = false, track, rng_ep) (DDPG.jl:186-242) and inference(env; track = 1) (memory_plotting_saving.jl:62-89,
+ * 1439 / 2999 / 4319 steps from reset!(rng = -1)) for every instance of `env`, by ONE call: act(normalize(s)) [+ GNoise when
+ * sigma > 0] -> scale_action -> step!, n_steps times.  One learner at widths l1 <= 256, l2 <= 512 runs as a single persistent
+ * thread-block-cluster kernel (csrc/actor_rollout.cu: the actor's W2 stays in shared memory for the whole episode, 8 instances per
+ * cluster, no launch and no host round trip per step); populations and wider nets take one act + step! launch pair per step.
+ * The 100 evaluation episodes of run_episodes (DDPG.jl:266-279) are one call on an environment handle with 100 instances.
+ *   ep_return_dev [N] double or NULL: reward_eps (:223);  trace_dev [T][23][N] double or NULL: the `results` rows of track = 1
+ *   (:207-208);  act_traj_dev [T][2][N] float or NULL: the unscaled actions a.  Seeds as ddpg_episode; reset! stays with the caller. */
+SHEMS_API int32_t ddpg_rollout(Ddpg* h, ShemsEnv* env, int32_t n_steps, float sigma, uint64_t seed, int64_t env_id_base,
+                               double* ep_return_dev, double* trace_dev, float* act_traj_dev);
 /* replay() (DDPG.jl:121-145) n_updates times: sample -> TD target -> critic step -> actor step
- * -> Polyak.  idx_host ([n_updates][batch], 0-based logical indices) or NULL -> Philox(seed, update counter). */
+ * -> Polyak.  idx_host ([n_updates][batch], 0-based logical indices) or NULL -> Philox(seed, draw j, counter u = index of the
+ * update inside this call): replay(rng_rpl = r) trains on the minibatch replay_sample(seed = r) returns, as getData(rng) is one
+ * sample in both of its uses (memory_plotting_saving.jl:31-42). */
 SHEMS_API int32_t ddpg_update(Ddpg* h, ShemsReplay* rp, int32_t n_updates, const int32_t* idx_host, uint64_t seed);
 /* the same update on a caller-supplied minibatch (device, [9][B],[2][B],[B],[9][B],[B]) */
 SHEMS_API int32_t ddpg_update_batch(Ddpg* h, const float* s_dev, const float* a_dev, const float* r_dev,
@@ -353,6 +372,21 @@ SHEMS_API int32_t ddpg_get_grad(Ddpg* h, int32_t net, int32_t layer, float* w_ho
 /* flat fp32 gradient buffer on the device: critic gradient at [0, nc), actor gradient at [roundup(nc, 64), roundup(nc, 64) + na),
  * zero padding between them; *n = roundup(nc, 64) + na (nc, na = ddpg_num_params of critic / actor) */
 SHEMS_API int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n);
+
+/* Full learner snapshot — what the reference never saves (saveBSON writes the actor and the score arrays only,
+ * memory_plotting_saving.jl:263-270, so its runs cannot be resumed): of the learner chosen by ddpg_select_learner,
+ *   state_host [ddpg_state_floats()] = [actor | critic | actor_target | critic_target | m_actor | v_actor | m_critic | v_critic |
+ *                                       s_min (9) | s_max (9)]   (nets in the flat Flux layout of ddpg_get_layer, ADAM moments alike)
+ *   opt_host [8] doubles             = [βp_critic[1], βp_critic[2], βp_actor[1], βp_actor[2] (Flux.ADAM's β^t), update counter, 0, 0, 0]
+ * A learner restored with ddpg_set_state continues bit-identically (tests/test_resume_gpu.py); the replay memory is saved with
+ * replay_get and restored with replay_push into a fresh memory of the same capacity (sampling uses logical indices). */
+SHEMS_API int64_t ddpg_state_floats(const Ddpg* h);
+SHEMS_API int32_t ddpg_get_state(Ddpg* h, float* state_host, double* opt_host);
+SHEMS_API int32_t ddpg_set_state(Ddpg* h, const float* state_host, const double* opt_host);
+/* OUNoise.X of ddpg_episode's instances ([2][n], input.jl:234; the reference never resets it): *n_out = instance count (0 before the
+ * first OU episode), x_host may be NULL to query it; ddpg_set_ou_state (re)allocates for n instances. */
+SHEMS_API int32_t ddpg_get_ou_state(Ddpg* h, float* x_host, int64_t* n_out);
+SHEMS_API int32_t ddpg_set_ou_state(Ddpg* h, const float* x_host, int64_t n);
 
 /* ------------------------------------------------ tensor-core GEMM (test / benchmark entry point)
  * The TF32 tcgen05 kernel behind the large-batch DDPG update, exposed for unit tests and roofline measurements:

@@ -40,7 +40,7 @@ class ShemsRolloutArgs(C.Structure):
     _fields_ = [
         ("policy", C.c_int32), ("n_steps", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_int64),
         ("tape_dev", C.c_void_p), ("ep_return_dev", C.c_void_p), ("replay", C.c_void_p), ("trace_dev", C.c_void_p),
-        ("obs_traj_dev", C.c_void_p), ("reward_traj_dev", C.c_void_p),
+        ("obs_traj_dev", C.c_void_p), ("reward_traj_dev", C.c_void_p), ("tape_unscaled", C.c_int32),
     ]
 
 
@@ -75,7 +75,7 @@ SIGNATURES = {
     "shems_set_stream": (I32, [VP, VP]),
     "shems_sync": (I32, [VP]),
     "shems_reset": (I32, [VP, I32, PI, PF, U64, I64]),
-    "shems_step": (I32, [VP, VP, I32, VP, VP, VP]),
+    "shems_step": (I32, [VP, VP, I32, VP, VP, VP, VP]),
     "shems_action_rule": (I32, [VP, VP]),
     "shems_action_drl": (I32, [VP, VP, VP]),
     "shems_finished": (I32, [VP, PI]),
@@ -112,7 +112,7 @@ SIGNATURES = {
     "ddpg_act_soa": (I32, [VP, VP, I64, F32, U64, I64, I64, VP, VP, VP]),
     "ddpg_act_ou": (I32, [VP, VP, I64, F32, F32, F32, F32, VP, U64, I64, I64, VP, VP, VP]),
     "ddpg_set_noise": (I32, [VP, I32, F32, F32, F32]),
-    "ddpg_episode": (I32, [VP, VP, C.POINTER(VP), I32, I32, F32, U64, I32, I64, VP]),
+    "ddpg_episode": (I32, [VP, VP, C.POINTER(VP), I32, I32, F32, U64, I32, I64, VP, VP]),
     "ddpg_update": (I32, [VP, VP, I32, PI, U64]),
     "ddpg_update_phase": (I32, [VP, VP, I32, PI, U64, F32]),
     "ddpg_update_batch": (I32, [VP, VP, VP, VP, VP, VP]),
@@ -127,6 +127,12 @@ SIGNATURES = {
     "ddpg_update_population": (I32, [VP, C.POINTER(VP), I32, PI, C.POINTER(U64)]),
     "shems_tc_gemm": (I32, [VP, I64, I32, VP, I64, I32, VP, I64, I32, I32, I32, I32, VP, VP, I64, I32, VP, VP]),
     "ddpg_grad_buffer": (I32, [VP, C.POINTER(VP), C.POINTER(I64)]),
+    "ddpg_rollout": (I32, [VP, VP, I32, F32, U64, I64, VP, VP, VP]),
+    "ddpg_state_floats": (I64, [VP]),
+    "ddpg_get_state": (I32, [VP, PF, PD]),
+    "ddpg_set_state": (I32, [VP, PF, PD]),
+    "ddpg_get_ou_state": (I32, [VP, PF, C.POINTER(I64)]),
+    "ddpg_set_ou_state": (I32, [VP, PF, I64]),
 }
 
 _lib = None

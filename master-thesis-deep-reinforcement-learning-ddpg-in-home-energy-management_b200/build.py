@@ -9,7 +9,7 @@ LIB = os.path.join(HERE, "libshems_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-ccbin", "/usr/bin/g++"]
 # env.cu restates Julia scalar arithmetic: no a*b+c contraction allowed there
-UNITS = [("env.cu", ["-fmad=false"]), ("replay.cu", []), ("ddpg.cu", []), ("ddpg_fused.cu", []), ("tc_gemm.cu", []), ("series.cu", [])]
+UNITS = [("env.cu", ["-fmad=false"]), ("replay.cu", []), ("ddpg.cu", []), ("ddpg_fused.cu", []), ("actor_rollout.cu", ["-fmad=false"]), ("tc_gemm.cu", []), ("series.cu", [])]
 
 
 def _newer(target, deps):

@@ -4,7 +4,7 @@
 #pragma once
 #include "philox.cuh"
 
-struct ActOut { float a0, a1, s0, s1; };
+struct ActOut { float a0, a1, s0, s1; float noise_mean; };  // noise_mean = mean(noise) of the two components (act returns it, DDPG.jl:172)
 // noise: (nz0, nz1) given when have_noise, else σ·N(0,1) by Box-Muller on Philox(seed, env id, step) when sigma > 0, else none
 __device__ __forceinline__ ActOut act_gauss_epilogue(float y0, float y1, bool have_noise, float nz0, float nz1, float sigma, unsigned long long seed,
                                                      long long step, long long env_id, float lo0, float lo1, float hi0, float hi1) {
@@ -22,6 +22,7 @@ __device__ __forceinline__ ActOut act_gauss_epilogue(float y0, float y1, bool ha
     }
   }
   ActOut o;
+  o.noise_mean = __fmul_rn(__fadd_rn(nz0, nz1), 0.5f);   // mean(Float32[nz0, nz1])
   float a0 = __fadd_rn(y0, nz0), a1 = __fadd_rn(y1, nz1);
   a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
   a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);

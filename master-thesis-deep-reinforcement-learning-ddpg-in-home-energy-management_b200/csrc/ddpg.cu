@@ -532,9 +532,10 @@ struct Ddpg {
   void* dp_opened[2 * DP_MAX_WORLD]; int dp_n_opened;
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
   // ddpg_episode scratch: a, scaled [2][N], s_prev [9][N], r [N]
-  float *ep_a, *ep_scaled, *ep_sprev, *ep_r; long long ep_cap;
+  float *ep_a, *ep_scaled, *ep_sprev, *ep_r; double* ep_r64; long long ep_cap;
   // cluster-fused small-batch update (csrc/ddpg_fused.cu): per-cluster partial gradients [batch/8][n_params] of actor / critic
   bool fused; float* parts[2];
+  bool rollout_ok;   // ddpg_rollout may run as the persistent cluster kernel (one learner, widths within the shared-memory plan)
   int noise_kind; float ou_theta, ou_mu, ou_dt;   // ddpg_set_noise
   float* ou_x; long long ou_cap;                   // OUNoise.X of every instance of ddpg_episode's environment ([2][N])
 };
@@ -637,6 +638,11 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
     DMALLOC(h->parts[0], (long long)(B / FUSED_ROWS) * na);
     DMALLOC(h->parts[1], (long long)(B / FUSED_ROWS) * nc);
     h->fused = !(ev && ev[0] == '0');
+  }
+  if (pop == 1 && ddpg_fused_shape_ok(FUSED_ROWS, p->l1, p->l2)) {
+    int s_ = actor_rollout_prepare();
+    if (s_) { ddpg_destroy(h); return s_; }
+    h->rollout_ok = true;
   }
   DMALLOC(h->ctrl, pop);
   DMALLOC(h->rings_dev, pop);
@@ -758,6 +764,15 @@ extern "C" int32_t ddpg_set_norm(Ddpg* h, const float* s_min_host, const float* 
   return SHEMS_OK;
 }
 
+// βp of both optimisers of learner l (Flux.ADAM state: βp = β^t after t - 1 updates) into the device control block, with the
+// reciprocals the optimiser kernels use; [0] = critic, [1] = actor
+static int write_opt_state(Ddpg* h, int l, double c_b1, double c_b2, double a_b1, double a_b2) {
+  double v[8] = {c_b1, c_b2, a_b1, a_b2, 1.0 / (1.0 - c_b1), 1.0 / (1.0 - c_b2), 1.0 / (1.0 - a_b1), 1.0 / (1.0 - a_b2)};
+  CUDA_TRY(cudaMemcpyAsync((char*)(h->ctrl + l) + offsetof(DdpgCtrl, bp), v, sizeof(v), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));   // v lives on this stack frame
+  return SHEMS_OK;
+}
+
 // init: glorot_uniform hidden layers / U(-3e-3, 3e-3) last layer / zero bias (DDPG.jl:21-22, 30-46)
 __global__ void ddpg_init_kernel(float* __restrict__ w, long long n, int in, int out, int last, unsigned long long seed, unsigned layer_id) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -783,8 +798,13 @@ extern "C" int32_t ddpg_init(Ddpg* h, uint64_t seed) {
       }
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaMemcpyAsync(h->net[n + 2] + lo, h->net[n] + lo, sizeof(float) * (size_t)d.n_params, cudaMemcpyDeviceToDevice, h->stream));  // deepcopy :38,:46
+      // fresh optimisers (opt_crit = ADAM(η_crit), opt_act = ADAM(η_act), input.jl:126-127): no moments, βp = β
+      CUDA_TRY(cudaMemsetAsync(h->adam_m[n] + lo, 0, sizeof(float) * (size_t)d.n_params, h->stream));
+      CUDA_TRY(cudaMemsetAsync(h->adam_v[n] + lo, 0, sizeof(float) * (size_t)d.n_params, h->stream));
     }
+    { const int st_ = write_opt_state(h, l, h->p.adam_beta1, h->p.adam_beta2, h->p.adam_beta1, h->p.adam_beta2); if (st_) return st_; }
   }
+  h->n_updates = 0;
   return SHEMS_OK;
 }
 
@@ -1537,7 +1557,9 @@ static int stage_update_inputs(Ddpg* h, ShemsReplay* const* rps, const uint64_t*
         const int32_t v = idx_host[(long long)l * per_learner + j];
         REQUIRE(v >= 0 && v < rp->length, SHEMS_ERR_INVALID, "ddpg_update: idx[%d][%lld]=%d outside 0..%lld", l, j, v, (long long)rp->length - 1);
       }
-    hp[l].seed = seeds[l]; hp[l].update = (unsigned)h->n_updates; hp[l].use_idx = idx_host ? 1 : 0;
+    // minibatch stream: Philox(seed, draw j, counter = index of the update inside THIS call) — replay(rng_rpl = r) trains on the
+    // minibatch replay_sample(seed = r) returns, as getData(rng) is one sample in both uses (memory_plotting_saving.jl:31-42)
+    hp[l].seed = seeds[l]; hp[l].update = 0u; hp[l].use_idx = idx_host ? 1 : 0;
     hp[l].len = rp->length; hp[l].head = rp->head; hp[l].cap = rp->capacity; hp[l].idx_cursor = 0; hp[l].blocks_done = 0;
     rings[l] = rp->ring;
   }
@@ -1750,9 +1772,11 @@ ddpg_normalize_kernel(const float* __restrict__ obs, long long n, const float* _
 __global__ void __launch_bounds__(256)
 ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float sigma, unsigned long long seed, long long step,
                          long long env_id_base, const float* __restrict__ noise, float lo0, float lo1, float hi0, float hi1,
-                         float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride, long long asl, long long ask) {
+                         float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride, long long asl, long long ask,
+                         float* __restrict__ noise_acc, int noise_first) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  if (noise_acc) noise_acc += (long long)blockIdx.y * n;   // [P*n], instance j of learner l at l*n + j
   {  // blockIdx.y = learner l of a population: component k of its instance j sits at [l*asl + k*ask + j] in noise / a / scaled
      // (packed [P][2][n]: asl = 2n, ask = n; SoA over all instances: asl = n, ask = N); noise streams are keyed by the global env id
     const long long l = blockIdx.y;
@@ -1765,6 +1789,7 @@ ddpg_act_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, fl
                                       env_id_base + j, lo0, lo1, hi0, hi1);
   a_out[j] = o.a0; a_out[ask + j] = o.a1;
   if (scaled_out) { scaled_out[j] = o.s0; scaled_out[ask + j] = o.s1; }
+  if (noise_acc) noise_acc[j] = __fadd_rn(noise_first ? 0.0f : noise_acc[j], o.noise_mean);   // noise_eps += noise (DDPG.jl:224)
 }
 
 // OUNoise (DDPG.jl:49-55, input.jl:190-234) with Julia's types: θ, μ, σ, dt and X are Float32, randn is Float64:
@@ -1776,9 +1801,10 @@ __global__ void __launch_bounds__(256)
 ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n, float theta, float mu, float sigma, float dt, float* __restrict__ ou_x,
                             unsigned long long seed, long long step, long long env_id_base, const double* __restrict__ z, float lo0, float lo1,
                             float hi0, float hi1, float* __restrict__ a_out, float* __restrict__ scaled_out, long long act_stride,
-                            long long asl, long long ask) {
+                            long long asl, long long ask, float* __restrict__ noise_acc, int noise_first) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  if (noise_acc) noise_acc += (long long)blockIdx.y * n;
   {  // learner l = blockIdx.y; component k of its instance j at [l*asl + k*ask + j] (packed: asl = 2n, ask = n; SoA: asl = n, ask = N)
     const long long l = blockIdx.y;
     y += l * act_stride; a_out += l * asl; ou_x += l * asl; env_id_base += l * n;
@@ -1806,6 +1832,7 @@ ddpg_act_ou_epilogue_kernel(const float* __restrict__ y /*[n][2]*/, long long n,
     nz[k] = __fadd_rn(x, dx);
     ou_x[k * ask + j] = nz[k];
   }
+  if (noise_acc) noise_acc[j] = __fadd_rn(noise_first ? 0.0f : noise_acc[j], __fmul_rn(__fadd_rn(nz[0], nz[1]), 0.5f));   // mean(Float32.(ou.X))
   float a0 = __fadd_rn(y[j * 2 + 0], nz[0]), a1 = __fadd_rn(y[j * 2 + 1], nz[1]);
   a0 = a0 > 1.0f ? 1.0f : (a0 < -1.0f ? -1.0f : a0);
   a1 = a1 > 1.0f ? 1.0f : (a1 < -1.0f ? -1.0f : a1);
@@ -1871,7 +1898,8 @@ static int act_forward(Ddpg* h, const float* obs_dev, int64_t n, long long osl, 
 
 // sprev_dev (optional, [9][N]): receives a copy of the raw states — the episode loop's s for `remember`
 static int act_gauss(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint64_t seed, int64_t step, int64_t env_id_base,
-                     const float* noise_dev, float* a_dev, float* scaled_dev, bool soa, float* sprev_dev = nullptr) {
+                     const float* noise_dev, float* a_dev, float* scaled_dev, bool soa, float* sprev_dev = nullptr, float* noise_acc = nullptr,
+                     int noise_first = 0) {
   REQUIRE(h && obs_dev && a_dev, SHEMS_ERR_INVALID, "ddpg_act: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act: n=%lld", (long long)n);
   GUARD(h->device);
@@ -1881,7 +1909,7 @@ static int act_gauss(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint
     a.a_out = a_dev; a.scaled_out = scaled_dev; a.noise = noise_dev; a.ask = n;
     a.sigma = sigma; a.seed = seed; a.step = step; a.env_id_base = env_id_base;
     a.lo0 = h->p.act_lo[0]; a.lo1 = h->p.act_lo[1]; a.hi0 = h->p.act_hi[0]; a.hi1 = h->p.act_hi[1];
-    a.sprev = sprev_dev;
+    a.sprev = sprev_dev; a.noise_acc = noise_acc; a.noise_first = noise_first;
     return ddpg_fused_act(h->stream, a);
   }
   if (sprev_dev) CUDA_TRY(cudaMemcpyAsync(sprev_dev, obs_dev, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
@@ -1889,7 +1917,7 @@ static int act_gauss(Ddpg* h, const float* obs_dev, int64_t n, float sigma, uint
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, sigma, seed, step, env_id_base, noise_dev, h->p.act_lo[0], h->p.act_lo[1],
                                                       h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev, h->act_stride, soa ? n : 2 * n,
-                                                      soa ? N : n);
+                                                      soa ? N : n, noise_acc, noise_first);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1905,7 +1933,8 @@ extern "C" int32_t ddpg_act_soa(Ddpg* h, const float* obs_dev, int64_t n, float 
 }
 
 static int act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float mu, float sigma, float dt, float* ou_x_dev, uint64_t seed,
-                  int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev, bool soa) {
+                  int64_t step, int64_t env_id_base, const double* z_dev, float* a_dev, float* scaled_dev, bool soa, float* noise_acc = nullptr,
+                  int noise_first = 0) {
   REQUIRE(h && obs_dev && a_dev && ou_x_dev, SHEMS_ERR_INVALID, "ddpg_act_ou: NULL argument");
   REQUIRE(n >= 1 && n < (1ll << 31), SHEMS_ERR_INVALID, "ddpg_act_ou: n=%lld", (long long)n);
   REQUIRE(dt >= 0.0f, SHEMS_ERR_INVALID, "ddpg_act_ou: dt=%g (sqrt(dt) raises DomainError in the reference)", (double)dt);
@@ -1915,7 +1944,7 @@ static int act_ou(Ddpg* h, const float* obs_dev, int64_t n, float theta, float m
   const dim3 gn((unsigned)((n + 255) / 256), h->pop);
   ddpg_act_ou_epilogue_kernel<<<gn, 256, 0, h->stream>>>(h->act_y, n, theta, mu, sigma, dt, ou_x_dev, seed, step, env_id_base, z_dev,
                                                          h->p.act_lo[0], h->p.act_lo[1], h->p.act_hi[0], h->p.act_hi[1], a_dev, scaled_dev,
-                                                         h->act_stride, soa ? n : 2 * n, soa ? N : n);
+                                                         h->act_stride, soa ? n : 2 * n, soa ? N : n, noise_acc, noise_first);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -1933,12 +1962,13 @@ extern "C" int32_t ddpg_set_noise(Ddpg* h, int32_t kind, float theta, float mu, 
 }
 
 // ----------------------------------------------------------------------------- episode!
-// reward_eps += r (DDPG.jl:223; Float64 accumulation of the Float32 step rewards as the vectorised loop sees them)
+// reward_eps += r (DDPG.jl:223): the Float64 env.reward of every step (shems_LU1.jl:171) is summed in Float64; the replay memory
+// keeps Float32(r), which is what `cu` makes of it when getData uploads the minibatch (memory_plotting_saving.jl:37)
 __global__ void __launch_bounds__(256)
-ddpg_accum_return_kernel(const float* __restrict__ r, double* __restrict__ ret, long long n, int first) {
+ddpg_accum_return_kernel(const double* __restrict__ r, double* __restrict__ ret, long long n, int first) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  ret[i] = (first ? 0.0 : ret[i]) + (double)r[i];
+  ret[i] = (first ? 0.0 : ret[i]) + r[i];
 }
 
 // One learner's episode loop, after step!: remember (DDPG.jl:229 — the n transitions go to ring slots head .. head+n-1), reward_eps += r
@@ -1946,8 +1976,9 @@ ddpg_accum_return_kernel(const float* __restrict__ r, double* __restrict__ ret, 
 // passed BY VALUE: one launch in place of two kernels and three small host-to-device copies per step.
 __global__ void __launch_bounds__(256)
 ddpg_episode_post_step_kernel(float* __restrict__ ring, long long cap, long long head, const float* __restrict__ s, const float* __restrict__ a,
-                              const float* __restrict__ r, const float* __restrict__ s2, long long n, double* __restrict__ ep_ret, int first,
-                              DdpgCtrl* __restrict__ ctrl, CtrlHostPart hp, const float** __restrict__ rings_dev) {
+                              const float* __restrict__ r, const double* __restrict__ r64, const float* __restrict__ s2, long long n,
+                              double* __restrict__ ep_ret, int first, DdpgCtrl* __restrict__ ctrl, CtrlHostPart hp,
+                              const float** __restrict__ rings_dev) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && ctrl) { *reinterpret_cast<CtrlHostPart*>(ctrl) = hp; rings_dev[0] = ring; }
   if (i >= n) return;
@@ -1963,7 +1994,7 @@ ddpg_episode_post_step_kernel(float* __restrict__ ring, long long cap, long long
 #pragma unroll
   for (int k = 0; k < 9; ++k) q[(RING_S2 + k) * 32] = s2[k * n + i];
   q[RING_DONE * 32] = 0.0f;
-  if (ep_ret) ep_ret[i] = (first ? 0.0 : ep_ret[i]) + (double)ri;
+  if (ep_ret) ep_ret[i] = (first ? 0.0 : ep_ret[i]) + r64[i];
 }
 
 // episode!(env; NUM_STEPS, train, track = 0, rng_ep) (DDPG.jl:186-242) for all instances of `env`, enqueued in one call with no host
@@ -1973,7 +2004,7 @@ ddpg_episode_post_step_kernel(float* __restrict__ ring, long long cap, long long
 // (keyed by the global env id) and, as rng_step + l, learner l's minibatch stream — the same rule the Python Driver uses.
 // All three handles must be bound to the same CUDA stream.  ep_return_dev [N] (Float64) receives the summed rewards, or NULL.
 extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps, int32_t n_steps, int32_t train, float sigma, uint64_t seed,
-                                int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev) {
+                                int32_t updates_per_step, int64_t env_id_base, double* ep_return_dev, float* noise_eps_dev) {
   REQUIRE(h && env, SHEMS_ERR_INVALID, "ddpg_episode: NULL argument");
   REQUIRE(n_steps >= 1 && updates_per_step >= 0, SHEMS_ERR_INVALID, "ddpg_episode: n_steps=%d updates_per_step=%d", n_steps, updates_per_step);
   REQUIRE(!train || rps, SHEMS_ERR_INVALID, "ddpg_episode: training needs the replay memories");
@@ -1992,8 +2023,9 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
   if (h->ep_cap < N) {
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     cudaFree(h->ep_a); h->ep_a = nullptr; h->ep_cap = 0;
-    CUDA_TRY(cudaMalloc(&h->ep_a, sizeof(float) * 14 * (size_t)N));
+    CUDA_TRY(cudaMalloc(&h->ep_a, sizeof(float) * 16 * (size_t)N));
     h->ep_scaled = h->ep_a + 2 * N; h->ep_sprev = h->ep_a + 4 * N; h->ep_r = h->ep_a + 13 * N;
+    h->ep_r64 = reinterpret_cast<double*>(h->ep_a + 14 * N);   // 8-byte aligned: cudaMalloc base + 56 N bytes
     h->ep_cap = N;
   }
   if (train && h->noise_kind == 1 && h->ou_cap != N) {  // first use (or another environment size): X = zeros (input.jl:234)
@@ -2007,13 +2039,14 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
   for (int step = 1; step <= n_steps; ++step) {
     const uint64_t rng_step = (seed * 1000003ull + (uint64_t)step) & 0x7fffffffffffffffull;
     if (train && h->noise_kind == 1) {
-      TRY(act_ou(h, env->obs, n, h->ou_theta, h->ou_mu, sigma, h->ou_dt, h->ou_x, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true));
+      TRY(act_ou(h, env->obs, n, h->ou_theta, h->ou_mu, sigma, h->ou_dt, h->ou_x, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true,
+                 noise_eps_dev, step == 1));
       CUDA_TRY(cudaMemcpyAsync(h->ep_sprev, env->obs, sizeof(float) * 9 * (size_t)N, cudaMemcpyDeviceToDevice, h->stream));
     } else {
       TRY(act_gauss(h, env->obs, n, train ? sigma : 0.0f, rng_step, step, env_id_base, nullptr, h->ep_a, h->ep_scaled, true,
-                    train ? h->ep_sprev : nullptr));
+                    train ? h->ep_sprev : nullptr, noise_eps_dev, step == 1));
     }
-    TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, nullptr, nullptr));
+    TRY(shems_step(env, h->ep_scaled, 0, h->ep_r, h->ep_r64, nullptr, nullptr));
     if (train && h->pop == 1 && !h->dp_on) {  // one learner: remember + reward_eps + the next replay()'s control block in one launch
       ShemsReplay* rp = rps[0];
       REQUIRE(rp && rp->device == h->device, SHEMS_ERR_INVALID, "ddpg_episode: replay memory missing or on another device");
@@ -2021,10 +2054,10 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
       const long long head = rp->head;
       replay_after_rollout(rp, N);
       CtrlHostPart hp; memset(&hp, 0, sizeof(hp));
-      hp.seed = rng_step; hp.update = (unsigned)h->n_updates; hp.use_idx = 0;
+      hp.seed = rng_step; hp.update = 0u; hp.use_idx = 0;
       hp.len = rp->length; hp.head = rp->head; hp.cap = rp->capacity;
       ddpg_episode_post_step_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(rp->ring, rp->capacity, head, h->ep_sprev, h->ep_a, h->ep_r,
-                                                                                       env->obs, N, ep_return_dev, step == 1,
+                                                                                       h->ep_r64, env->obs, N, ep_return_dev, step == 1,
                                                                                        updates_per_step > 0 ? h->ctrl : nullptr, hp, h->rings_dev);
       CUDA_TRY(cudaGetLastError());
       if (updates_per_step > 0) {
@@ -2035,15 +2068,78 @@ extern "C" int32_t ddpg_episode(Ddpg* h, ShemsEnv* env, ShemsReplay* const* rps,
       continue;
     }
     if (ep_return_dev) {
-      ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r, ep_return_dev, N, step == 1);
+      ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r64, ep_return_dev, N, step == 1);
       CUDA_TRY(cudaGetLastError());
     }
     if (train) {
       TRY(replay_push_groups(rps, h->pop, h->ep_sprev, h->ep_a, h->ep_r, env->obs, nullptr, n));   // the unscaled action is stored (:229)
-      if (updates_per_step > 0) {
+      if (updates_per_step > 0 && h->dp_on) {
+        // a connected data-parallel learner: every rank steps its own instances and memory, the update exchanges gradients
+        // (all ranks make the same calls) — never the local-only graph, which would let the replicas drift apart
+        TRY(ddpg_update_dp(h, rps[0], updates_per_step, nullptr, rng_step));
+      } else if (updates_per_step > 0) {
         for (int l = 0; l < h->pop; ++l) seeds[l] = rng_step + (uint64_t)l;
         TRY(ddpg_update_population(h, rps, updates_per_step, nullptr, seeds.data()));                  // replay(rng_rpl = rng_step) (:231)
       }
+    }
+  }
+  return SHEMS_OK;
+}
+
+// episode!(env; NUM_STEPS, train = false, track, rng_ep) (DDPG.jl:186-242) / inference(env; track = 1) (memory_plotting_saving.jl:62-89)
+// for every instance of `env`: act(normalize(s)) [+ GNoise when sigma > 0] -> scale_action -> step!, n_steps times, by ONE call.
+// One learner at the fused shapes: a single persistent cluster kernel per group of instances (csrc/actor_rollout.cu) — no launch,
+// no host round trip per step.  Populations / wider nets: one act + step! launch pair per step.
+extern "C" int32_t ddpg_rollout(Ddpg* h, ShemsEnv* env, int32_t n_steps, float sigma, uint64_t seed, int64_t env_id_base, double* ep_return_dev,
+                                double* trace_dev, float* act_traj_dev) {
+  REQUIRE(h && env, SHEMS_ERR_INVALID, "ddpg_rollout: NULL argument");
+  REQUIRE(n_steps >= 1, SHEMS_ERR_INVALID, "ddpg_rollout: n_steps=%d", n_steps);
+  REQUIRE(env->device == h->device, SHEMS_ERR_INVALID, "ddpg_rollout: env on device %d, learner on %d", env->device, h->device);
+  REQUIRE(env->n % h->pop == 0, SHEMS_ERR_INVALID, "ddpg_rollout: %lld instances do not split over %d learners", (long long)env->n, h->pop);
+  REQUIRE(env->stream == h->stream, SHEMS_ERR_STATE, "ddpg_rollout: bind the environment and the learner to one CUDA stream");
+  REQUIRE(env->was_reset, SHEMS_ERR_STATE, "ddpg_rollout: reset! must come first");
+  if (ensure_rows(env, n_steps)) {
+    shems_set_error("BoundsError: rollout of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", n_steps, env->max_idx,
+                    env->nrows);
+    return SHEMS_ERR_BOUNDS;
+  }
+  GUARD(h->device);
+  const long long N = env->n, n = N / h->pop;
+  if (h->pop == 1 && h->rollout_ok) {
+    const NetDims& dA = h->dims[0]; const NetDims& dC = h->dims[1];
+    ActorRolloutArgs a; memset(&a, 0, sizeof(a));
+    a.actor = h->net[DDPG_NET_ACTOR];
+    a.ao = FusedNetOff{(int)dA.l[0].w_off, (int)dA.l[0].b_off, (int)dA.l[1].w_off, (int)dA.l[1].b_off, (int)dA.l[2].w_off, (int)dA.l[2].b_off};
+    a.l1 = h->p.l1; a.l2 = h->p.l2;
+    a.vec16 = (h->p.l2 % 4 == 0 && dA.l[1].w_off % 4 == 0 && dC.l[1].w_off % 4 == 0) ? 1 : 0;
+    a.norm = h->norm; a.N = N; a.obs = env->obs; a.idx = env->idx; a.T = n_steps; a.step0 = env->step;
+    a.sigma = sigma; a.seed = seed; a.env_id_base = env_id_base;
+    a.lo0 = h->p.act_lo[0]; a.lo1 = h->p.act_lo[1]; a.hi0 = h->p.act_hi[0]; a.hi1 = h->p.act_hi[1];
+    a.ep_return = ep_return_dev; a.trace = trace_dev; a.act_traj = act_traj_dev;
+    for (int g = 0; g < env->n_groups; ++g) {
+      a.P = env->gdp[g]; a.series = env->gseries[g]; a.n0 = env->gstart[g]; a.n1 = env->gstart[g + 1];
+      TRY(actor_rollout_launch(h->stream, a));
+    }
+    env->max_idx += n_steps; env->step += n_steps; env->consistent = true;
+    return SHEMS_OK;
+  }
+  if (h->ep_cap < N) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    cudaFree(h->ep_a); h->ep_a = nullptr; h->ep_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->ep_a, sizeof(float) * 16 * (size_t)N));
+    h->ep_scaled = h->ep_a + 2 * N; h->ep_sprev = h->ep_a + 4 * N; h->ep_r = h->ep_a + 13 * N;
+    h->ep_r64 = reinterpret_cast<double*>(h->ep_a + 14 * N);
+    h->ep_cap = N;
+  }
+  for (int t = 0; t < n_steps; ++t) {
+    const int step = env->step + 1;
+    const uint64_t rng_step = (seed * 1000003ull + (uint64_t)step) & 0x7fffffffffffffffull;
+    float* a_out = act_traj_dev ? act_traj_dev + (size_t)t * 2 * N : h->ep_a;
+    TRY(act_gauss(h, env->obs, n, sigma, rng_step, step, env_id_base, nullptr, a_out, h->ep_scaled, true, nullptr));
+    TRY(shems_step(env, h->ep_scaled, trace_dev ? 1 : 0, nullptr, h->ep_r64, nullptr, trace_dev ? trace_dev + (size_t)t * SHEMS_TRACE_COLS * N : nullptr));
+    if (ep_return_dev) {
+      ddpg_accum_return_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->ep_r64, ep_return_dev, N, t == 0);
+      CUDA_TRY(cudaGetLastError());
     }
   }
   return SHEMS_OK;
@@ -2053,5 +2149,75 @@ extern "C" int32_t ddpg_grad_buffer(Ddpg* h, float** grad_dev, int64_t* n) {
   REQUIRE(h && grad_dev && n, SHEMS_ERR_INVALID, "ddpg_grad_buffer: NULL argument");
   *grad_dev = h->gradbuf;
   *n = (h->grad[0] - h->gradbuf) + h->dims[0].n_params;
+  return SHEMS_OK;
+}
+
+// ----------------------------------------------------------------------------- full learner snapshot (resume)
+// What the reference never saves (saveBSON writes the actor and the score arrays only, memory_plotting_saving.jl:263-270, so a
+// run cannot be resumed): the four nets, both optimisers' moments and β powers, the update counter and the normalisation
+// constants of the selected learner.  Layout of state_host (floats):
+//   [actor | critic | actor_target | critic_target | m_actor | v_actor | m_critic | v_critic | s_min (9) | s_max (9)]
+// opt_host (doubles): [βp_critic[0], βp_critic[1], βp_actor[0], βp_actor[1], number of updates, 0, 0, 0]
+extern "C" int64_t ddpg_state_floats(const Ddpg* h) {
+  if (!h) return 0;
+  return 4 * h->dims[0].n_params + 4 * h->dims[1].n_params + 18;
+}
+static int state_copy(Ddpg* h, float* host, bool to_host) {
+  const long long na = h->dims[0].n_params, nc = h->dims[1].n_params, lo = sel_off(h);
+  float* const parts[9] = {h->net[0], h->net[1], h->net[2], h->net[3], h->adam_m[0], h->adam_v[0], h->adam_m[1], h->adam_v[1], h->norm};
+  const long long counts[9] = {na, nc, na, nc, na, na, nc, nc, 18};
+  long long off = 0;
+  for (int i = 0; i < 9; ++i) {
+    if (to_host) CUDA_TRY(cudaMemcpy(host + off, parts[i] + lo, sizeof(float) * (size_t)counts[i], cudaMemcpyDeviceToHost));
+    else CUDA_TRY(cudaMemcpy(parts[i] + lo, host + off, sizeof(float) * (size_t)counts[i], cudaMemcpyHostToDevice));
+    off += counts[i];
+  }
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_get_state(Ddpg* h, float* state_host, double* opt_host) {
+  REQUIRE(h && state_host && opt_host, SHEMS_ERR_INVALID, "ddpg_get_state: NULL argument");
+  GUARD(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  TRY(state_copy(h, state_host, true));
+  DdpgCtrl c;
+  CUDA_TRY(cudaMemcpy(&c, h->ctrl + h->sel, sizeof(c), cudaMemcpyDeviceToHost));
+  opt_host[0] = c.bp[0][0]; opt_host[1] = c.bp[0][1]; opt_host[2] = c.bp[1][0]; opt_host[3] = c.bp[1][1];
+  opt_host[4] = (double)h->n_updates; opt_host[5] = opt_host[6] = opt_host[7] = 0.0;
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_set_state(Ddpg* h, const float* state_host, const double* opt_host) {
+  REQUIRE(h && state_host && opt_host, SHEMS_ERR_INVALID, "ddpg_set_state: NULL argument");
+  for (int i = 0; i < 4; ++i)
+    REQUIRE(opt_host[i] > 0.0 && opt_host[i] < 1.0, SHEMS_ERR_INVALID, "ddpg_set_state: beta power %d = %g outside (0, 1)", i, opt_host[i]);
+  REQUIRE(opt_host[4] >= 0.0, SHEMS_ERR_INVALID, "ddpg_set_state: update counter %g", opt_host[4]);
+  GUARD(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  TRY(state_copy(h, const_cast<float*>(state_host), false));
+  TRY(write_opt_state(h, h->sel, opt_host[0], opt_host[1], opt_host[2], opt_host[3]));
+  h->n_updates = (long long)opt_host[4];   // one counter per handle (the learners of a population advance together)
+  return SHEMS_OK;
+}
+// OUNoise.X of ddpg_episode's instances ([2][n], input.jl:234; never reset by the reference): n_out receives the instance count
+// (0 before the first OU episode); x_host may be NULL to query it.  ddpg_set_ou_state (re)allocates for n instances.
+extern "C" int32_t ddpg_get_ou_state(Ddpg* h, float* x_host, int64_t* n_out) {
+  REQUIRE(h && n_out, SHEMS_ERR_INVALID, "ddpg_get_ou_state: NULL argument");
+  GUARD(h->device);
+  *n_out = h->ou_cap;
+  if (x_host && h->ou_cap > 0) {
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(x_host, h->ou_x, sizeof(float) * 2 * (size_t)h->ou_cap, cudaMemcpyDeviceToHost));
+  }
+  return SHEMS_OK;
+}
+extern "C" int32_t ddpg_set_ou_state(Ddpg* h, const float* x_host, int64_t n) {
+  REQUIRE(h && x_host && n >= 1, SHEMS_ERR_INVALID, "ddpg_set_ou_state: NULL argument or n=%lld", (long long)n);
+  GUARD(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->ou_cap != n) {
+    cudaFree(h->ou_x); h->ou_x = nullptr; h->ou_cap = 0;
+    CUDA_TRY(cudaMalloc(&h->ou_x, sizeof(float) * 2 * (size_t)n));
+    h->ou_cap = n;
+  }
+  CUDA_TRY(cudaMemcpy(h->ou_x, x_host, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice));
   return SHEMS_OK;
 }

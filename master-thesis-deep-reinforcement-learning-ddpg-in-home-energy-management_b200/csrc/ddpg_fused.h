@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "common.h"
 
 #define FUSED_CLUSTER 8        // CTAs per cluster (the portable maximum); a cluster owns FUSED_ROWS minibatch rows
 #define FUSED_ROWS 8
@@ -60,8 +61,26 @@ struct FusedActArgs {
   float* a_out; float* scaled_out; const float* noise; long long ask;
   float sigma; unsigned long long seed; long long step, env_id_base; float lo0, lo1, hi0, hi1;
   float* sprev;
+  float* noise_acc; int noise_first;             // noise_eps += mean(noise) per instance (DDPG.jl:224), [n]; first: start from 0f0
 };
 int ddpg_fused_act(cudaStream_t st, const FusedActArgs& a);
 int ddpg_fused_prepare();                                    // shared-memory attribute of both kernels on the current device
 int ddpg_fused_critic(cudaStream_t st, const FusedArgs& a);  // targets, TD target, critic forward/backward -> part (critic)
 int ddpg_fused_actor(cudaStream_t st, const FusedArgs& a);   // actor-loss forward/backward through the critic -> part (actor)
+
+// episode!(env; train = false) / inference(track = 1) for the instances n0 .. n1-1 of an environment handle as one persistent cluster
+// kernel (csrc/actor_rollout.cu): act(normalize(s)) -> scale_action -> step! for T steps, 8 instances per cluster
+struct ActorRolloutArgs {
+  const float* actor; FusedNetOff ao; int l1, l2, vec16;
+  const float* norm;
+  DevParams P; const float4* series;
+  long long N, n0, n1;       // SoA stride of the handle's arrays; instance range of this launch (one group of constants)
+  float* obs; int32_t* idx;  // env.state [9][N], env.idx [N]: read at the start, written back at the end
+  int T, step0;              // steps to take; env.step before the first one (per-step seeds follow ddpg_episode's rule)
+  float sigma; unsigned long long seed; long long env_id_base; float lo0, lo1, hi0, hi1;
+  double* ep_return;         // [N] reward_eps (Float64) or NULL
+  double* trace;             // [T][23][N] `results` rows or NULL
+  float* act_traj;           // [T][2][N] the unscaled actions a or NULL
+};
+int actor_rollout_prepare();
+int actor_rollout_launch(cudaStream_t st, const ActorRolloutArgs& a);

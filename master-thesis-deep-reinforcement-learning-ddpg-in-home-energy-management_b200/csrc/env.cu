@@ -26,7 +26,7 @@ void shems_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* shems_last_error(void) { return g_err; }
-extern "C" int32_t shems_version(void) { return 100; }
+extern "C" int32_t shems_version(void) { return 200; }
 extern "C" int32_t shems_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -227,7 +227,8 @@ template <bool FROM_SERIES, bool WANT_TRACE>
 __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                   int32_t* __restrict__ idx_arr, const float* __restrict__ act, int track_neg,
-                  float* __restrict__ reward_out, float* __restrict__ obs_out, double* __restrict__ trace, long long n0, long long n1) {
+                  float* __restrict__ reward_out, double* __restrict__ reward64_out, float* __restrict__ obs_out, double* __restrict__ trace,
+                  long long n0, long long n1) {
   const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n1) return;
   const int idx = idx_arr[n];
@@ -268,6 +269,7 @@ shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, f
   obs[8 * N + n] = nx.season;
   idx_arr[n] = idx + 1;  // :456
   if (reward_out) reward_out[n] = (float)o.reward;
+  if (reward64_out) reward64_out[n] = o.reward;  // env.reward::Float64 (:171, :467-470)
   if (obs_out) {
     obs_out[0 * N + n] = o.Soc_b; obs_out[1 * N + n] = Soc_ev_new; obs_out[2 * N + n] = nx.cd; obs_out[3 * N + n] = nx.d_e;
     obs_out[4 * N + n] = nx.g_e; obs_out[5 * N + n] = nx.p_buy; obs_out[6 * N + n] = nx.h_cos; obs_out[7 * N + n] = nx.h_sin;
@@ -324,7 +326,7 @@ template <int POLICY, bool WANT_TRACE>
 __global__ void __launch_bounds__(ROLLOUT_THREADS, ROLLOUT_MIN_BLOCKS)
 shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                      int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
-                     const float* __restrict__ tape, RolloutSinks S, long long n0, long long n1) {
+                     const float* __restrict__ tape, int tape_unscaled, RolloutSinks S, long long n0, long long n1) {
   const long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n1) return;
   int idx = idx_arr[n];
@@ -362,6 +364,10 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
         Bt = tape[((size_t)t * 2 + 0) * N + n];
         EVt = tape[((size_t)t * 2 + 1) * N + n];
         a_raw0 = Bt; a_raw1 = EVt;
+        if (tape_unscaled) {  // the tape holds what `remember` stores (DDPG.jl:229): a in [-1,1]; scale_action with bounds (0,0)/(1,1)
+          Bt = (float)(((double)a_raw0 + 1.0) * 0.5);   // Float32.(lo .+ (a .+ ones(2)) .* 0.5 .* (hi .- lo))  (:178-184)
+          EVt = (float)(((double)a_raw1 + 1.0) * 0.5);
+        }
       }
       shems_action_drl(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
     }
@@ -560,7 +566,8 @@ extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_ho
   return SHEMS_OK;
 }
 
-extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, float* reward_dev, float* obs_dev, double* trace_dev) {
+extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, float* reward_dev, double* reward64_dev, float* obs_dev,
+                              double* trace_dev) {
   REQUIRE(e && act_dev, SHEMS_ERR_INVALID, "shems_step: NULL argument");
   REQUIRE(e->was_reset, SHEMS_ERR_STATE, "shems_step: reset! (or shems_set_state) must come first");
   if (ensure_rows(e, 1)) {
@@ -571,7 +578,7 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
   const int tn = track < 0 ? 1 : 0;
 #define LAUNCH_STEP(FS, TR)                                                                                                             \
   shems_step_kernel<FS, TR><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, \
-                                                                                            act_dev, tn, reward_dev, obs_dev, trace_dev, n0, n1)
+                                                                                            act_dev, tn, reward_dev, reward64_dev, obs_dev, trace_dev, n0, n1)
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
     if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
@@ -642,6 +649,9 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
   REQUIRE(a->n_steps >= 1, SHEMS_ERR_INVALID, "shems_rollout: n_steps=%d", a->n_steps);
   REQUIRE(a->policy >= 0 && a->policy <= 2, SHEMS_ERR_INVALID, "shems_rollout: unknown policy %d", a->policy);
   REQUIRE(a->policy != SHEMS_POLICY_TAPE || a->tape_dev, SHEMS_ERR_INVALID, "shems_rollout: POLICY_TAPE needs tape_dev");
+  // remember() stores the UNSCALED action (DDPG.jl:229): a tape of scaled targets must not feed a training memory
+  REQUIRE(!(a->policy == SHEMS_POLICY_TAPE && a->replay && !a->tape_unscaled), SHEMS_ERR_INVALID,
+          "shems_rollout: POLICY_TAPE with a replay sink needs tape_unscaled = 1 (actions in [-1,1], as remember() stores them)");
   if (ensure_rows(e, a->n_steps)) {
     shems_set_error("BoundsError: rollout of %d steps from row %d leaves the %d-row series (next_state!, shems_LU1.jl:266-268)", a->n_steps,
                     e->max_idx, e->nrows);
@@ -666,7 +676,7 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
   }
 #define LAUNCH_RO(POL, TR)                                                                                                          \
   shems_rollout_kernel<POL, TR><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                                  \
-      e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, a->n_steps, e->step, a->seed, a->env_id_base, a->tape_dev, S, n0, n1)
+      e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, a->n_steps, e->step, a->seed, a->env_id_base, a->tape_dev, a->tape_unscaled, S, n0, n1)
   const bool tr = a->trace_dev != nullptr;
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];

@@ -77,7 +77,7 @@ __device__ __forceinline__ void shems_action_rule(const DevParams& P, float Soc_
 // step! :343-485 given the feasible (B, EV) and the recorded EV target.  track_neg <=> track < 0
 // (no penalty in the reward, :466-471).
 // w * discomfort^pot (shems_LU1 / shems_LU7) or (discomfort * w)^pot (shems_LU1_input0607) for the exponents other than LU1's 2
-__device__ __noinline__ double shems_discomfort_term(int reward_form, double dw, double pot, double dd) {
+static __device__ __noinline__ double shems_discomfort_term(int reward_form, double dw, double pot, double dd) {
   if (!reward_form) return dw * ((pot == 2.0) ? dd * dd : (pot == 1.0) ? dd : pow(dd, pot));
   const double dwd = dd * dw;
   return (pot == 1.0) ? dwd : (pot == 2.0) ? dwd * dwd : pow(dwd, pot);

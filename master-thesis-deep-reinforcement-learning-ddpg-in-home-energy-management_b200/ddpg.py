@@ -215,18 +215,61 @@ class Learner:
         """noise_type of the native episode loop: "gn" or "ou" (OUNoise state is kept per instance inside the handle)."""
         L.check(self.lib.ddpg_set_noise(self._h, {"gn": 0, "ou": 1}[kind], float(theta), float(mu), float(dt)))
 
-    def episode(self, env, memories, n_steps, train=True, sigma=0.1, rng_ep=0, updates_per_step=1):
+    def episode(self, env, memories, n_steps, train=True, sigma=0.1, rng_ep=0, updates_per_step=1, want_noise=False):
         """ddpg_episode: episode!(env; train, track = 0) for all instances of `env`, enqueued by one call (no host round trip per
-        step).  memories: the learners' Replay objects (one for a single learner) or None when train is False.  Returns reward_eps [N] float64."""
+        step).  memories: the learners' Replay objects (one for a single learner) or None when train is False.  Returns reward_eps
+        [N] float64 (and, with want_noise, noise_eps [N] float32: the per-step mean(noise) summed over the episode, DDPG.jl:224)."""
         ret = torch.empty(env.n_envs, dtype=torch.float64, device=self._dev)
+        nz = torch.zeros(env.n_envs, dtype=torch.float32, device=self._dev) if want_noise else None
         hs = None
         if memories is not None:
             mems = list(memories) if isinstance(memories, (list, tuple)) else [memories]
             assert len(mems) == self.population
             hs = (C.c_void_p * self.population)(*[m._h for m in mems])
         L.check(self.lib.ddpg_episode(self._h, env._h, hs, int(n_steps), 1 if train else 0, float(sigma), int(rng_ep) & (2**64 - 1),
-                                      int(updates_per_step), int(env.env_id_base), _ptr(ret)))
-        return ret
+                                      int(updates_per_step), int(env.env_id_base), _ptr(ret), _ptr(nz)))
+        return (ret, nz) if want_noise else ret
+
+    def rollout(self, env, n_steps, sigma=0.0, rng_ep=0, want_trace=False, want_actions=False):
+        """ddpg_rollout: episode!(env; train = false, track) / inference(env; track = 1) for all instances of `env` by one call —
+        a single persistent cluster kernel for one learner at the reference's widths.  reset! stays with the caller.
+        Returns a dict: ep_return [N] float64, trace [T][23][N] float64 (want_trace), actions [T][2][N] (want_actions)."""
+        n, T = env.n_envs, int(n_steps)
+        out = {"ep_return": torch.empty(n, dtype=torch.float64, device=self._dev)}
+        if want_trace:
+            out["trace"] = torch.empty((T, 23, n), dtype=torch.float64, device=self._dev)
+        if want_actions:
+            out["actions"] = torch.empty((T, 2, n), dtype=torch.float32, device=self._dev)
+        L.check(self.lib.ddpg_rollout(self._h, env._h, T, float(sigma), int(rng_ep) & (2**64 - 1), int(env.env_id_base),
+                                      _ptr(out["ep_return"]), _ptr(out.get("trace")), _ptr(out.get("actions"))))
+        return out
+
+    # ---- full snapshot (nets, targets, ADAM moments, β powers, update counter, s_min/s_max): resume where the run stopped
+    def get_state(self):
+        n = int(self.lib.ddpg_state_floats(self._h))
+        st = np.empty(n, np.float32)
+        opt = np.zeros(8, np.float64)
+        L.check(self.lib.ddpg_get_state(self._h, st.ctypes.data_as(L.PF), opt.ctypes.data_as(L.PD)))
+        return st, opt
+
+    def set_state(self, state, opt):
+        st = np.ascontiguousarray(state, np.float32)
+        op = np.ascontiguousarray(opt, np.float64)
+        assert st.size == int(self.lib.ddpg_state_floats(self._h)) and op.size == 8
+        L.check(self.lib.ddpg_set_state(self._h, st.ctypes.data_as(L.PF), op.ctypes.data_as(L.PD)))
+
+    def get_ou_state(self):
+        n = C.c_int64()
+        L.check(self.lib.ddpg_get_ou_state(self._h, None, C.byref(n)))
+        if n.value == 0:
+            return None
+        x = np.empty((2, n.value), np.float32)
+        L.check(self.lib.ddpg_get_ou_state(self._h, x.ctypes.data_as(L.PF), C.byref(n)))
+        return x
+
+    def set_ou_state(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        L.check(self.lib.ddpg_set_ou_state(self._h, x.ctypes.data_as(L.PF), x.shape[-1]))
 
     def replay(self, memory, rng_rpl=0, n_updates=1, idx=None):
         """replay(; rng_rpl) (DDPG.jl:121-145), n_updates times back to back.  Population handles: `memory` is the list of the
@@ -359,15 +402,21 @@ class Driver:
         T = self.ep_length if num_steps is None else num_steps
         env.reset(rng=rng_ep)
         n = env.n_envs
-        if track == 0 and self.native:
+        if track == 0 and train and self.native:
             # the whole loop below as one native call (ddpg_episode): same seeds, same kernels, no host round trip per step
-            r = self.learner.episode(env, self.memory if train else None, T, train=train, sigma=self.sigma, rng_ep=rng_ep,
-                                     updates_per_step=self.updates_per_step)
-            if train:
-                self.n_env_steps += n * T
-            return r, T, 0.0
+            r, nz = self.learner.episode(env, self.memory, T, train=True, sigma=self.sigma, rng_ep=rng_ep,
+                                         updates_per_step=self.updates_per_step, want_noise=True)
+            self.n_env_steps += n * T
+            return r, T, nz
+        if track >= 0 and not train and self.native:
+            # evaluation / DRL inference: one persistent cluster kernel for the whole episode (ddpg_rollout)
+            out = self.learner.rollout(env, T, sigma=0.0, rng_ep=rng_ep, want_trace=(track != 0))
+            if track == 0:
+                return out["ep_return"], T, torch.zeros(n, dtype=torch.float32, device=env._torch_dev)
+            return out["ep_return"], out["trace"]
         reward_eps = torch.zeros(n, dtype=torch.float64, device=env._torch_dev)
-        noise_eps = 0.0
+        r64 = torch.empty(n, dtype=torch.float64, device=env._torch_dev)
+        noise_eps = torch.zeros(n, dtype=torch.float32, device=env._torch_dev)
         traces = []
         s_prev = torch.empty((9, n), dtype=torch.float32, device=env._torch_dev)
         for step in range(1, T + 1):
@@ -375,7 +424,7 @@ class Driver:
             s = env.state_tensor()
             if track < 0:
                 a = env.action(track)  # DDPG.jl:210
-                r, s2, tr = env.step(a, track=track)
+                r, s2, tr = env.step(a, track=track, reward64_out=r64)
                 traces.append(tr)
             else:
                 if train and self.noise_type == "ou":
@@ -388,11 +437,11 @@ class Driver:
                 if train:
                     s_prev.copy_(s)
                 if track == 0:
-                    r, s2 = env.step(scaled)
+                    r, s2 = env.step(scaled, reward64_out=r64)
                 else:
-                    r, s2, tr = env.step(scaled, track=track)
+                    r, s2, tr = env.step(scaled, track=track, reward64_out=r64)
                     traces.append(tr)
-            reward_eps += r.double()
+            reward_eps += r64  # reward_eps += r with the Float64 env.reward (DDPG.jl:223)
             if train:
                 self.memory.push(s_prev, a, r, s2)  # remember(s, a, r, s′, finished) :229
                 self.learner.replay(self.memory, rng_rpl=rng_step, n_updates=self.updates_per_step)  # :231
@@ -401,21 +450,39 @@ class Driver:
             return reward_eps, T, noise_eps
         return reward_eps, torch.stack(traces)
 
-    # run_episodes — DDPG.jl:244-298 (periodic evaluation on env_eval every `test_every` episodes)
-    def run_episodes(self, num_ep, test_every=100, test_runs=100, seed_ini=123):
-        total_reward = np.zeros((num_ep, self.env_train.n_envs))
-        score_mean = []
-        for i in range(1, num_ep + 1):
-            rng_ep = self.rng_run * 100003 + i
-            r, _, _ = self.episode(self.env_train, train=True, rng_ep=rng_ep)
-            total_reward[i - 1] = r.cpu().numpy()
-            if self.env_eval is not None and i % test_every == 1:
-                score_all = 0.0
-                for test_ep in range(1, test_runs + 1):
+    # run_episodes(env_train, env_eval, total_reward, score_mean, best_run, noise_mean, test_every, render, rng) — DDPG.jl:244-298
+    def run_episodes(self, num_ep, test_every=100, test_runs=100, seed_ini=123, on_best=None, start_ep=1, state=None):
+        """The training loop with the reference's bookkeeping: total_reward[i] / noise_mean[i] per training episode (:255), every
+        `test_every` episodes (i % test_every == 1, :261) `test_runs` evaluation episodes of EP_LENGTH["train"] steps on env_eval
+        (train = false, :266-271) -> score_mean[idx]; a new best score calls on_best(i, score) — the reference's
+        saveBSON(actor, ...; idx = i, path = "temp") (:282-289) — and sets best_run = i.  The evaluation episodes run as instances
+        of ONE env_eval handle (the reference runs them one after the other): test_runs is rounded up to whole batches of
+        env_eval.n_envs.  `state` / `start_ep` continue a loop that was interrupted (the returned dict is that state).
+        Seeds: rng_ep = rng_run * 100003 + i, rng_test = seed_ini * 1000 + test_ep (Julia's string concatenation feeds
+        MersenneTwister; here the integers key Philox streams)."""
+        n = self.env_train.n_envs
+        st = state if state is not None else dict(total_reward=np.zeros((num_ep, n)), noise_mean=np.zeros((num_ep, n), np.float32),
+                                                  score_mean=np.zeros(-(-num_ep // test_every)), best_run=0, best_score=-100000.0)
+        for i in range(start_ep, num_ep + 1):
+            rng_ep = self.rng_run * 100003 + i                                        # :252
+            r, _, nz = self.episode(self.env_train, train=True, rng_ep=rng_ep)        # :255
+            st["total_reward"][i - 1] = r.cpu().numpy()
+            st["noise_mean"][i - 1] = nz.cpu().numpy() if torch.is_tensor(nz) else nz
+            if self.env_eval is not None and i % test_every == 1:                     # :261
+                idx = -(-i // test_every)                                             # ceil(Int32, i / test_every) :266
+                score_all, runs, test_ep = 0.0, 0, 1
+                while runs < test_runs:
                     sc, _, _ = self.episode(self.env_eval, train=False, num_steps=self.ep_length, rng_ep=seed_ini * 1000 + test_ep)
-                    score_all += float(sc.mean())
-                score_mean.append(score_all / test_runs)
-        return total_reward, np.array(score_mean)
+                    score_all += float(sc.sum())
+                    runs += self.env_eval.n_envs
+                    test_ep += 1
+                st["score_mean"][idx - 1] = score_all / runs                          # :273
+                if st["score_mean"][idx - 1] > st["best_score"]:                     # :282-289
+                    if on_best is not None:
+                        on_best(i, st["score_mean"][idx - 1])
+                    st["best_score"] = float(st["score_mean"][idx - 1])
+                    st["best_run"] = i
+        return st
 
     # inference(env; track) — memory_plotting_saving.jl:62-89: full-dataset deterministic rollout with the 23-column trace
     def inference(self, env, num_steps, track=1):

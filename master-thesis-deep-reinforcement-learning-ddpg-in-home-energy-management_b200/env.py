@@ -161,9 +161,10 @@ class Shems:
         self.a = ShemsAction()
         return self
 
-    def step(self, a, track=0, reward_out=None, obs_out=None, trace_out=None):
+    def step(self, a, track=0, reward_out=None, obs_out=None, trace_out=None, reward64_out=None):
         """step!(env, s, a; track): `a` is a device tensor [2][N] (targets for track >= 0, (B, EV) for track < 0).
-        Returns (reward tensor [N], state tensor [9][N]) — plus the trace tensor [23][N] (float64) when track != 0."""
+        Returns (reward tensor [N], state tensor [9][N]) — plus the trace tensor [23][N] (float64) when track != 0.
+        reward64_out (float64 [N]): env.reward as the reference holds it (Float64, shems_LU1.jl:171); `reward` is its Float32 value."""
         if not torch.is_tensor(a):
             a = torch.as_tensor(np.ascontiguousarray(a, np.float32).reshape(2, self.n_envs), device=self._torch_dev)
         assert a.dtype == torch.float32 and a.is_contiguous() and a.numel() == 2 * self.n_envs and a.is_cuda
@@ -171,7 +172,9 @@ class Shems:
         if track != 0 and trace_out is None:
             trace_out = torch.empty((23, self.n_envs), dtype=torch.float64, device=self._torch_dev)
         tn = -1 if track < 0 else (1 if track > 0 else 0)
-        L.check(self.lib.shems_step(self._h, _ptr(a), tn, _ptr(rw), _ptr(obs_out), _ptr(trace_out)))
+        if reward64_out is not None:
+            assert reward64_out.dtype == torch.float64 and reward64_out.numel() == self.n_envs and reward64_out.is_cuda
+        L.check(self.lib.shems_step(self._h, _ptr(a), tn, _ptr(rw), _ptr(reward64_out), _ptr(obs_out), _ptr(trace_out)))
         self.reward = rw
         s2 = obs_out if obs_out is not None else self.state_tensor()
         if track == 0:
@@ -194,8 +197,9 @@ class Shems:
 
     # ------------------------------------------------------------------ fused rollouts
     def rollout(self, policy, n_steps, seed=0, tape=None, want_return=True, replay=None, want_trace=False, want_obs=False,
-                want_reward=False):
-        """T fused steps (episode!/populate_memory/inference loops).  Returns a dict of device tensors."""
+                want_reward=False, tape_unscaled=False):
+        """T fused steps (episode!/populate_memory/inference loops).  Returns a dict of device tensors.
+        tape_unscaled: the tape holds actions in [-1,1] as `remember` stores them (required with a replay sink)."""
         self._bind_stream()
         n, T = self.n_envs, int(n_steps)
         dev = self._torch_dev
@@ -205,6 +209,7 @@ class Shems:
         if tape is not None:
             assert tape.is_cuda and tape.dtype == torch.float32 and tape.numel() == T * 2 * n
             args.tape_dev = tape.data_ptr()
+            args.tape_unscaled = 1 if tape_unscaled else 0
         if want_return:
             out["ep_return"] = torch.empty(n, dtype=torch.float64, device=dev)
             args.ep_return_dev = out["ep_return"].data_ptr()

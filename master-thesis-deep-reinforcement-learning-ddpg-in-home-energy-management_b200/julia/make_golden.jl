@@ -1,6 +1,6 @@
 # make_golden.jl — golden vectors from the UNMODIFIED reference (RL-SHEMS), for the parity tests of this repository.
 #
-# The build image of this repository has no Julia, so its oracle (oracle/*.c) is pinned only by hand-derived vectors and by an
+# The build image of this repository has no Julia, so its CPU oracle is pinned only by hand-derived vectors and by an
 # independent numpy restatement.  This script closes that gap wherever Julia 1.6 and the reference's packages are available:
 # it `include`s the reference's own files, runs them on the committed inputs under tests/golden/julia_inputs/ and writes
 # tests/golden/reference_julia/*.csv.  tests/test_julia_golden.py consumes those files when present (bit-exact for the

@@ -69,7 +69,7 @@ def test_invalid_arguments(sb):
     # nrows - maxsteps < 1: rand(1:(nrow-maxsteps)) is empty in the reference (shems_LU1.jl:225)
     assert L.lib().shems_create(ctypes.byref(p), ser.ctypes.data_as(L.PF), 72, 72, 1, 0, ctypes.byref(h)) == L.ERR_INVALID
     assert L.lib().shems_create(None, None, 72, 10, 1, 0, ctypes.byref(h)) == L.ERR_INVALID
-    assert L.lib().shems_step(None, None, 0, None, None, None) == L.ERR_INVALID
+    assert L.lib().shems_step(None, None, 0, None, None, None, None) == L.ERR_INVALID
     assert L.lib().replay_create(0, 0, ctypes.byref(h)) == L.ERR_INVALID
 
 

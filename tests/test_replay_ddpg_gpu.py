@@ -241,8 +241,14 @@ def test_driver_short_training_run(sb, train_series):
     assert len(drv.memory) == 32 * 72 * 2
     mn, mx = drv.min_max_buffer()
     assert np.all(mx >= mn) and mx[5] == mn[5] == np.float32(0.4)  # p_buy is constant -> normalises to 0
-    tot, score = drv.run_episodes(2, test_every=2, test_runs=2)
+    best = []
+    st = drv.run_episodes(2, test_every=2, test_runs=2, on_best=lambda i, sc: best.append((i, sc)))
+    tot, score = st["total_reward"], st["score_mean"]
     assert tot.shape == (2, 32) and np.isfinite(tot).all() and len(score) == 1 and np.isfinite(score).all()
+    # episode 1 is evaluated (1 % test_every == 1), its score beats the initial -100000 -> the "temp" checkpoint hook fires (DDPG.jl:282-289)
+    assert st["best_run"] == 1 and best == [(1, score[0])] and st["best_score"] == score[0]
+    assert st["noise_mean"].shape == (2, 32) and np.abs(st["noise_mean"]).max() > 0   # sum over 72 steps of mean(N(0, 0.1) x 2)
+    assert np.abs(st["noise_mean"]).max() < 72 * 0.1 * 4
     ret, trace = drv.inference(ev, 1439, track=-0.5)
     assert trace.shape == (1439, 23, 4) and torch.isfinite(ret).all()
     ret2, trace2 = drv.inference(ev, 50, track=1)
@@ -292,7 +298,7 @@ def test_closed_loop_episode_parity(sb, O, train_series):
         ret_ref += r_ref
         S = np.concatenate([S, s_ref], 1); A = np.concatenate([A, oa], 1); R = np.concatenate([R, r_ref.astype(np.float32)])
         S2 = np.concatenate([S2, s2_ref], 1); D = np.concatenate([D, np.zeros(n, np.float32)])
-        idx = O.sample_indices(1000 + step, step, S.shape[1], B)   # Philox counter = the learner's cumulative update number
+        idx = O.sample_indices(1000 + step, 0, S.shape[1], B)   # Philox counter = index of the update inside the call (one per replay())
         orc.update_batch(S[:, idx], A[:, idx], R[idx], S2[:, idx], D[idx])
         # Stated tolerances.  The CPU oracle itself is insensitive to rounding here (1-ulp perturbations of its initial weights
         # move its actions by < 2e-8 over these 40 steps), so the loop is compared directly: the fp32 summation order of the
