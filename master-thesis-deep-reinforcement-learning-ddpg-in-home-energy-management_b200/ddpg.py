@@ -562,14 +562,15 @@ class PopulationDriver:
                 self.n_env_steps += self.N * self.ep_length
             return ret.view(self.P, self.n_envs).mean(dim=1)
         ret = torch.zeros(self.N, dtype=torch.float64, device=self._dev)
+        r64 = torch.empty(self.N, dtype=torch.float64, device=self._dev)
         for step in range(1, self.ep_length + 1):
             rng_step = (rng_ep * 1000003 + step) & (2**63 - 1)
             obs = env.state_tensor()
             a, scaled = self.learner.act(obs, train=train, sigma=self.sigma, rng_act=rng_step, step=step, env_id_base=env.env_id_base, soa=True)
             if train:
                 self._s_prev.copy_(obs)
-            r, s2 = env.step(scaled)
-            ret += r.double()
+            r, s2 = env.step(scaled, reward64_out=r64)
+            ret += r64                                              # reward_eps += r: the Float64 env.reward (DDPG.jl:223)
             if train:
                 push_groups(self.mems, self._s_prev, a, r, s2)      # remember(s, a, r, s′, done) — the unscaled action (DDPG.jl:229)
                 self.learner.replay(self.mems, rng_rpl=rng_step, n_updates=updates_per_step)

@@ -7,6 +7,10 @@
 #     env.state, env.a, env.reward, env.step, env.idx, env.maxsteps, env.path
 # unchanged.  All arithmetic happens in CUDA kernels behind the C ABI; this file only marshals.
 #
+# `Shems` is an ABSTRACT type here and `Shems(maxsteps, path)` returns the concrete `ShemsCuda <: Shems`: every reference method
+# written for `env::Shems` (episode!, run_episodes, populate_memory, inference) still applies, and DdpgB200.jl overrides the hot
+# ones with methods for `env::ShemsCuda`, which win by dispatch whatever the order in which the driver includes the files.
+#
 # NOTE: Julia is not installed in the build/CI image of this repository, so this file is reviewed but
 # never executed there; every code path it calls is exercised through the identical C ABI by the
 # Python ctypes harness (tests/test_env_gpu.py).  It is written against Julia 1.6 / CUDA.jl 2.6 like
@@ -17,7 +21,7 @@ using Reinforce: AbstractEnvironment
 import Reinforce: reset!, action, finished, step!, state, actions
 using CSV, DataFrames
 
-export Shems, reset!, step!, action, finished, state, actions, track, ShemsState, ShemsAction
+export Shems, ShemsCuda, reset!, step!, action, finished, state, actions, track, ShemsState, ShemsAction
 
 const LIB = get(ENV, "SHEMS_B200_LIB", "libshems_b200")
 
@@ -68,7 +72,8 @@ Base.maximum(::ShemsAction) = (1f0, 1f0)
 Base.getindex(a::ShemsAction, i::Int) = getfield(a, i)
 
 # ---------------------------------------------------------------- the environment (shems_LU1.jl:169-203)
-mutable struct Shems <: AbstractEnvironment
+abstract type Shems <: AbstractEnvironment end
+mutable struct ShemsCuda <: Shems
     handle::Ptr{Cvoid}
     state::ShemsState{Float32}
     reward::Float64
@@ -83,7 +88,8 @@ end
 const SERIES_COLS = (:soc_ev, :h_countdown, :electkwh, :PV_generation, :p_buy, :hour_cos, :hour_sin, :season)
 
 # Shems(maxsteps, path): the CSV is parsed ONCE here (the reference re-parses it on every reset/step, :217, :265)
-function Shems(maxsteps, path; n_envs::Int=1, device::Int=parse(Int, get(ENV, "GPU_ID", "0")))
+Shems(maxsteps, path; kw...) = ShemsCuda(maxsteps, path; kw...)
+function ShemsCuda(maxsteps, path; n_envs::Int=1, device::Int=parse(Int, get(ENV, "GPU_ID", "0")))
     df = CSV.read(path, DataFrame)
     nrows = nrow(df)
     series = Matrix{Float32}(undef, nrows, 8)            # column-major: [8][nrows] in C order
@@ -94,13 +100,13 @@ function Shems(maxsteps, path; n_envs::Int=1, device::Int=parse(Int, get(ENV, "G
     check(ccall((:shems_create, LIB), Cint,
                 (Ref{ShemsParams}, Ptr{Cfloat}, Cint, Cint, Int64, Cint, Ref{Ptr{Cvoid}}),
                 params, series, nrows, maxsteps, n_envs, device, h))
-    env = Shems(h[], ShemsState(), 0.0, ShemsAction(), 0, maxsteps, 1, path, n_envs)
+    env = ShemsCuda(h[], ShemsState(), 0.0, ShemsAction(), 0, maxsteps, 1, path, n_envs)
     finalizer(e -> ccall((:shems_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle), env)
     return env
 end
 
 # copy instance 1 of the device state into the Julia-visible fields (n_envs == 1 is the reference's use)
-function pull!(env::Shems)
+function pull!(env::ShemsCuda)
     obs = Matrix{Float32}(undef, env.n_envs, 9)
     idx = Vector{Int32}(undef, env.n_envs)
     check(ccall((:shems_get_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Cfloat}, Ptr{Int32}), env.handle, obs, idx))
@@ -115,7 +121,7 @@ end
 # reset!(env; rng) (shems_LU1.jl:206-262).  rng == -1: deterministic start.  Otherwise the two draws the
 # reference takes from MersenneTwister(rng) (:224-225) are made HERE, in Julia, and handed to the library
 # (mode 1 = SHEMS_RESET_HOST_DRAWS), so the start row and Soc_b are bit-identical to the reference run.
-function reset!(env::Shems; rng=0)
+function reset!(env::ShemsCuda; rng=0)
     if rng == -1
         check(ccall((:shems_reset, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Cfloat}, UInt64, Int64),
                     env.handle, 0, C_NULL, C_NULL, 0, 0))
@@ -133,14 +139,14 @@ function reset!(env::Shems; rng=0)
 end
 
 # step!(env, s, a; track=0) (shems_LU1.jl:343-485): a = targets (track >= 0) or (B, EV) (track < 0)
-function step!(env::Shems, s, a; track=0)
+function step!(env::ShemsCuda, s, a; track=0)
     n = env.n_envs
     act = CUDA.CuArray(reshape(Float32.(collect(a)), n, 2))          # [2][N] in C order
-    rew = CUDA.zeros(Float32, n)
+    rew = CUDA.zeros(Float64, n)                                     # env.reward::Float64 (shems_LU1.jl:171)
     trace = track == 0 ? nothing : CUDA.zeros(Float64, n, 23)
     check(ccall((:shems_step, LIB), Cint,
-                (Ptr{Cvoid}, CUDA.CuPtr{Cfloat}, Cint, CUDA.CuPtr{Cfloat}, CUDA.CuPtr{Cfloat}, CUDA.CuPtr{Cdouble}),
-                env.handle, act, track < 0 ? -1 : (track > 0 ? 1 : 0), rew, CUDA.CU_NULL,
+                (Ptr{Cvoid}, CUDA.CuPtr{Cfloat}, Cint, CUDA.CuPtr{Cfloat}, CUDA.CuPtr{Cdouble}, CUDA.CuPtr{Cfloat}, CUDA.CuPtr{Cdouble}),
+                env.handle, act, track < 0 ? -1 : (track > 0 ? 1 : 0), CUDA.CU_NULL, rew, CUDA.CU_NULL,
                 trace === nothing ? CUDA.CU_NULL : trace))
     check(ccall((:shems_sync, LIB), Cint, (Ptr{Cvoid},), env.handle))
     pull!(env)
@@ -149,8 +155,7 @@ function step!(env::Shems, s, a; track=0)
     else
         env.a = ShemsAction(0f0, 0f0)
     end
-    # env.reward is Float64 in the reference; the Float64 value is column 6 of the trace, the step API returns Float32(reward)
-    env.reward = trace === nothing ? Float64(Array(rew)[1]) : Array(trace)[1, 6]
+    env.reward = Array(rew)[1]                                       # the Float64 reward of the reference (:467-470)
     if track == 0
         return env.reward, Vector{Float32}(env.state)
     else
@@ -159,12 +164,12 @@ function step!(env::Shems, s, a; track=0)
 end
 
 # action(env, a::ShemsAction) (:283-316) and action(env, track) (:318-340)
-function action(env::Shems, a::ShemsAction)
+function action(env::ShemsCuda, a::ShemsAction)
     tgt = CUDA.CuArray(Float32[a.B, a.EV]); out = CUDA.zeros(Float32, 2 * env.n_envs)
     check(ccall((:shems_action_drl, LIB), Cint, (Ptr{Cvoid}, CUDA.CuPtr{Cfloat}, CUDA.CuPtr{Cfloat}), env.handle, tgt, out))
     return Array(out)[1:env.n_envs:end]
 end
-function action(env::Shems, track=-1)
+function action(env::ShemsCuda, track=-1)
     out = CUDA.zeros(Float32, 2 * env.n_envs)
     check(ccall((:shems_action_rule, LIB), Cint, (Ptr{Cvoid}, CUDA.CuPtr{Cfloat}), env.handle, out))
     return Array(out)[1:env.n_envs:end]

@@ -147,17 +147,29 @@ static void normalize_into(const OracleDdpg* h, const float* s, int B, float* x,
 
 /* Dense forward for B samples: x [B][in] -> y [B][out]; z kept only through y (relu/tanh invertible enough) */
 static void dense_fwd(const Layer* L, const float* x, int B, float* y) {
+  /* every output (b, o) is the Float64 sum over i = 0, 1, ... of W[o, i] * x[b, i], in that order; the loops run o innermost so that
+   * the column-major Flux weight is walked contiguously (same sums, same order per element) */
 #pragma omp parallel for schedule(static)
-  for (int b = 0; b < B; ++b)
-    for (int o = 0; o < L->out; ++o) {
-      double acc = 0.0;
-      for (int i = 0; i < L->in; ++i) acc += (double)L->W[(size_t)o + (size_t)L->out * i] * (double)x[(size_t)b * L->in + i];
-      float z = (float)acc;   /* W*x */
-      z = z + L->b[o];        /* .+ b */
-      if (L->act == ACT_RELU) z = z > 0.f ? z : 0.f;
-      else if (L->act == ACT_TANH) z = tanhf(z);
-      y[(size_t)b * L->out + o] = z;
+  for (int b = 0; b < B; ++b) {
+    double acc[2048];
+    const int out = L->out;
+    for (int o0 = 0; o0 < out; o0 += 2048) {
+      const int on = out - o0 < 2048 ? out - o0 : 2048;
+      for (int o = 0; o < on; ++o) acc[o] = 0.0;
+      for (int i = 0; i < L->in; ++i) {
+        const double xv = (double)x[(size_t)b * L->in + i];
+        const float* w = L->W + (size_t)out * i + o0;
+        for (int o = 0; o < on; ++o) acc[o] += (double)w[o] * xv;
+      }
+      for (int o = 0; o < on; ++o) {
+        float z = (float)acc[o];   /* W*x */
+        z = z + L->b[o0 + o];      /* .+ b */
+        if (L->act == ACT_RELU) z = z > 0.f ? z : 0.f;
+        else if (L->act == ACT_TANH) z = tanhf(z);
+        y[(size_t)b * out + o0 + o] = z;
+      }
     }
+  }
 }
 /* dy (grad wrt layer output) -> dz in place, then gW, gb, and dx (if dx != NULL) */
 static void dense_bwd(const Layer* L, const float* x, const float* y, float* dy, int B, float* gW, float* gb, float* dx) {
@@ -169,12 +181,20 @@ static void dense_bwd(const Layer* L, const float* x, const float* y, float* dy,
     }
   if (gW) {
 #pragma omp parallel for schedule(static)
-    for (int i = 0; i < L->in; ++i)
-      for (int o = 0; o < L->out; ++o) {
-        double acc = 0.0;
-        for (int b = 0; b < B; ++b) acc += (double)dy[(size_t)b * L->out + o] * (double)x[(size_t)b * L->in + i];
-        gW[(size_t)o + (size_t)L->out * i] = (float)acc;
+    for (int i = 0; i < L->in; ++i) {   /* gW[o, i] = sum over b = 0, 1, ... of dy[b, o] * x[b, i] (o innermost: contiguous, same sums) */
+      double acc[2048];
+      const int out = L->out;
+      for (int o0 = 0; o0 < out; o0 += 2048) {
+        const int on = out - o0 < 2048 ? out - o0 : 2048;
+        for (int o = 0; o < on; ++o) acc[o] = 0.0;
+        for (int b = 0; b < B; ++b) {
+          const double xv = (double)x[(size_t)b * L->in + i];
+          const float* d = dy + (size_t)b * out + o0;
+          for (int o = 0; o < on; ++o) acc[o] += (double)d[o] * xv;
+        }
+        for (int o = 0; o < on; ++o) gW[(size_t)(o0 + o) + (size_t)out * i] = (float)acc[o];
       }
+    }
     for (int o = 0; o < L->out; ++o) {
       double acc = 0.0;
       for (int b = 0; b < B; ++b) acc += (double)dy[(size_t)b * L->out + o];

@@ -130,11 +130,15 @@ def test_rollout_parity_72_steps(sb, O, P98, train_series, cuda_ok, policy):
     env = sb.Shems(T, train_series, n_envs=n)
     ref.reset(mode=2, seed=3)
     env.reset(rng=3)
-    tape = np.random.default_rng(1).uniform(0, 1, (T, 2, n)).astype(np.float32) if policy == "tape" else None
+    # a tape that feeds a training memory holds the UNSCALED actions remember() stores (DDPG.jl:229); the oracle is given scale_action(a)
+    raw = np.random.default_rng(1).uniform(-1, 1, (T, 2, n)).astype(np.float32) if policy == "tape" else None
+    tape = ((raw.astype(np.float64) + 1.0) * 0.5).astype(np.float32) if policy == "tape" else None
     want = ref.rollout(pol, T, seed=9, tape=tape, want_transitions=True, want_trace=True)
+    if policy == "tape":
+        want["a"] = raw
     mem = sb.Replay(T * n)
-    got = env.rollout(pol, T, seed=9, tape=dev(tape) if tape is not None else None, replay=mem, want_trace=True, want_obs=True,
-                      want_reward=True)
+    got = env.rollout(pol, T, seed=9, tape=dev(raw) if raw is not None else None, replay=mem, want_trace=True, want_obs=True,
+                      want_reward=True, tape_unscaled=policy == "tape")
     np.testing.assert_array_equal(got["obs"].cpu().numpy(), want["s2"])          # closed-loop, 72 steps, bit-exact
     np.testing.assert_array_equal(got["reward"].cpu().numpy(), want["r"])
     np.testing.assert_allclose(got["trace"].cpu().numpy(), want["trace"], rtol=1e-12, atol=0)
