@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[2], the configuration the metric is quoted on): 
 rollout, 2^20 instances per GPU x 8760 hourly steps on a synthetic ChargerID98-shaped 8761-row year series,
 every transition (s, a, r, s', done) written into the device-resident replay ring as populate_memory does
 (memory_plotting_saving.jl:9-29).  One bench "step" = one reset + one fused 8760-step rollout of all instances.
-Instances shard across ranks with no collective (global env id keys the RNG), per-GPU work fixed: "weak".
+Instances shard across ranks with no collective (global env id keys the RNG), per-GPU work fixed: "weak".  For N > 1 the line
+also carries `strong_scaling`: configs[2] as written, 2^20 instances in TOTAL split over the ranks.
 """
 import argparse
 import json
@@ -518,10 +519,12 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    launches0 = int(sb._lib.lib().shems_env_kernel_launches())
     ev[0].record()
     for k in range(args.steps):
         device_step(1000 + k, True)
     ev[1].record()
+    launches_timed = int(sb._lib.lib().shems_env_kernel_launches()) - launches0   # counted by the library at its launch sites
     barrier()
     ms = ev[0].elapsed_time(ev[1])
     # ---- end-to-end through the public API with host buffers (`e2e`) ----
@@ -543,6 +546,34 @@ def main():
     total_steps = float(world) * n * T * args.steps
     value = total_steps / (ms * 1e-3)
     e2e_value = total_steps / (ms_e2e * 1e-3)
+
+    # ---- BASELINE configs[2] as written: 2^20 instances in TOTAL, sharded over the ranks (strong scaling; N > 1 only) ----
+    strong = None
+    if world > 1:
+        total = args.envs_per_gpu
+        lo, cnt = sharding.shard_range(total, rank, world)
+        env_s = sb.Shems(T, ser, n_envs=cnt, device=local_rank, env_id_base=lo)
+
+        def strong_step(seed):
+            env_s.reset(rng=seed)
+            env_s.rollout(sb.POLICY_RANDOM, T, seed=seed, replay=mem, want_return=True)
+        for w in range(args.warmup):
+            strong_step(300 + w)
+        barrier()
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        es[0].record()
+        for k in range(args.steps):
+            strong_step(3000 + k)
+        es[1].record()
+        barrier()
+        ts = torch.tensor([es[0].elapsed_time(es[1])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item())
+        strong = dict(scaling="strong", envs_total=total, envs_per_gpu=cnt, value=float(total) * T * args.steps / (ms_s * 1e-3), unit=UNIT,
+                      ms_per_step=ms_s / args.steps, vs_weak_value=float(total) * T * args.steps / (ms_s * 1e-3) / value,
+                      note="2^20 instances in total (configs[2] as written), contiguous env-id ranges per rank, no collective; vs_weak_value = "
+                           "this throughput / the weak-scaling value of the same run (1.0 = no loss from the smaller per-GPU grids)")
+        env_s.close()
 
     ddpg_dp = ddpg_pop = None
     if not args.skip_ddpg:
@@ -589,7 +620,7 @@ def main():
                 roofline=roofline, clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=int(8 * n), d2h_bytes_per_step=int(8 * n),
                          note="reset draws (idx0, Soc_b0) from pinned host memory and episode returns back to pinned host memory every step"),
-                gpu_launches=int(2 * args.steps * 2))
+                gpu_launches=launches_timed)
     if not args.skip_ddpg:
         try:
             line["ddpg"] = ddpg_updates_per_s(sb, torch, sb.series.synth_charger98(4320, seed=98))
@@ -611,6 +642,8 @@ def main():
             line["ddpg_large_batch"] = ddpg_large_batch(sb, torch, sb.series.synth_charger98(4320, seed=98))
         except Exception as e:
             line["ddpg_large_batch"] = dict(error=str(e))
+    if strong is not None:
+        line["strong_scaling"] = strong
     if ddpg_dp is not None:
         line["ddpg_data_parallel"] = ddpg_dp
     if ddpg_pop is not None:

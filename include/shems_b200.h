@@ -48,6 +48,8 @@ enum {
 
 SHEMS_API const char* shems_last_error(void);
 SHEMS_API int32_t shems_version(void);
+/* environment kernels (reset / step / action / rollout) this process has launched so far — a real counter for benchmarks' launch counts */
+SHEMS_API int64_t shems_env_kernel_launches(void);
 /* number of visible CUDA devices (0 on a CPU-only box; never an error) */
 SHEMS_API int32_t shems_device_count(void);
 

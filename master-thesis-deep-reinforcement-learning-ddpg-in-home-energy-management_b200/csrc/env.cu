@@ -12,6 +12,7 @@
 #include <vector>
 #include <string.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "philox.cuh"
@@ -27,6 +28,10 @@ void shems_set_error(const char* fmt, ...) {
 }
 extern "C" const char* shems_last_error(void) { return g_err; }
 extern "C" int32_t shems_version(void) { return 200; }
+// environment kernels (reset / step / action / rollout) launched by this process so far: what bench.py reports as gpu_launches
+static long long g_env_launches = 0;
+extern "C" int64_t shems_env_kernel_launches(void) { return __atomic_load_n(&g_env_launches, __ATOMIC_RELAXED); }
+#define COUNT_LAUNCH() __atomic_add_fetch(&g_env_launches, 1, __ATOMIC_RELAXED)
 extern "C" int32_t shems_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -322,8 +327,11 @@ struct RolloutSinks {
 #ifndef ROLLOUT_MIN_BLOCKS
 #define ROLLOUT_MIN_BLOCKS 6
 #endif
-template <int POLICY, bool WANT_TRACE>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, ROLLOUT_MIN_BLOCKS)
+// MINB = resident CTAs per SM the register budget is cut for (6: 80 registers, 7: 72, 8: 64).  6 is the fastest per wave; 7 or 8 are
+// chosen when they save a mostly empty last wave (e.g. 2^20 instances over 8 GPUs = 1024 CTAs per GPU: 1.15 waves of 148 x 6 CTAs,
+// but ONE wave of 148 x 7) — see rollout_min_blocks().
+template <int POLICY, bool WANT_TRACE, int MINB>
+__global__ void __launch_bounds__(ROLLOUT_THREADS, MINB)
 shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                      int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
                      const float* __restrict__ tape, int tape_unscaled, RolloutSinks S, long long n0, long long n1) {
@@ -418,6 +426,34 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
 
 // ----------------------------------------------------------------------------- C ABI
 static inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// Resident CTAs per SM for a rollout over n instances.  A wave of 148 x b CTAs takes about the same time for b = 6, 7, 8 per CTA slot
+// (measured: 6 is 1-3 % faster per instance, profiles/r1_rollout_sweep.md), but a sparsely filled LAST wave runs its few warps at a
+// fraction of the issue rate: cost model = full waves + the last wave's fill, floored at 0.45 (a lone warp per scheduler is latency
+// bound), times the per-instance penalty of the tighter register budget.  SHEMS_ROLLOUT_MIN_BLOCKS=6|7|8 overrides.
+static int rollout_min_blocks(int device, long long n) {
+  static int forced = -1;
+  if (forced < 0) { const char* ev = getenv("SHEMS_ROLLOUT_MIN_BLOCKS"); forced = ev ? atoi(ev) : 0; }
+  if (forced == 6 || forced == 7 || forced == 8) return forced;
+  static int sms[64];
+  if (device >= 0 && device < 64 && sms[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+    sms[device] = v;
+  }
+  const int nsm = (device >= 0 && device < 64) ? sms[device] : 148;
+  const double ctas = (double)((n + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS);
+  int best = ROLLOUT_MIN_BLOCKS; double best_cost = 1e300;
+  for (int b = 6; b <= 8; ++b) {
+    const double waves = ctas / ((double)nsm * b);
+    const double full = floor(waves), frac = waves - full;
+    const double last = frac > 0.0 ? (frac < 0.45 ? 0.45 : frac) : 0.0;
+    const double penalty = b == 6 ? 1.0 : (b == 7 ? 1.015 : 1.03);
+    const double cost = (full + last) * b * penalty;   // time ~ waves x (instances per wave ~ b)
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
+  }
+  return best;
+}
 
 // Shems(maxsteps, path) for G groups of instances (group g: group_sizes[g] consecutive instances with params[g] and, when
 // series_per_group, its own series): several chargers in one handle.  Every kernel is launched once per group on its slice.
@@ -547,6 +583,7 @@ extern "C" int32_t shems_reset(ShemsEnv* e, int32_t mode, const int32_t* idx0_ho
   CUDA_TRY(cudaMemsetAsync(e->d_maxidx, 0, sizeof(int32_t), e->stream));
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
+    COUNT_LAUNCH();
     shems_reset_kernel<<<grid_for(n1 - n0, 256), 256, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->nrows, e->maxsteps, e->n, mode, e->scratch_i,
                                                                      e->scratch_f, seed, env_id_base, e->obs, e->idx, e->d_maxidx, n0, n1);
   }
@@ -577,12 +614,13 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
   GUARD(e->device);
   const int tn = track < 0 ? 1 : 0;
 #define LAUNCH_STEP(FS, TR)                                                                                                             \
+  COUNT_LAUNCH();                                                                                                                       \
   shems_step_kernel<FS, TR><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, \
                                                                                             act_dev, tn, reward_dev, reward64_dev, obs_dev, trace_dev, n0, n1)
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
-    if (e->consistent) { if (trace_dev) LAUNCH_STEP(true, true); else LAUNCH_STEP(true, false); }
-    else { if (trace_dev) LAUNCH_STEP(false, true); else LAUNCH_STEP(false, false); }
+    if (e->consistent) { if (trace_dev) { LAUNCH_STEP(true, true); } else { LAUNCH_STEP(true, false); } }
+    else { if (trace_dev) { LAUNCH_STEP(false, true); } else { LAUNCH_STEP(false, false); } }
   }
 #undef LAUNCH_STEP
   CUDA_TRY(cudaGetLastError());
@@ -595,7 +633,7 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
 extern "C" int32_t shems_action_rule(ShemsEnv* e, float* bev_dev) {
   REQUIRE(e && bev_dev, SHEMS_ERR_INVALID, "shems_action_rule: NULL argument");
   GUARD(e->device);
-  for (int g = 0; g < e->n_groups; ++g)
+  for (int g = 0; g < e->n_groups; ++g, COUNT_LAUNCH())
     shems_action_kernel<true><<<grid_for(e->gstart[g + 1] - e->gstart[g], 256), 256, 0, e->stream>>>(e->gdp[g], e->n, e->obs, nullptr, bev_dev,
                                                                                                     e->gstart[g], e->gstart[g + 1]);
   CUDA_TRY(cudaGetLastError());
@@ -604,7 +642,7 @@ extern "C" int32_t shems_action_rule(ShemsEnv* e, float* bev_dev) {
 extern "C" int32_t shems_action_drl(ShemsEnv* e, const float* target_dev, float* bev_dev) {
   REQUIRE(e && target_dev && bev_dev, SHEMS_ERR_INVALID, "shems_action_drl: NULL argument");
   GUARD(e->device);
-  for (int g = 0; g < e->n_groups; ++g)
+  for (int g = 0; g < e->n_groups; ++g, COUNT_LAUNCH())
     shems_action_kernel<false><<<grid_for(e->gstart[g + 1] - e->gstart[g], 256), 256, 0, e->stream>>>(e->gdp[g], e->n, e->obs, target_dev, bev_dev,
                                                                                                      e->gstart[g], e->gstart[g + 1]);
   CUDA_TRY(cudaGetLastError());
@@ -674,18 +712,28 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
     REQUIRE(e->n <= rp->capacity, SHEMS_ERR_INVALID, "shems_rollout: replay capacity %lld < n_envs %lld", (long long)rp->capacity, (long long)e->n);
     S.ring = rp->ring; S.cap = rp->capacity; S.head = rp->head;
   }
-#define LAUNCH_RO(POL, TR)                                                                                                          \
-  shems_rollout_kernel<POL, TR><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                                  \
+#define LAUNCH_RO(POL, TR, MB)                                                                                                      \
+  shems_rollout_kernel<POL, TR, MB><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                              \
       e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, a->n_steps, e->step, a->seed, a->env_id_base, a->tape_dev, a->tape_unscaled, S, n0, n1)
+#define LAUNCH_RO_MB(POL)                                                                                                           \
+  do {                                                                                                                              \
+    if (tr) LAUNCH_RO(POL, true, ROLLOUT_MIN_BLOCKS);                                                                               \
+    else if (mb == 7) LAUNCH_RO(POL, false, 7);                                                                                     \
+    else if (mb == 8) LAUNCH_RO(POL, false, 8);                                                                                     \
+    else LAUNCH_RO(POL, false, ROLLOUT_MIN_BLOCKS);                                                                                 \
+  } while (0)
   const bool tr = a->trace_dev != nullptr;
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
+    const int mb = rollout_min_blocks(e->device, n1 - n0);
+    COUNT_LAUNCH();
     switch (a->policy) {
-      case SHEMS_POLICY_RULE: if (tr) LAUNCH_RO(SHEMS_POLICY_RULE, true); else LAUNCH_RO(SHEMS_POLICY_RULE, false); break;
-      case SHEMS_POLICY_RANDOM: if (tr) LAUNCH_RO(SHEMS_POLICY_RANDOM, true); else LAUNCH_RO(SHEMS_POLICY_RANDOM, false); break;
-      default: if (tr) LAUNCH_RO(SHEMS_POLICY_TAPE, true); else LAUNCH_RO(SHEMS_POLICY_TAPE, false); break;
+      case SHEMS_POLICY_RULE: LAUNCH_RO_MB(SHEMS_POLICY_RULE); break;
+      case SHEMS_POLICY_RANDOM: LAUNCH_RO_MB(SHEMS_POLICY_RANDOM); break;
+      default: LAUNCH_RO_MB(SHEMS_POLICY_TAPE); break;
     }
   }
+#undef LAUNCH_RO_MB
 #undef LAUNCH_RO
   CUDA_TRY(cudaGetLastError());
   e->max_idx += a->n_steps;
