@@ -709,6 +709,11 @@ extern "C" int32_t ddpg_sync(Ddpg* h) {
   REQUIRE(h, SHEMS_ERR_INVALID, "ddpg_sync: NULL handle");
   GUARD(h->device);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->dp_on) {  // a gradient exchange that gave up (a peer never arrived) skipped its update on purpose: tell the caller
+    int e = 0;
+    CUDA_TRY(cudaMemcpy(&e, &h->ctrl->dp_error, sizeof(int), cudaMemcpyDeviceToHost));
+    REQUIRE(e == 0, SHEMS_ERR_STATE, "ddpg_sync: a data-parallel gradient exchange timed out (a peer did not arrive); the replicas' updates were skipped");
+  }
   return SHEMS_OK;
 }
 extern "C" int32_t ddpg_set_fused(Ddpg* h, int32_t on) {
@@ -999,33 +1004,21 @@ adam_polyak_parts_kernel(float* __restrict__ x, const float* __restrict__ parts,
   if (advance) adam_advance(ctrl, b1, b2);
 }
 
-// data-parallel learner on the cluster-fused path: this rank's gradient = the fixed-order sum of its per-cluster partial copies,
-// written to the flat gradient buffer the peers read
-__global__ void __launch_bounds__(256)
-parts_reduce_kernel(const float* __restrict__ parts, int nparts, long long part_stride, float* __restrict__ g_out, long long n) {
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  float gj = 0.0f;
-  for (int c0 = 0; c0 < nparts; c0 += 8) {
-    float t[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
-  }
-  g_out[j] = gj;
-}
-
 // Data-parallel learner: gradient all-reduce FUSED into the optimiser step, over NVLink peer memory (no NCCL call, no
-// reduced-gradient round trip through HBM).  Every rank runs this kernel at the same point of its stream:
-//   1. block 0 publishes "my gradient segment is final" by writing the exchange number into every peer's flag array
-//      (st.release.sys after a system fence; the gradient itself was written by earlier kernels of the stream);
-//   2. every block waits until all ranks have published that number (ld.acquire.sys on its own flag array, bounded spin);
-//   3. element j: g = (sum over ranks r = 0..W-1 of peer_grad[r][j]) / W, read straight from the peers' buffers in rank order
-//      (same order everywhere -> bit-identical replicas), then ADAM (+ Polyak) as in adam_polyak_kernel.
+// reduced-gradient round trip through HBM).  Every rank runs this ONE kernel per gradient segment at the same point of its stream:
+//   0. (cluster-fused path) this rank's gradient = the fixed-order sum of its per-cluster partial copies, written to the flat
+//      gradient buffer the peers read — formerly a kernel of its own;
+//   1. the LAST block to finish step 0 publishes "my segment is final" by writing the exchange number into every peer's flag array
+//      (st.release.sys after a system fence);
+//   2. every block waits until all ranks have published that number (ld.acquire.sys on its own, LOCAL flag array);
+//   3. element j: g = (sum over ranks r = 0..W-1 of peer_grad[r][j]) / W.  The W loads of an element are independent and issued
+//      together (W is a template parameter: the loop is unrolled, one NVLink round trip per element instead of W serialised ones);
+//      they are summed in rank order (same order everywhere -> bit-identical replicas); then ADAM (+ Polyak) as in adam_polyak_kernel.
 // A rank may overwrite a gradient segment only after the NEXT exchange (critic and actor segments alternate), which every peer
 // signals after it finished reading this one — so no second barrier is needed.
+// A peer that never arrives: ONLY block 0 runs the clock; when it gives up it records the abort for this exchange number in the
+// control block, every other block sees it in its wait loop, and NO block applies the step (a half-updated parameter vector would
+// silently break the replicas' identity).  dp_error stays set; ddpg_sync / ddpg_dp_status report it.
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -1034,57 +1027,169 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ float ld_peer(const float* p) {  // never served from a stale local cache line
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ float ld_peer(const float* p) {  // never served from a stale local cache line; no memory clobber: independent
+  float v;                                                   // loads may be issued back to back
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];\n" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// -DDP_TRACE (tools/time_dp.py --trace builds that variant): globaltimer stamps of block 0 / the publishing block per segment
+#ifdef DP_TRACE
+__device__ unsigned long long dp_trace[2][8];
+#define DP_STAMP(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); dp_trace[opt][i] = t_; } } while (0)
+extern "C" __attribute__((visibility("default"))) int ddpg_dp_trace_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, dp_trace, sizeof(dp_trace));
+}
+#else
+#define DP_STAMP(i) do { } while (0)
+#endif
+template <int W>
 __global__ void __launch_bounds__(256)
-adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
+adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, const float* __restrict__ parts, int nparts, long long part_stride,
+                      float* __restrict__ g_own, float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, long long n, double b1,
                       double b2, double eps, float eta, DdpgCtrl* __restrict__ ctrl, int opt, float* __restrict__ target, float tau,
                       float* __restrict__ target2, const float* __restrict__ model2, long long n2, int advance) {
-  __shared__ int ok_s;
+  __shared__ int ok_s, last_s;
+  // the fused actor pass is a programmatic dependent of the critic exchange: its actor forward pass (which does not read the critic)
+  // may run beside this kernel; all blocks of this grid are resident before the dependent can start, so the waits below stay safe
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
   const unsigned epoch = ctrl->dp_epoch + 1u;
-  const int W = peers.world;
-  if (blockIdx.x == 0 && threadIdx.x < W) {
-    __threadfence_system();
-    st_release_sys(peers.flags[threadIdx.x] + peers.rank, epoch);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0) DP_STAMP(0);
+  // 0. this rank's gradient segment from its per-cluster partial copies (fixed order)
+  if (parts) {
+    for (long long j = tid0; j < n; j += stride) {
+      float gj = 0.0f;
+      for (int c0 = 0; c0 < nparts; c0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
+      }
+      g_own[j] = gj;
+    }
   }
-  if (threadIdx.x == 0) ok_s = 1;
+  // 1. the last block to get here publishes (its fence orders every block's gradient stores, seen through the counter, before the flag)
   __syncthreads();
+  if (blockIdx.x == 0) DP_STAMP(1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned arrived = atomicAdd(&ctrl->dp_ready, 1u);
+    last_s = (arrived == gridDim.x - 1);
+    if (last_s) { ctrl->dp_ready = 0; DP_STAMP(2); }
+    ok_s = 1;
+  }
+  __syncthreads();
+  // Publishing: lane r tells rank r.  A system-scope release costs a ~2 us round trip EACH (measured: W back-to-back st.release.sys
+  // from ONE thread took 4.2 us at W = 2 — the negative scaling of the first version); issued by the W lanes of one warp they are one
+  // instruction and one round trip.  (Measured and dropped: one fence + relaxed flag stores — the relaxed stores reached the peer
+  // 10-16 us later; a release store is pushed out at once.)  The barrier above carries thread 0's observation of the other blocks'
+  // gradient stores to these lanes.
+  if (last_s && threadIdx.x < W) {
+    st_release_sys(peers.flags[threadIdx.x] + peers.rank, epoch);
+    DP_STAMP(3);
+  }
+  // 2. wait for every rank's flag (local memory); block 0 alone decides to give up
   if (threadIdx.x < W) {
     const unsigned* f = peers.flags[peers.rank] + threadIdx.x;
     unsigned long long t0 = 0, t = 0;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+    unsigned spins = 0;
     while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-      if (t - t0 > DP_TIMEOUT_NS) { ok_s = 0; ctrl->dp_error = 1; break; }
-      __nanosleep(100);
+      if ((++spins & 63u) == 0u) {
+        if (ld_volatile_u32(&ctrl->dp_abort) == epoch) { ok_s = 0; break; }
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+        if (blockIdx.x == 0 && t - t0 > DP_TIMEOUT_NS) {
+          if ((int)(ld_acquire_sys(f) - epoch) >= 0) break;   // it arrived after all
+          ctrl->dp_abort = epoch; ctrl->dp_error = 1;
+          __threadfence();
+          ok_s = 0;
+          break;
+        }
+        if (blockIdx.x != 0 && t - t0 > 4ull * DP_TIMEOUT_NS) { ok_s = 0; break; }   // backstop: block 0 never ran its clock
+      }
     }
   }
+  __syncthreads();
+  if (blockIdx.x == 0) DP_STAMP(4);
+  if (ok_s && ld_volatile_u32(&ctrl->dp_abort) == epoch) ok_s = 0;   // racing with block 0's abort: stay uniform
   __syncthreads();
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
   const float omt = __fsub_rn(1.0f, tau), inv_w = 1.0f / (float)W;
-  const long long stride = (long long)gridDim.x * blockDim.x;
   if (ok_s) {
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-      float gs = ld_peer(peers.grad[0] + seg_off + j);
-      for (int r = 1; r < W; ++r) gs = __fadd_rn(gs, ld_peer(peers.grad[r] + seg_off + j));
-      const float xn = adam_element<false>(x[j], __fmul_rn(gs, inv_w), m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
-      x[j] = xn;
-      if (target) target[j] = __fadd_rn(__fmul_rn(omt, target[j]), __fmul_rn(tau, xn));
+    for (long long j = tid0; j < n || j < n2; j += stride) {
+      const bool in1 = j < n, in2 = j < n2;
+      float t2 = 0.0f, w2 = 0.0f, xj = 0.0f, tj = 0.0f, gr[W];
+      if (in1) {
+#pragma unroll
+        for (int r = 0; r < W; ++r) gr[r] = ld_peer(peers.grad[r] + seg_off + j);   // W independent loads in flight
+        xj = x[j];
+        if (target) tj = target[j];
+      }
+      if (in2) { t2 = target2[j]; w2 = model2[j]; }
+      if (in1) {
+        float gs = gr[0];
+#pragma unroll
+        for (int r = 1; r < W; ++r) gs = __fadd_rn(gs, gr[r]);
+        const float xn = adam_element<false>(xj, __fmul_rn(gs, inv_w), m + j, v + j, b1, b2, eps, eta, c1, c2, r1, r2);
+        x[j] = xn;
+        if (target) target[j] = __fadd_rn(__fmul_rn(omt, tj), __fmul_rn(tau, xn));
+      }
+      if (in2) target2[j] = __fadd_rn(__fmul_rn(omt, t2), __fmul_rn(tau, w2));
     }
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride)
-      target2[j] = __fadd_rn(__fmul_rn(omt, target2[j]), __fmul_rn(tau, model2[j]));
   }
   __syncthreads();
+  if (blockIdx.x == 0) DP_STAMP(5);
   if (threadIdx.x == 0) {  // the last block closes this exchange
     __threadfence();
     const unsigned done = atomicAdd(&ctrl->dp_blocks_done, 1u);
-    if (done == gridDim.x - 1) { ctrl->dp_blocks_done = 0; ctrl->dp_epoch = epoch; }
+    if (done == gridDim.x - 1) { ctrl->dp_blocks_done = 0; ctrl->dp_epoch = epoch; DP_STAMP(6); }
   }
   if (advance) adam_advance(ctrl, b1, b2);
+}
+// host-side dispatch on the world size (the gather loop is unrolled per W); grid: one element per thread, capped at the number
+// of blocks that are co-resident (the blocks wait for one another in step 1)
+static int dp_grid_cap = 0;
+static int launch_adam_dp(cudaStream_t st, const DpPeers& peers, long long seg_off, const float* parts, int nparts, long long part_stride, float* g_own,
+                          float* x, float* m, float* v, long long n, double b1, double b2, double eps, float eta, DdpgCtrl* ctrl, int opt,
+                          float* target, float tau, float* target2, const float* model2, long long n2, int advance) {
+#define DP_CASE(WW)                                                                                                                          \
+  case WW: {                                                                                                                                 \
+    if (!dp_grid_cap) {                                                                                                                      \
+      int per_sm = 0, dev = 0, sms = 0;                                                                                                      \
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_polyak_dp_kernel<WW>, 256, 0));                                   \
+      CUDA_TRY(cudaGetDevice(&dev));                                                                                                         \
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                                           \
+      dp_grid_cap = per_sm * sms > 0 ? per_sm * sms : 148;                                                                                   \
+    }                                                                                                                                        \
+    const long long want = ((n > n2 ? n : n2) + 255) / 256;                                                                                  \
+    const unsigned grid = (unsigned)(want < dp_grid_cap ? want : dp_grid_cap);                                                               \
+    adam_polyak_dp_kernel<WW><<<grid, 256, 0, st>>>(peers, seg_off, parts, nparts, part_stride, g_own, x, m, v, n, b1, b2, eps, eta, ctrl, opt, \
+                                                    target, tau, target2, model2, n2, advance);                                              \
+  } break;
+  switch (peers.world) {
+    DP_CASE(1) DP_CASE(2) DP_CASE(3) DP_CASE(4) DP_CASE(5) DP_CASE(6) DP_CASE(7) DP_CASE(8) DP_CASE(16)
+    default: shems_set_error("ddpg_update_dp: world size %d has no kernel instance (1-8, 16)", peers.world); return SHEMS_ERR_INVALID;
+  }
+#undef DP_CASE
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
 }
 
 // ----------------------------------------------------------------------------- update sequence
@@ -1347,10 +1452,10 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   GemmProblem g[4];
   // P10: ADAM(η_crit) on the critic
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);  // one element per thread: the Float64 div/sqrt chains need TLP
-  if (dp)  // gradient exchange over NVLink fused into the optimiser step (critic segment = first nc floats of the flat buffer)
-    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
-                                                      p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
-  else if (h->tc)
+  if (dp) {  // gradient exchange over NVLink fused into the optimiser step (critic segment = first nc floats of the flat buffer)
+    TRY(launch_adam_dp(st, h->dp, 0, nullptr, 0, 0, h->grad[1], critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
+                       p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0));
+  } else if (h->tc)
     adam_polyak_kernel<true><<<dim3((adam_grid.x + 3) / 4, h->pop), 256, 0, st>>>(critic, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2,
                                                        p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   else
@@ -1428,10 +1533,10 @@ static int enqueue_phase2(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);
   // P19: ADAM(η_act) on the actor + soft_update! of both targets (:140-143)
-  if (dp)
-    adam_polyak_dp_kernel<<<adam_grid.x, 256, 0, st>>>(h->dp, h->grad[0] - h->gradbuf, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                                      p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
-  else if (h->tc)
+  if (dp) {
+    TRY(launch_adam_dp(st, h->dp, h->grad[0] - h->gradbuf, nullptr, 0, 0, h->grad[0], actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1,
+                       p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1));
+  } else if (h->tc)
     adam_polyak_kernel<true><<<dim3((adam_grid.x + 3) / 4, h->pop), 256, 0, st>>>(actor, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
                                                        p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1, gscale, h->pop_stride);
   else
@@ -1462,17 +1567,15 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
   // every slab buffer starts on a 256-byte boundary: W2 rows are 16-byte aligned iff l2 and both W2 offsets are multiples of 4 floats
   a.vec16 = (p.l2 % 4 == 0 && da.l[1].w_off % 4 == 0 && dc.l[1].w_off % 4 == 0) ? 1 : 0;
   const int nparts = p.batch / FUSED_ROWS;
-  const unsigned adam_blocks = (unsigned)((dc.n_params + 255) / 256);
 #ifndef ADAM_PARTS_THREADS
 #define ADAM_PARTS_THREADS 256
 #endif
   const unsigned ap_blocks = (unsigned)((dc.n_params + ADAM_PARTS_THREADS - 1) / ADAM_PARTS_THREADS);   // one element per thread
   a.part = h->parts[1]; a.part_stride = dc.n_params;
   TRY(ddpg_fused_critic(st, a));
-  if (dp) {  // gradient exchange over NVLink fused into the optimiser step, as on the tiled path (enqueue_phase1)
-    parts_reduce_kernel<<<adam_blocks, 256, 0, st>>>(h->parts[1], nparts, dc.n_params, h->grad[1], dc.n_params);
-    adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, 0, critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1, p.adam_beta2, p.adam_eps,
-                                                      p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
+  if (dp) {  // partial-sum reduction, gradient exchange over NVLink and the optimiser step in ONE kernel
+    TRY(launch_adam_dp(st, h->dp, 0, h->parts[1], nparts, dc.n_params, h->grad[1], critic, h->adam_m[1], h->adam_v[1], dc.n_params, p.adam_beta1,
+                       p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0));
   } else {
     adam_polyak_parts_kernel<<<ap_blocks, ADAM_PARTS_THREADS, 0, st>>>(critic, h->parts[1], nparts, dc.n_params, h->grad[1], h->adam_m[1], h->adam_v[1], dc.n_params,
                                                            p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0);
@@ -1481,9 +1584,8 @@ static int enqueue_update_fused(Ddpg* h, cudaStream_t st, bool dp, const GatherS
   a.part = h->parts[0]; a.part_stride = da.n_params;
   TRY(ddpg_fused_actor(st, a));
   if (dp) {
-    parts_reduce_kernel<<<adam_blocks, 256, 0, st>>>(h->parts[0], nparts, da.n_params, h->grad[0], da.n_params);
-    adam_polyak_dp_kernel<<<adam_blocks, 256, 0, st>>>(h->dp, h->grad[0] - h->gradbuf, actor, h->adam_m[0], h->adam_v[0], da.n_params, p.adam_beta1, p.adam_beta2,
-                                                      p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1);
+    TRY(launch_adam_dp(st, h->dp, h->grad[0] - h->gradbuf, h->parts[0], nparts, da.n_params, h->grad[0], actor, h->adam_m[0], h->adam_v[0], da.n_params,
+                       p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic, dc.n_params, 1));
   } else {
     adam_polyak_parts_kernel<<<ap_blocks, ADAM_PARTS_THREADS, 0, st>>>(actor, h->parts[0], nparts, da.n_params, h->grad[0], h->adam_m[0], h->adam_v[0], da.n_params,
                                                            p.adam_beta1, p.adam_beta2, p.adam_eps, p.lr_actor, h->ctrl, 1, actor_t, p.tau, critic_t, critic,

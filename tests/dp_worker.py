@@ -59,6 +59,23 @@ def main():
                 else:  # TF32 products on both sides, different tiling of the batch: ADAM sign noise on near-zero gradients
                     d = np.abs(w - wf)
                     assert d.max() <= 2.0 * lrs[net] * K + 1e-6 and np.quantile(d, 0.99) <= 0.1 * lrs[net] * K + 1e-7, (net, k, d.max())
+    # a native training episode on a connected learner (ddpg_episode): every rank steps ITS OWN instances (different env ids ->
+    # different noise, different transitions), every replay() exchanges gradients -> the replicas must stay bit-identical
+    env2 = sb.Shems(T, ser, n_envs=4, device=device, env_id_base=rank * 4)
+    env2.reset(rng=5)
+    le.dp_prepare(0)
+    ret = le.episode(env2, mem, 6, train=True, sigma=0.1, rng_ep=5, updates_per_step=1)
+    assert le.dp_status() == 0
+    mine = ([le.get_layer(net, k) for net in range(4) for k in range(3)], ret.cpu().numpy())
+    everyone = [None] * world if rank == 0 else None
+    dist.gather_object(mine, everyone, dst=0)
+    if rank == 0:
+        for r in range(1, world):
+            for (w0, b0), (w, b) in zip(everyone[0][0], everyone[r][0]):
+                np.testing.assert_array_equal(w, w0)
+                np.testing.assert_array_equal(b, b0)
+            if world > 1 and torch.cuda.device_count() >= 1:
+                assert not np.array_equal(everyone[0][1], everyone[r][1])          # the ranks really saw different episodes
         print("DP_OK world=%d devices=%d batch=%d tc=%d" % (world, torch.cuda.device_count(), B, tc), flush=True)
     dist.barrier()
     dist.destroy_process_group()
