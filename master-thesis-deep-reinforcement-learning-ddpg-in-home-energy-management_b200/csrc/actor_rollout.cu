@@ -80,9 +80,9 @@ actor_rollout_kernel(const ActorRolloutArgs a) {
       s.Soc_b = raw[r * 12 + 0]; s.Soc_ev = raw[r * 12 + 1]; s.c_ev = raw[r * 12 + 2]; s.d_e = raw[r * 12 + 3]; s.g_e = raw[r * 12 + 4];
       s.p_buy = raw[r * 12 + 5];
       float B, EV;
-      shems_action_drl(a.P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, o.s0, o.s1, B, EV);
+      shems_action_drl<false>(a.P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, o.s0, o.s1, B, EV);
       StepTrace tr;
-      const StepOut so = shems_flows<WANT_TRACE>(a.P, s, B, EV, o.s1, false, &tr);
+      const StepOut so = shems_flows<WANT_TRACE, false>(a.P, s, B, EV, o.s1, false, &tr);
       const int idx = s_idx[r];
       const float4 ra = __ldg(a.series + 2 * (size_t)idx), rb = __ldg(a.series + 2 * (size_t)idx + 1);   // row idx + 1 (next_state! :264-281)
       float Soc_ev_new = so.Soc_ev;

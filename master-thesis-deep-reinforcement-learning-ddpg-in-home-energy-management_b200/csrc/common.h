@@ -62,6 +62,9 @@ struct DevParams {
   double r_eta_d, r_C_d;     // 1/Float64(eta), 1/Float64(C)
   int fast_eta_f, fast_span_f;  // host-verified over all 2^23 significands: the 3-op sequence == IEEE division
   int fast_d;                   // eta_d and C_d are Float32-valued: the 3-op sequence is provably correctly rounded
+  double span_d, r_span_d;      // Float64(span), 1/Float64(span): the Float32 quotient Soc_b / span through Float64 (fdiv_const_wide)
+  int fast_all;                 // fast_d && span Float32-valued && Float32 penalty weight && shems_LU1's reward form: kernels take the
+                                // FAST instantiation (no flag tests, no guarded division sequences) — same results
 };
 
 // ---- replay ring layout: 22 fields per transition, tiled so that one transition's fields sit at fixed

@@ -148,6 +148,8 @@ static DevParams make_dev_params(const ShemsParams& p) {
   d.fast_span_f = verify_fdiv_const(d.span);
   // eta_d and C_d are converted Float32 values by construction (<= 24 significant bits): see ddiv_const
   d.fast_d = ((double)(float)d.eta_d == d.eta_d) && ((double)(float)d.C_d == d.C_d) && d.eta_d != 0.0 && d.C_d != 0.0;
+  d.span_d = (double)d.span; d.r_span_d = 1.0 / d.span_d;
+  d.fast_all = d.fast_d && d.span_d != 0.0 && d.span == d.span && fabs(d.span_d) < 1e30 && !d.pen_f64 && d.reward_mode == 0;
   return d;
 }
 
@@ -221,14 +223,14 @@ shems_reset_kernel(DevParams P, const float4* __restrict__ series, int nrows, in
 // step!(env, s, a; track) for one instance per thread.  FROM_SERIES: the exogenous state fields are
 // taken from series row idx (they equal env.state there after reset!/step!); otherwise from obs
 // (after shems_set_state injected an arbitrary state).
-// measured (profiles/r1_step_kernel.md): 128 threads x 12 blocks/SM (40 registers) is the fastest of the sweep
+// measured (profiles/r2_step_kernel.md): 128 threads x 10 blocks/SM (48 registers, no spills) is the fastest of the sweep
 #ifndef STEP_THREADS
 #define STEP_THREADS 128
 #endif
 #ifndef STEP_MIN_BLOCKS
-#define STEP_MIN_BLOCKS 12
+#define STEP_MIN_BLOCKS 10
 #endif
-template <bool FROM_SERIES, bool WANT_TRACE>
+template <bool FROM_SERIES, bool WANT_TRACE, bool FAST>
 __global__ void __launch_bounds__(STEP_THREADS, STEP_MIN_BLOCKS)
 shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                   int32_t* __restrict__ idx_arr, const float* __restrict__ act, int track_neg,
@@ -253,12 +255,12 @@ shems_step_kernel(DevParams P, const float4* __restrict__ series, long long N, f
   float B, EV, Bt, EVt;
   if (!track_neg) {  // :346-349
     Bt = a0; EVt = a1;
-    shems_action_drl(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
+    shems_action_drl<FAST>(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
   } else {           // :350-353
     Bt = 0.0f; EVt = 0.0f; B = a0; EV = a1;
   }
   StepTrace tr;
-  const StepOut o = shems_flows<WANT_TRACE>(P, s, B, EV, EVt, track_neg != 0, &tr);
+  const StepOut o = shems_flows<WANT_TRACE, FAST>(P, s, B, EV, EVt, track_neg != 0, &tr);
   // next_state! :264-281
   const Row8 nx = load_row(series, idx + 1);
   float Soc_ev_new = o.Soc_ev;
@@ -301,7 +303,7 @@ shems_action_kernel(DevParams P, long long N, const float* __restrict__ obs, con
   if (n >= n1) return;
   float B, EV;
   if (RULE) shems_action_rule(P, obs[0 * N + n], obs[1 * N + n], obs[3 * N + n], obs[4 * N + n], B, EV);
-  else shems_action_drl(P, obs[0 * N + n], obs[1 * N + n], obs[2 * N + n], obs[3 * N + n], obs[4 * N + n], target[n], target[N + n], B, EV);
+  else shems_action_drl<false>(P, obs[0 * N + n], obs[1 * N + n], obs[2 * N + n], obs[3 * N + n], obs[4 * N + n], target[n], target[N + n], B, EV);
   bev[n] = B;
   bev[N + n] = EV;
 }
@@ -330,7 +332,7 @@ struct RolloutSinks {
 // MINB = resident CTAs per SM the register budget is cut for (6: 80 registers, 7: 72, 8: 64).  6 is the fastest per wave; 7 or 8 are
 // chosen when they save a mostly empty last wave (e.g. 2^20 instances over 8 GPUs = 1024 CTAs per GPU: 1.15 waves of 148 x 6 CTAs,
 // but ONE wave of 148 x 7) — see rollout_min_blocks().
-template <int POLICY, bool WANT_TRACE, int MINB>
+template <int POLICY, bool WANT_TRACE, int MINB, bool FAST>
 __global__ void __launch_bounds__(ROLLOUT_THREADS, MINB)
 shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N, float* __restrict__ obs,
                      int32_t* __restrict__ idx_arr, int T, int step0, unsigned long long seed, long long env_id_base,
@@ -377,10 +379,10 @@ shems_rollout_kernel(DevParams P, const float4* __restrict__ series, long long N
           EVt = (float)(((double)a_raw1 + 1.0) * 0.5);
         }
       }
-      shems_action_drl(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
+      shems_action_drl<FAST>(P, s.Soc_b, s.Soc_ev, s.c_ev, s.d_e, s.g_e, Bt, EVt, B, EV);
     }
     StepTrace tr;
-    const StepOut o = shems_flows<WANT_TRACE>(P, s, B, EV, EVt, track_neg, &tr);
+    const StepOut o = shems_flows<WANT_TRACE, FAST>(P, s, B, EV, EVt, track_neg, &tr);
     const Row8 nx = load_row(series, idx + 1);
     float Soc_ev_new = o.Soc_ev;
     if (nx.cd >= 0.0f && cd_here == -1.0f) Soc_ev_new = nx.soc_ev;
@@ -615,8 +617,12 @@ extern "C" int32_t shems_step(ShemsEnv* e, const float* act_dev, int32_t track, 
   const int tn = track < 0 ? 1 : 0;
 #define LAUNCH_STEP(FS, TR)                                                                                                             \
   COUNT_LAUNCH();                                                                                                                       \
-  shems_step_kernel<FS, TR><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, \
-                                                                                            act_dev, tn, reward_dev, reward64_dev, obs_dev, trace_dev, n0, n1)
+  if (!TR && e->gdp[g].fast_all)                                                                                                        \
+    shems_step_kernel<FS, false, true><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(                                   \
+        e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, act_dev, tn, reward_dev, reward64_dev, obs_dev, trace_dev, n0, n1);              \
+  else                                                                                                                                  \
+    shems_step_kernel<FS, TR, false><<<grid_for(n1 - n0, STEP_THREADS), STEP_THREADS, 0, e->stream>>>(                                     \
+        e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, act_dev, tn, reward_dev, reward64_dev, obs_dev, trace_dev, n0, n1)
   for (int g = 0; g < e->n_groups; ++g) {
     const long long n0 = e->gstart[g], n1 = e->gstart[g + 1];
     if (e->consistent) { if (trace_dev) { LAUNCH_STEP(true, true); } else { LAUNCH_STEP(true, false); } }
@@ -712,9 +718,11 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
     REQUIRE(e->n <= rp->capacity, SHEMS_ERR_INVALID, "shems_rollout: replay capacity %lld < n_envs %lld", (long long)rp->capacity, (long long)e->n);
     S.ring = rp->ring; S.cap = rp->capacity; S.head = rp->head;
   }
-#define LAUNCH_RO(POL, TR, MB)                                                                                                      \
-  shems_rollout_kernel<POL, TR, MB><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                              \
+#define LAUNCH_RO_F(POL, TR, MB, FA)                                                                                                \
+  shems_rollout_kernel<POL, TR, MB, FA><<<grid_for(n1 - n0, ROLLOUT_THREADS), ROLLOUT_THREADS, 0, e->stream>>>(                          \
       e->gdp[g], e->gseries[g], e->n, e->obs, e->idx, a->n_steps, e->step, a->seed, a->env_id_base, a->tape_dev, a->tape_unscaled, S, n0, n1)
+#define LAUNCH_RO(POL, TR, MB)                                                                                                      \
+  do { if (!TR && e->gdp[g].fast_all) LAUNCH_RO_F(POL, false, MB, true); else LAUNCH_RO_F(POL, TR, MB, false); } while (0)
 #define LAUNCH_RO_MB(POL)                                                                                                           \
   do {                                                                                                                              \
     if (tr) LAUNCH_RO(POL, true, ROLLOUT_MIN_BLOCKS);                                                                               \
@@ -735,6 +743,7 @@ extern "C" int32_t shems_rollout(ShemsEnv* e, const ShemsRolloutArgs* a) {
   }
 #undef LAUNCH_RO_MB
 #undef LAUNCH_RO
+#undef LAUNCH_RO_F
   CUDA_TRY(cudaGetLastError());
   e->max_idx += a->n_steps;
   e->step += a->n_steps;

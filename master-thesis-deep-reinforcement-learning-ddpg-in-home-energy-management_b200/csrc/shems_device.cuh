@@ -38,6 +38,16 @@ __device__ __forceinline__ float fdiv_const(float x, float d, float r, int ok) {
   const float e = fmaf(-q, d, x);
   return fmaf(e, r, q);
 }
+// The same Float32 quotient through Float64, branch-free and without a guard: RN32(RN64(x / d)) == RN32(x / d) for every pair of
+// Float32 operands (double rounding is innocuous for division once the wide format has >= 2p + 2 = 50 significant bits), and
+// RN64(x / d) is what ddiv_const (below) delivers for a Float32-valued constant divisor.  Every Float32 — subnormals included — is
+// a normal double, so no operand needs the IEEE fallback; x = 0 gives 0.  xd = (double)x is passed in because the callers need it anyway.
+__device__ __forceinline__ double ddiv_const(double x, double d, double r, int ok);
+__device__ __forceinline__ float fdiv_const_wide(double xd, double d_d, double r_d) {
+  const double q = xd * r_d;
+  const double e = fma(-q, d_d, xd);
+  return (float)fma(e, r_d, q);
+}
 // Float64 with a divisor that is a converted Float32 (<= 24 significant bits): q + e*r differs from x/d by
 // < 2^-105 relative, while x/d is either exactly representable-or-farther than 2^-77 relative from any
 // rounding midpoint (x - m*d lies on a grid of 2^-76 |x| and cannot vanish for a 54-bit odd m), so
@@ -49,10 +59,16 @@ __device__ __forceinline__ double ddiv_const(double x, double d, double r, int o
   return fma(e, r, q);
 }
 
+// FAST (template parameter of everything below) = the constants are in their usual state — P.fast_all: Float32-valued divisors,
+// Float32 penalty weight, shems_LU1's reward form — so the flag tests, the fall-back branches and the guarded Float32 division
+// sequences are compiled out (the Float32 quotients go through fdiv_const_wide).  Both instantiations give the same bits.
+
 // action(env, a::ShemsAction) :283-316 -> Float32.([B, EV])
+template <bool FAST>
 __device__ __forceinline__ void shems_action_drl(const DevParams& P, float Soc_b, float Soc_ev, float c_ev, float d_e,
                                                  float g_e, float Bt, float EVt, float& B, float& EV) {
-  const float perc = fdiv_const(Soc_b - P.smin, P.span, P.r_span_f, P.fast_span_f);       // :288
+  const float sb0 = Soc_b - P.smin;
+  const float perc = FAST ? fdiv_const_wide((double)sb0, P.span_d, P.r_span_d) : fdiv_const(sb0, P.span, P.r_span_f, P.fast_span_f);   // :288
   EV = (c_ev > -1.0f && Soc_ev < EVt) ? jl_minf(P.evR, (EVt - Soc_ev) * P.C) : 0.0f;      // :292-297
   const float pv = (g_e - d_e) - EV;                                                      // :301
   // :304-313 evaluated branch-free: charge request / discharge request / nothing
@@ -83,7 +99,7 @@ static __device__ __noinline__ double shems_discomfort_term(int reward_form, dou
   return (pot == 1.0) ? dwd : (pot == 2.0) ? dwd * dwd : pow(dwd, pot);
 }
 
-template <bool WANT_TRACE>
+template <bool WANT_TRACE, bool FAST>
 __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn& s, float B, float EV, float EVt,
                                                bool track_neg, StepTrace* tr) {
   const float eta = P.b_eta;
@@ -100,14 +116,14 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   const float PV_EV = A ? (A1 ? EV : pvr) : 0.0f;   // :372 / :375
   const float pv = A1 ? (pvr - EV) : 0.0f;   // :373 / :376 / :390  (Float32, or the Int 0)
   // battery stage 1 (branch B only): the residual demand dB   :392-408
-  const float q1 = fdiv_const(dB, eta, P.r_eta_f, P.fast_eta_f);
+  const float q1 = FAST ? fdiv_const_wide((double)dB, eta_d, P.r_eta_d) : fdiv_const(dB, eta, P.r_eta_f, P.fast_eta_f);
   const bool cover1 = (!A) && (BD0 > (double)q1);
   const double B_DE = A ? 0.0 : (cover1 ? (double)dB : BD0 * eta_d);              // :393 / :404
   const double GR_DE = (A || cover1) ? 0.0 : ((double)dB - B_DE);                 // :406
   const double BD1 = A ? BD0 : (cover1 ? BD0 - (double)q1 : 0.0);                 // :394 / :405
   // battery stage 2: the EV share not served by PV — x2 = EV - PV_EV (:377-384); in branch B it is EV itself (:395-402)
   const float x2 = EV - PV_EV;
-  const float q2 = fdiv_const(x2, eta, P.r_eta_f, P.fast_eta_f);
+  const float q2 = FAST ? fdiv_const_wide((double)x2, eta_d, P.r_eta_d) : fdiv_const(x2, eta, P.r_eta_f, P.fast_eta_f);
   const bool act2 = A ? (!A1) : cover1;
   const bool cover2 = act2 && (BD1 > (double)q2);
   const double B_EV = cover2 ? (double)x2 : (act2 ? BD1 * eta_d : 0.0);           // :378/:396, :381/:399
@@ -120,7 +136,7 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   double PV_B = 0.0, X = (double)s.Soc_b, pv_d = (double)pv;
   if (B > 0.01f) {
     const double BC = jl_clampd((double)B, 0.001, jl_mind(P.R, (double)(P.smax - s.Soc_b)));   // :413
-    const double thr = ddiv_const(BC, eta_d, P.r_eta_d, P.fast_d);
+    const double thr = ddiv_const(BC, eta_d, P.r_eta_d, FAST ? 1 : P.fast_d);
     const bool c1 = pv_d > thr;              // :414
     const float pvb = pv * eta;              // :418 stays Float32 (pv_ is Float32 or the Int 0)
     PV_B = c1 ? BC : (double)pvb;
@@ -130,8 +146,8 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   // :432  (1 - loss) * (Soc_b + PV_B + GR_B - (B_DE + B_EV + B_GR) / eta)
   double Y = 0.0;
   if (BD0 > 0.0) {  // without a discharge budget B_DE = B_EV = 0 and the quotient is 0
-    const double Yd = ddiv_const(B_DE + B_EV, eta_d, P.r_eta_d, P.fast_d);
-    const float Yf = fdiv_const(f32sum, eta, P.r_eta_f, P.fast_eta_f);
+    const double Yd = ddiv_const(B_DE + B_EV, eta_d, P.r_eta_d, FAST ? 1 : P.fast_d);
+    const float Yf = FAST ? fdiv_const_wide((double)f32sum, eta_d, P.r_eta_d) : fdiv_const(f32sum, eta, P.r_eta_f, P.fast_eta_f);
     Y = leafB1a ? (double)Yf : Yd;
   }
   StepOut o;
@@ -139,7 +155,7 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   // :435  Soc_ev + (PV_EV + B_EV + GR_EV) / (ev.soc_max - ev.soc_min)
   const double T = leafA2a ? (double)f32sum : (((double)PV_EV + B_EV) + GR_EV);
   float Soc_ev_new = s.Soc_ev;
-  if (T != 0.0) Soc_ev_new = (float)((double)s.Soc_ev + ddiv_const(T, P.C_d, P.r_C_d, P.fast_d));
+  if (T != 0.0) Soc_ev_new = (float)((double)s.Soc_ev + ddiv_const(T, P.C_d, P.r_C_d, FAST ? 1 : P.fast_d));
   // :438-449
   float disc = 0.0f, EX_EV = 0.0f;
   double pen = 0.0;
@@ -152,7 +168,7 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
     // shems_LU1: Float32 product with penalty_weight::Float32; LU7 / input0607: penalty_weight is a Float64 -> Float64 product
     const float om = 1.0f - EVt;
     pen = (double)(om * P.pw);
-    if (P.pen_f64) pen = (double)om * P.pw_d;
+    if (!FAST && P.pen_f64) pen = (double)om * P.pw_d;
   }
   o.Soc_ev = Soc_ev_new;
   // :464  profit = (sell * p_buy * (PV_GR + B_GR)) - (p_buy * (GR_DE + GR_B + GR_EV + EX_EV))   [Float64]
@@ -161,7 +177,7 @@ __device__ __forceinline__ StepOut shems_flows(const DevParams& P, const StepIn&
   const double dd = (double)disc;
   // Float32^Float64 promotes; x*x is exact for F32 x, x^1.0 is x
   double dterm = P.dw * (dd * dd);                                   // reward_mode 0: shems_LU1's w * discomfort^2
-  if (P.reward_mode != 0) dterm = shems_discomfort_term(P.reward_form, P.dw, P.pot, dd);      // every other combination (uniform branch, off the hot path)
+  if (!FAST && P.reward_mode != 0) dterm = shems_discomfort_term(P.reward_form, P.dw, P.pot, dd);      // every other combination (uniform branch, off the hot path)
   const double base = profit - dterm;
   if (track_neg) pen = 0.0;  // :466-468
   o.reward = track_neg ? base : (base - pen);
