@@ -602,13 +602,13 @@ def main():
     achieved = ALG_BYTES_PER_ENV_STEP * n * T / (kern_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture, scaled per env-step
     traffic = traffic_src = None
-    tpath = os.path.join(ROOT, "profiles", "r1_rollout_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_rollout_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_per_env_step"] * n * T
-        traffic_src = f"profiles/r1_rollout_traffic.json: {tj['dram_bytes_per_env_step']:.2f} DRAM B/env-step ({tj['capture']}) x env-steps of this launch"
+        traffic_src = f"profiles/r2_rollout_traffic.json: {tj['dram_bytes_per_env_step']:.2f} DRAM B/env-step ({tj['capture']}) x env-steps of this launch"
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
-                    kernel="shems_rollout_kernel<POLICY_RANDOM>", kernel_ms=kern_ms,
+                    kernel="shems_rollout_kernel<POLICY_RANDOM, no trace, FAST>", kernel_ms=kern_ms,
                     algorithmic_bytes_per_launch=ALG_BYTES_PER_ENV_STEP * n * T, peak_source=peak_src)
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=DTYPE, data="synthetic",

@@ -25,19 +25,54 @@ CAPACITIES = {
 }
 
 
-class Consts:
-    """pv, b, ev, m and penalty_weight of the module (:40-43, :67-99) for one charger id (JOB_ID digits, :45)."""
+# shems_LU7.jl:42-55: ev_capacities::Dict{Int, Float64} of Float32 literals (ids 1-9, 98, 99)
+LU7_EV_CAPACITIES = {k: F64(v[0]) for k, v in CAPACITIES.items() if k != 97}
+LU7_EV_CAPACITIES[99] = F64(F32(35.816))
 
-    def __init__(self, charger_id=98):
-        cap = CAPACITIES[charger_id]                      # KeyError like the reference (:95)
+
+class Consts:
+    """pv, b, ev, m and penalty_weight of the module (:40-43, :67-99) for one charger id (JOB_ID digits, :45).
+    variant: "LU1" (shems_LU1.jl), "LU7" (shems_LU7.jl) or "INPUT0607" (shems_LU1_input0607.jl with fourth ternary digit 0) — the
+    sibling files differ in these constants and in the reward line only (reward_line below)."""
+
+    def __init__(self, charger_id=98, variant="LU1"):
+        self.variant = variant
         self.pv_eta = F32(1)                              # PV(1f0) :92
-        self.b_eta, self.b_soc_min, self.b_soc_max = F32(0.95), F32(0), cap[1]   # Battery(0.95f0, 0f0, cap, rate, 0.00003f0) :95
-        self.b_rate_max, self.b_loss = cap[2], F32(0.00003)
-        self.ev_soc_min, self.ev_soc_max, self.ev_rate_max = F32(0), cap[0], F32(11)   # :97
+        self.ev_soc_min, self.ev_rate_max, self.b_loss = F32(0), F32(11), F32(0.00003)
+        self.b_eta, self.b_soc_min = F32(0.95), F32(0)
+        if variant == "LU7":
+            # Battery(0.95f0, 0f0, 10f0, 4.6f0, 0.00003f0) shems_LU7.jl:91 (rate_max::Float64 <- 4.6f0); Market(0.3f0, 1) :94
+            self.b_soc_max, self.b_rate_max = F32(10), F64(F32(4.6))
+            self.ev_soc_max = F32(LU7_EV_CAPACITIES[charger_id])      # ::Float32 field <- the Float64 dict value
+            self.sell_discount = F64(F32(0.3))
+            self.discomfort_weight_ev = F64(1)            # DISCOMFORT_WEIGHT_EV = 1 (Int) -> Float64 field
+            self.disc_pot = None                          # the struct has no disc_pot: the reward line is linear (:465-468)
+            self.penalty_weight = F64(0.1)                # penalty_weight = 0.1 (Float64) :35
+            return
+        cap = CAPACITIES[charger_id]                      # KeyError like the reference (:95)
+        if variant == "INPUT0607" and charger_id == 97:
+            raise KeyError(97)                            # shems_LU1_input0607.jl:57-68 has no charger 97
+        self.b_soc_max, self.b_rate_max = cap[1], cap[2]  # Battery(0.95f0, 0f0, cap, rate, 0.00003f0) :95
+        self.ev_soc_max = cap[0]                          # :97
         self.sell_discount = F64(F32(0.2))                # Market(0.2f0, DISCOMFORT_WEIGHT_EV, DISC_POT) with Float64 fields :85-89, :99
-        self.discomfort_weight_ev = F64(F32(0.01))
-        self.disc_pot = F64(F32(2))
-        self.penalty_weight = F32(0.1)                    # :43
+        if variant == "INPUT0607":
+            self.discomfort_weight_ev = F64(F32(0.1))     # fourth ternary digit 0 (shems_LU1_input0607.jl:38-47)
+            self.disc_pot = F64(F32(1))                   # DISC_POT = 1f0 (:49)
+            self.penalty_weight = F64(0.1)                # penalty_weight = 0.1 (Float64) (:52)
+        else:
+            self.discomfort_weight_ev = F64(F32(0.01))
+            self.disc_pot = F64(F32(2))
+            self.penalty_weight = F32(0.1)                # :43
+
+    def discomfort_term(self, discomfort):
+        """the discomfort part of the reward line: shems_LU1.jl:467-470 w * discomfort^pot; shems_LU7.jl:465-468 discomfort * w;
+        shems_LU1_input0607.jl:481-484 (discomfort * w)^pot.  discomfort is the Int 0 or a Float32."""
+        if self.variant == "LU7":
+            return discomfort * self.discomfort_weight_ev                     # Int/Float32 * Float64 -> Float64
+        d = F64(0) if isinstance(discomfort, int) else F64(discomfort)        # promotion of Int / Float32 next to a Float64
+        if self.variant == "INPUT0607":
+            return (d * self.discomfort_weight_ev) ** self.disc_pot
+        return self.discomfort_weight_ev * (d ** self.disc_pot)
 
 
 def jl_min(x, y):
@@ -211,15 +246,12 @@ def step(K, series, state, idx, a, track=0):
                  F32(col["season"][nidx - 1])]
     # reward :464-471 (p_buy is the pre-step price)
     profit = (K.sell_discount * p_buy * (PV_GR + B_GR)) - (p_buy * (GR_DE + GR_B + GR_EV + EX_EV))
-    if isinstance(discomfort, int):
-        disc_pow = F64(0) ** K.disc_pot                                             # 0::Int ^ 2.0 -> 0.0
-    else:
-        disc_pow = F64(discomfort) ** K.disc_pot                                    # Float32 ^ Float64 promotes
+    dterm = K.discomfort_term(discomfort)                                           # 0::Int ^ 2.0 -> 0.0; Float32 ^ Float64 promotes
     if track < 0:
-        reward = profit - K.discomfort_weight_ev * disc_pow
+        reward = profit - dterm
         penalty = 0
     else:
-        reward = profit - K.discomfort_weight_ev * disc_pow - penalty
+        reward = profit - dterm - penalty
     results = [nidx, c_ev, EV_target, EV, Soc_ev, reward, profit, discomfort, penalty, PV_DE, B_DE, GR_DE,
                PV_B, PV_GR, PV_EV, B_EV, GR_EV, EX_EV, GR_B, B_GR, B, B_target, Soc_b]                    # :476-478
     return F64(reward), np.array(new_state, F32), nidx, np.array([F64(v) for v in results], F64), tags

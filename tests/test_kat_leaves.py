@@ -98,11 +98,33 @@ def test_other_chargers_bit_for_bit(O, charger98_test_series, cid):
         assert r == ro and s2.tobytes() == so.tobytes() and np.array_equal(tr, tro), i
 
 
+@pytest.mark.parametrize("variant,vid,cid", [("LU7", 1, 98), ("LU7", 1, 4), ("INPUT0607", 2, 98), ("INPUT0607", 2, 6)])
+def test_sibling_envs_bit_for_bit(O, charger98_test_series, variant, vid, cid):
+    """shems_LU7.jl / shems_LU1_input0607.jl: other constants, a Float64 penalty weight and another reward line"""
+    ser = charger98_test_series
+    K, P = J.Consts(cid, variant), O.params_for_env(vid, cid)
+    assert float(K.b_soc_max) == P.b_soc_max and float(K.ev_soc_max) == P.ev_soc_max and float(K.b_rate_max) == P.b_rate_max
+    assert float(K.sell_discount) == P.sell_discount
+    cs = Cs.make_cases(ser, 3000, seed=100 + cid, charger_id=98)
+    cs["state"][:, 0] = np.minimum(cs["state"][:, 0], np.float32(K.b_soc_max))
+    seen = set()
+    for i in range(3000):
+        r, s2, i2, tr, tags = J.step(K, ser, cs["state"][i], int(cs["idx"][i]), cs["a"][i], cs["track"][i])
+        ro, so, io, tro = O.step_single(P, ser, cs["state"][i], int(cs["idx"][i]), cs["a"][i], cs["track"][i])
+        assert r == ro and s2.tobytes() == so.tobytes() and np.array_equal(tr, tro), (i, tags, r, ro)
+        seen.add(tags["tail"])
+    assert seen == Cs.TAILS
+
+
 def test_unknown_charger_is_a_key_error(O):
     with pytest.raises(KeyError):
         J.Consts(42)
     with pytest.raises(KeyError):
         O.params_for_charger(42)
+    with pytest.raises(KeyError):
+        J.Consts(97, "INPUT0607")
+    with pytest.raises(KeyError):
+        O.params_for_env(2, 97)
 
 
 def test_reset_bit_for_bit(O, P98, charger98_test_series):
