@@ -511,6 +511,7 @@ struct Ddpg {
   bool ctrl_init;
   int ld1, ld2;    // leading dimensions of the [B][l1] / [B][l2] activation buffers (l1, l2 rounded up to 32 floats = 128 bytes)
   bool tc;         // layer-2 contractions on TF32 tensor cores (use_tensor_cores, batch >= 256, operands 16-byte aligned)
+  bool chain;      // one learner in tensor-core mode at widths l1 <= 256, l2 <= 512: a net's whole forward pass is ONE kernel (tc_fwd_chain)
   unsigned* counters;  // [WS_COUNTERS] arrival counters of the fused slab reductions (zero between kernels)
   float* ws;       // split-K workspace (tensor-core dW, SIMT dW with K = batch >= 1024, bias-gradient partial sums)
   long long ws_floats;
@@ -544,6 +545,7 @@ static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows
 #define TC_MIN_ROWS 256
 #endif
 #define SPLITK_MIN_BATCH 1024
+#define CHAIN_MIN_BATCH 6144
 #define SPLITK_MAX 32
 #define WS_COUNTERS 1024
 
@@ -611,6 +613,13 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
     if (e_ != cudaSuccess) { shems_set_error("ddpg_create: side stream/events -> %s", cudaGetErrorString(e_)); ddpg_destroy(h); return SHEMS_ERR_CUDA; }
   }
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
+  {
+    const char* ev = getenv("SHEMS_TC_CHAIN");
+    // measured (tools/time_ddpg_large.py): 227 vs 252 us per update at B = 8192 and 336 vs 412 at 16384, but 175 vs 171 at 4096 and 144 vs 119 at 1024 (8 tiles per net leave the
+    // per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
+    h->chain = h->tc && pop == 1 && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
+               (ev ? ev[0] != '0' : p->batch >= CHAIN_MIN_BATCH);
+  }
   // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
   struct Carve { float** ptr; long long count; };
@@ -1351,6 +1360,18 @@ static int side_join(Ddpg* h, cudaStream_t st) {                     // `st` con
   return SHEMS_OK;
 }
 static inline bool use_tc(const Ddpg* h, long long rows) { return h->tc && rows * h->pop >= TC_MIN_ROWS; }
+// forward-chain problem q: net `w` (flat Flux buffer, dims d) on the inputs X [B][11] (first K1 columns)
+static inline void chain_set(TcFwdChainArgs& a, int q, const float* X, const float* w, const NetDims& d, float* H1, float* H2, int mode, float* out, int ldo) {
+  a.X[q] = X; a.K1[q] = d.l[0].in;
+  a.W1[q] = w + d.l[0].w_off; a.b1[q] = w + d.l[0].b_off; a.W2[q] = w + d.l[1].w_off; a.b2[q] = w + d.l[1].b_off;
+  a.W3[q] = w + d.l[2].w_off; a.b3[q] = w + d.l[2].b_off; a.J[q] = d.l[2].out;
+  a.H1[q] = H1; a.H2[q] = H2; a.out_mode[q] = mode; a.out[q] = out; a.ldo[q] = ldo;
+}
+static inline TcFwdChainArgs chain_args(const Ddpg* h, int nprob) {
+  TcFwdChainArgs a; memset(&a, 0, sizeof(a));
+  a.M = h->p.batch; a.L1 = h->p.l1; a.L2 = h->p.l2; a.nprob = nprob; a.ldx = 11; a.ldh1 = h->ld1; a.ldh2 = h->ld2;
+  return a;
+}
 
 // one replay() after the minibatch has been gathered ("DDPG update"), in three phases so that a data-parallel
 // learner can all-reduce the flat gradient buffer between them:
@@ -1367,6 +1388,20 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC], *actor_t = h->net[DDPG_NET_ACTOR_TARGET], *critic_t = h->net[DDPG_NET_CRITIC_TARGET];
   GemmProblem g[4];
+  if (tc && h->chain) {
+    // the forward passes as whole-net kernels (csrc/tc_gemm.cu tc_fwd_chain_kernel): layer 1 -> tcgen05 layer 2 -> output layer
+    // actor_target(s'_n) -> a' | critic(s_n, a) -> q | actor(s_n) -> vcat(s_n, actions)      (DDPG.jl:131, :114, :117)
+    TcFwdChainArgs a = chain_args(h, 3);
+    chain_set(a, 0, h->xs2, actor_t, da, nullptr, nullptr, TC_OUT_TANH, h->xs2 + 9, 11);
+    chain_set(a, 1, h->xs, critic, dc, h->c_h1, h->c_h2, TC_OUT_ID, h->q, 1);
+    chain_set(a, 2, h->xs, actor, da, h->a_h1, h->a_h2, TC_OUT_TANH, h->xspi + 9, 11);
+    TRY(tc_fwd_chain(st, a));
+    // q' = critic_target(vcat(s'_n, a'));  y = r + gamma (1 - done) q';  dq = 2 (q - y) / B     (:132-133)
+    TcFwdChainArgs t = chain_args(h, 1);
+    chain_set(t, 0, h->xs2, critic_t, dc, nullptr, nullptr, TC_OUT_TD, h->y, 1);
+    t.td_r = h->r; t.td_done = h->done; t.td_q = h->q; t.td_dq = h->dq; t.gamma = p.gamma; t.inv_batch = 1.0f / (float)B;
+    TRY(tc_fwd_chain(st, t));
+  } else {
   // P1-P3: actor_target(s'_n) | critic(s_n, a) | actor(s_n)     (DDPG.jl:131, :114, :117)
   if (big) {
     const float* X[3] = {h->xs2, h->xs, h->xs}; const float* nets[3] = {actor_t, critic, actor};
@@ -1411,6 +1446,7 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
   g[0] = gp_fwd(h->tc_h2, l2, B, critic_t, dc.l[2], h->y, 1, EPI_TD_TARGET);
   g[0].aux = h->r; g[0].aux2 = h->done; g[0].aux3 = h->q; g[0].out2 = h->dq; g[0].alpha = p.gamma; g[0].inv_batch = 1.0f / (float)B;
   TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
+  }
   // P7-P9: critic backward (:137, :105-108)
   if (big) {
     // the dX chain (dz2 -> dz1 -> dW1) is the critical path; dW3, dW2 and their bias sums run beside it on the side stream
@@ -1463,14 +1499,20 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
                                                         p.adam_eps, p.lr_critic, h->ctrl, 0, nullptr, 0.0f, nullptr, nullptr, 0, 0, gscale, h->pop_stride);
   CUDA_TRY(cudaGetLastError());
   // P11-P13: critic(vcat(s_n, actor(s_n))) with the UPDATED critic (:116-119); loss_act = -mean(q) => dq = -1/B
-  if (big) {
+  const bool chain = tc && h->chain;
+  if (chain) {  // one kernel: p_h1, p_h2 (for the backward pass) and q(s, actor(s)) itself (reporting)
+    TcFwdChainArgs a = chain_args(h, 1);
+    chain_set(a, 0, h->xspi, critic, dc, h->p_h1, h->p_h2, TC_OUT_ID, h->qpi, 1);
+    TRY(tc_fwd_chain(st, a));
+  } else if (big) {
     const float* X[1] = {h->xspi}; const float* nets[1] = {critic}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->p_h1};
     TRY(big_l1(st, 1, X, 11, B, nets, Ls, Y, l1, h->pop, h->pop_stride, h->pop_stride));
   } else {
     g[0] = gp_fwd(h->xspi, 11, B, critic, dc.l[0], h->p_h1, l1, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
-  if (tc) TRY(tc_fwd(h, st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, h->pop_stride));
+  if (chain) { }
+  else if (tc) TRY(tc_fwd(h, st, h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, h->pop_stride));
   else {
     g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
@@ -1493,8 +1535,10 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   if (big) {  // as in the critic's backward pass: dW3, dW2 (and the reporting-only q(s, actor(s))) beside the dX chain
     TRY(side_after(h, st, h->ev_fork));                                                                       // dza3 is ready
     TRY(out_bwd_dw(h, h->side, h->a_h2, l2, h->dza3, 2, B, da.l[2], h->grad[0], true));
-    g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
-    TRY(launch_gemms(h->side, g, 1, h->pop, h->pop_stride, h->pop_stride));
+    if (!chain) {
+      g[0] = gp_fwd(h->p_h2, l2, B, critic, dc.l[2], h->qpi, 1, EPI_BIAS_ID);
+      TRY(launch_gemms(h->side, g, 1, h->pop, h->pop_stride, h->pop_stride));
+    }
     TRY(launch_outer_mask(h, st, h->dza3, 2, actor + da.l[2].w_off, h->a_h2, l2, B, p.l2, h->dza2));
     TRY(side_after(h, st, h->ev_mid));                                                                        // dza2 is ready
     if (tc) {

@@ -336,6 +336,226 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------- forward chain
+// One net's WHOLE forward pass for a 128-row tile of a large minibatch in one CTA (large-batch replay(), DDPG.jl:131-132, :114, :117):
+//   h1 = relu(x W1 + b1)        fp32 SIMT by 8 producer warps (thread = 4 rows x 4 columns of a k-block, the rows' inputs held in
+//                               registers for the whole kernel, W1 and b1 in shared memory), written k-block by k-block straight into the
+//                               128B-swizzled K-major A operand in shared memory (128 KB, resident for both column halves); when the
+//                               backward pass needs h1 the finished k-blocks are sent to HBM by TMA stores FROM that operand
+//   h2 = relu(h1 W2 + b2)       tcgen05.mma kind::tf32, 128 x 256 x 8 per instruction, W2 streamed by TMA (MN-major, as Flux stores it)
+//                               through a 3-stage ring of 16-k slabs; the two 256-column halves have their own TMEM accumulators, so the
+//                               epilogue of half 0 runs under the MMAs of half 1
+//   out = f(h2 W3 + b3)         in the epilogue: a thread owns one row and both halves, so the output layer's dot product (1 or 2
+//                               units) never leaves its registers; f = tanh (actor -> written into the critic's input rows), identity
+//                               (q), or the TD target y = r + gamma (1 - done) q' with dq = 2 (q - y) / B (DDPG.jl:133)
+// Replaces l1_fwd_kernel + tc_gemm_kernel + gemm_skinny_kernel (3 launches and two round trips of the activations through HBM per net).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocation + MMA issue (+ the h1 stores), warps 2-9 layer-1 producers,
+// warps 2-5 epilogue.
+constexpr int FC_THREADS = 320, FC_N = 256, FC_KB = 8, FC_BSTAGES = 3, FC_BK = 16;
+constexpr int FC_A_BYTES = FC_KB * TILE_BYTES;                 // 8 k-blocks x 16 KB
+constexpr int FC_B_STAGE = FC_N * FC_BK * 4;                   // 16 KB: 8 chunks of [16 k][32 columns]
+constexpr int FC_SMEM = FC_A_BYTES + FC_BSTAGES * FC_B_STAGE + 4 * 4096 + 1024;
+constexpr int FC_G = 2 * FC_KB * (BLOCK_K / FC_BK);            // B slabs per tile: 2 halves x 16
+
+// -DFC_TRACE: globaltimer stamps of CTA 0 (tools/time_ddpg_large.py with a *fctrace* build): [0..31] TMA slab issued, [32..63] MMA slab
+// committed, [64..71] layer-1 k-block written (warp 2), [72] start, [73] acc 0 seen, [74] epilogue half 0 done, [75] acc 1 seen, [76] end
+#ifdef FC_TRACE
+__device__ unsigned long long fc_trace[96];
+#define FC_STAMP(i) do { if (blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); fc_trace[i] = t_; } } while (0)
+#else
+#define FC_STAMP(i) do { } while (0)
+#endif
+__global__ void __launch_bounds__(FC_THREADS, 1)
+tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + FC_A_BYTES;
+  uint8_t* staging = sB + FC_BSTAGES * FC_B_STAGE;
+  __shared__ uint64_t a_full[FC_KB], b_full[FC_BSTAGES], b_empty[FC_BSTAGES], acc_full[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float w1s[12][FC_KB * BLOCK_K];   // rows 0..K1-1: W1 (zero beyond l1), rows K1..10: zero, row 11: b1 (its input is 1)
+  __shared__ __align__(16) float b2s[2 * FC_N];
+  __shared__ __align__(16) float w3s[2][2 * FC_N];            // W3[:, j] (zero beyond l2)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int prob = blockIdx.x / mt, m0 = (blockIdx.x - prob * mt) * BLOCK_M;
+  const int K1 = p.K1[prob], J = p.J[prob];
+  for (int e = threadIdx.x; e < 12 * FC_KB * BLOCK_K; e += FC_THREADS) {
+    const int i = e / (FC_KB * BLOCK_K), n = e - i * (FC_KB * BLOCK_K);
+    float v = 0.0f;
+    if (n < p.L1) v = i < K1 ? __ldg(p.W1[prob] + (long long)i * p.L1 + n) : (i == 11 ? __ldg(p.b1[prob] + n) : 0.0f);
+    w1s[i][n] = v;
+  }
+  for (int n = threadIdx.x; n < 2 * FC_N; n += FC_THREADS) {
+    const bool ok = n < p.L2;
+    b2s[n] = ok ? __ldg(p.b2[prob] + n) : 0.0f;
+    w3s[0][n] = ok ? __ldg(p.W3[prob] + (long long)n * J) : 0.0f;
+    w3s[1][n] = (ok && J == 2) ? __ldg(p.W3[prob] + (long long)n * J + 1) : 0.0f;
+  }
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < FC_KB; ++k) mbar_init(&a_full[k], 8);          // one arrival per producer warp
+    for (int s = 0; s < FC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b[prob]) : "memory");
+    if (p.H1[prob]) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[prob]) : "memory");
+    if (p.H2[prob]) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.d[prob]) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===== TMA producer: W2[16-k slab][column half] as the MN-major B operand, 8 boxes of {32 columns, 16 k} per slab =====
+    if (elect_one()) {
+      for (int g = 0; g < FC_G; ++g) {
+        const int h = g / (FC_G / 2), k16 = g - h * (FC_G / 2), s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+        mbar_wait(&b_empty[s], ph ^ 1);
+        FC_STAMP(g);
+        mbar_expect_tx(&b_full[s], FC_B_STAGE);
+        uint8_t* sb = sB + s * FC_B_STAGE;
+#pragma unroll
+        for (int j = 0; j < FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], h * FC_N + j * 32, k16 * FC_BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(FC_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    if (elect_one()) {
+      const bool store_h1 = p.H1[prob] != nullptr;
+      for (int g = 0; g < FC_G; ++g) {
+        const int h = g / (FC_G / 2), k16 = g - h * (FC_G / 2), kb = k16 >> 1, s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+        if (h == 0 && (k16 & 1) == 0) {
+          mbar_wait(&a_full[kb], 0);                        // layer-1 producers have written (and fenced) this k-block of the A operand
+          if (store_h1 && kb * BLOCK_K < p.ldh1) {          // ... which is also h1[m0 .. m0+127][kb*32 .. +31]: send it to HBM as it lies
+            tma_store_3d(&maps.a[prob], sA + kb * TILE_BYTES, kb * BLOCK_K, m0, 0);
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+        }
+        mbar_wait(&b_full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t sa = smem_u32(sA + kb * TILE_BYTES) + (uint32_t)((k16 & 1) * (FC_BK / UMMA_K) * 32), sb = smem_u32(sB + s * FC_B_STAGE);
+#pragma unroll
+        for (int kk = 0; kk < FC_BK / UMMA_K; ++kk) {
+          const uint64_t ad = make_smem_desc(sa + kk * 32, 16, 1024, 2);                   // K-major, SWIZZLE_128B
+          const uint64_t bd = make_smem_desc(sb + kk * 1024, FC_BK * 128, 512, 1);         // MN-major, SWIZZLE_128B_BASE32B: 32-column chunks 2 KB apart
+          umma_tf32(tmem_base + (uint32_t)(h * FC_N), ad, bd, idesc, (k16 | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&b_empty[s]);
+        FC_STAMP(32 + g);
+        if (k16 == FC_G / 2 - 1) umma_commit(&acc_full[h]);
+      }
+      if (store_h1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the A operand must outlive the stores' reads
+    }
+  } else {
+    // ===== layer-1 producers (warps 2-9): thread = rows {lane, lane+32, lane+64, lane+96} x 4 columns (cg = warp - 2) of every k-block =====
+    const int cg = warp - 2;
+    float x[4][12];
+    if (warp == 2 && lane == 0) FC_STAMP(72);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int row = m0 + lane + 32 * rr;
+#pragma unroll
+      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + (long long)row * p.ldx + i) : 0.0f;
+      x[rr][11] = 1.0f;                                     // the bias row of w1s: fma(1, b, sum) == sum + b
+    }
+    for (int kb = 0; kb < FC_KB; ++kb) {
+      const int n0 = kb * BLOCK_K + cg * 4;
+      float4 w[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) w[i] = *reinterpret_cast<const float4*>(&w1s[i][n0]);   // same address across the warp: broadcast
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          o0 = fmaf(x[rr][i], w[i].x, o0); o1 = fmaf(x[rr][i], w[i].y, o1); o2 = fmaf(x[rr][i], w[i].z, o2); o3 = fmaf(x[rr][i], w[i].w, o3);
+        }
+        const int r = lane + 32 * rr;                       // SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7); units beyond l1 are relu(0) = 0
+        *reinterpret_cast<float4*>(sA + kb * TILE_BYTES + r * 128 + ((cg ^ (r & 7)) << 4)) =
+            make_float4(fmaxf(o0, 0.0f), fmaxf(o1, 0.0f), fmaxf(o2, 0.0f), fmaxf(o3, 0.0f));
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[kb]);
+      if (warp == 2 && lane == 0) FC_STAMP(64 + kb);
+    }
+    if (warp < 6) {
+      // ===== epilogue (warps 2-5; TMEM lane quarter = warp % 4): a thread owns one row for both column halves =====
+      const int q = warp & 3;
+      const int erow = m0 + q * 32 + lane;
+      uint8_t* buf = staging + q * 4096;
+      const bool store = p.H2[prob] != nullptr;
+      float d0 = 0.0f, d1 = 0.0f;
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&acc_full[h], 0);
+        if (warp == 2 && lane == 0) FC_STAMP(73 + 2 * h);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < FC_N / 32; ++c) {
+          const int nc = h * FC_N + c * 32;
+          if (nc >= p.L2) break;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nc, v);
+          float4 o[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {   // columns beyond l2: accumulator 0 (TMA zero fill), b2 = W3 = 0 -> h2 = 0, no contribution
+            const float4 bv = *reinterpret_cast<const float4*>(&b2s[nc + j4 * 4]);
+            const float4 wa = *reinterpret_cast<const float4*>(&w3s[0][nc + j4 * 4]);
+            const float4 wb = *reinterpret_cast<const float4*>(&w3s[1][nc + j4 * 4]);
+            o[j4].x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.0f); o[j4].y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.0f);
+            o[j4].z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.0f); o[j4].w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.0f);
+            d0 = fmaf(o[j4].x, wa.x, d0); d0 = fmaf(o[j4].y, wa.y, d0); d0 = fmaf(o[j4].z, wa.z, d0); d0 = fmaf(o[j4].w, wa.w, d0);
+            d1 = fmaf(o[j4].x, wb.x, d1); d1 = fmaf(o[j4].y, wb.y, d1); d1 = fmaf(o[j4].z, wb.z, d1); d1 = fmaf(o[j4].w, wb.w, d1);
+          }
+          if (store) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous chunk's store has read the buffer
+            __syncwarp();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&maps.d[prob], buf, nc, m0 + q * 32, 0);
+              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            }
+          }
+        }
+        if (warp == 2 && lane == 0) FC_STAMP(74 + 2 * h);
+      }
+      if (erow < p.M) {
+        const float* __restrict__ b3 = p.b3[prob];
+        const float z0 = d0 + __ldg(b3);
+        if (p.out_mode[prob] == TC_OUT_TANH) {
+          float* o = p.out[prob] + (long long)erow * p.ldo[prob];
+          o[0] = tanhf(z0);
+          if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
+        } else if (p.out_mode[prob] == TC_OUT_ID) {
+          p.out[prob][(long long)erow * p.ldo[prob]] = z0;
+        } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
+          const float y = p.td_r[erow] + (p.gamma * (1.0f - p.td_done[erow])) * z0;
+          p.out[prob][(long long)erow * p.ldo[prob]] = y;
+          p.td_dq[erow] = 2.0f * (p.td_q[erow] - y) * p.inv_batch;
+        }
+      }
+      if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // deterministic second pass of a split-K GEMM: D[m][n] = sum_s W[s][m][n] (fixed order)
 __global__ void __launch_bounds__(256)
 tc_splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, float* __restrict__ D, long long n_elems) {
@@ -428,6 +648,7 @@ int tc_gemm_prepare() {
   if ((s = set_smem_attr<true, false>())) return s;
   if ((s = set_smem_attr<true, true>())) return s;
   REQUIRE(get_encode(), SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
+  CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
   return SHEMS_OK;
 }
 
@@ -479,6 +700,48 @@ int tc_gemm_multi(cudaStream_t st, int nprob, const TcOperand* A, const TcOperan
     tc_splitk_reduce_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(workspace, a.split_stride, splits, D[0], ne);
     CUDA_TRY(cudaGetLastError());
   }
+  return SHEMS_OK;
+}
+
+
+// One launch = the forward pass of up to 3 nets (same widths) over the whole minibatch, 128 rows per CTA (see tc_fwd_chain_kernel)
+#ifdef FC_TRACE
+extern "C" __attribute__((visibility("default"))) int tc_fwd_chain_trace_read(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, fc_trace, sizeof(fc_trace));
+}
+#endif
+int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
+  REQUIRE(a.nprob >= 1 && a.nprob <= TC_MAX_PROBLEMS && a.M >= 1, SHEMS_ERR_INVALID, "tc_fwd_chain: nprob=%d M=%d", a.nprob, a.M);
+  REQUIRE(a.L1 >= 1 && a.L1 <= FC_KB * BLOCK_K && a.L2 >= 1 && a.L2 <= 2 * FC_N && a.L2 % 4 == 0, SHEMS_ERR_INVALID,
+          "tc_fwd_chain: widths %d/%d outside the kernel's plan (l1 <= 256, l2 <= 512, l2 %% 4 == 0)", a.L1, a.L2);
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int s;
+  for (int q = 0; q < a.nprob; ++q) {
+    REQUIRE(a.K1[q] >= 1 && a.K1[q] <= 11 && (a.J[q] == 1 || a.J[q] == 2), SHEMS_ERR_INVALID, "tc_fwd_chain: K1=%d J=%d", a.K1[q], a.J[q]);
+    REQUIRE(!a.H1[q] || (a.ldh1 % 4 == 0 && ((uintptr_t)a.H1[q] & 15) == 0 && a.ldh1 >= a.L1), SHEMS_ERR_INVALID,
+            "tc_fwd_chain: h1 needs 16-byte aligned rows of at least l1 floats (a multiple of 4)");
+    if ((s = make_tmap(&maps.b[q], a.W2[q], a.L2, a.L1, a.L2, 32, FC_BK, true, 1, 0))) return s;       // MN-major: dim0 = columns, dim1 = k
+    if (a.H1[q]) {   // h1 leaves through TMA stores from the swizzled A operand: box {32 columns, 128 rows}, SWIZZLE_128B
+      EncodeTiledFn enc = get_encode();
+      cuuint64_t dims[3] = {(cuuint64_t)a.ldh1, (cuuint64_t)a.M, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)a.ldh1 * 4, (cuuint64_t)a.ldh1 * 4 * (cuuint64_t)a.M};
+      cuuint32_t box[3] = {32, 128, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = enc(&maps.a[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.H1[q], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      REQUIRE(r == CUDA_SUCCESS, SHEMS_ERR_CUDA, "tc_fwd_chain: cuTensorMapEncodeTiled(h1) failed (%d)", (int)r);
+    }
+    if (a.H2[q] && (s = make_tmap_out(&maps.d[q], a.H2[q], a.L2, a.M, 1, a.ldh2, 0))) return s;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    attr_set = true;
+  }
+  const int mt = (a.M + BLOCK_M - 1) / BLOCK_M;
+  tc_fwd_chain_kernel<<<(unsigned)(mt * a.nprob), FC_THREADS, FC_SMEM, st>>>(maps, a);
+  CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
 

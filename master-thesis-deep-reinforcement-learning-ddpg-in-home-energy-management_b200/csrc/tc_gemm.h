@@ -29,3 +29,19 @@ int tc_gemm_multi(cudaStream_t st, int nprob, const TcOperand* A, const TcOperan
                   const float* const* bias, const float* const* aux, long long auxld, int splits, float* workspace, const TcBatch& batch = TcBatch());
 // sets the kernels' shared-memory attribute on the current device; call once per device before capturing launches in a graph
 int tc_gemm_prepare();
+
+// The whole forward pass of up to TC_MAX_PROBLEMS nets (same widths l1 <= 256, l2 <= 512) over a large minibatch in ONE launch:
+// layer 1 (fp32 SIMT) -> layer 2 (tcgen05, TF32) -> output layer (1 or 2 units) in the epilogue; 128 rows per CTA.
+enum { TC_OUT_TANH = 0, TC_OUT_ID = 1, TC_OUT_TD = 2 };
+struct TcFwdChainArgs {
+  int M, L1, L2, nprob, ldx, ldh1, ldh2;
+  const float* X[TC_MAX_PROBLEMS]; int K1[TC_MAX_PROBLEMS];        // inputs [M][ldx] (K1 <= 12 columns used)
+  const float *W1[TC_MAX_PROBLEMS], *b1[TC_MAX_PROBLEMS];          // Flux layout Wt[in][out]
+  const float *W2[TC_MAX_PROBLEMS], *b2[TC_MAX_PROBLEMS];
+  const float *W3[TC_MAX_PROBLEMS], *b3[TC_MAX_PROBLEMS]; int J[TC_MAX_PROBLEMS];
+  float* H1[TC_MAX_PROBLEMS];                                      // [M][ldh1] layer-1 activations, or NULL (target nets: no backward pass)
+  float* H2[TC_MAX_PROBLEMS];                                      // [M][ldh2] layer-2 activations, or NULL
+  int out_mode[TC_MAX_PROBLEMS]; float* out[TC_MAX_PROBLEMS]; int ldo[TC_MAX_PROBLEMS];   // out[row*ldo + j]
+  const float *td_r, *td_done, *td_q; float* td_dq; float gamma, inv_batch;               // TC_OUT_TD
+};
+int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a);

@@ -400,3 +400,29 @@ def test_learned_returns_match_oracle_at_reference_shape(sb, O, train_series, ch
         print("episode %d: train return %.6f / %.6f, eval score %.6f / %.6f (CUDA / oracle)" % (ep + 1, ret_gpu, ret_ref, score, score_ref))
     print("worst relative deviation: eval %.2e, train %.2e; worst action difference %.2e" % (worst_eval, worst_train, worst_action))
     assert worst_eval < 1e-3 and worst_train < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------ large-batch forward chain
+@pytest.mark.parametrize("B,l1,l2", [(1024, 250, 500), (8192, 250, 500), (1000, 250, 500), (384, 64, 128), (2048, 256, 512)])
+def test_forward_chain_kernel_equals_layerwise_path(sb, train_series, monkeypatch, B, l1, l2):
+    """tc_fwd_chain_kernel (layer 1 by SIMT into the swizzled A operand, tcgen05 layer 2, output layer in the epilogue: one kernel per
+    net) against the layer-by-layer tensor-core path (l1_fwd + tc_gemm + gemm_skinny): same TF32 products in the same k order, so
+    activations agree to fp32 rounding of the output layer's differently ordered dot product; one whole update is compared."""
+    mem = _memory(sb, train_series, n=256, seed=4)
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
+    idx = np.random.default_rng(1).integers(0, len(mem), B).astype(np.int32)
+    res = []
+    for chain in ("1", "0"):
+        monkeypatch.setenv("SHEMS_TC_CHAIN", chain)
+        le = sb.Learner(params=sb.default_ddpg_params(batch=B, l1=l1, l2=l2, use_tensor_cores=1))
+        le.init(6)
+        le.set_norm(mn, mx)
+        le.replay(mem, n_updates=1, idx=idx)
+        grads = [le.get_grad(net, k) for net in (0, 1) for k in range(3)]
+        res.append((le.losses(), grads, le.get_state()[0]))
+    (lc1, la1), g1, st1 = res[0]
+    (lc0, la0), g0, st0 = res[1]
+    assert lc1 == pytest.approx(lc0, rel=1e-5) and la1 == pytest.approx(la0, rel=1e-5, abs=1e-7)
+    for (w1, b1), (w0, b0) in zip(g1, g0):
+        scale = np.abs(w0).max() + 1e-12
+        assert np.abs(w1 - w0).max() <= 2e-5 * scale and np.abs(b1 - b0).max() <= 2e-5 * (np.abs(b0).max() + 1e-12)
