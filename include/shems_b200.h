@@ -42,8 +42,7 @@ enum {
   SHEMS_ERR_CUDA = -2,     /* CUDA runtime error, or no device                          */
   SHEMS_ERR_BOUNDS = -3,   /* row idx+1 > nrows: Julia BoundsError, shems_LU1.jl:266-268 */
   SHEMS_ERR_KEY = -4,      /* unknown charger id: Julia KeyError, shems_LU1.jl:95        */
-  SHEMS_ERR_STATE = -5,    /* call order (e.g. step before reset, sample from empty)    */
-  SHEMS_ERR_NCCL = -6
+  SHEMS_ERR_STATE = -5     /* call order (e.g. step before reset, sample from empty); a data-parallel gradient exchange that timed out */
 };
 
 SHEMS_API const char* shems_last_error(void);

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHEMS_B200_LIB", os.path.join(HERE, "libshems_b200.so"))  # override: kernel-variant sweeps (tools/)
 
-OK, ERR_INVALID, ERR_CUDA, ERR_BOUNDS, ERR_KEY, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_INVALID, ERR_CUDA, ERR_BOUNDS, ERR_KEY, ERR_STATE = 0, -1, -2, -3, -4, -5
 RESET_DETERMINISTIC, RESET_HOST_DRAWS, RESET_DEVICE_PHILOX = 0, 1, 2
 POLICY_RULE, POLICY_RANDOM, POLICY_TAPE = 0, 1, 2
 ENV_LU1, ENV_LU7, ENV_LU1_INPUT0607 = 0, 1, 2

@@ -6,8 +6,8 @@
 //   K-major  : element (row, k) at  ptr[row*ld + k]   (k contiguous)   — activations as the M operand of forward / dX
 //   MN-major : element (row, k) at  ptr[k*ld + row]   (row contiguous) — Flux weights Wt[in][out] as the N operand of the
 //              forward pass, and both operands of dW = X^T · dZ
-// One CTA computes one 128×128 output tile (optionally one K-split of it).  Warp roles (192 threads):
-//   warp 0   : TMA producer — cp.async.bulk.tensor into a 3-stage ring of 128B-swizzled tiles, mbarrier expect_tx
+// Persistent CTAs (one per SM) work through 128×128 output tiles (optionally K-splits of them).  Warp roles (192 threads):
+//   warp 0   : TMA producer — cp.async.bulk.tensor into a 5-stage ring of 128B-swizzled tiles (running across tile boundaries), mbarrier expect_tx
 //   warp 1   : TMEM allocator + MMA issuer — one elected lane issues 4 tcgen05.mma.kind::tf32 (K = 8 each) per 32-wide
 //              k-block, tcgen05.commit releases the smem stage / signals the epilogue
 //   warps 2-5: epilogue — tcgen05.ld (32 lanes × 32 columns per instruction) TMEM -> registers -> fused epilogue -> HBM
