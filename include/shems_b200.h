@@ -355,7 +355,8 @@ SHEMS_API int32_t ddpg_select_learner(Ddpg* h, int32_t learner);
 SHEMS_API int32_t ddpg_population(const Ddpg* h);
 SHEMS_API int32_t ddpg_update_population(Ddpg* h, ShemsReplay* const* rps, int32_t n_updates, const int32_t* idx_host, const uint64_t* seeds);
 /* Data-parallel learner with the gradient all-reduce fused into the optimiser kernels over NVLink peer memory (one process per
- * GPU).  Each rank exports DDPG_DP_HANDLE_BYTES (CUDA IPC handles of its gradient buffer and flag array), the caller gathers the
+ * GPU).  Each rank exports DDPG_DP_HANDLE_BYTES (the CUDA IPC handle of its exchange box: per-block flags and one inbound row of
+ * gradient sums per peer, which the peers write), the caller gathers the
  * ranks' blobs in rank order (any transport: torch.distributed, MPI, a file) and hands them to ddpg_dp_connect.  ddpg_update_dp is
  * replay() with both exchanges done in-kernel: no NCCL call, no host synchronisation; all ranks must issue the same calls.
  * A peer that does not arrive within 4 s makes the kernel give up (ddpg_dp_status reports 1) instead of hanging the GPU. */

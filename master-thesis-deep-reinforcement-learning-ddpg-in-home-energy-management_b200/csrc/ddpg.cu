@@ -482,7 +482,9 @@ struct NetDims { LayerDims l[3]; long long n_params; };
 #define DP_MAX_WORLD 16
 #define DP_TIMEOUT_NS 4000000000ull
 // peers of a data-parallel learner: rank r's flat gradient buffer and flag array, mapped into this process (CUDA IPC over NVLink)
-struct DpPeers { const float* grad[DP_MAX_WORLD]; unsigned* flags[DP_MAX_WORLD]; int world, rank; };
+// box[r]: rank r's exchange box = DP_BOX_FLAG_WORDS flag words (one per source rank), then [DP_MAX_WORLD][in_stride] inbound gradient sums
+struct DpPeers { unsigned* box[DP_MAX_WORLD]; long long in_stride; int world, rank; };
+#define DP_BOX_FLAG_WORDS 64ll
 
 struct Ddpg {
   int device;
@@ -529,7 +531,7 @@ struct Ddpg {
   // data-parallel learner over NVLink peer memory (ddpg_dp_export / ddpg_dp_connect / ddpg_update_dp)
   DpPeers dp;
   bool dp_on;
-  unsigned* dp_flags;      // [DP_MAX_WORLD] exchange numbers published by the ranks (written by the peers)
+  unsigned* dp_box;        // this rank's exchange box (allocated by ddpg_dp_export; written by the peers)
   void* dp_opened[2 * DP_MAX_WORLD]; int dp_n_opened;
   cudaGraph_t graph_dp; cudaGraphExec_t graph_dp_exec;
   // ddpg_episode scratch: a, scaled [2][N], s_prev [9][N], r [N]
@@ -655,7 +657,6 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   }
   DMALLOC(h->ctrl, pop);
   DMALLOC(h->rings_dev, pop);
-  DMALLOC(h->dp_flags, DP_MAX_WORLD);
   {
     std::vector<float> c((size_t)B, -1.0f / (float)B);
     float nm[18];
@@ -690,7 +691,7 @@ extern "C" int32_t ddpg_destroy(Ddpg* h) {
   if (h->graph_dp_exec) cudaGraphExecDestroy(h->graph_dp_exec);
   if (h->graph_dp) cudaGraphDestroy(h->graph_dp);
   for (int i = 0; i < h->dp_n_opened; ++i) cudaIpcCloseMemHandle(h->dp_opened[i]);
-  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_flags); cudaFree(h->counters);
+  cudaFree(h->ctrl); cudaFree(h->idx_dev); cudaFree(h->ws); cudaFree((void*)h->rings_dev); cudaFree(h->dp_box); cudaFree(h->counters);
   cudaFree(h->ws_side); cudaFree(h->counters_side);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_mid) cudaEventDestroy(h->ev_mid);
@@ -1014,20 +1015,25 @@ adam_polyak_parts_kernel(float* __restrict__ x, const float* __restrict__ parts,
 }
 
 // Data-parallel learner: gradient all-reduce FUSED into the optimiser step, over NVLink peer memory (no NCCL call, no
-// reduced-gradient round trip through HBM).  Every rank runs this ONE kernel per gradient segment at the same point of its stream:
-//   0. (cluster-fused path) this rank's gradient = the fixed-order sum of its per-cluster partial copies, written to the flat
-//      gradient buffer the peers read — formerly a kernel of its own;
-//   1. the LAST block to finish step 0 publishes "my segment is final" by writing the exchange number into every peer's flag array
-//      (st.release.sys after a system fence);
-//   2. every block waits until all ranks have published that number (ld.acquire.sys on its own, LOCAL flag array);
-//   3. element j: g = (sum over ranks r = 0..W-1 of peer_grad[r][j]) / W.  The W loads of an element are independent and issued
-//      together (W is a template parameter: the loop is unrolled, one NVLink round trip per element instead of W serialised ones);
-//      they are summed in rank order (same order everywhere -> bit-identical replicas); then ADAM (+ Polyak) as in adam_polyak_kernel.
-// A rank may overwrite a gradient segment only after the NEXT exchange (critic and actor segments alternate), which every peer
-// signals after it finished reading this one — so no second barrier is needed.
+// reduced-gradient round trip through HBM).  Every rank runs this ONE kernel per gradient segment at the same point of its stream,
+// with the same grid.  The exchange is PUSH style:
+//   0. every block sums its elements of this rank's gradient (cluster-fused path: the fixed-order sum of the per-cluster partial
+//      copies), keeps them in the flat gradient buffer and writes them into row [rank] of every peer's inbox — posted NVLink
+//      stores that travel while the rest of the grid is still summing;
+//   1. the LAST block to finish step 0 publishes "rank `rank` is in": st.release.sys of the exchange number into every peer's flag
+//      word [rank];
+//   2. every block waits for all peers' flags in its own, LOCAL flag words (ld.acquire.sys);
+//   3. element j: g = (sum over ranks r = 0..W-1 of [own sum | inbox[r][j]]) / W — all LOCAL loads, summed in rank order (the same
+//      order everywhere -> bit-identical replicas); then ADAM (+ Polyak) as in adam_polyak_kernel.
+// (Round 1 / early round 2 pulled: after the flags, W peer loads per element — one more NVLink round trip on every element's
+// critical path, and at W = 8 a read burst of 7 x 516 KB per rank right when everybody waits for it.)
+// An inbox segment is rewritten two exchanges later (critic and actor segments alternate).  By then the writer has completed the
+// exchange in between, i.e. has seen that exchange's flags of every peer, and a peer starts an exchange kernel only after its previous
+// one — all its inbox reads — has finished: no second barrier is needed.
 // A peer that never arrives: ONLY block 0 runs the clock; when it gives up it records the abort for this exchange number in the
-// control block, every other block sees it in its wait loop, and NO block applies the step (a half-updated parameter vector would
-// silently break the replicas' identity).  dp_error stays set; ddpg_sync / ddpg_dp_status report it.
+// control block, every other block sees it in its wait loop (or, having passed it, before it applies anything: see below), and NO
+// block applies the step (a half-updated parameter vector would silently break the replicas' identity).  dp_error stays set;
+// ddpg_sync / ddpg_dp_status report it.
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -1057,12 +1063,14 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 // -DDP_TRACE (tools/time_dp.py --trace builds that variant): globaltimer stamps of block 0 / the publishing block per segment
 #ifdef DP_TRACE
 __device__ unsigned long long dp_trace[2][8];
-#define DP_STAMP(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); dp_trace[opt][i] = t_; } } while (0)
+#define DP_STAMP_T(i) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); dp_trace[opt][i] = t_; } while (0)
+#define DP_STAMP(i) do { if (threadIdx.x == 0) DP_STAMP_T(i); } while (0)
 extern "C" __attribute__((visibility("default"))) int ddpg_dp_trace_read(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, dp_trace, sizeof(dp_trace));
 }
 #else
 #define DP_STAMP(i) do { } while (0)
+#define DP_STAMP_T(i) do { } while (0)
 #endif
 template <int W>
 __global__ void __launch_bounds__(256)
@@ -1077,45 +1085,56 @@ adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, const float* __res
   const unsigned epoch = ctrl->dp_epoch + 1u;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rank = peers.rank;
+  if (threadIdx.x == 0) ok_s = 1;
   if (blockIdx.x == 0) DP_STAMP(0);
-  // 0. this rank's gradient segment from its per-cluster partial copies (fixed order)
-  if (parts) {
+  // 0. this rank's sums of the block's elements: kept locally, pushed into row [rank] of every peer's inbox
+  {
+    float* out[W];
+#pragma unroll
+    for (int r = 0; r < W; ++r)
+      out[r] = reinterpret_cast<float*>(peers.box[r] + DP_BOX_FLAG_WORDS) + (long long)rank * peers.in_stride + seg_off;
     for (long long j = tid0; j < n; j += stride) {
-      float gj = 0.0f;
-      for (int c0 = 0; c0 < nparts; c0 += 8) {
-        float t[8];
+      float gj;
+      if (parts) {
+        gj = 0.0f;
+        for (int c0 = 0; c0 < nparts; c0 += 8) {
+          float t[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
+          for (int q = 0; q < 8; ++q) t[q] = (c0 + q < nparts) ? parts[(long long)(c0 + q) * part_stride + j] : 0.0f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
+          for (int q = 0; q < 8; ++q)
+            if (c0 + q < nparts) gj = (c0 + q == 0) ? t[q] : __fadd_rn(gj, t[q]);
+        }
+        g_own[j] = gj;
+      } else {
+        gj = g_own[j];
       }
-      g_own[j] = gj;
+#pragma unroll
+      for (int r = 0; r < W; ++r)
+        if (r != rank) out[r][j] = gj;
     }
   }
-  // 1. the last block to get here publishes (its fence orders every block's gradient stores, seen through the counter, before the flag)
+  // 1. the last block to get here publishes: its system-scope release covers every block's inbox stores (each block fenced them
+  //    before it counted itself in).  Lane r tells rank r — W - 1 lanes = one ~2 us system round trip, not W - 1 serialised ones.
+  //    (Measured and dropped: a flag per block — 500 blocks x (W - 1) release stores at once took 3.5-4 us each and the slowest
+  //    10 us; one fence + relaxed flag stores — the relaxed stores reached the peer 10-16 us later.)
   __syncthreads();
   if (blockIdx.x == 0) DP_STAMP(1);
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned arrived = atomicAdd(&ctrl->dp_ready, 1u);
     last_s = (arrived == gridDim.x - 1);
-    if (last_s) { ctrl->dp_ready = 0; DP_STAMP(2); }
-    ok_s = 1;
+    if (last_s) { ctrl->dp_ready = 0; DP_STAMP_T(2); }
   }
   __syncthreads();
-  // Publishing: lane r tells rank r.  A system-scope release costs a ~2 us round trip EACH (measured: W back-to-back st.release.sys
-  // from ONE thread took 4.2 us at W = 2 — the negative scaling of the first version); issued by the W lanes of one warp they are one
-  // instruction and one round trip.  (Measured and dropped: one fence + relaxed flag stores — the relaxed stores reached the peer
-  // 10-16 us later; a release store is pushed out at once.)  The barrier above carries thread 0's observation of the other blocks'
-  // gradient stores to these lanes.
-  if (last_s && threadIdx.x < W) {
-    st_release_sys(peers.flags[threadIdx.x] + peers.rank, epoch);
-    DP_STAMP(3);
+  if (last_s && threadIdx.x < W && (int)threadIdx.x != rank) {
+    st_release_sys(peers.box[threadIdx.x] + rank, epoch);
+    if ((int)threadIdx.x == (rank == 0 ? 1 : 0)) DP_STAMP_T(3);
   }
-  // 2. wait for every rank's flag (local memory); block 0 alone decides to give up
-  if (threadIdx.x < W) {
-    const unsigned* f = peers.flags[peers.rank] + threadIdx.x;
+  // 2. lane r waits for rank r's flag (local memory); block 0 alone decides to give up
+  if (threadIdx.x < W && (int)threadIdx.x != rank) {
+    const unsigned* f = peers.box[rank] + threadIdx.x;
     unsigned long long t0 = 0, t = 0;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
     unsigned spins = 0;
@@ -1136,18 +1155,21 @@ adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, const float* __res
   }
   __syncthreads();
   if (blockIdx.x == 0) DP_STAMP(4);
-  if (ok_s && ld_volatile_u32(&ctrl->dp_abort) == epoch) ok_s = 0;   // racing with block 0's abort: stay uniform
-  __syncthreads();
+  // block 0 gave up on this exchange while this block's own flags were in: skip as well.  (Uniform over the grid whenever a peer is
+  // absent altogether — the failure the clock is for: then no block of any rank gets past its wait.  A peer whose blocks publish more
+  // than the timeout apart can leave the step half applied; dp_error is set either way and the replica must be restored.)
+  const bool ok = ok_s && ld_volatile_u32(&ctrl->dp_abort) != epoch;
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
   const float omt = __fsub_rn(1.0f, tau), inv_w = 1.0f / (float)W;
-  if (ok_s) {
+  if (ok) {
+    const float* in = reinterpret_cast<const float*>(peers.box[rank] + DP_BOX_FLAG_WORDS) + seg_off;
     for (long long j = tid0; j < n || j < n2; j += stride) {
       const bool in1 = j < n, in2 = j < n2;
       float t2 = 0.0f, w2 = 0.0f, xj = 0.0f, tj = 0.0f, gr[W];
       if (in1) {
 #pragma unroll
-        for (int r = 0; r < W; ++r) gr[r] = ld_peer(peers.grad[r] + seg_off + j);   // W independent loads in flight
+        for (int r = 0; r < W; ++r) gr[r] = ld_peer((r == rank ? g_own : in + (long long)r * peers.in_stride) + j);   // local, past L1
         xj = x[j];
         if (target) tj = target[j];
       }
@@ -1770,22 +1792,28 @@ extern "C" int32_t ddpg_update_phase(Ddpg* h, ShemsReplay* rp, int32_t phase, co
 
 // ---- data-parallel learner over NVLink peer memory
 struct DpExport {  // what one rank tells the others (ddpg_dp_export), DDPG_DP_HANDLE_BYTES bytes
-  cudaIpcMemHandle_t slab, flags;
-  long long grad_off;              // floats from the slab base to the flat gradient buffer
-  unsigned long long raw_grad, raw_flags;  // the same addresses for peers living in THIS process (tests: two handles, one process)
+  cudaIpcMemHandle_t box;          // the rank's exchange box (flags + inbox rows), written by its peers
+  unsigned long long raw_box;      // the same address for peers living in THIS process (tests: two handles, one process)
+  long long in_stride;             // floats per inbox row (the flat gradient buffer's length): must agree between the ranks
   int pid, device;
 };
 static_assert(sizeof(DpExport) <= DDPG_DP_HANDLE_BYTES, "DDPG_DP_HANDLE_BYTES too small");
+static inline long long dp_in_stride(const Ddpg* h) { return (((h->grad[0] - h->gradbuf) + h->dims[0].n_params) + 63) & ~63ll; }
 
 extern "C" int32_t ddpg_dp_export(Ddpg* h, void* handle_out) {
   REQUIRE(h && handle_out, SHEMS_ERR_INVALID, "ddpg_dp_export: NULL argument");
   REQUIRE(h->pop == 1, SHEMS_ERR_INVALID, "ddpg_dp_export: not available for a population handle");
   GUARD(h->device);
+  if (!h->dp_box) {  // flags, then one inbox row per possible source rank; zeroed: exchange numbers start at 1
+    const size_t bytes = sizeof(unsigned) * (size_t)DP_BOX_FLAG_WORDS + sizeof(float) * (size_t)DP_MAX_WORLD * (size_t)dp_in_stride(h);
+    CUDA_TRY(cudaMalloc((void**)&h->dp_box, bytes));
+    CUDA_TRY(cudaMemset(h->dp_box, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
   DpExport e; memset(&e, 0, sizeof(e));
-  CUDA_TRY(cudaIpcGetMemHandle(&e.slab, h->slab));
-  CUDA_TRY(cudaIpcGetMemHandle(&e.flags, h->dp_flags));
-  e.grad_off = h->gradbuf - h->slab;
-  e.raw_grad = (unsigned long long)(uintptr_t)h->gradbuf; e.raw_flags = (unsigned long long)(uintptr_t)h->dp_flags;
+  CUDA_TRY(cudaIpcGetMemHandle(&e.box, h->dp_box));
+  e.raw_box = (unsigned long long)(uintptr_t)h->dp_box;
+  e.in_stride = dp_in_stride(h);
   e.pid = (int)getpid(); e.device = h->device;
   memset(handle_out, 0, DDPG_DP_HANDLE_BYTES);
   memcpy(handle_out, &e, sizeof(e));
@@ -1796,13 +1824,16 @@ extern "C" int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const v
   REQUIRE(h && handles, SHEMS_ERR_INVALID, "ddpg_dp_connect: NULL argument");
   REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, SHEMS_ERR_INVALID, "ddpg_dp_connect: rank=%d world=%d (max %d)", rank, world, DP_MAX_WORLD);
   REQUIRE(h->pop == 1 && !h->dp_on, SHEMS_ERR_STATE, "ddpg_dp_connect: population handle, or already connected");
+  REQUIRE(h->dp_box, SHEMS_ERR_STATE, "ddpg_dp_connect: call ddpg_dp_export on this handle first");
   GUARD(h->device);
   memset(&h->dp, 0, sizeof(h->dp));
-  h->dp.world = world; h->dp.rank = rank;
+  h->dp.world = world; h->dp.rank = rank; h->dp.in_stride = dp_in_stride(h);
   for (int r = 0; r < world; ++r) {
     DpExport e;
     memcpy(&e, (const char*)handles + (size_t)r * DDPG_DP_HANDLE_BYTES, sizeof(e));
-    if (r == rank) { h->dp.grad[r] = h->gradbuf; h->dp.flags[r] = h->dp_flags; continue; }
+    REQUIRE(e.in_stride == h->dp.in_stride, SHEMS_ERR_INVALID, "ddpg_dp_connect: rank %d has a different network shape (%lld gradient floats, here %lld)", r,
+            e.in_stride, h->dp.in_stride);
+    if (r == rank) { h->dp.box[r] = h->dp_box; continue; }
     if (e.pid == (int)getpid()) {  // same process: plain pointers (peer access between the two devices if they differ)
       if (e.device != h->device) {
         int can = 0;
@@ -1812,15 +1843,13 @@ extern "C" int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const v
         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(pe);
         cudaGetLastError();
       }
-      h->dp.grad[r] = (const float*)(uintptr_t)e.raw_grad; h->dp.flags[r] = (unsigned*)(uintptr_t)e.raw_flags;
+      h->dp.box[r] = (unsigned*)(uintptr_t)e.raw_box;
       continue;
     }
-    void *ps = nullptr, *pf = nullptr;
-    CUDA_TRY(cudaIpcOpenMemHandle(&ps, e.slab, cudaIpcMemLazyEnablePeerAccess));
-    h->dp_opened[h->dp_n_opened++] = ps;
-    CUDA_TRY(cudaIpcOpenMemHandle(&pf, e.flags, cudaIpcMemLazyEnablePeerAccess));
-    h->dp_opened[h->dp_n_opened++] = pf;
-    h->dp.grad[r] = (const float*)ps + e.grad_off; h->dp.flags[r] = (unsigned*)pf;
+    void* pb = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&pb, e.box, cudaIpcMemLazyEnablePeerAccess));
+    h->dp_opened[h->dp_n_opened++] = pb;
+    h->dp.box[r] = (unsigned*)pb;
   }
   h->dp_on = true;
   return SHEMS_OK;

@@ -23,7 +23,7 @@ struct DdpgCtrl {  // device-side control block read by the gather kernel (graph
   unsigned dp_epoch;    // data-parallel learner: number of gradient exchanges completed (two per update)
   unsigned dp_blocks_done;
   int dp_error;         // set when a peer's signal did not arrive within DP_TIMEOUT_NS
-  unsigned dp_ready;    // blocks of the exchange kernel that have written their share of this rank's gradient segment
+  unsigned dp_ready;    // blocks of the exchange kernel that have pushed their share of this rank's gradient segment
   unsigned dp_abort;    // exchange number block 0 gave up on (every block skips that update: the decision is grid-uniform)
 };
 

@@ -52,8 +52,8 @@ for fused in (True, False):
         sb._lib.lib().ddpg_dp_trace_read(buf)
         for seg, name in ((0, "critic"), (1, "actor")):
             st = list(buf[seg * 8: seg * 8 + 8])
-            print("rank %d %s segment (ns from kernel start): own-sum done %d, last block publishes %d, published %d, all flags seen %d, "
-                  "gather+ADAM done %d, grid done %d" % (rank, name, st[1] - st[0], st[2] - st[0], st[3] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0]),
+            print("rank %d %s segment, (ns from kernel start): block 0's sums pushed %d, all blocks in %d, flags released %d, "
+                  "all peers' flags seen %d, gather+ADAM done %d, grid done %d" % (rank, name, st[1] - st[0], st[2] - st[0], st[3] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0]),
                   file=sys.stderr, flush=True)
     out["cluster_fused" if fused else "tiled_gemm"] = dict(us_per_update=1e3 * float(t.item()) / n_updates, status=le.dp_status(),
                                                           replicas_bit_identical=bool(ok.item() == 1.0))
