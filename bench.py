@@ -446,7 +446,7 @@ def ddpg_dp_updates_per_s(sb, torch, dist, rank, ser_train, n_updates=300):
         lf.replay_fused_dp(mem, rng_rpl=100 + rank, n_updates=20)
         ms = timed(lambda: lf.replay_fused_dp(mem, rng_rpl=1000 + rank, n_updates=n_updates))
         out["fused_peer"] = dict(updates_per_s=n_updates / (ms * 1e-3), us_per_update=1e3 * ms / n_updates, exchange_status=lf.dp_status(),
-                                 peer_bytes_read_per_update=4 * int(lf.grad_tensor().numel()) * dist.get_world_size(),
+                                 peer_bytes_pushed_per_update=4 * int(lf.grad_tensor().numel()) * (dist.get_world_size() - 1),
                                  replicas_bit_identical=in_sync(lf))
     except Exception as e:
         out["fused_peer"] = dict(error=str(e))

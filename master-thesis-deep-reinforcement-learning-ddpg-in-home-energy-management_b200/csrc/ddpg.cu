@@ -547,7 +547,7 @@ static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows
 #define TC_MIN_ROWS 256
 #endif
 #define SPLITK_MIN_BATCH 1024
-#define CHAIN_MIN_BATCH 6144
+#define CHAIN_MIN_BATCH 4096
 #define SPLITK_MAX 32
 #define WS_COUNTERS 1024
 
@@ -617,8 +617,8 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   {
     const char* ev = getenv("SHEMS_TC_CHAIN");
-    // measured (tools/time_ddpg_large.py): 227 vs 252 us per update at B = 8192 and 336 vs 412 at 16384, but 175 vs 171 at 4096 and 144 vs 119 at 1024 (8 tiles per net leave the
-    // per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
+    // measured (tools/time_ddpg_large.py): 217 vs 252 us per update at B = 8192, 323 vs 412 at 16384 and 168 vs 172 at 4096, but 157 vs 154 at 3072 and 148 vs 140 at 2048 (few
+    // tiles per net leave the per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
     h->chain = h->tc && pop == 1 && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
                (ev ? ev[0] != '0' : p->batch >= CHAIN_MIN_BATCH);
   }

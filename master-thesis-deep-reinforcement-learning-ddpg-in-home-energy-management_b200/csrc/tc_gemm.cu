@@ -340,26 +340,30 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs p) {
 // ---------------------------------------------------------------------------------------------------------------- forward chain
 // One net's WHOLE forward pass for a 128-row tile of a large minibatch in one CTA (large-batch replay(), DDPG.jl:131-132, :114, :117):
 //   h1 = relu(x W1 + b1)        fp32 SIMT by 8 producer warps (thread = 4 rows x 4 columns of a k-block, the rows' inputs held in
-//                               registers for the whole kernel, W1 and b1 in shared memory), written k-block by k-block straight into the
-//                               128B-swizzled K-major A operand in shared memory (128 KB, resident for both column halves); when the
-//                               backward pass needs h1 the finished k-blocks are sent to HBM by TMA stores FROM that operand
-//   h2 = relu(h1 W2 + b2)       tcgen05.mma kind::tf32, 128 x 256 x 8 per instruction, W2 streamed by TMA (MN-major, as Flux stores it)
-//                               through a 3-stage ring of 16-k slabs; the two 256-column halves have their own TMEM accumulators, so the
-//                               epilogue of half 0 runs under the MMAs of half 1
-//   out = f(h2 W3 + b3)         in the epilogue: a thread owns one row and both halves, so the output layer's dot product (1 or 2
-//                               units) never leaves its registers; f = tanh (actor -> written into the critic's input rows), identity
-//                               (q), or the TD target y = r + gamma (1 - done) q' with dq = 2 (q - y) / B (DDPG.jl:133)
+//                               registers for the whole kernel, W1 and b1 in shared memory), written k-block by k-block straight into a
+//                               3-deep ring of 128B-swizzled K-major A-operand blocks in shared memory; when the backward pass needs h1
+//                               the finished k-blocks are sent to HBM by TMA stores FROM the operand
+//   h2 = relu(h1 W2 + b2)       tcgen05.mma kind::tf32, 128 x 256 x 8 per instruction; BOTH 256-column halves accumulate in TMEM at once
+//                               (all 512 columns), so the tile makes ONE pass over k: W2 is streamed by TMA (MN-major, as Flux stores it)
+//                               through a 4-stage ring of [16 k][512 columns] slabs = 128 KB in flight per SM.  (The first version kept the
+//                               whole A operand resident — 128 KB — and walked k once per half behind a 48 KB ring: 48 KB / L2 latency =
+//                               40 GB/s per SM, 19.4 us per tile.)
+//   out = f(h2 W3 + b3)         in the epilogue (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4): bias + ReLU, h2 to HBM
+//                               by TMA stores staged in the then idle W2 ring (4 chunks in flight per warp), and the output layer's dot
+//                               product (1 or 2 units) in registers, the two halves' partial sums joined through shared memory;
+//                               f = tanh (actor -> written into the critic's input rows), identity (q), or the TD target
+//                               y = r + gamma (1 - done) q' with dq = 2 (q - y) / B (DDPG.jl:133)
 // Replaces l1_fwd_kernel + tc_gemm_kernel + gemm_skinny_kernel (3 launches and two round trips of the activations through HBM per net).
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocation + MMA issue (+ the h1 stores), warps 2-9 layer-1 producers,
-// warps 2-5 epilogue.
-constexpr int FC_THREADS = 320, FC_N = 256, FC_KB = 8, FC_BSTAGES = 3, FC_BK = 16;
-constexpr int FC_A_BYTES = FC_KB * TILE_BYTES;                 // 8 k-blocks x 16 KB
-constexpr int FC_B_STAGE = FC_N * FC_BK * 4;                   // 16 KB: 8 chunks of [16 k][32 columns]
-constexpr int FC_SMEM = FC_A_BYTES + FC_BSTAGES * FC_B_STAGE + 4 * 4096 + 1024;
-constexpr int FC_G = 2 * FC_KB * (BLOCK_K / FC_BK);            // B slabs per tile: 2 halves x 16
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocation + MMA issue (+ the h1 stores), warps 2-9 layer-1 producers, then
+// the epilogue.
+constexpr int FC_THREADS = 320, FC_N = 256, FC_KB = 8, FC_ASTAGES = 3, FC_BSTAGES = 4, FC_BK = 16;
+constexpr int FC_A_BYTES = FC_ASTAGES * TILE_BYTES;            // 3 k-blocks x 16 KB
+constexpr int FC_B_STAGE = 2 * FC_N * FC_BK * 4;               // 32 KB: 16 chunks of [16 k][32 columns], column half h at h * 16 KB
+constexpr int FC_SMEM = FC_A_BYTES + FC_BSTAGES * FC_B_STAGE + 1024;
+static_assert(FC_BSTAGES * FC_B_STAGE >= 8 * 4 * 4096, "the epilogue stages 4 chunks per warp in the W2 ring");
 
-// -DFC_TRACE: globaltimer stamps of CTA 0 (tools/time_ddpg_large.py with a *fctrace* build): [0..31] TMA slab issued, [32..63] MMA slab
-// committed, [64..71] layer-1 k-block written (warp 2), [72] start, [73] acc 0 seen, [74] epilogue half 0 done, [75] acc 1 seen, [76] end
+// -DFC_TRACE: globaltimer stamps of CTA 0 (tools/time_ddpg_large.py with a *fctrace* build): [0..15] TMA slab issued, [32..47] MMA slab
+// committed, [64..71] layer-1 k-block written (warp 2), [72] start, [73] accumulators seen, [74] warp 2's chunks done, [76] end
 #ifdef FC_TRACE
 __device__ unsigned long long fc_trace[96];
 #define FC_STAMP(i) do { if (blockIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t_)); fc_trace[i] = t_; } } while (0)
@@ -372,16 +376,28 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + FC_A_BYTES;
-  uint8_t* staging = sB + FC_BSTAGES * FC_B_STAGE;
-  __shared__ uint64_t a_full[FC_KB], b_full[FC_BSTAGES], b_empty[FC_BSTAGES], acc_full[2];
+  __shared__ uint64_t a_full[FC_ASTAGES], a_empty[FC_ASTAGES], b_full[FC_BSTAGES], b_empty[FC_BSTAGES], acc_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float w1s[12][FC_KB * BLOCK_K];   // rows 0..K1-1: W1 (zero beyond l1), rows K1..10: zero, row 11: b1 (its input is 1)
   __shared__ __align__(16) float b2s[2 * FC_N];
   __shared__ __align__(16) float w3s[2][2 * FC_N];            // W3[:, j] (zero beyond l2)
+  __shared__ float dpart[2][BLOCK_M];                         // the upper column half's share of the output layer's dot products
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int prob = blockIdx.x / mt, m0 = (blockIdx.x - prob * mt) * BLOCK_M;
   const int K1 = p.K1[prob], J = p.J[prob];
+  const int nkb = (p.L1 + BLOCK_K - 1) / BLOCK_K, nslab = (p.L1 + FC_BK - 1) / FC_BK;   // k-blocks of 32 / W2 slabs of 16 that hold real units
+  if (warp == 2 && lane == 0) FC_STAMP(72);
+  float x[4][12];   // layer-1 producers: the inputs of rows {lane, lane+32, lane+64, lane+96}, requested first so that they arrive under the staging below
+  if (warp >= 2) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int row = m0 + lane + 32 * rr;
+#pragma unroll
+      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + (long long)row * p.ldx + i) : 0.0f;
+      x[rr][11] = 1.0f;                                     // the bias row of w1s: fma(1, b, sum) == sum + b
+    }
+  }
   for (int e = threadIdx.x; e < 12 * FC_KB * BLOCK_K; e += FC_THREADS) {
     const int i = e / (FC_KB * BLOCK_K), n = e - i * (FC_KB * BLOCK_K);
     float v = 0.0f;
@@ -395,9 +411,9 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     w3s[1][n] = (ok && J == 2) ? __ldg(p.W3[prob] + (long long)n * J + 1) : 0.0f;
   }
   if (threadIdx.x == 0) {
-    for (int k = 0; k < FC_KB; ++k) mbar_init(&a_full[k], 8);          // one arrival per producer warp
+    for (int k = 0; k < FC_ASTAGES; ++k) { mbar_init(&a_full[k], 8); mbar_init(&a_empty[k], 1); }   // a_full: one arrival per producer warp
     for (int s = 0; s < FC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b[prob]) : "memory");
     if (p.H1[prob]) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[prob]) : "memory");
@@ -413,16 +429,16 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===== TMA producer: W2[16-k slab][column half] as the MN-major B operand, 8 boxes of {32 columns, 16 k} per slab =====
+    // ===== TMA producer: W2[16-k slab][all columns] as the MN-major B operand, 16 boxes of {32 columns, 16 k} per slab =====
     if (elect_one()) {
-      for (int g = 0; g < FC_G; ++g) {
-        const int h = g / (FC_G / 2), k16 = g - h * (FC_G / 2), s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+      for (int g = 0; g < nslab; ++g) {
+        const int s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
         mbar_wait(&b_empty[s], ph ^ 1);
         FC_STAMP(g);
         mbar_expect_tx(&b_full[s], FC_B_STAGE);
         uint8_t* sb = sB + s * FC_B_STAGE;
 #pragma unroll
-        for (int j = 0; j < FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], h * FC_N + j * 32, k16 * FC_BK, 0);
+        for (int j = 0; j < 2 * FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], j * 32, g * FC_BK, 0);
       }
     }
   } else if (warp == 1) {
@@ -430,124 +446,131 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(FC_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     if (elect_one()) {
       const bool store_h1 = p.H1[prob] != nullptr;
-      for (int g = 0; g < FC_G; ++g) {
-        const int h = g / (FC_G / 2), k16 = g - h * (FC_G / 2), kb = k16 >> 1, s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
-        if (h == 0 && (k16 & 1) == 0) {
-          mbar_wait(&a_full[kb], 0);                        // layer-1 producers have written (and fenced) this k-block of the A operand
+      for (int g = 0; g < nslab; ++g) {
+        const int kb = g >> 1, sa_i = kb % FC_ASTAGES, s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+        if ((g & 1) == 0) {
+          mbar_wait(&a_full[sa_i], (kb / FC_ASTAGES) & 1);   // layer-1 producers have written (and fenced) this k-block of the A operand
           if (store_h1 && kb * BLOCK_K < p.ldh1) {          // ... which is also h1[m0 .. m0+127][kb*32 .. +31]: send it to HBM as it lies
-            tma_store_3d(&maps.a[prob], sA + kb * TILE_BYTES, kb * BLOCK_K, m0, 0);
+            tma_store_3d(&maps.a[prob], sA + sa_i * TILE_BYTES, kb * BLOCK_K, m0, 0);
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
           }
         }
         mbar_wait(&b_full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t sa = smem_u32(sA + kb * TILE_BYTES) + (uint32_t)((k16 & 1) * (FC_BK / UMMA_K) * 32), sb = smem_u32(sB + s * FC_B_STAGE);
+        const uint32_t sa = smem_u32(sA + sa_i * TILE_BYTES) + (uint32_t)((g & 1) * (FC_BK / UMMA_K) * 32), sb = smem_u32(sB + s * FC_B_STAGE);
 #pragma unroll
-        for (int kk = 0; kk < FC_BK / UMMA_K; ++kk) {
-          const uint64_t ad = make_smem_desc(sa + kk * 32, 16, 1024, 2);                   // K-major, SWIZZLE_128B
-          const uint64_t bd = make_smem_desc(sb + kk * 1024, FC_BK * 128, 512, 1);         // MN-major, SWIZZLE_128B_BASE32B: 32-column chunks 2 KB apart
-          umma_tf32(tmem_base + (uint32_t)(h * FC_N), ad, bd, idesc, (k16 | kk) != 0 ? 1u : 0u);
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+          for (int kk = 0; kk < FC_BK / UMMA_K; ++kk) {
+            const uint64_t ad = make_smem_desc(sa + kk * 32, 16, 1024, 2);                                  // K-major, SWIZZLE_128B
+            const uint64_t bd = make_smem_desc(sb + h * (FC_N * FC_BK * 4) + kk * 1024, FC_BK * 128, 512, 1);   // MN-major, SWIZZLE_128B_BASE32B: 32-column chunks 2 KB apart
+            umma_tf32(tmem_base + (uint32_t)(h * FC_N), ad, bd, idesc, (g | kk) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&b_empty[s]);
         FC_STAMP(32 + g);
-        if (k16 == FC_G / 2 - 1) umma_commit(&acc_full[h]);
+        if ((g & 1) == 1 || g == nslab - 1) {   // last slab of this k-block: its ring slot is free once these MMAs (and the h1 store's read) are done
+          if (store_h1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          umma_commit(&a_empty[sa_i]);
+        }
       }
-      if (store_h1) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the A operand must outlive the stores' reads
+      umma_commit(&acc_full);
     }
   } else {
     // ===== layer-1 producers (warps 2-9): thread = rows {lane, lane+32, lane+64, lane+96} x 4 columns (cg = warp - 2) of every k-block =====
     const int cg = warp - 2;
-    float x[4][12];
-    if (warp == 2 && lane == 0) FC_STAMP(72);
+    {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int n0 = kb * BLOCK_K + cg * 4, sa_i = kb % FC_ASTAGES;
+        float4 w[12];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int row = m0 + lane + 32 * rr;
+        for (int i = 0; i < 12; ++i) w[i] = *reinterpret_cast<const float4*>(&w1s[i][n0]);   // same address across the warp: broadcast
+        float4 o[4];
 #pragma unroll
-      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + (long long)row * p.ldx + i) : 0.0f;
-      x[rr][11] = 1.0f;                                     // the bias row of w1s: fma(1, b, sum) == sum + b
-    }
-    for (int kb = 0; kb < FC_KB; ++kb) {
-      const int n0 = kb * BLOCK_K + cg * 4;
-      float4 w[12];
+        for (int rr = 0; rr < 4; ++rr) {
+          float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) w[i] = *reinterpret_cast<const float4*>(&w1s[i][n0]);   // same address across the warp: broadcast
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          o0 = fmaf(x[rr][i], w[i].x, o0); o1 = fmaf(x[rr][i], w[i].y, o1); o2 = fmaf(x[rr][i], w[i].z, o2); o3 = fmaf(x[rr][i], w[i].w, o3);
+          for (int i = 0; i < 12; ++i) {
+            o0 = fmaf(x[rr][i], w[i].x, o0); o1 = fmaf(x[rr][i], w[i].y, o1); o2 = fmaf(x[rr][i], w[i].z, o2); o3 = fmaf(x[rr][i], w[i].w, o3);
+          }
+          o[rr] = make_float4(fmaxf(o0, 0.0f), fmaxf(o1, 0.0f), fmaxf(o2, 0.0f), fmaxf(o3, 0.0f));
         }
-        const int r = lane + 32 * rr;                       // SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7); units beyond l1 are relu(0) = 0
-        *reinterpret_cast<float4*>(sA + kb * TILE_BYTES + r * 128 + ((cg ^ (r & 7)) << 4)) =
-            make_float4(fmaxf(o0, 0.0f), fmaxf(o1, 0.0f), fmaxf(o2, 0.0f), fmaxf(o3, 0.0f));
+        if (kb >= FC_ASTAGES) mbar_wait(&a_empty[sa_i], ((kb / FC_ASTAGES) - 1) & 1);   // the MMAs (and the h1 store) of k-block kb - 3 have read the slot
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = lane + 32 * rr;                       // SWIZZLE_128B: 16-byte chunk j of row r at j ^ (r & 7); units beyond l1 are relu(0) = 0
+          *reinterpret_cast<float4*>(sA + sa_i * TILE_BYTES + r * 128 + ((cg ^ (r & 7)) << 4)) = o[rr];
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa_i]);
+        if (warp == 2 && lane == 0) FC_STAMP(64 + kb);
       }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[kb]);
-      if (warp == 2 && lane == 0) FC_STAMP(64 + kb);
     }
-    if (warp < 6) {
-      // ===== epilogue (warps 2-5; TMEM lane quarter = warp % 4): a thread owns one row for both column halves =====
-      const int q = warp & 3;
-      const int erow = m0 + q * 32 + lane;
-      uint8_t* buf = staging + q * 4096;
-      const bool store = p.H2[prob] != nullptr;
-      float d0 = 0.0f, d1 = 0.0f;
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(&acc_full[h], 0);
-        if (warp == 2 && lane == 0) FC_STAMP(73 + 2 * h);
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // ===== epilogue (the same 8 warps; TMEM lane quarter = warp % 4, column half hh): a thread owns one row of one half =====
+    const int q = warp & 3, hh = cg >> 2;
+    const int erow = m0 + q * 32 + lane;
+    uint8_t* buf = sB + cg * (4 * 4096);                      // the W2 ring is idle once the accumulators are final: 4 staging chunks per warp
+    const bool store = p.H2[prob] != nullptr;
+    float d0 = 0.0f, d1 = 0.0f;
+    mbar_wait(&acc_full, 0);
+    if (warp == 2 && lane == 0) FC_STAMP(73);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-        for (int c = 0; c < FC_N / 32; ++c) {
-          const int nc = h * FC_N + c * 32;
-          if (nc >= p.L2) break;
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nc, v);
-          float4 o[8];
+    for (int c = 0; c < FC_N / 32; ++c) {
+      const int nc = hh * FC_N + c * 32;
+      if (nc >= p.L2) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nc, v);
+      float4 o[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {   // columns beyond l2: accumulator 0 (TMA zero fill), b2 = W3 = 0 -> h2 = 0, no contribution
-            const float4 bv = *reinterpret_cast<const float4*>(&b2s[nc + j4 * 4]);
-            const float4 wa = *reinterpret_cast<const float4*>(&w3s[0][nc + j4 * 4]);
-            const float4 wb = *reinterpret_cast<const float4*>(&w3s[1][nc + j4 * 4]);
-            o[j4].x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.0f); o[j4].y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.0f);
-            o[j4].z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.0f); o[j4].w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.0f);
-            d0 = fmaf(o[j4].x, wa.x, d0); d0 = fmaf(o[j4].y, wa.y, d0); d0 = fmaf(o[j4].z, wa.z, d0); d0 = fmaf(o[j4].w, wa.w, d0);
-            d1 = fmaf(o[j4].x, wb.x, d1); d1 = fmaf(o[j4].y, wb.y, d1); d1 = fmaf(o[j4].z, wb.z, d1); d1 = fmaf(o[j4].w, wb.w, d1);
-          }
-          if (store) {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous chunk's store has read the buffer
-            __syncwarp();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(buf + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&maps.d[prob], buf, nc, m0 + q * 32, 0);
-              asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-            }
-          }
-        }
-        if (warp == 2 && lane == 0) FC_STAMP(74 + 2 * h);
+      for (int j4 = 0; j4 < 8; ++j4) {   // columns beyond l2: accumulator 0 (TMA zero fill), b2 = W3 = 0 -> h2 = 0, no contribution
+        const float4 bv = *reinterpret_cast<const float4*>(&b2s[nc + j4 * 4]);
+        const float4 wa = *reinterpret_cast<const float4*>(&w3s[0][nc + j4 * 4]);
+        const float4 wb = *reinterpret_cast<const float4*>(&w3s[1][nc + j4 * 4]);
+        o[j4].x = fmaxf(__uint_as_float(v[j4 * 4 + 0]) + bv.x, 0.0f); o[j4].y = fmaxf(__uint_as_float(v[j4 * 4 + 1]) + bv.y, 0.0f);
+        o[j4].z = fmaxf(__uint_as_float(v[j4 * 4 + 2]) + bv.z, 0.0f); o[j4].w = fmaxf(__uint_as_float(v[j4 * 4 + 3]) + bv.w, 0.0f);
+        d0 = fmaf(o[j4].x, wa.x, d0); d0 = fmaf(o[j4].y, wa.y, d0); d0 = fmaf(o[j4].z, wa.z, d0); d0 = fmaf(o[j4].w, wa.w, d0);
+        d1 = fmaf(o[j4].x, wb.x, d1); d1 = fmaf(o[j4].y, wb.y, d1); d1 = fmaf(o[j4].z, wb.z, d1); d1 = fmaf(o[j4].w, wb.w, d1);
       }
-      if (erow < p.M) {
-        const float* __restrict__ b3 = p.b3[prob];
-        const float z0 = d0 + __ldg(b3);
-        if (p.out_mode[prob] == TC_OUT_TANH) {
-          float* o = p.out[prob] + (long long)erow * p.ldo[prob];
-          o[0] = tanhf(z0);
-          if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
-        } else if (p.out_mode[prob] == TC_OUT_ID) {
-          p.out[prob][(long long)erow * p.ldo[prob]] = z0;
-        } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
-          const float y = p.td_r[erow] + (p.gamma * (1.0f - p.td_done[erow])) * z0;
-          p.out[prob][(long long)erow * p.ldo[prob]] = y;
-          p.td_dq[erow] = 2.0f * (p.td_q[erow] - y) * p.inv_batch;
+      if (store) {
+        uint8_t* b = buf + (c & 3) * 4096;
+        if (c >= 4) {   // the store of chunk c - 4 has read this buffer (at most the 3 newer ones still pending)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;\n" ::: "memory");
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(b + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps.d[prob], b, nc, m0 + q * 32, 0);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
-      if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     }
+    if (warp == 2 && lane == 0) FC_STAMP(74);
+    if (hh == 1) { dpart[0][q * 32 + lane] = d0; dpart[1][q * 32 + lane] = d1; }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");          // the 8 epilogue warps
+    if (hh == 0 && erow < p.M) {
+      d0 += dpart[0][q * 32 + lane]; d1 += dpart[1][q * 32 + lane];
+      const float* __restrict__ b3 = p.b3[prob];
+      const float z0 = d0 + __ldg(b3);
+      if (p.out_mode[prob] == TC_OUT_TANH) {
+        float* o = p.out[prob] + (long long)erow * p.ldo[prob];
+        o[0] = tanhf(z0);
+        if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
+      } else if (p.out_mode[prob] == TC_OUT_ID) {
+        p.out[prob][(long long)erow * p.ldo[prob]] = z0;
+      } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
+        const float y = p.td_r[erow] + (p.gamma * (1.0f - p.td_done[erow])) * z0;
+        p.out[prob][(long long)erow * p.ldo[prob]] = y;
+        p.td_dq[erow] = 2.0f * (p.td_q[erow] - y) * p.inv_batch;
+      }
+    }
+    if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    if (warp == 2 && lane == 0) FC_STAMP(76);
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {

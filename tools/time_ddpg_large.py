@@ -47,7 +47,7 @@ if "fctrace" in os.environ.get("SHEMS_B200_LIB", ""):   # a -DFC_TRACE build: ti
     sb._lib.lib().tc_fwd_chain_trace_read(buf)
     t0 = buf[72]
     rel = [int(x) - int(t0) for x in buf]
-    print("TMA slab issued (ns):", rel[0:32])
-    print("MMA slab committed:", rel[32:64])
+    print("TMA slab issued (ns):", rel[0:16])
+    print("MMA slab committed:", rel[32:48])
     print("layer-1 k-block written:", rel[64:72])
-    print("acc0 seen %d, epilogue half 0 done %d, acc1 seen %d, end %d" % (rel[73], rel[74], rel[75], rel[76]))
+    print("accumulators seen %d, warp 2's chunks done %d, end %d" % (rel[73], rel[74], rel[76]))
