@@ -619,8 +619,9 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
     const char* ev = getenv("SHEMS_TC_CHAIN");
     // measured (tools/time_ddpg_large.py): 217 vs 252 us per update at B = 8192, 323 vs 412 at 16384 and 168 vs 172 at 4096, but 157 vs 154 at 3072 and 148 vs 140 at 2048 (few
     // tiles per net leave the per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
-    h->chain = h->tc && pop == 1 && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
-               (ev ? ev[0] != '0' : p->batch >= CHAIN_MIN_BATCH);
+    // a population (grid.y = learner): the same rule on the rows of all learners together
+    h->chain = h->tc && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
+               (ev ? ev[0] != '0' : (long long)p->batch * pop >= CHAIN_MIN_BATCH);
   }
   // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
@@ -1392,6 +1393,7 @@ static inline void chain_set(TcFwdChainArgs& a, int q, const float* X, const flo
 static inline TcFwdChainArgs chain_args(const Ddpg* h, int nprob) {
   TcFwdChainArgs a; memset(&a, 0, sizeof(a));
   a.M = h->p.batch; a.L1 = h->p.l1; a.L2 = h->p.l2; a.nprob = nprob; a.ldx = 11; a.ldh1 = h->ld1; a.ldh2 = h->ld2;
+  a.pop = h->pop; a.pop_stride = h->pop_stride;
   return a;
 }
 

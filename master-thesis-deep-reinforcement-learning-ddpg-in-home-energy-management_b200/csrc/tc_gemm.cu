@@ -386,6 +386,8 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
   const int mt = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int prob = blockIdx.x / mt, m0 = (blockIdx.x - prob * mt) * BLOCK_M;
   const int K1 = p.K1[prob], J = p.J[prob];
+  const int learner = blockIdx.y;                              // a population: the learner's slab starts lo floats further, TMA coordinate 2
+  const long long lo = (long long)learner * p.pop_stride;
   const int nkb = (p.L1 + BLOCK_K - 1) / BLOCK_K, nslab = (p.L1 + FC_BK - 1) / FC_BK;   // k-blocks of 32 / W2 slabs of 16 that hold real units
   if (warp == 2 && lane == 0) FC_STAMP(72);
   float x[4][12];   // layer-1 producers: the inputs of rows {lane, lane+32, lane+64, lane+96}, requested first so that they arrive under the staging below
@@ -394,21 +396,21 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     for (int rr = 0; rr < 4; ++rr) {
       const int row = m0 + lane + 32 * rr;
 #pragma unroll
-      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + (long long)row * p.ldx + i) : 0.0f;
+      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + lo + (long long)row * p.ldx + i) : 0.0f;
       x[rr][11] = 1.0f;                                     // the bias row of w1s: fma(1, b, sum) == sum + b
     }
   }
   for (int e = threadIdx.x; e < 12 * FC_KB * BLOCK_K; e += FC_THREADS) {
     const int i = e / (FC_KB * BLOCK_K), n = e - i * (FC_KB * BLOCK_K);
     float v = 0.0f;
-    if (n < p.L1) v = i < K1 ? __ldg(p.W1[prob] + (long long)i * p.L1 + n) : (i == 11 ? __ldg(p.b1[prob] + n) : 0.0f);
+    if (n < p.L1) v = i < K1 ? __ldg(p.W1[prob] + lo + (long long)i * p.L1 + n) : (i == 11 ? __ldg(p.b1[prob] + lo + n) : 0.0f);
     w1s[i][n] = v;
   }
   for (int n = threadIdx.x; n < 2 * FC_N; n += FC_THREADS) {
     const bool ok = n < p.L2;
-    b2s[n] = ok ? __ldg(p.b2[prob] + n) : 0.0f;
-    w3s[0][n] = ok ? __ldg(p.W3[prob] + (long long)n * J) : 0.0f;
-    w3s[1][n] = (ok && J == 2) ? __ldg(p.W3[prob] + (long long)n * J + 1) : 0.0f;
+    b2s[n] = ok ? __ldg(p.b2[prob] + lo + n) : 0.0f;
+    w3s[0][n] = ok ? __ldg(p.W3[prob] + lo + (long long)n * J) : 0.0f;
+    w3s[1][n] = (ok && J == 2) ? __ldg(p.W3[prob] + lo + (long long)n * J + 1) : 0.0f;
   }
   if (threadIdx.x == 0) {
     for (int k = 0; k < FC_ASTAGES; ++k) { mbar_init(&a_full[k], 8); mbar_init(&a_empty[k], 1); }   // a_full: one arrival per producer warp
@@ -438,7 +440,7 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
         mbar_expect_tx(&b_full[s], FC_B_STAGE);
         uint8_t* sb = sB + s * FC_B_STAGE;
 #pragma unroll
-        for (int j = 0; j < 2 * FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], j * 32, g * FC_BK, 0);
+        for (int j = 0; j < 2 * FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], j * 32, g * FC_BK, learner);
       }
     }
   } else if (warp == 1) {
@@ -451,7 +453,7 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
         if ((g & 1) == 0) {
           mbar_wait(&a_full[sa_i], (kb / FC_ASTAGES) & 1);   // layer-1 producers have written (and fenced) this k-block of the A operand
           if (store_h1 && kb * BLOCK_K < p.ldh1) {          // ... which is also h1[m0 .. m0+127][kb*32 .. +31]: send it to HBM as it lies
-            tma_store_3d(&maps.a[prob], sA + sa_i * TILE_BYTES, kb * BLOCK_K, m0, 0);
+            tma_store_3d(&maps.a[prob], sA + sa_i * TILE_BYTES, kb * BLOCK_K, m0, learner);
             asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
           }
         }
@@ -544,7 +546,7 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&maps.d[prob], b, nc, m0 + q * 32, 0);
+          tma_store_3d(&maps.d[prob], b, nc, m0 + q * 32, learner);
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
@@ -554,18 +556,18 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     asm volatile("bar.sync 1, 256;\n" ::: "memory");          // the 8 epilogue warps
     if (hh == 0 && erow < p.M) {
       d0 += dpart[0][q * 32 + lane]; d1 += dpart[1][q * 32 + lane];
-      const float* __restrict__ b3 = p.b3[prob];
+      const float* __restrict__ b3 = p.b3[prob] + lo;
       const float z0 = d0 + __ldg(b3);
       if (p.out_mode[prob] == TC_OUT_TANH) {
-        float* o = p.out[prob] + (long long)erow * p.ldo[prob];
+        float* o = p.out[prob] + lo + (long long)erow * p.ldo[prob];
         o[0] = tanhf(z0);
         if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
       } else if (p.out_mode[prob] == TC_OUT_ID) {
-        p.out[prob][(long long)erow * p.ldo[prob]] = z0;
+        p.out[prob][lo + (long long)erow * p.ldo[prob]] = z0;
       } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
-        const float y = p.td_r[erow] + (p.gamma * (1.0f - p.td_done[erow])) * z0;
-        p.out[prob][(long long)erow * p.ldo[prob]] = y;
-        p.td_dq[erow] = 2.0f * (p.td_q[erow] - y) * p.inv_batch;
+        const float y = p.td_r[lo + erow] + (p.gamma * (1.0f - p.td_done[lo + erow])) * z0;
+        p.out[prob][lo + (long long)erow * p.ldo[prob]] = y;
+        p.td_dq[lo + erow] = 2.0f * (p.td_q[lo + erow] - y) * p.inv_batch;
       }
     }
     if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
@@ -737,6 +739,8 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
   REQUIRE(a.nprob >= 1 && a.nprob <= TC_MAX_PROBLEMS && a.M >= 1, SHEMS_ERR_INVALID, "tc_fwd_chain: nprob=%d M=%d", a.nprob, a.M);
   REQUIRE(a.L1 >= 1 && a.L1 <= FC_KB * BLOCK_K && a.L2 >= 1 && a.L2 <= 2 * FC_N && a.L2 % 4 == 0, SHEMS_ERR_INVALID,
           "tc_fwd_chain: widths %d/%d outside the kernel's plan (l1 <= 256, l2 <= 512, l2 %% 4 == 0)", a.L1, a.L2);
+  const int pop = a.pop > 1 ? a.pop : 1;
+  REQUIRE(pop == 1 || a.pop_stride % 4 == 0, SHEMS_ERR_INVALID, "tc_fwd_chain: the learners' slabs must be a multiple of 16 bytes apart");
   TcMaps maps;
   memset(&maps, 0, sizeof(maps));
   int s;
@@ -744,18 +748,18 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
     REQUIRE(a.K1[q] >= 1 && a.K1[q] <= 11 && (a.J[q] == 1 || a.J[q] == 2), SHEMS_ERR_INVALID, "tc_fwd_chain: K1=%d J=%d", a.K1[q], a.J[q]);
     REQUIRE(!a.H1[q] || (a.ldh1 % 4 == 0 && ((uintptr_t)a.H1[q] & 15) == 0 && a.ldh1 >= a.L1), SHEMS_ERR_INVALID,
             "tc_fwd_chain: h1 needs 16-byte aligned rows of at least l1 floats (a multiple of 4)");
-    if ((s = make_tmap(&maps.b[q], a.W2[q], a.L2, a.L1, a.L2, 32, FC_BK, true, 1, 0))) return s;       // MN-major: dim0 = columns, dim1 = k
+    if ((s = make_tmap(&maps.b[q], a.W2[q], a.L2, a.L1, a.L2, 32, FC_BK, true, pop, a.pop_stride))) return s;   // MN-major: dim0 = columns, dim1 = k, dim2 = learner
     if (a.H1[q]) {   // h1 leaves through TMA stores from the swizzled A operand: box {32 columns, 128 rows}, SWIZZLE_128B
       EncodeTiledFn enc = get_encode();
-      cuuint64_t dims[3] = {(cuuint64_t)a.ldh1, (cuuint64_t)a.M, 1};
-      cuuint64_t strides[2] = {(cuuint64_t)a.ldh1 * 4, (cuuint64_t)a.ldh1 * 4 * (cuuint64_t)a.M};
+      cuuint64_t dims[3] = {(cuuint64_t)a.ldh1, (cuuint64_t)a.M, (cuuint64_t)pop};
+      cuuint64_t strides[2] = {(cuuint64_t)a.ldh1 * 4, (cuuint64_t)(pop > 1 ? a.pop_stride : a.ldh1 * (long long)a.M) * 4};
       cuuint32_t box[3] = {32, 128, 1};
       cuuint32_t estr[3] = {1, 1, 1};
       CUresult r = enc(&maps.a[q], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a.H1[q], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       REQUIRE(r == CUDA_SUCCESS, SHEMS_ERR_CUDA, "tc_fwd_chain: cuTensorMapEncodeTiled(h1) failed (%d)", (int)r);
     }
-    if (a.H2[q] && (s = make_tmap_out(&maps.d[q], a.H2[q], a.L2, a.M, 1, a.ldh2, 0))) return s;
+    if (a.H2[q] && (s = make_tmap_out(&maps.d[q], a.H2[q], a.L2, a.M, pop, a.ldh2, a.pop_stride))) return s;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -763,7 +767,7 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
     attr_set = true;
   }
   const int mt = (a.M + BLOCK_M - 1) / BLOCK_M;
-  tc_fwd_chain_kernel<<<(unsigned)(mt * a.nprob), FC_THREADS, FC_SMEM, st>>>(maps, a);
+  tc_fwd_chain_kernel<<<dim3((unsigned)(mt * a.nprob), (unsigned)pop), FC_THREADS, FC_SMEM, st>>>(maps, a);
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }

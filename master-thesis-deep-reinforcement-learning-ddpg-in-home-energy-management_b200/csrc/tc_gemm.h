@@ -43,5 +43,6 @@ struct TcFwdChainArgs {
   float* H2[TC_MAX_PROBLEMS];                                      // [M][ldh2] layer-2 activations, or NULL
   int out_mode[TC_MAX_PROBLEMS]; float* out[TC_MAX_PROBLEMS]; int ldo[TC_MAX_PROBLEMS];   // out[row*ldo + j]
   const float *td_r, *td_done, *td_q; float* td_dq; float gamma, inv_batch;               // TC_OUT_TD
+  int pop; long long pop_stride;   // a population of learners (grid.y): every pointer above moves by pop_stride floats per learner
 };
 int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a);

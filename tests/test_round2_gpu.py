@@ -426,3 +426,35 @@ def test_forward_chain_kernel_equals_layerwise_path(sb, train_series, monkeypatc
     for (w1, b1), (w0, b0) in zip(g1, g0):
         scale = np.abs(w0).max() + 1e-12
         assert np.abs(w1 - w0).max() <= 2e-5 * scale and np.abs(b1 - b0).max() <= 2e-5 * (np.abs(b0).max() + 1e-12)
+
+
+@pytest.mark.parametrize("P,B,l1,l2", [(3, 96, 48, 64), (5, 120, 250, 500)])
+def test_forward_chain_kernel_population(sb, train_series, monkeypatch, P, B, l1, l2):
+    """The same kernel with the learner as grid.y (BASELINE configs[4]: one 128-row tile per learner and net, every pointer and TMA
+    coordinate moved to the learner's slab) against the population's layer-by-layer path: per learner the same TF32 products."""
+    mems = [_memory(sb, train_series, n=64, seed=10 + l) for l in range(P)]
+    norms = [m.min_max_buffer(len(m), rng_mm=l) for l, m in enumerate(mems)]
+    idx = np.stack([np.random.default_rng(l).integers(0, len(mems[l]), (2, B)) for l in range(P)]).astype(np.int32)
+    res = []
+    for chain in ("1", "0"):
+        monkeypatch.setenv("SHEMS_TC_CHAIN", chain)
+        pop = sb.Learner(params=sb.default_ddpg_params(population=P, batch=B, l1=l1, l2=l2, use_tensor_cores=1))
+        pop.init(60)
+        for l in range(P):
+            pop.select(l).set_norm(*norms[l])
+        pop.replay(mems, n_updates=2, idx=idx)
+        out = []
+        for l in range(P):
+            pop.select(l)
+            out.append((pop.losses(), [pop.get_grad(net, k) for net in (0, 1) for k in range(3)], [pop.get_layer(net, 1)[0] for net in range(4)]))
+        res.append(out)
+        pop.close()
+    for l in range(P):
+        (lc1, la1), g1, w1s = res[0][l]
+        (lc0, la0), g0, w0s = res[1][l]
+        assert lc1 == pytest.approx(lc0, rel=2e-4) and la1 == pytest.approx(la0, rel=2e-4, abs=1e-6), l
+        for (w1, b1), (w0, b0) in zip(g1, g0):
+            assert np.abs(w1 - w0).max() <= 1e-3 * (np.abs(w0).max() + 1e-12) and np.abs(b1 - b0).max() <= 1e-3 * (np.abs(b0).max() + 1e-12), l
+        for w1, w0 in zip(w1s, w0s):
+            assert np.abs(w1 - w0).max() <= 2e-5, l
+        assert not np.array_equal(res[0][l][2][1], res[0][(l + 1) % P][2][1])   # the learners are different learners
