@@ -359,7 +359,8 @@ SHEMS_API int32_t ddpg_update_population(Ddpg* h, ShemsReplay* const* rps, int32
  * gradient sums per peer, which the peers write), the caller gathers the
  * ranks' blobs in rank order (any transport: torch.distributed, MPI, a file) and hands them to ddpg_dp_connect.  ddpg_update_dp is
  * replay() with both exchanges done in-kernel: no NCCL call, no host synchronisation; all ranks must issue the same calls.
- * A peer that does not arrive within 4 s makes the kernel give up (ddpg_dp_status reports 1) instead of hanging the GPU. */
+ * A peer that does not arrive within 4 s (environment SHEMS_DP_TIMEOUT_MS at connect time) makes the kernel give up without applying the
+ * step (ddpg_dp_status reports 1, ddpg_sync fails) instead of hanging the GPU. */
 #define DDPG_DP_HANDLE_BYTES 192
 SHEMS_API int32_t ddpg_dp_export(Ddpg* h, void* handle_out /* [DDPG_DP_HANDLE_BYTES] */);
 SHEMS_API int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const void* handles /* [world][DDPG_DP_HANDLE_BYTES] */);

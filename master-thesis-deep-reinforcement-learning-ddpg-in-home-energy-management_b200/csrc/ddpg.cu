@@ -483,7 +483,7 @@ struct NetDims { LayerDims l[3]; long long n_params; };
 #define DP_TIMEOUT_NS 4000000000ull
 // peers of a data-parallel learner: rank r's flat gradient buffer and flag array, mapped into this process (CUDA IPC over NVLink)
 // box[r]: rank r's exchange box = DP_BOX_FLAG_WORDS flag words (one per source rank), then [DP_MAX_WORLD][in_stride] inbound gradient sums
-struct DpPeers { unsigned* box[DP_MAX_WORLD]; long long in_stride; int world, rank; };
+struct DpPeers { unsigned* box[DP_MAX_WORLD]; long long in_stride; unsigned long long timeout_ns; int world, rank; };
 #define DP_BOX_FLAG_WORDS 64ll
 
 struct Ddpg {
@@ -1143,14 +1143,14 @@ adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, const float* __res
       if ((++spins & 63u) == 0u) {
         if (ld_volatile_u32(&ctrl->dp_abort) == epoch) { ok_s = 0; break; }
         asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-        if (blockIdx.x == 0 && t - t0 > DP_TIMEOUT_NS) {
+        if (blockIdx.x == 0 && t - t0 > peers.timeout_ns) {
           if ((int)(ld_acquire_sys(f) - epoch) >= 0) break;   // it arrived after all
           ctrl->dp_abort = epoch; ctrl->dp_error = 1;
           __threadfence();
           ok_s = 0;
           break;
         }
-        if (blockIdx.x != 0 && t - t0 > 4ull * DP_TIMEOUT_NS) { ok_s = 0; break; }   // backstop: block 0 never ran its clock
+        if (blockIdx.x != 0 && t - t0 > 4ull * peers.timeout_ns) { ok_s = 0; break; }   // backstop: block 0 never ran its clock
       }
     }
   }
@@ -1830,6 +1830,11 @@ extern "C" int32_t ddpg_dp_connect(Ddpg* h, int32_t rank, int32_t world, const v
   GUARD(h->device);
   memset(&h->dp, 0, sizeof(h->dp));
   h->dp.world = world; h->dp.rank = rank; h->dp.in_stride = dp_in_stride(h);
+  h->dp.timeout_ns = DP_TIMEOUT_NS;
+  if (const char* ev = getenv("SHEMS_DP_TIMEOUT_MS")) {   // tests: a short clock for the missing-peer case
+    const long long ms = atoll(ev);
+    if (ms > 0) h->dp.timeout_ns = (unsigned long long)ms * 1000000ull;
+  }
   for (int r = 0; r < world; ++r) {
     DpExport e;
     memcpy(&e, (const char*)handles + (size_t)r * DDPG_DP_HANDLE_BYTES, sizeof(e));

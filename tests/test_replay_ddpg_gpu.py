@@ -502,6 +502,35 @@ def test_fused_peer_allreduce_world1_equals_plain_update(sb, O, train_series, cl
                 np.testing.assert_array_equal(x, y)
 
 
+def test_fused_peer_exchange_gives_up_on_a_missing_peer(sb, train_series, monkeypatch):
+    """A rank whose peer never launches its exchange kernel: the bounded spin ends (SHEMS_DP_TIMEOUT_MS, 4 s by default), NO block
+    applies the optimiser step (nets, targets untouched), ddpg_dp_status reports 1 and ddpg_sync fails instead of hanging the GPU."""
+    monkeypatch.setenv("SHEMS_DP_TIMEOUT_MS", "30")
+    n, T, B = 64, 72, 64
+    env = sb.Shems(T, train_series, n_envs=n)
+    mem = sb.Replay(n * T)
+    env.reset(rng=2)
+    env.rollout(sb.POLICY_RANDOM, T, seed=2, replay=mem, want_return=False)
+    mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
+    here, absent = (sb.Learner(params=sb.default_ddpg_params(batch=B)) for _ in range(2))
+    for le in (here, absent):
+        le.init(3)
+        le.set_norm(mn, mx)
+    blobs = [here.dp_export(), absent.dp_export()]
+    here.dp_connect(0, 2, blobs)
+    here.dp_prepare()
+    before = [here.get_layer(net, k) for net in range(4) for k in range(3)]
+    here.replay_fused_dp(mem, rng_rpl=5, n_updates=1)
+    torch.cuda.synchronize()
+    assert here.dp_status() == 1
+    with pytest.raises(sb.ShemsError):
+        here.sync()
+    after = [here.get_layer(net, k) for net in range(4) for k in range(3)]
+    for (w0, b0), (w1, b1) in zip(before, after):
+        np.testing.assert_array_equal(w0, w1)
+        np.testing.assert_array_equal(b0, b1)
+
+
 @pytest.mark.parametrize("batch,tc", [(32, 0), (512, 1)])
 def test_fused_peer_allreduce_two_processes(batch, tc):
     """(512, 1): the large-batch tensor-core path under the fused exchange.  Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
