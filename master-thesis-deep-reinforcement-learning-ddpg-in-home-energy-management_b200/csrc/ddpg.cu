@@ -1156,9 +1156,8 @@ adam_polyak_dp_kernel(const DpPeers peers, long long seg_off, const float* __res
   }
   __syncthreads();
   if (blockIdx.x == 0) DP_STAMP(4);
-  // block 0 gave up on this exchange while this block's own flags were in: skip as well.  (Uniform over the grid whenever a peer is
-  // absent altogether — the failure the clock is for: then no block of any rank gets past its wait.  A peer whose blocks publish more
-  // than the timeout apart can leave the step half applied; dp_error is set either way and the replica must be restored.)
+  // Every block waits for the same W - 1 flags and only block 0 runs the clock, so the decision is the grid's: if block 0 gave up on this
+  // exchange, a block whose own polls happened to see the flags later skips as well (dp_error is set; the replica must be restored).
   const bool ok = ok_s && ld_volatile_u32(&ctrl->dp_abort) != epoch;
   const double c1 = 1.0 - ctrl->bp[opt][0], c2 = 1.0 - ctrl->bp[opt][1];
   const double r1 = ctrl->rc[opt][0], r2 = ctrl->rc[opt][1];
