@@ -233,7 +233,7 @@ class OracleDdpg:
         self.h = lib().oracle_ddpg_create(C.byref(p))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:   # module globals may be gone at interpreter exit
             lib().oracle_ddpg_destroy(self.h)
             self.h = None
 

@@ -337,9 +337,11 @@ def test_learned_returns_match_oracle_at_reference_shape(sb, O, train_series, ch
 
     STATED TOLERANCE: evaluation and training returns within 1e-3 relative (+1e-3 absolute).  The fp32 summation order of the CUDA
     kernels differs from the oracle's Float64 accumulation; ADAM's normalised step turns that rounding noise into weight differences
-    of a few per cent of lr per update, which 360 updates compound — the measured deviation is printed."""
+    of a few per cent of lr per update, which 360 updates compound — the measured deviation is printed.  Longer horizons (SHEMS_G1_EPISODES,
+    tests/learned_returns_divergence.py): past ~400 updates the closed loop amplifies rounding tenfold per episode, for CUDA against the oracle
+    exactly as for the two CUDA update paths against each other (profiles/r2_learned_returns.md) — hence 5 episodes here."""
     O.set_threads(max(1, min(16, (os.cpu_count() or 2) // 2)))
-    T, B, EPISODES = 72, 120, 5
+    T, B, EPISODES = 72, 120, int(os.environ.get("SHEMS_G1_EPISODES", "5"))   # longer horizons: profiles/r2_learned_returns.md
     rng = np.random.default_rng(2024)
     warm = _memory(sb, train_series, n=64, T=T, seed=12)             # a warm-up memory both sides share (random policy)
     S, A, R, S2, D = warm.get()
