@@ -430,6 +430,7 @@ template <int J>
 __global__ void __launch_bounds__(256)
 outer_mask_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const float* __restrict__ H, long long ld, int B, int N,
                   float* __restrict__ dX, long long pop_stride) {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // the dX product after it sets itself up under this kernel (tc_gemm.cu)
   {  // blockIdx.y = learner of a population
     const long long lo = (long long)blockIdx.y * pop_stride;
     dZ += lo; W += lo; H += lo; dX += lo;
@@ -617,7 +618,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   {
     const char* ev = getenv("SHEMS_TC_CHAIN");
-    // measured (tools/time_ddpg_large.py): 217 vs 252 us per update at B = 8192, 323 vs 412 at 16384 and 168 vs 172 at 4096, but 157 vs 154 at 3072 and 148 vs 140 at 2048 (few
+    // measured (tools/time_ddpg_large.py): 209 vs 249 us per update at B = 8192, 313 vs 407 at 16384 and 163 vs 171 at 4096, but 157 vs 154 at 3072 and 148 vs 140 at 2048 (few
     // tiles per net leave the per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
     // a population (grid.y = learner): the same rule on the rows of all learners together
     h->chain = h->tc && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
@@ -834,6 +835,7 @@ ddpg_gather_kernel(const float* const* __restrict__ rings, const float* __restri
                    const float* __restrict__ rs2, const float* __restrict__ rd, long long ld, DdpgCtrl* __restrict__ ctrl,
                    const int32_t* __restrict__ idx, long long idx_stride, const float* __restrict__ norm, int B, float* __restrict__ xs,
                    float* __restrict__ xs2, float* __restrict__ xspi, float* __restrict__ r, float* __restrict__ done, long long pop_stride) {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // the forward-chain launch after it stages its weights under this kernel
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = g / 9, k = g - j * 9;
   if (j >= B) return;
@@ -1307,6 +1309,7 @@ static int tc_fwd(const Ddpg* h, cudaStream_t st, const float* X, int ldx, int M
 static int tc_dx(const Ddpg* h, cudaStream_t st, const float* dZ, int lddz, int M, const float* net, const LayerDims& L, float* dX, int lddx, const float* H, int ldh) {
   TcOperand A{dZ, lddz, false}, Bo{net + L.w_off, L.out, false};
   TcBatch bt; bt.count = h->pop; bt.sA = bt.sB = bt.sD = bt.sAux = h->pop_stride;
+  bt.pdl = true;   // a programmatic dependent of the outer_mask launch before it: its set-up (barriers, TMEM, tensor maps) runs under that kernel's tail
   return tc_gemm(st, A, Bo, dX, lddx, M, L.in, L.out, TC_EPI_RELU_MASK, nullptr, H, ldh, 1, nullptr, bt);
 }
 // dW = X^T · dZ (both MN-major, K = batch, split-K for one large-batch learner), db = column sums of dZ
@@ -1418,11 +1421,16 @@ static int enqueue_phase0(Ddpg* h, cudaStream_t st) {
     chain_set(a, 0, h->xs2, actor_t, da, nullptr, nullptr, TC_OUT_TANH, h->xs2 + 9, 11);
     chain_set(a, 1, h->xs, critic, dc, h->c_h1, h->c_h2, TC_OUT_ID, h->q, 1);
     chain_set(a, 2, h->xs, actor, da, h->a_h1, h->a_h2, TC_OUT_TANH, h->xspi + 9, 11);
+    // Programmatic dependent launches (the tcgen05 kernels only: their set-up is worth hiding, and a CTA of theirs fills an SM, so
+    // a grid scheduled early takes nothing from the side branch.  The thin kernels as dependents were measured and dropped: their
+    // early-resident blocks starve the side branch, 209 -> 226 us).  After the gather only the rows' inputs are its output:
+    a.pdl = 1; a.early_weights = 1;
     TRY(tc_fwd_chain(st, a));
     // q' = critic_target(vcat(s'_n, a'));  y = r + gamma (1 - done) q';  dq = 2 (q - y) / B     (:132-133)
     TcFwdChainArgs t = chain_args(h, 1);
     chain_set(t, 0, h->xs2, critic_t, dc, nullptr, nullptr, TC_OUT_TD, h->y, 1);
     t.td_r = h->r; t.td_done = h->done; t.td_q = h->q; t.td_dq = h->dq; t.gamma = p.gamma; t.inv_batch = 1.0f / (float)B;
+    t.pdl = 1; t.early_weights = 1;   // after the three-net launch: a' and q are its output, critic_target's weights are not
     TRY(tc_fwd_chain(st, t));
   } else {
   // P1-P3: actor_target(s'_n) | critic(s_n, a) | actor(s_n)     (DDPG.jl:131, :114, :117)
@@ -1526,6 +1534,7 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   if (chain) {  // one kernel: p_h1, p_h2 (for the backward pass) and q(s, actor(s)) itself (reporting)
     TcFwdChainArgs a = chain_args(h, 1);
     chain_set(a, 0, h->xspi, critic, dc, h->p_h1, h->p_h2, TC_OUT_ID, h->qpi, 1);
+    a.pdl = 1; a.early_weights = 0;   // after ADAM(critic): the weights are the predecessor's output
     TRY(tc_fwd_chain(st, a));
   } else if (big) {
     const float* X[1] = {h->xspi}; const float* nets[1] = {critic}; const LayerDims* Ls[1] = {&dc.l[0]}; float* Y[1] = {h->p_h1};

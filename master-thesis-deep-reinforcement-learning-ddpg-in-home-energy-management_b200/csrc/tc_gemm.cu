@@ -140,6 +140,9 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs p) {
   const int total_tiles = mt * nt * nz * p.nprob;  // several same-shape problems (own tensor maps / pointers) share one launch
   const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_per = (kb_total + p.splits - 1) / p.splits;
+  // programmatic dependent launch (when the host asks for it): a successor may be scheduled while this grid runs, and this grid's own
+  // set-up (barriers, TMEM, tensor maps) runs under the tail of its predecessor; nothing the predecessor wrote is touched before the wait
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -159,6 +162,7 @@ tc_gemm_kernel(const __grid_constant__ TcMaps maps, const TcGemmArgs p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
 // tile -> (m0, n0, split, bz, first k-block, number of k-blocks); m-tiles vary fastest so that concurrently running CTAs share B tiles in L2
 #define TILE_COORDS(tile)                                                               \
@@ -390,15 +394,23 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
   const long long lo = (long long)learner * p.pop_stride;
   const int nkb = (p.L1 + BLOCK_K - 1) / BLOCK_K, nslab = (p.L1 + FC_BK - 1) / FC_BK;   // k-blocks of 32 / W2 slabs of 16 that hold real units
   if (warp == 2 && lane == 0) FC_STAMP(72);
-  float x[4][12];   // layer-1 producers: the inputs of rows {lane, lane+32, lane+64, lane+96}, requested first so that they arrive under the staging below
-  if (warp >= 2) {
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const int row = m0 + lane + 32 * rr;
-#pragma unroll
-      for (int i = 0; i < 11; ++i) x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + lo + (long long)row * p.ldx + i) : 0.0f;
-      x[rr][11] = 1.0f;                                     // the bias row of w1s: fma(1, b, sum) == sum + b
-    }
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");   // see tc_gemm_kernel
+  // Programmatic dependent launch: what did the predecessor in the stream write?  Normally only the rows' inputs (early_weights): the
+  // weights are staged under its tail, then the wait, then the inputs.  After an optimiser step the weights are its output: wait first
+  // (then the inputs are requested before the staging so that they arrive under it).
+  float x[4][12];   // layer-1 producers: the inputs of rows {lane, lane+32, lane+64, lane+96}
+#define FC_LOAD_X()                                                                                                                       \
+  if (warp >= 2) {                                                                                                                        \
+    _Pragma("unroll") for (int rr = 0; rr < 4; ++rr) {                                                                                    \
+      const int row = m0 + lane + 32 * rr;                                                                                                \
+      _Pragma("unroll") for (int i = 0; i < 11; ++i)                                                                                      \
+        x[rr][i] = (row < p.M && i < K1) ? __ldg(p.X[prob] + lo + (long long)row * p.ldx + i) : 0.0f;                                     \
+      x[rr][11] = 1.0f; /* the bias row of w1s: fma(1, b, sum) == sum + b */                                                              \
+    }                                                                                                                                     \
+  }
+  if (!p.early_weights) {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    FC_LOAD_X();
   }
   for (int e = threadIdx.x; e < 12 * FC_KB * BLOCK_K; e += FC_THREADS) {
     const int i = e / (FC_KB * BLOCK_K), n = e - i * (FC_KB * BLOCK_K);
@@ -412,6 +424,11 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     w3s[0][n] = ok ? __ldg(p.W3[prob] + lo + (long long)n * J) : 0.0f;
     w3s[1][n] = (ok && J == 2) ? __ldg(p.W3[prob] + lo + (long long)n * J + 1) : 0.0f;
   }
+  if (p.early_weights) {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    FC_LOAD_X();
+  }
+#undef FC_LOAD_X
   if (threadIdx.x == 0) {
     for (int k = 0; k < FC_ASTAGES; ++k) { mbar_init(&a_full[k], 8); mbar_init(&a_empty[k], 1); }   // a_full: one arrival per producer warp
     for (int s = 0; s < FC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -658,7 +675,18 @@ int launch_variant(cudaStream_t st, const TcMaps& maps, const TcGemmArgs& a) {
     CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);  // persistent: one CTA per SM, tiles dealt round-robin
-  tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(maps, a);
+  if (a.pdl) {   // a programmatic dependent of its predecessor in the stream
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<A_MN, B_MN>, maps, a));
+  } else {
+    tc_gemm_kernel<A_MN, B_MN><<<grid, 192, SMEM_BYTES, st>>>(maps, a);
+  }
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
@@ -692,7 +720,7 @@ int tc_gemm_multi(cudaStream_t st, int nprob, const TcOperand* A, const TcOperan
   TcGemmArgs a;
   memset(&a, 0, sizeof(a));
   a.M = M; a.N = N; a.K = K; a.splits = splits; a.epi = epi; a.auxld = auxld; a.nprob = nprob;
-  a.batch = bt.count; a.bs_bias = bt.sBias; a.bs_aux = bt.sAux;
+  a.batch = bt.count; a.bs_bias = bt.sBias; a.bs_aux = bt.sAux; a.pdl = bt.pdl ? 1 : 0;
   if (splits == 1) { a.ldd = ldd; a.split_stride = bt.count > 1 ? bt.sD : 0; }
   else { a.ldd = N; a.split_stride = (long long)M * N; }
   const int nz = bt.count > 1 ? bt.count : splits;
@@ -767,7 +795,18 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
     attr_set = true;
   }
   const int mt = (a.M + BLOCK_M - 1) / BLOCK_M;
-  tc_fwd_chain_kernel<<<dim3((unsigned)(mt * a.nprob), (unsigned)pop), FC_THREADS, FC_SMEM, st>>>(maps, a);
+  if (a.pdl) {   // a programmatic dependent of its predecessor in the stream (captured as such in the update's graph)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(mt * a.nprob), (unsigned)pop); cfg.blockDim = dim3(FC_THREADS); cfg.dynamicSmemBytes = FC_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fwd_chain_kernel, maps, a));
+  } else {
+    tc_fwd_chain_kernel<<<dim3((unsigned)(mt * a.nprob), (unsigned)pop), FC_THREADS, FC_SMEM, st>>>(maps, a);
+  }
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }

@@ -12,7 +12,7 @@ struct TcOperand {
 };
 #define TC_MAX_PROBLEMS 3
 struct TcGemmArgs {
-  int M, N, K, splits, epi, tma_store, batch, nprob;
+  int M, N, K, splits, epi, tma_store, batch, nprob, pdl;
   float* D[TC_MAX_PROBLEMS]; long long ldd, split_stride;
   const float* bias[TC_MAX_PROBLEMS]; const float* aux[TC_MAX_PROBLEMS]; long long auxld, bs_bias, bs_aux;
 };
@@ -20,6 +20,7 @@ struct TcGemmArgs {
 struct TcBatch {
   int count = 1;
   long long sA = 0, sB = 0, sD = 0, sBias = 0, sAux = 0;
+  bool pdl = false;   // launch as a programmatic dependent of the predecessor in the stream (the kernel waits before touching its operands)
 };
 // D[M×N] (row-major, ldd) = epilogue(sum_k A(m,k) · B(n,k))
 int tc_gemm(cudaStream_t st, const TcOperand& A, const TcOperand& B, float* D, long long ldd, int M, int N, int K, int epi,
@@ -43,6 +44,7 @@ struct TcFwdChainArgs {
   float* H2[TC_MAX_PROBLEMS];                                      // [M][ldh2] layer-2 activations, or NULL
   int out_mode[TC_MAX_PROBLEMS]; float* out[TC_MAX_PROBLEMS]; int ldo[TC_MAX_PROBLEMS];   // out[row*ldo + j]
   const float *td_r, *td_done, *td_q; float* td_dq; float gamma, inv_batch;               // TC_OUT_TD
+  int pdl, early_weights;          // programmatic dependent launch; early_weights: the predecessor in the stream did not write the net's weights
   int pop; long long pop_stride;   // a population of learners (grid.y): every pointer above moves by pop_stride floats per learner
 };
 int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a);
