@@ -97,7 +97,8 @@ def cpu_baseline(ser, horizon, sample_envs=0, target_s=15.0):
     rate, dt = cpu_rollout_rate(ser, horizon, sample_envs)
     return dict(value=rate, unit=UNIT, cores=cores, kind="port",
                 sample=f"{sample_envs} instances x {horizon} steps (same series, same Philox actions), OpenMP over instances, {dt:.1f} s; "
-                       "the reference's Julia cannot run here (not installed), this is the repo's C restatement of it"), dt
+                       "the reference's Julia cannot run here (not installed), this is the repo's C restatement of it; it accumulates the episode returns but "
+                       "does not write the 88-byte transitions, i.e. it does LESS work per step than the GPU arm"), dt
 
 
 def run_reference(args, rank, world):
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
                             series_rows=args.horizon + 1, charger=98, sample_envs_per_step=n,
                             note="the same rollout (same series, same Philox action streams) on the host cores, a bounded sample of the instances per step"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{n} instances x {args.horizon} steps per step, OpenMP over instances"),
+                                  sample=f"{n} instances x {args.horizon} steps per step, OpenMP over instances; returns only (no transition writes: less work than the GPU arm)"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
 
