@@ -1517,6 +1517,9 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
   const NetDims& da = h->dims[0]; const NetDims& dc = h->dims[1];
   float *actor = h->net[DDPG_NET_ACTOR], *critic = h->net[DDPG_NET_CRITIC];
   GemmProblem g[4];
+  // the fused dX chain through the critic below: with few row tiles two CTAs share a tile and ADD their shares of the action-input gradient
+  const int bwd_split = (tc && h->chain && h->pop == 1 && ((B + 127) / 128) * 2 <= 148) ? 2 : 1;
+  if (bwd_split == 2) CUDA_TRY(cudaMemsetAsync(h->dza3, 0, sizeof(float) * 2 * (size_t)B, st));
   // P10: ADAM(η_crit) on the critic
   const dim3 adam_grid((unsigned)((dc.n_params + 255) / 256), h->pop);  // one element per thread: the Float64 div/sqrt chains need TLP
   if (dp) {  // gradient exchange over NVLink fused into the optimiser step (critic segment = first nc floats of the flat buffer)
@@ -1549,20 +1552,31 @@ static int enqueue_phase1(Ddpg* h, cudaStream_t st, float gscale, bool dp = fals
     g[0] = gp_fwd(h->p_h1, l1, B, critic, dc.l[1], h->p_h2, l2, EPI_BIAS_RELU);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
-  if (big) {                                                                                               // dX through the critic only
-    TRY(launch_outer_mask(h, st, h->dqpi, 1, critic + dc.l[2].w_off, h->p_h2, l2, B, p.l2, h->dzp2));
+  if (chain) {
+    // dX through the critic only, as ONE kernel (csrc/tc_gemm.cu tc_bwd_chain_kernel): dq -> dz2 -> dz1 -> the action inputs, times tanh';
+    // nothing of it is kept (no weight gradient of the critic in the actor's loss)
+    TcBwdChainArgs b; memset(&b, 0, sizeof(b));
+    b.M = B; b.L1 = p.l1; b.L2 = p.l2; b.J = 1; b.ldh1 = l1; b.ldh2 = l2; b.pdl = 1; b.nsplit = bwd_split;
+    b.dout = h->dqpi; b.W3 = critic + dc.l[2].w_off; b.W2 = critic + dc.l[1].w_off; b.H2 = h->p_h2; b.H1 = h->p_h1;
+    b.W1a = critic + dc.l[0].w_off + 9ll * p.l1; b.act = h->xspi + 9; b.ld_act = 11; b.dA = h->dza3;
+    b.pop = h->pop; b.pop_stride = h->pop_stride;
+    TRY(tc_bwd_chain(st, b));
   } else {
-    g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, p.l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);
+    if (big) {                                                                                               // dX through the critic only
+      TRY(launch_outer_mask(h, st, h->dqpi, 1, critic + dc.l[2].w_off, h->p_h2, l2, B, p.l2, h->dzp2));
+    } else {
+      g[0] = gp_dx(h->dqpi, 1, B, critic, dc.l[2], 0, p.l2, h->dzp2, l2, EPI_RELU_MASK, h->p_h2, l2);
+      TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
+    }
+    // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
+    if (tc) TRY(tc_dx(h, st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
+    else {
+      g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, p.l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
+      TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
+    }
+    g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
     TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   }
-  // P14-P15: back through critic layers 2, 1 down to the action inputs, times tanh'
-  if (tc) TRY(tc_dx(h, st, h->dzp2, l2, B, critic, dc.l[1], h->dzp1, l1, h->p_h1, l1));
-  else {
-    g[0] = gp_dx(h->dzp2, l2, B, critic, dc.l[1], 0, p.l1, h->dzp1, l1, EPI_RELU_MASK, h->p_h1, l1);
-    TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
-  }
-  g[0] = gp_dx(h->dzp1, l1, B, critic, dc.l[0], 9, 2, h->dza3, 2, EPI_TANH_GRAD, h->xspi + 9, 11);
-  TRY(launch_gemms(st, g, 1, h->pop, h->pop_stride, h->pop_stride));
   // P16-P18: actor backward
   if (big) {  // as in the critic's backward pass: dW3, dW2 (and the reporting-only q(s, actor(s))) beside the dX chain
     TRY(side_after(h, st, h->ev_fork));                                                                       // dza3 is ready

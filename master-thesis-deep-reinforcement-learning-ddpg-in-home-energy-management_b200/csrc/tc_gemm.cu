@@ -598,6 +598,212 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- backward chain
+// The dX chain of a net for a 128-row tile in one CTA (see tc_gemm.h).  Per k-block of 32 layer-2 units: the h2 tile block arrives by TMA
+// in the 128B-swizzled K-major operand layout, 8 warps turn it IN PLACE into dz2 = (sum_j dout[row][j] W3[n][j]) * (h2 > 0), the MMA warp
+// (optionally) sends the finished block to HBM by a TMA store from the operand and issues tcgen05.mma 128 x 256 x 8 against the W2 block
+// [256 layer-1 units][32 layer-2 units] (K-major as Flux stores W2; units beyond l1 are zero-filled by TMA).  The epilogue (8 warps: TMEM
+// lane quarter x column half) masks with relu'(h1), stores dz1 through TMA from the then idle W2 ring, and folds the product with the two
+// action rows of W1 into registers.  Replaces outer_mask_kernel + tc_gemm_kernel<0,0> (+ gemm_skinny_kernel).
+constexpr int BC_THREADS = 320, BC_N = 256, BC_ASTAGES = 4, BC_BSTAGES = 4;   // BC_N: layer-1 units per row tile; a CTA takes all of them or (NS = 2) half
+constexpr int BC_B_STAGE = BC_N * BLOCK_K * 4;                 // 32 KB: [256 rows][32 k]
+constexpr int BC_SMEM = BC_ASTAGES * TILE_BYTES + BC_BSTAGES * BC_B_STAGE + 1024;
+static_assert(BC_BSTAGES * BC_B_STAGE >= 8 * 4 * 4096, "the epilogue stages 4 chunks per warp in the W2 ring");
+
+// NS = 2: two CTAs per row tile, each with 128 of the layer-1 units (half of the W2 stream; the h2 block and its dz2 are computed by both,
+// stored by the first; the action-input gradient is the sum of the two CTAs' shares: two atomic adds onto zeros — commutative, hence
+// deterministic).  For minibatches whose row tiles alone would leave more than half of the SMs idle.
+template <int NS>
+__global__ void __launch_bounds__(BC_THREADS, 1)
+tc_bwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcBwdChainArgs p) {
+  constexpr int NC = BC_N / NS;                                // layer-1 units (accumulator columns) of this CTA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + BC_ASTAGES * TILE_BYTES;
+  __shared__ uint64_t h_full[BC_ASTAGES], a_full[BC_ASTAGES], a_empty[BC_ASTAGES], b_full[BC_BSTAGES], b_empty[BC_BSTAGES], acc_full;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float w3s[2][2 * BC_N];            // W3[:, j] (zero beyond l2)
+  __shared__ __align__(16) float w1a[2][BC_N];                // the two action rows of W1 (zero beyond l1)
+  __shared__ float dpart[2][BLOCK_M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = (blockIdx.x / NS) * BLOCK_M, nh = blockIdx.x % NS, learner = blockIdx.y, J = p.J;   // nh: which half of the layer-1 units
+  const long long lo = (long long)learner * p.pop_stride;
+  const int nkb = (p.L2 + BLOCK_K - 1) / BLOCK_K;              // k-blocks of 32 layer-2 units
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < BC_ASTAGES; ++k) { mbar_init(&h_full[k], 1); mbar_init(&a_full[k], 8); mbar_init(&a_empty[k], 1); }
+    for (int s = 0; s < BC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(&acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b[0]) : "memory");
+    if (p.DZ2 && nh == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[1]) : "memory");
+    if (p.DZ1) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.d[0]) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(NC));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_smem;
+  // everything this kernel reads may be its predecessor's output (the optimiser step, the forward pass): set-up above, data below
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+  if (warp >= 2) {   // W3 and the action rows of W1 for the 8 producer / epilogue warps, while the TMA warp already streams the first blocks
+    const int t = threadIdx.x - 64;
+    for (int n = t; n < 2 * BC_N; n += BC_THREADS - 64) {
+      const bool ok = n < p.L2;
+      w3s[0][n] = ok ? __ldg(p.W3 + lo + (long long)n * J) : 0.0f;
+      w3s[1][n] = (ok && J == 2) ? __ldg(p.W3 + lo + (long long)n * J + 1) : 0.0f;
+    }
+    if (p.dA) {
+      for (int n = t; n < 2 * BC_N; n += BC_THREADS - 64) {
+        const int j = n / BC_N, i = n - j * BC_N;
+        w1a[j][i] = (i < NC && nh * NC + i < p.L1) ? __ldg(p.W1a + lo + (long long)j * p.L1 + nh * NC + i) : 0.0f;   // this CTA's units
+      }
+    }
+    asm volatile("bar.sync 2, 256;\n" ::: "memory");
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: the h2 block [128 rows][32 units] and the W2 block [256 layer-1 units][32 layer-2 units] of every k-block =====
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % BC_ASTAGES, pa = (kb / BC_ASTAGES) & 1, sb = kb % BC_BSTAGES, pb = (kb / BC_BSTAGES) & 1;
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        mbar_expect_tx(&h_full[sa], TILE_BYTES);
+        tma_load_3d(sA + sa * TILE_BYTES, &maps.a[0], &h_full[sa], kb * BLOCK_K, m0, learner);
+        mbar_wait(&b_empty[sb], pb ^ 1);
+        mbar_expect_tx(&b_full[sb], BC_B_STAGE / NS);
+        tma_load_3d(sB + sb * BC_B_STAGE, &maps.b[0], &b_full[sb], kb * BLOCK_K, nh * NC, learner);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (+ the dz2 stores from the operand) =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    if (elect_one()) {
+      const bool store = p.DZ2 != nullptr && nh == 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % BC_ASTAGES, pa = (kb / BC_ASTAGES) & 1, sb = kb % BC_BSTAGES, pb = (kb / BC_BSTAGES) & 1;
+        mbar_wait(&a_full[sa], pa);                         // the 8 warps have turned this block into dz2 (and fenced it)
+        if (store) {
+          tma_store_3d(&maps.a[1], sA + sa * TILE_BYTES, kb * BLOCK_K, m0, learner);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+        mbar_wait(&b_full[sb], pb);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t a0 = smem_u32(sA + sa * TILE_BYTES), b0 = smem_u32(sB + sb * BC_B_STAGE);
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          const uint64_t ad = make_smem_desc(a0 + kk * 32, 16, 1024, 2);   // K-major, SWIZZLE_128B
+          const uint64_t bd = make_smem_desc(b0 + kk * 32, 16, 1024, 2);   // K-major, SWIZZLE_128B: 256 rows of 128 bytes
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&b_empty[sb]);
+        if (kb > 0) {   // block kb - 1: its MMAs are covered by this commit; its store (all but the newest) has read the operand
+          if (store) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+          umma_commit(&a_empty[(kb - 1) % BC_ASTAGES]);
+        }
+      }
+      if (store) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+      umma_commit(&a_empty[(nkb - 1) % BC_ASTAGES]);
+      umma_commit(&acc_full);
+    }
+  } else {
+    // ===== dz2 producers (warps 2-9): thread = rows {lane, lane+32, lane+64, lane+96} x the 16-byte chunk cg = warp - 2 of every block =====
+    const int cg = warp - 2;
+    {
+      float dz[4][2];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int row = m0 + lane + 32 * rr;
+        dz[rr][0] = row < p.M ? __ldcg(p.dout + lo + (long long)row * J) : 0.0f;
+        dz[rr][1] = (row < p.M && J == 2) ? __ldcg(p.dout + lo + (long long)row * J + 1) : 0.0f;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % BC_ASTAGES, pa = (kb / BC_ASTAGES) & 1, n0 = kb * BLOCK_K + cg * 4;
+        const float4 wa = *reinterpret_cast<const float4*>(&w3s[0][n0]);
+        const float4 wb = *reinterpret_cast<const float4*>(&w3s[1][n0]);
+        mbar_wait(&h_full[sa], pa);
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = lane + 32 * rr;
+          float4* q4 = reinterpret_cast<float4*>(sA + sa * TILE_BYTES + r * 128 + ((cg ^ (r & 7)) << 4));
+          const float4 hv = *q4;
+          float4 o;   // the same order as outer_mask_kernel: fma(dz[1], w[1], fma(dz[0], w[0], 0))
+          o.x = hv.x > 0.0f ? fmaf(dz[rr][1], wb.x, fmaf(dz[rr][0], wa.x, 0.0f)) : 0.0f;
+          o.y = hv.y > 0.0f ? fmaf(dz[rr][1], wb.y, fmaf(dz[rr][0], wa.y, 0.0f)) : 0.0f;
+          o.z = hv.z > 0.0f ? fmaf(dz[rr][1], wb.z, fmaf(dz[rr][0], wa.z, 0.0f)) : 0.0f;
+          o.w = hv.w > 0.0f ? fmaf(dz[rr][1], wb.w, fmaf(dz[rr][0], wa.w, 0.0f)) : 0.0f;
+          *q4 = o;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
+      }
+    }
+    // ===== epilogue (the same 8 warps; TMEM lane quarter = warp % 4, column half hh of this CTA's layer-1 units) =====
+    const int q = warp & 3, hh = cg >> 2;
+    const int erow = m0 + q * 32 + lane;
+    uint8_t* buf = sB + cg * (4 * 4096);
+    const bool store = p.DZ1 != nullptr, want_da = p.dA != nullptr;
+    const float* __restrict__ h1row = p.H1 + lo + (long long)(erow < p.M ? erow : 0) * p.ldh1;
+    float d0 = 0.0f, d1 = 0.0f;
+    mbar_wait(&acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+    for (int c = 0; c < NC / 64; ++c) {
+      const int lc = hh * (NC / 2) + c * 32, nc = nh * NC + lc;   // column of this CTA's accumulator / layer-1 unit
+      if (nc >= p.L1) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)lc, v);
+      float4 o[8];
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {   // units beyond l1: W2 rows zero-filled -> accumulator 0
+        const float4 hv = __ldcg(reinterpret_cast<const float4*>(h1row + nc + j4 * 4));
+        o[j4].x = hv.x > 0.0f ? __uint_as_float(v[j4 * 4 + 0]) : 0.0f; o[j4].y = hv.y > 0.0f ? __uint_as_float(v[j4 * 4 + 1]) : 0.0f;
+        o[j4].z = hv.z > 0.0f ? __uint_as_float(v[j4 * 4 + 2]) : 0.0f; o[j4].w = hv.w > 0.0f ? __uint_as_float(v[j4 * 4 + 3]) : 0.0f;
+        if (want_da) {
+          const float4 ua = *reinterpret_cast<const float4*>(&w1a[0][lc + j4 * 4]);
+          const float4 ub = *reinterpret_cast<const float4*>(&w1a[1][lc + j4 * 4]);
+          d0 = fmaf(o[j4].x, ua.x, d0); d0 = fmaf(o[j4].y, ua.y, d0); d0 = fmaf(o[j4].z, ua.z, d0); d0 = fmaf(o[j4].w, ua.w, d0);
+          d1 = fmaf(o[j4].x, ub.x, d1); d1 = fmaf(o[j4].y, ub.y, d1); d1 = fmaf(o[j4].z, ub.z, d1); d1 = fmaf(o[j4].w, ub.w, d1);
+        }
+      }
+      if (store) {
+        uint8_t* b = buf + c * 4096;   // 4 chunks per warp: a buffer each
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(b + lane * 128 + ((j4 ^ (lane & 7)) << 4)) = o[j4];
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&maps.d[0], b, nc, m0 + q * 32, learner);
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      }
+    }
+    if (want_da) {
+      if (hh == 1) { dpart[0][q * 32 + lane] = d0; dpart[1][q * 32 + lane] = d1; }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");        // the 8 epilogue warps
+      if (hh == 0 && erow < p.M) {   // times tanh'(z) = 1 - a^2 (the actor's output layer; EPI_TANH_GRAD of the layer-by-layer path)
+        const float a0 = __ldcg(p.act + lo + (long long)erow * p.ld_act), a1 = __ldcg(p.act + lo + (long long)erow * p.ld_act + 1);
+        const float g0 = (d0 + dpart[0][q * 32 + lane]) * (1.0f - a0 * a0), g1 = (d1 + dpart[1][q * 32 + lane]) * (1.0f - a1 * a1);
+        if (NS == 1) { p.dA[lo + (long long)erow * 2] = g0; p.dA[lo + (long long)erow * 2 + 1] = g1; }
+        else { atomicAdd(p.dA + lo + (long long)erow * 2, g0); atomicAdd(p.dA + lo + (long long)erow * 2 + 1, g1); }   // onto zeros (the host clears dA)
+      }
+    }
+    if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(NC));
+  }
+}
+
 // deterministic second pass of a split-K GEMM: D[m][n] = sum_s W[s][m][n] (fixed order)
 __global__ void __launch_bounds__(256)
 tc_splitk_reduce_kernel(const float* __restrict__ ws, long long split_stride, int splits, float* __restrict__ D, long long n_elems) {
@@ -702,6 +908,8 @@ int tc_gemm_prepare() {
   if ((s = set_smem_attr<true, true>())) return s;
   REQUIRE(get_encode(), SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
   CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
   return SHEMS_OK;
 }
 
@@ -807,6 +1015,41 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
   } else {
     tc_fwd_chain_kernel<<<dim3((unsigned)(mt * a.nprob), (unsigned)pop), FC_THREADS, FC_SMEM, st>>>(maps, a);
   }
+  CUDA_TRY(cudaGetLastError());
+  return SHEMS_OK;
+}
+
+// One launch = the dX chain of a net over the whole minibatch, 128 rows per CTA (see tc_bwd_chain_kernel)
+int tc_bwd_chain(cudaStream_t st, const TcBwdChainArgs& a) {
+  REQUIRE(a.M >= 1 && a.L1 >= 1 && a.L1 <= BC_N && a.L2 >= 1 && a.L2 <= 2 * BC_N && a.L2 % 4 == 0 && (a.J == 1 || a.J == 2), SHEMS_ERR_INVALID,
+          "tc_bwd_chain: M=%d widths %d/%d J=%d outside the kernel's plan (l1 <= 256, l2 <= 512, l2 %% 4 == 0)", a.M, a.L1, a.L2, a.J);
+  REQUIRE(a.dout && a.W3 && a.W2 && a.H2 && a.H1 && a.ldh1 % 32 == 0 && a.ldh2 % 4 == 0 && (!a.dA || (a.W1a && a.act)), SHEMS_ERR_INVALID,
+          "tc_bwd_chain: NULL operand, or activation rows that are not whole 128-byte lines");
+  const int pop = a.pop > 1 ? a.pop : 1;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int s;
+  if ((s = make_tmap(&maps.a[0], a.H2, a.L2, a.M, a.ldh2, BLOCK_K, BLOCK_M, false, pop, a.pop_stride))) return s;   // h2 blocks: K-major, SWIZZLE_128B
+  if (a.DZ2 && (s = make_tmap(&maps.a[1], a.DZ2, a.L2, a.M, a.ldh2, BLOCK_K, BLOCK_M, false, pop, a.pop_stride))) return s;
+  const int tiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int ns = a.nsplit == 2 ? 2 : 1;
+  if ((s = make_tmap(&maps.b[0], a.W2, a.L2, a.L1, a.L2, BLOCK_K, BC_N / ns, false, pop, a.pop_stride))) return s;   // W2 [l1][l2]: K-major B, rows beyond l1 zero
+  if (a.DZ1 && (s = make_tmap_out(&maps.d[0], a.DZ1, a.L1, a.M, pop, a.ldh1, a.pop_stride))) return s;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(tiles * ns), (unsigned)pop); cfg.blockDim = dim3(BC_THREADS); cfg.dynamicSmemBytes = BC_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = a.pdl ? 1 : 0;
+  if (ns == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_bwd_chain_kernel<2>, maps, a));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_bwd_chain_kernel<1>, maps, a));
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }

@@ -48,3 +48,25 @@ struct TcFwdChainArgs {
   int pop; long long pop_stride;   // a population of learners (grid.y): every pointer above moves by pop_stride floats per learner
 };
 int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a);
+
+// The backward pass of a net from its output layer down to layer 1 (the dX chain) for a large minibatch in ONE launch, 128 rows per CTA:
+//   dz2 = (dout W3^T) masked by relu'(h2)        fp32 SIMT, in place on the TMA-loaded h2 tile = the tcgen05 A operand (optionally stored: DZ2)
+//   dz1 = (dz2 W2^T) masked by relu'(h1)         tcgen05, TF32 (optionally stored: DZ1)
+//   dA  = (dz1 W1[rows 9, 10]^T) (1 - a^2)       in the epilogue (critic inside the actor loss: the gradient w.r.t. the action inputs)
+struct TcBwdChainArgs {
+  int M, L1, L2, J, ldh1, ldh2, pdl;
+  int nsplit;             // 2: two CTAs per row tile, half of the layer-1 units each (dA must be zero on entry: the halves add their shares)
+  const float* dout;      // [M][J] gradient w.r.t. the net's output (J = 1 or 2)
+  const float* W3;        // Flux layout [L2][J]
+  const float* W2;        // Flux layout [L1][L2]
+  const float* H2;        // [M][ldh2]
+  const float* H1;        // [M][ldh1]
+  float* DZ2;             // [M][ldh2] or NULL
+  float* DZ1;             // [M][ldh1] or NULL
+  const float* W1a;       // W1 rows of the two action inputs ([2][L1], row stride L1) or NULL
+  const float* act;       // a = tanh output [M] rows, 2 columns, row stride ld_act
+  float* dA;              // [M][2]
+  int ld_act;
+  int pop; long long pop_stride;
+};
+int tc_bwd_chain(cudaStream_t st, const TcBwdChainArgs& a);
