@@ -548,7 +548,7 @@ static inline int round_ld(int x) { return (x + 31) & ~31; }  // activation rows
 #define TC_MIN_ROWS 256
 #endif
 #define SPLITK_MIN_BATCH 1024
-#define CHAIN_MIN_BATCH 4096
+#define CHAIN_MIN_BATCH 2048
 #define SPLITK_MAX 32
 #define WS_COUNTERS 1024
 
@@ -618,8 +618,8 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
   if (h->tc) { int s_ = tc_gemm_prepare(); if (s_) { ddpg_destroy(h); return s_; } }
   {
     const char* ev = getenv("SHEMS_TC_CHAIN");
-    // measured (tools/time_ddpg_large.py): 209 vs 249 us per update at B = 8192, 313 vs 407 at 16384 and 163 vs 171 at 4096, but 157 vs 154 at 3072 and 148 vs 140 at 2048 (few
-    // tiles per net leave the per-tile latency of the chain kernel exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
+    // measured (tools/time_ddpg_large.py): 196 vs 249 us per update at B = 8192, 291 vs 407 at 16384, 153 vs 171 at 4096 and 130 vs 141 at 2048, but 120 vs 116 at 1024 (few
+    // tiles per net leave the per-tile latency of the chain kernels exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
     // a population (grid.y = learner): the same rule on the rows of all learners together
     h->chain = h->tc && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
                (ev ? ev[0] != '0' : (long long)p->batch * pop >= CHAIN_MIN_BATCH);
@@ -1396,6 +1396,8 @@ static inline TcFwdChainArgs chain_args(const Ddpg* h, int nprob) {
   TcFwdChainArgs a; memset(&a, 0, sizeof(a));
   a.M = h->p.batch; a.L1 = h->p.l1; a.L2 = h->p.l2; a.nprob = nprob; a.ldx = 11; a.ldh1 = h->ld1; a.ldh2 = h->ld2;
   a.pop = h->pop; a.pop_stride = h->pop_stride;
+  // few row tiles: two CTAs (a cluster) per tile, half of the layer-2 units each, so that the launch covers the SMs
+  a.nsplit = (long long)((h->p.batch + 127) / 128) * nprob * h->pop * 2 <= 148 ? 2 : 1;
   return a;
 }
 

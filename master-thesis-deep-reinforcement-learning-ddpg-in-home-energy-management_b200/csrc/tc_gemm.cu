@@ -374,21 +374,30 @@ __device__ unsigned long long fc_trace[96];
 #else
 #define FC_STAMP(i) do { } while (0)
 #endif
+// NS = 2: a cluster of two CTAs per row tile, each with 256 of the layer-2 units (half of the W2 stream; layer 1 is computed by both, h1
+// stored by the first); the second CTA hands its share of the output layer's dot products to the first through distributed shared
+// memory.  For launches whose row tiles alone would leave more than half of the SMs idle.
+template <int NS>
 __global__ void __launch_bounds__(FC_THREADS, 1)
 tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p) {
+  constexpr int NCOL = 2 * FC_N / NS;                          // layer-2 units (accumulator columns) of this CTA
+  constexpr int HN = NCOL / FC_N;                              // 256-column MMA halves of this CTA
+  constexpr int BST = FC_BSTAGES * NS, BSTAGE = FC_B_STAGE / NS;   // the W2 ring: the same 128 KB, in slabs of [16 k][NCOL columns]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + FC_A_BYTES;
-  __shared__ uint64_t a_full[FC_ASTAGES], a_empty[FC_ASTAGES], b_full[FC_BSTAGES], b_empty[FC_BSTAGES], acc_full;
+  __shared__ uint64_t a_full[FC_ASTAGES], a_empty[FC_ASTAGES], b_full[BST], b_empty[BST], acc_full;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float w1s[12][FC_KB * BLOCK_K];   // rows 0..K1-1: W1 (zero beyond l1), rows K1..10: zero, row 11: b1 (its input is 1)
   __shared__ __align__(16) float b2s[2 * FC_N];
   __shared__ __align__(16) float w3s[2][2 * FC_N];            // W3[:, j] (zero beyond l2)
   __shared__ float dpart[2][BLOCK_M];                         // the upper column half's share of the output layer's dot products
+  __shared__ float xpart[2][BLOCK_M];                         // NS = 2: the second CTA's share, written by it through DSMEM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int prob = blockIdx.x / mt, m0 = (blockIdx.x - prob * mt) * BLOCK_M;
+  const int bx = blockIdx.x / NS, nh = blockIdx.x % NS;        // nh: which half of the layer-2 units (= the rank in the cluster of two)
+  const int prob = bx / mt, m0 = (bx - prob * mt) * BLOCK_M;
   const int K1 = p.K1[prob], J = p.J[prob];
   const int learner = blockIdx.y;                              // a population: the learner's slab starts lo floats further, TMA coordinate 2
   const long long lo = (long long)learner * p.pop_stride;
@@ -431,42 +440,45 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
 #undef FC_LOAD_X
   if (threadIdx.x == 0) {
     for (int k = 0; k < FC_ASTAGES; ++k) { mbar_init(&a_full[k], 8); mbar_init(&a_empty[k], 1); }   // a_full: one arrival per producer warp
-    for (int s = 0; s < FC_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.b[prob]) : "memory");
-    if (p.H1[prob]) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[prob]) : "memory");
+    if (p.H1[prob] && nh == 0) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.a[prob]) : "memory");
     if (p.H2[prob]) asm volatile("prefetch.tensormap [%0];\n" ::"l"(&maps.d[prob]) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_smem)), "n"(NCOL));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_smem;
+  const int q = warp & 3, erow = m0 + q * 32 + lane;          // epilogue: TMEM lane quarter and row of this thread
+  float d0 = 0.0f, d1 = 0.0f;                                  // its share of the output layer's dot products
+  bool fin = false;                                            // this thread finishes a row (warps 2-5)
 
   if (warp == 0) {
     // ===== TMA producer: W2[16-k slab][all columns] as the MN-major B operand, 16 boxes of {32 columns, 16 k} per slab =====
     if (elect_one()) {
       for (int g = 0; g < nslab; ++g) {
-        const int s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+        const int s = g % BST, ph = (g / BST) & 1;
         mbar_wait(&b_empty[s], ph ^ 1);
         FC_STAMP(g);
-        mbar_expect_tx(&b_full[s], FC_B_STAGE);
-        uint8_t* sb = sB + s * FC_B_STAGE;
+        mbar_expect_tx(&b_full[s], BSTAGE);
+        uint8_t* sb = sB + s * BSTAGE;
 #pragma unroll
-        for (int j = 0; j < 2 * FC_N / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], j * 32, g * FC_BK, learner);
+        for (int j = 0; j < NCOL / 32; ++j) tma_load_3d(sb + j * (FC_BK * 128), &maps.b[prob], &b_full[s], nh * NCOL + j * 32, g * FC_BK, learner);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(FC_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     if (elect_one()) {
-      const bool store_h1 = p.H1[prob] != nullptr;
+      const bool store_h1 = p.H1[prob] != nullptr && nh == 0;
       for (int g = 0; g < nslab; ++g) {
-        const int kb = g >> 1, sa_i = kb % FC_ASTAGES, s = g % FC_BSTAGES, ph = (g / FC_BSTAGES) & 1;
+        const int kb = g >> 1, sa_i = kb % FC_ASTAGES, s = g % BST, ph = (g / BST) & 1;
         if ((g & 1) == 0) {
           mbar_wait(&a_full[sa_i], (kb / FC_ASTAGES) & 1);   // layer-1 producers have written (and fenced) this k-block of the A operand
           if (store_h1 && kb * BLOCK_K < p.ldh1) {          // ... which is also h1[m0 .. m0+127][kb*32 .. +31]: send it to HBM as it lies
@@ -476,9 +488,9 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
         }
         mbar_wait(&b_full[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t sa = smem_u32(sA + sa_i * TILE_BYTES) + (uint32_t)((g & 1) * (FC_BK / UMMA_K) * 32), sb = smem_u32(sB + s * FC_B_STAGE);
+        const uint32_t sa = smem_u32(sA + sa_i * TILE_BYTES) + (uint32_t)((g & 1) * (FC_BK / UMMA_K) * 32), sb = smem_u32(sB + s * BSTAGE);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < HN; ++h) {
 #pragma unroll
           for (int kk = 0; kk < FC_BK / UMMA_K; ++kk) {
             const uint64_t ad = make_smem_desc(sa + kk * 32, 16, 1024, 2);                                  // K-major, SWIZZLE_128B
@@ -527,20 +539,18 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
       }
     }
     // ===== epilogue (the same 8 warps; TMEM lane quarter = warp % 4, column half hh): a thread owns one row of one half =====
-    const int q = warp & 3, hh = cg >> 2;
-    const int erow = m0 + q * 32 + lane;
+    const int hh = cg >> 2;
     uint8_t* buf = sB + cg * (4 * 4096);                      // the W2 ring is idle once the accumulators are final: 4 staging chunks per warp
     const bool store = p.H2[prob] != nullptr;
-    float d0 = 0.0f, d1 = 0.0f;
     mbar_wait(&acc_full, 0);
     if (warp == 2 && lane == 0) FC_STAMP(73);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 #pragma unroll 1
-    for (int c = 0; c < FC_N / 32; ++c) {
-      const int nc = hh * FC_N + c * 32;
+    for (int c = 0; c < NCOL / 64; ++c) {
+      const int lc = hh * (NCOL / 2) + c * 32, nc = nh * NCOL + lc;   // column of this CTA's accumulator / layer-2 unit
       if (nc >= p.L2) break;
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)nc, v);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)lc, v);
       float4 o[8];
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {   // columns beyond l2: accumulator 0 (TMA zero fill), b2 = W3 = 0 -> h2 = 0, no contribution
@@ -571,30 +581,43 @@ tc_fwd_chain_kernel(const __grid_constant__ TcMaps maps, const TcFwdChainArgs p)
     if (warp == 2 && lane == 0) FC_STAMP(74);
     if (hh == 1) { dpart[0][q * 32 + lane] = d0; dpart[1][q * 32 + lane] = d1; }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");          // the 8 epilogue warps
-    if (hh == 0 && erow < p.M) {
-      d0 += dpart[0][q * 32 + lane]; d1 += dpart[1][q * 32 + lane];
-      const float* __restrict__ b3 = p.b3[prob] + lo;
-      const float z0 = d0 + __ldg(b3);
-      if (p.out_mode[prob] == TC_OUT_TANH) {
-        float* o = p.out[prob] + lo + (long long)erow * p.ldo[prob];
-        o[0] = tanhf(z0);
-        if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
-      } else if (p.out_mode[prob] == TC_OUT_ID) {
-        p.out[prob][lo + (long long)erow * p.ldo[prob]] = z0;
-      } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
-        const float y = p.td_r[lo + erow] + (p.gamma * (1.0f - p.td_done[lo + erow])) * z0;
-        p.out[prob][lo + (long long)erow * p.ldo[prob]] = y;
-        p.td_dq[lo + erow] = 2.0f * (p.td_q[lo + erow] - y) * p.inv_batch;
-      }
-    }
+    if (hh == 0) { d0 += dpart[0][q * 32 + lane]; d1 += dpart[1][q * 32 + lane]; fin = true; }
     if (store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-    if (warp == 2 && lane == 0) FC_STAMP(76);
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   }
+  if (NS == 2) {   // the second CTA's share of the dot products -> the first CTA's shared memory; every thread of both CTAs meets at the cluster barrier
+    if (fin && nh == 1) {
+      uint32_t r0, r1;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r0) : "r"(smem_u32(&xpart[0][q * 32 + lane])), "r"(0));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r1) : "r"(smem_u32(&xpart[1][q * 32 + lane])), "r"(0));
+      asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(r0), "f"(d0) : "memory");
+      asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(r1), "f"(d1) : "memory");
+    }
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    if (fin && nh == 0) { d0 += xpart[0][q * 32 + lane]; d1 += xpart[1][q * 32 + lane]; }
+  }
+  if (fin && nh == 0 && erow < p.M) {
+    const float* __restrict__ b3 = p.b3[prob] + lo;
+    const float z0 = d0 + __ldg(b3);
+    if (p.out_mode[prob] == TC_OUT_TANH) {
+      float* o = p.out[prob] + lo + (long long)erow * p.ldo[prob];
+      o[0] = tanhf(z0);
+      if (J == 2) o[1] = tanhf(d1 + __ldg(b3 + 1));
+    } else if (p.out_mode[prob] == TC_OUT_ID) {
+      p.out[prob][lo + (long long)erow * p.ldo[prob]] = z0;
+    } else {  // TC_OUT_TD: y = r + gamma (1 - done) q'; dq = 2 (q - y) / B   (DDPG.jl:133, d mse / d q)
+      const float y = p.td_r[lo + erow] + (p.gamma * (1.0f - p.td_done[lo + erow])) * z0;
+      p.out[prob][lo + (long long)erow * p.ldo[prob]] = y;
+      p.td_dq[lo + erow] = 2.0f * (p.td_q[lo + erow] - y) * p.inv_batch;
+    }
+  }
+  if (warp == 2 && lane == 0) FC_STAMP(76);
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(NCOL));
   }
 }
 
@@ -907,7 +930,8 @@ int tc_gemm_prepare() {
   if ((s = set_smem_attr<true, false>())) return s;
   if ((s = set_smem_attr<true, true>())) return s;
   REQUIRE(get_encode(), SHEMS_ERR_CUDA, "tc_gemm: cuTensorMapEncodeTiled is not available from this driver");
-  CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(tc_bwd_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
   return SHEMS_OK;
@@ -999,22 +1023,29 @@ int tc_fwd_chain(cudaStream_t st, const TcFwdChainArgs& a) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(tc_fwd_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM));
     attr_set = true;
   }
-  const int mt = (a.M + BLOCK_M - 1) / BLOCK_M;
-  if (a.pdl) {   // a programmatic dependent of its predecessor in the stream (captured as such in the update's graph)
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(mt * a.nprob), (unsigned)pop); cfg.blockDim = dim3(FC_THREADS); cfg.dynamicSmemBytes = FC_SMEM; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fwd_chain_kernel, maps, a));
-  } else {
-    tc_fwd_chain_kernel<<<dim3((unsigned)(mt * a.nprob), (unsigned)pop), FC_THREADS, FC_SMEM, st>>>(maps, a);
+  const int mt = (a.M + BLOCK_M - 1) / BLOCK_M, ns = a.nsplit == 2 ? 2 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(mt * a.nprob * ns), (unsigned)pop); cfg.blockDim = dim3(FC_THREADS); cfg.dynamicSmemBytes = FC_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (ns == 2) {   // the two CTAs of a row tile form a cluster (distributed shared memory for the output layer's partial sums)
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (a.pdl) {     // a programmatic dependent of its predecessor in the stream (captured as such in the update's graph)
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  if (ns == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fwd_chain_kernel<2>, maps, a));
+  else CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_fwd_chain_kernel<1>, maps, a));
   CUDA_TRY(cudaGetLastError());
   return SHEMS_OK;
 }
