@@ -531,9 +531,10 @@ def test_fused_peer_exchange_gives_up_on_a_missing_peer(sb, train_series, monkey
         np.testing.assert_array_equal(b0, b1)
 
 
-@pytest.mark.parametrize("batch,tc", [(32, 0), (512, 1)])
+@pytest.mark.parametrize("batch,tc", [(32, 0), (512, 1), (2048, 1)])
 def test_fused_peer_allreduce_two_processes(batch, tc):
-    """(512, 1): the large-batch tensor-core path under the fused exchange.  Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
+    """(512, 1): the large-batch tensor-core path under the fused exchange; (2048, 1): with the forward / backward chain kernels and their
+    programmatic dependent launches behind the exchange kernels.  Two ranks as two processes (torch.distributed.run, gloo for the handle exchange; CUDA IPC for the gradients): replicas
     bit-identical and equal to one learner on the full minibatch — checked inside tests/dp_worker.py.  On a one-GPU box both
     ranks share the device (time-sliced contexts): the same IPC code path, just slower."""
     import os
