@@ -408,8 +408,11 @@ def test_learned_returns_match_oracle_at_reference_shape(sb, O, train_series, ch
 @pytest.mark.parametrize("B,l1,l2", [(1024, 250, 500), (8192, 250, 500), (1000, 250, 500), (384, 64, 128), (2048, 256, 512)])
 def test_forward_chain_kernel_equals_layerwise_path(sb, train_series, monkeypatch, B, l1, l2):
     """tc_fwd_chain_kernel (layer 1 by SIMT into the swizzled A operand, tcgen05 layer 2, output layer in the epilogue: one kernel per
-    net) against the layer-by-layer tensor-core path (l1_fwd + tc_gemm + gemm_skinny): same TF32 products in the same k order, so
-    activations agree to fp32 rounding of the output layer's differently ordered dot product; one whole update is compared."""
+    net; with few row tiles a cluster of two CTAs per tile) and tc_bwd_chain_kernel (the dX chain through the critic in the actor pass:
+    dz2 in place on the TMA-loaded h2 block, tcgen05 against W2, relu' mask and the action rows of W1 in the epilogue) against the
+    layer-by-layer tensor-core path (l1_fwd + tc_gemm + gemm_skinny, outer_mask + tc_gemm + gemm_skinny): same TF32 products in the same k
+    order, so activations agree to fp32 rounding of the differently ordered thin dot products; one whole update is compared.  The shapes
+    cover one and two CTAs per tile, ragged last tiles (1000 rows), narrow nets and the widest ones the kernels take."""
     mem = _memory(sb, train_series, n=256, seed=4)
     mn, mx = mem.min_max_buffer(len(mem), rng_mm=1)
     idx = np.random.default_rng(1).integers(0, len(mem), B).astype(np.int32)
