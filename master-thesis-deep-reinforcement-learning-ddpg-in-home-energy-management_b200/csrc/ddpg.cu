@@ -622,7 +622,7 @@ extern "C" int32_t ddpg_create(const DdpgParams* p, int32_t device, Ddpg** out) 
     // tiles per net leave the per-tile latency of the chain kernels exposed) — on from CHAIN_MIN_BATCH rows; SHEMS_TC_CHAIN=0 / 1 forces it off / on
     // a population (grid.y = learner): the same rule on the rows of all learners together
     h->chain = h->tc && p->l1 <= 256 && p->l2 <= 512 && p->l2 % 4 == 0 &&
-               (ev ? ev[0] != '0' : (long long)p->batch * pop >= CHAIN_MIN_BATCH);
+               (ev ? ev[0] != '0' : (long long)p->batch * pop >= (pop > 1 ? CHAIN_MIN_BATCH / 2 : CHAIN_MIN_BATCH));   // populations: 10 x 120 rows already win (132 vs 135 us)
   }
   // one slab per learner: every buffer is carved at a 256-byte boundary (TMA operands, float4 accesses)
   const long long na = h->dims[0].n_params, nc = h->dims[1].n_params;
